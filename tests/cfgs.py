@@ -1,0 +1,68 @@
+"""Shared test configurations ("mini" = the reference architecture at reduced width/depth).
+
+The mini UNet keeps the head dims of the real model (d = 40 / 80 / 160 / 160) by using 4 heads on
+(160, 320, 640, 640) channels, so the same kernel instantiations run in the tests as at full size.
+"""
+import torch
+
+from oracle.ref_ddim import default_scheduler_config
+from oracle.ref_unet import default_unet_config
+from oracle.ref_vae import default_vae_config
+
+CLIP_DIM = 1024
+MINI_UNET_VARIANTS = ("base", "ip", "cam")
+MINI_VAE = default_vae_config(block_out_channels=(32, 64, 128, 128), layers_per_block=1)
+SCHED_V = default_scheduler_config()
+SCHED_EPS = default_scheduler_config(prediction_type="epsilon", rescale_betas_zero_snr=False)
+
+_MM = dict(num_attention_heads=4, num_transformer_block=1, attention_block_types=("Temporal_Self", "Temporal_Self"),
+           temporal_position_encoding=True, temporal_position_encoding_max_len=24, temporal_attention_dim_div=1,
+           zero_initialize=True)
+
+
+def mini_unet_ref_kwargs(variant):
+    """Constructor kwargs accepted both by the reference UNet3DConditionModel (unet.py:43-103) and by ours."""
+    kw = dict(sample_size=16, in_channels=4, out_channels=4, block_out_channels=(160, 320, 640, 640),
+              layers_per_block=1, attention_head_dim=4, cross_attention_dim=768, norm_num_groups=32,
+              use_motion_module=True, motion_module_resolutions=(1, 2, 4, 8), unet_use_cross_frame_attention=False,
+              unet_use_temporal_attention=False, motion_module_type="Vanilla", motion_module_kwargs=dict(_MM))
+    if variant == "base":          # configs/inference/inference_img_embed_mask_condition_zero_snr_.yaml
+        kw.update(use_fps_condition=True, use_first_frame_mask_condition_concat=True)
+    elif variant == "ip":          # cfg3: base + IP-Adapter cross attention
+        kw.update(use_fps_condition=True, use_first_frame_mask_condition_concat=True,
+                  use_ip_cross_attention=True, scale=0.25, num_tokens=4)
+    elif variant == "cam":         # cfg5: training_magic_..._lora_32f_from_244k.yaml:7-38
+        mm = dict(_MM, temporal_position_encoding_max_len=32, add_temporal_lora=True, rank=4)
+        kw.update(use_ip_cross_attention=True, image_condition_dim=1024, scale=0.2, num_tokens=4,
+                  use_camera_motion_condition=True, motion_module_kwargs=mm, layers_per_block=2)
+    else:
+        raise KeyError(variant)
+    return kw
+
+
+def mini_unet_oracle_cfg(variant):
+    kw = mini_unet_ref_kwargs(variant)
+    mm = {k: v for k, v in kw["motion_module_kwargs"].items() if k != "zero_initialize"}
+    return default_unet_config(
+        block_out_channels=kw["block_out_channels"], layers_per_block=kw["layers_per_block"],
+        attention_head_dim=kw["attention_head_dim"], motion_module_kwargs=mm,
+        use_first_frame_mask_condition_concat=kw.get("use_first_frame_mask_condition_concat", False),
+        use_fps_condition=kw.get("use_fps_condition", False),
+        use_ip_cross_attention=kw.get("use_ip_cross_attention", False),
+        scale=kw.get("scale", 1.0), num_tokens=kw.get("num_tokens", 4),
+        use_camera_motion_condition=kw.get("use_camera_motion_condition", False))
+
+
+def unet_inputs(variant, b=2, f=4, h=16, w=16, seed=11):
+    g = torch.Generator().manual_seed(seed)
+    cin = 9 if variant in ("base", "ip") else 4
+    d = dict(sample=torch.randn(b, cin, f, h, w, generator=g), timestep=torch.tensor(501),
+             ctx=torch.randn(b, 77, 768, generator=g))
+    if variant in ("base", "ip"):
+        d["fps"] = torch.tensor([2, 2])
+        d["flow"] = torch.tensor([4, 4])
+    if variant in ("ip", "cam"):
+        d["clip"] = torch.randn(b, CLIP_DIM, generator=g)
+    if variant == "cam":
+        d["camera"] = torch.tensor([3, 3])
+    return d
