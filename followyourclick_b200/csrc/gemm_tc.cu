@@ -1,0 +1,522 @@
+// tcgen05 (5th-gen tensor core) GEMM / implicit-GEMM 3x3 convolution for sm_100a.
+//
+//   out[p, n] = epilogue( alpha * sum_{tap, c} X[pixel(p) + (dy,dx)(tap), c] * W[n, tap, c] )
+//
+// One persistent CTA per SM, 6 warps, warp-specialised:
+//   warp 0 (1 lane)  TMA producer : cp.async.bulk.tensor (4-D box for the activation patch, 3-D box for the weight
+//                                   slab) into a 4-stage 128B-swizzled shared-memory ring, mbarrier expect_tx
+//   warp 1 (1 lane)  MMA issuer   : tcgen05.mma.cta_group::1.kind::f16  128 x BN x 16, bf16 x bf16 -> fp32 in TMEM,
+//                                   tcgen05.commit releases smem stages / publishes the accumulator
+//   warps 2..5       epilogue     : tcgen05.ld (32x32b) TMEM -> registers, fused bias / time-embedding row bias /
+//                                   residual / GEGLU / alpha, vectorised global stores; double-buffered TMEM
+//                                   accumulators (2 x 256 columns) overlap the epilogue with the next tile's MMAs.
+// The 3x3 convolution never builds an im2col matrix: for each filter tap the producer loads the SAME 4-D box shifted
+// by (dy, dx); TMA's out-of-bounds zero fill implements the padding halo.  A plain GEMM is the 1-tap special case.
+// Stride-2 convolutions run on a parity-plane split of the input (fyc_space_to_planes), which turns every tap into
+// a unit-stride shifted read of one plane (tap_img selects the plane).
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128;            // UMMA M (rows = output pixels per tile)
+constexpr int BK = 64;             // K per stage = one 128-byte swizzle row of bf16
+constexpr int STAGES = 4;
+constexpr int MAX_BN = 256;
+constexpr int A_BYTES = BM * BK * 2;           // 16 KB
+constexpr int B_BYTES = MAX_BN * BK * 2;       // 32 KB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int NUM_THREADS = 192;
+
+struct TcParams {
+  // problem
+  int64_t M;                 // valid output rows (pixels)
+  int N, N_out;              // accumulator columns / stored columns (N/2 for GEGLU)
+  int taps, cin_blocks;      // K loop = taps x cin_blocks
+  int BN, n_tiles;
+  // output-pixel tiling: tile = bn images x bh rows x bw cols; Wt = ceil(Wo / bw) tiles per row, etc.
+  int bw, bh, bn, Wo, Ho, w_tiles, h_tiles;
+  int64_t m_tiles;
+  int tap_dy[9], tap_dx[9], tap_img[9];
+  // epilogue
+  const float* bias; const void* residual; const float* rowbias; void* out;
+  int64_t ldo, ldr, rows_per_group;
+  float alpha;
+  int flags;
+};
+
+// ---------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra.uni WAIT_DONE;\n\t"
+      "bra.uni WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T   (both operands K-major, 128B swizzle)
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);          // start address        bits [0,14)
+  d |= (uint64_t)0 << 16;                            // leading byte offset  bits [16,30)  (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset   bits [32,46)
+  d |= (uint64_t)1 << 46;                            // descriptor version 1 (Blackwell) bits [46,48)
+  d |= (uint64_t)2 << 61;                            // layout type SWIZZLE_128B         bits [61,64)
+  return d;
+}
+
+// ---------------------------------------------------------------------------------------------- kernel
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024 - (raw & 1023)) & 1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full = bars;                  // [STAGES]
+  uint64_t* empty = bars + STAGES;        // [STAGES]
+  uint64_t* tfull = bars + 2 * STAGES;    // [2]
+  uint64_t* tempty = bars + 2 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t num_tiles = p.m_tiles * p.n_tiles;
+  const int k_iters = p.taps * p.cin_blocks;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {   // TMEM: all 512 columns (2 accumulator stages x 256); this warp also frees them
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      const uint32_t tx_bytes = A_BYTES + (uint32_t)p.BN * BK * 2;
+      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int n_blk = (int)(tile % p.n_tiles);
+        const int64_t m_blk = tile / p.n_tiles;
+        const int wt = (int)(m_blk % p.w_tiles);
+        const int ht = (int)((m_blk / p.w_tiles) % p.h_tiles);
+        const int it = (int)(m_blk / ((int64_t)p.w_tiles * p.h_tiles));
+        const int ow0 = wt * p.bw, oh0 = ht * p.bh, img0 = it * p.bn;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          for (int cb = 0; cb < p.cin_blocks; ++cb) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            uint8_t* sa = smem + stage * STAGE_BYTES;
+            mbar_expect_tx(&full[stage], tx_bytes);
+            tma_load_4d(&map_a, &full[stage], sa, cb * BK, ow0 + p.tap_dx[tap], oh0 + p.tap_dy[tap], img0 + p.tap_img[tap]);
+            tma_load_3d(&map_w, &full[stage], sa + A_BYTES, cb * BK, tap, n_blk * p.BN);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================== MMA issuer
+    if (lane == 0) {
+      // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, K-major both, N>>3, M>>4
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t aphase = 0;
+      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[acc], aphase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * MAX_BN;
+        for (int k = 0; k < k_iters; ++k) {
+          mbar_wait(&full[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint64_t a_desc = make_sw128_desc(sa);
+          const uint64_t b_desc = make_sw128_desc(sa + A_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            // advance 16 elements (32 B) along K inside the 128B swizzle atom: +2 in the (addr >> 4) field
+            umma_bf16(d_tmem, a_desc + (uint64_t)(2 * kk), b_desc + (uint64_t)(2 * kk), idesc, (k > 0 || kk > 0) ? 1u : 0u);
+          }
+          tcgen05_commit(&empty[stage]);                     // frees the smem stage when these MMAs retire
+          if (k == k_iters - 1) tcgen05_commit(&tfull[acc]); // accumulator complete
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; aphase ^= 1; }
+      }
+    }
+  } else {
+    // ================================================================== epilogue (warps 2..5)
+    const int quarter = warp & 3;                      // TMEM lane quarter this warp may access
+    const int r = quarter * 32 + lane;                 // row of the tile handled by this thread
+    int acc = 0; uint32_t aphase = 0;
+    const bool geglu = (p.flags & FYC_EPI_GEGLU) != 0;
+    const bool out_f32 = (p.flags & FYC_EPI_OUT_F32) != 0;
+    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int n_blk = (int)(tile % p.n_tiles);
+      const int64_t m_blk = tile / p.n_tiles;
+      const int wt = (int)(m_blk % p.w_tiles);
+      const int ht = (int)((m_blk / p.w_tiles) % p.h_tiles);
+      const int it = (int)(m_blk / ((int64_t)p.w_tiles * p.h_tiles));
+      // row r of the tile = (image il, row hl, col wl) of the patch
+      const int wl = r % p.bw, hl = (r / p.bw) % p.bh, il = r / (p.bw * p.bh);
+      const int ow = wt * p.bw + wl, oh = ht * p.bh + hl, img = it * p.bn + il;
+      const int64_t pix = ((int64_t)img * p.Ho + oh) * p.Wo + ow;
+      const bool row_ok = (ow < p.Wo) && (oh < p.Ho) && (pix < p.M);
+      mbar_wait(&tfull[acc], aphase);
+      tcgen05_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * MAX_BN;
+      const int n0 = n_blk * p.BN;
+      const float* rb = (p.flags & FYC_EPI_ROWBIAS) ? p.rowbias + (row_ok ? pix / p.rows_per_group : 0) * p.N : nullptr;
+      if (!geglu) {
+        for (int c = 0; c < p.BN; c += 16) {
+          float v[16];
+          tmem_ld16(taddr + c, v);
+          const int n = n0 + c;
+          if (row_ok && n < p.N) {     // N is a multiple of 16 on this path
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] *= p.alpha;
+            if (p.flags & FYC_EPI_BIAS) {
+#pragma unroll
+              for (int i = 0; i < 16; i += 4) {
+                float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + i));
+                v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+              }
+            }
+            if (rb) {
+#pragma unroll
+              for (int i = 0; i < 16; i += 4) {
+                float4 b = __ldg(reinterpret_cast<const float4*>(rb + n + i));
+                v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+              }
+            }
+            if (p.flags & FYC_EPI_RESIDUAL) {
+              float f[16];
+              if (out_f32) {
+                Vec8<float>::load(reinterpret_cast<const float*>(p.residual) + pix * p.ldr + n, f);
+                Vec8<float>::load(reinterpret_cast<const float*>(p.residual) + pix * p.ldr + n + 8, f + 8);
+              } else {
+                Vec8<bf16>::load(reinterpret_cast<const bf16*>(p.residual) + pix * p.ldr + n, f);
+                Vec8<bf16>::load(reinterpret_cast<const bf16*>(p.residual) + pix * p.ldr + n + 8, f + 8);
+              }
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] += f[i];
+            }
+            if (out_f32) {
+              float* o = reinterpret_cast<float*>(p.out) + pix * p.ldo + n;
+              Vec8<float>::store(o, v); Vec8<float>::store(o + 8, v + 8);
+            } else {
+              bf16* o = reinterpret_cast<bf16*>(p.out) + pix * p.ldo + n;
+              Vec8<bf16>::store(o, v); Vec8<bf16>::store(o + 8, v + 8);
+            }
+          }
+        }
+      } else {
+        // GEGLU: columns [0,128) of the tile are `a`, [128,256) the matching `gate` (weight rows pre-interleaved)
+        for (int c = 0; c < 128; c += 16) {
+          float a[16], g[16];
+          tmem_ld16(taddr + c, a);
+          tmem_ld16(taddr + 128 + c, g);
+          if (row_ok) {
+            const int n = n0 + c;
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              float4 ba = __ldg(reinterpret_cast<const float4*>(p.bias + n + i));
+              float4 bg = __ldg(reinterpret_cast<const float4*>(p.bias + n + 128 + i));
+              a[i] += ba.x; a[i + 1] += ba.y; a[i + 2] += ba.z; a[i + 3] += ba.w;
+              g[i] += bg.x; g[i + 1] += bg.y; g[i + 2] += bg.z; g[i + 3] += bg.w;
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) a[i] *= gelu_erf_f(g[i]);
+            bf16* o = reinterpret_cast<bf16*>(p.out) + pix * p.ldo + n_blk * 128 + c;
+            Vec8<bf16>::store(o, a); Vec8<bf16>::store(o + 8, a + 8);
+          }
+        }
+      }
+      tcgen05_fence_before();
+      mbar_arrive(&tempty[acc]);
+      if (++acc == 2) { acc = 0; aphase ^= 1; }
+    }
+  }
+  __syncwarp();
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// parity-plane split for stride-2 convolutions: x [NB, H, W, C] -> planes [4, NB, H/2, W/2, C], plane = 2*(h&1) + (w&1)
+__global__ void space_to_planes_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int64_t NB, int64_t H, int64_t W, int64_t C) {
+  const int64_t cv = C / 8, H2 = H / 2, W2 = W / 2;
+  const int64_t total = NB * H * W * cv;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t c = (i % cv) * 8; int64_t t = i / cv;
+    int64_t w = t % W; t /= W;
+    int64_t h = t % H; int64_t n = t / H;
+    int64_t plane = 2 * (h & 1) + (w & 1);
+    bf16* dst = out + ((((plane * NB + n) * H2) + h / 2) * W2 + w / 2) * C + c;
+    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(x + i * 8);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    else
+      (void)cudaGetLastError();
+  }
+  return fn;
+}
+
+int32_t encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box) {
+  EncodeTiledFn fn = get_encode_fn();
+  FYC_CHECK(fn != nullptr, "tcgen05 path: cuTensorMapEncodeTiled driver entry point unavailable");
+  cuuint64_t gdim[5]; cuuint64_t gstr[4]; cuuint32_t bx[5]; cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FYC_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu %llu %llu %llu)", (int)r, rank,
+            (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)(rank > 2 ? dims[2] : 0),
+            (unsigned long long)(rank > 3 ? dims[3] : 0));
+  return FYC_OK;
+}
+
+int pick_bn(int64_t N, bool geglu) {
+  if (geglu) return 256;
+  for (int bn = 256; bn >= 64; bn -= 16)
+    if (N % bn == 0) return bn;
+  if (N <= 256) return (int)N;          // N % 16 == 0 checked by the caller
+  return 256;                           // ragged last tile (guarded stores)
+}
+
+int32_t launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, const TcParams& p, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    FYC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  int64_t tiles = p.m_tiles * p.n_tiles;
+  int grid = (int)(tiles < fyc_sm_count() ? tiles : fyc_sm_count());
+  gemm_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mw, p);
+  FYC_LAUNCH_CHECK();
+  return FYC_OK;
+}
+
+}  // namespace
+
+extern "C" int32_t fyc_tcgen05_available(void) { return get_encode_fn() != nullptr ? 1 : 0; }
+
+// Is this GEMM eligible for the tensor-core path?
+bool fyc_gemm_tc_eligible(const fyc_gemm_args* g) {
+  if (g->dtype != FYC_BF16) return false;
+  if (g->K % 8 || g->lda % 8 || g->ldw % 8 || g->N % 16 || g->M < 64) return false;
+  if (((uintptr_t)g->A | (uintptr_t)g->W) & 15) return false;
+  if (g->batch > 1 && ((g->strideA | g->strideW | g->strideO) % 8)) return false;
+  const int64_t n_out = (g->epilogue & FYC_EPI_GEGLU) ? g->N / 2 : g->N;
+  if (g->ldo % 8 || ((uintptr_t)g->out & 15)) return false;
+  if ((g->epilogue & FYC_EPI_RESIDUAL) && (g->ldr % 8 || ((uintptr_t)g->residual & 15))) return false;
+  if ((g->epilogue & FYC_EPI_GEGLU) && (g->N % 256 || !(g->epilogue & FYC_EPI_BIAS) || (g->epilogue & ~(FYC_EPI_GEGLU | FYC_EPI_BIAS)))) return false;
+  if ((g->epilogue & FYC_EPI_BIAS) && ((uintptr_t)g->bias & 15)) return false;
+  if ((g->epilogue & FYC_EPI_ROWBIAS) && ((uintptr_t)g->rowbias & 15)) return false;
+  (void)n_out;
+  return get_encode_fn() != nullptr;
+}
+
+int32_t fyc_gemm_tc(const fyc_gemm_args* g, cudaStream_t st) {
+  FYC_CHECK(fyc_gemm_tc_eligible(g), "gemm(tcgen05): shape/alignment not eligible (M=%lld N=%lld K=%lld)", (long long)g->M,
+            (long long)g->N, (long long)g->K);
+  const bool geglu = (g->epilogue & FYC_EPI_GEGLU) != 0;
+  const bool f32 = (g->epilogue & FYC_EPI_OUT_F32) != 0;
+  for (int64_t b = 0; b < g->batch; ++b) {
+    const bf16* A = (const bf16*)g->A + b * g->strideA;
+    const bf16* W = (const bf16*)g->W + b * g->strideW;
+    CUtensorMap ma, mw;
+    {
+      uint64_t dims[4] = {(uint64_t)g->K, (uint64_t)g->M, 1, 1};
+      uint64_t str[3] = {(uint64_t)g->lda * 2, (uint64_t)g->lda * 2 * (uint64_t)g->M, (uint64_t)g->lda * 2 * (uint64_t)g->M};
+      uint32_t box[4] = {BK, BM, 1, 1};
+      int32_t rc = encode_map(&ma, A, 4, dims, str, box);
+      if (rc) return rc;
+    }
+    TcParams p{};
+    p.M = g->M; p.N = (int)g->N; p.N_out = geglu ? (int)g->N / 2 : (int)g->N;
+    p.taps = 1; p.cin_blocks = (int)ceil_div64(g->K, BK);
+    p.BN = pick_bn(g->N, geglu); p.n_tiles = (int)ceil_div64(g->N, p.BN);
+    p.bw = BM; p.bh = 1; p.bn = 1; p.Wo = (int)g->M; p.Ho = 1;
+    p.w_tiles = (int)ceil_div64(g->M, BM); p.h_tiles = 1; p.m_tiles = p.w_tiles;
+    p.tap_dy[0] = p.tap_dx[0] = p.tap_img[0] = 0;
+    {
+      uint64_t dims[3] = {(uint64_t)g->K, 1, (uint64_t)g->N};
+      uint64_t str[2] = {(uint64_t)g->ldw * 2, (uint64_t)g->ldw * 2};
+      uint32_t box[3] = {BK, 1, (uint32_t)p.BN};
+      int32_t rc = encode_map(&mw, W, 3, dims, str, box);
+      if (rc) return rc;
+    }
+    FYC_CHECK(g->M < (1ll << 31), "gemm(tcgen05): M too large");
+    p.bias = g->bias; p.rowbias = g->rowbias; p.rows_per_group = g->rows_per_group > 0 ? g->rows_per_group : 1;
+    p.residual = g->residual ? (f32 ? (const void*)((const float*)g->residual + b * g->strideO) : (const void*)((const bf16*)g->residual + b * g->strideO)) : nullptr;
+    p.out = f32 ? (void*)((float*)g->out + b * g->strideO) : (void*)((bf16*)g->out + b * g->strideO);
+    p.ldo = g->ldo; p.ldr = g->ldr; p.alpha = g->alpha; p.flags = g->epilogue;
+    int32_t rc = launch_tc(ma, mw, p, st);
+    if (rc) return rc;
+  }
+  return FYC_OK;
+}
+
+// Tile shape for a conv output of Ho x Wo over NB images: bw*bh*bn == 128, all dividing evenly.
+static bool pick_patch(int64_t NB, int64_t Ho, int64_t Wo, int* bw, int* bh, int* bn) {
+  int w = 1; while (w < 128 && Wo % (w * 2) == 0) w *= 2;
+  int h = 1; while (w * h < 128 && Ho % (h * 2) == 0) h *= 2;
+  int n = 128 / (w * h);
+  if (w * h * n != 128 || NB % n != 0) return false;
+  *bw = w; *bh = h; *bn = n;
+  return true;
+}
+
+bool fyc_conv3x3_tc_eligible(const fyc_conv3x3_args* c) {
+  if (c->dtype != FYC_BF16 || c->upsample != 1) return false;
+  if (c->stride != 1 && c->stride != 2) return false;
+  if (c->Cin % 8 || c->Cout % 16) return false;
+  if (c->stride == 2 && (c->H % 2 || c->W % 2)) return false;
+  if (((uintptr_t)c->x | (uintptr_t)c->w | (uintptr_t)c->out) & 15) return false;
+  if ((c->epilogue & FYC_EPI_RESIDUAL) && ((uintptr_t)c->residual & 15)) return false;
+  if (c->epilogue & FYC_EPI_GEGLU) return false;
+  int bw, bh, bn;
+  if (!pick_patch(c->NB, c->H / c->stride, c->W / c->stride, &bw, &bh, &bn)) return false;
+  return get_encode_fn() != nullptr;
+}
+
+// x for stride 2 must already be the parity-plane split (see fyc_space_to_planes); H, W are the ORIGINAL dims.
+int32_t fyc_conv3x3_tc(const fyc_conv3x3_args* c, const void* x_planes, cudaStream_t st) {
+  FYC_CHECK(fyc_conv3x3_tc_eligible(c), "conv3x3(tcgen05): shape/alignment not eligible");
+  const int s = c->stride;
+  const int64_t Ho = c->H / s, Wo = c->W / s;
+  const bool f32 = (c->epilogue & FYC_EPI_OUT_F32) != 0;
+  TcParams p{};
+  pick_patch(c->NB, Ho, Wo, &p.bw, &p.bh, &p.bn);
+  p.M = c->NB * Ho * Wo; p.N = (int)c->Cout; p.N_out = p.N;
+  p.taps = 9; p.cin_blocks = (int)ceil_div64(c->Cin, BK);
+  p.BN = pick_bn(c->Cout, false); p.n_tiles = (int)ceil_div64(c->Cout, p.BN);
+  p.Wo = (int)Wo; p.Ho = (int)Ho; p.w_tiles = (int)(Wo / p.bw); p.h_tiles = (int)(Ho / p.bh);
+  p.m_tiles = (int64_t)p.w_tiles * p.h_tiles * (c->NB / p.bn);
+  CUtensorMap ma, mw;
+  const void* xa = c->x;
+  uint64_t imgs = (uint64_t)c->NB;
+  for (int t = 0; t < 9; ++t) {
+    int kh = t / 3, kw = t % 3;
+    if (s == 1) { p.tap_dy[t] = kh - 1; p.tap_dx[t] = kw - 1; p.tap_img[t] = 0; }
+    else {   // ih = 2*oh + kh - 1: kh=0 -> odd plane, row oh-1; kh=1 -> even plane, row oh; kh=2 -> odd plane, row oh
+      int ph = (kh == 1) ? 0 : 1, pw = (kw == 1) ? 0 : 1;
+      p.tap_dy[t] = (kh == 0) ? -1 : 0; p.tap_dx[t] = (kw == 0) ? -1 : 0;
+      p.tap_img[t] = (2 * ph + pw) * (int)c->NB;
+    }
+  }
+  if (s == 2) { xa = x_planes; imgs = 4ull * c->NB; FYC_CHECK(x_planes != nullptr, "conv3x3(tcgen05): stride 2 needs the plane-split input"); }
+  {
+    uint64_t dims[4] = {(uint64_t)c->Cin, (uint64_t)Wo, (uint64_t)Ho, imgs};
+    uint64_t str[3] = {(uint64_t)c->Cin * 2, (uint64_t)c->Cin * 2 * Wo, (uint64_t)c->Cin * 2 * Wo * Ho};
+    uint32_t box[4] = {BK, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
+    int32_t rc = encode_map(&ma, xa, 4, dims, str, box);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)c->Cin, 9, (uint64_t)c->Cout};
+    uint64_t str[2] = {(uint64_t)c->Cin * 2, (uint64_t)c->Cin * 2 * 9};
+    uint32_t box[3] = {BK, 1, (uint32_t)p.BN};
+    int32_t rc = encode_map(&mw, c->w, 3, dims, str, box);
+    if (rc) return rc;
+  }
+  p.bias = c->bias; p.rowbias = c->rowbias; p.residual = c->residual; p.out = c->out;
+  p.rows_per_group = (c->images_per_group > 0 ? c->images_per_group : 1) * Ho * Wo;
+  p.ldo = c->Cout; p.ldr = c->Cout; p.alpha = 1.0f; p.flags = c->epilogue;
+  (void)f32;
+  return launch_tc(ma, mw, p, st);
+}
+
+int32_t fyc_space_to_planes(const void* x, void* out, int64_t NB, int64_t H, int64_t W, int64_t C, cudaStream_t st) {
+  FYC_CHECK(H % 2 == 0 && W % 2 == 0 && C % 8 == 0, "space_to_planes: H, W must be even and C a multiple of 8");
+  int64_t total = NB * H * W * C / 8;
+  int64_t blocks = ceil_div64(total, 256), cap = (int64_t)fyc_sm_count() * 16;
+  space_to_planes_kernel<<<(unsigned)(blocks > cap ? cap : blocks), 256, 0, st>>>((const bf16*)x, (bf16*)out, NB, H, W, C);
+  FYC_LAUNCH_CHECK();
+  return FYC_OK;
+}

@@ -1,0 +1,170 @@
+/*
+ * libfyc_sm100a.so - C ABI of the B200-native FollowYourClick denoising engine.
+ *
+ * The reference (mayuelala/FollowYourClick) has no FFI: every GPU instruction it issues comes from
+ * PyTorch/cuDNN/cuBLAS call sites inside Python modules.  Each entry point below replaces one family of
+ * those call sites (cited as reference file:line, relative to the reference repo root); the Python classes
+ * in followyourclick_b200/ keep the reference call surface and hand raw device pointers to these functions.
+ *
+ * Conventions:
+ *   - caller owns every buffer (inputs, outputs, workspace); the library never allocates device memory,
+ *     never synchronises, never touches the default stream: all work is enqueued on `stream`;
+ *   - return value 0 = OK, non-zero = error, message via fyc_last_error() (thread-local);
+ *   - activations are channels-last "tokens": [images(B*F), H*W, C] contiguous unless a leading dimension
+ *     is passed; `dtype` selects the storage type of activations/weights (accumulation is always fp32);
+ *   - small per-channel vectors (bias, norm gamma/beta) are always fp32.
+ */
+#ifndef FYC_H_
+#define FYC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FYC_VERSION 100 /* 0.1.0 */
+
+enum { FYC_OK = 0, FYC_ERR_INVALID = 1, FYC_ERR_CUDA = 2, FYC_ERR_UNSUPPORTED = 3 };
+enum { FYC_F32 = 0, FYC_BF16 = 1 };
+/* GEMM / conv implementation selector */
+enum { FYC_IMPL_AUTO = 0, FYC_IMPL_SIMT = 1, FYC_IMPL_TCGEN05 = 2 };
+/* epilogue flags */
+enum {
+  FYC_EPI_BIAS = 1,      /* + bias[n]                                  */
+  FYC_EPI_RESIDUAL = 2,  /* + residual[m, n]                           */
+  FYC_EPI_ROWBIAS = 4,   /* + rowbias[m / rows_per_group, n]  (time embedding broadcast, resnet.py:307,319) */
+  FYC_EPI_GEGLU = 8,     /* out[m, j] = a * gelu_erf(gate); weight rows pre-interleaved in 128-col granules */
+  FYC_EPI_OUT_F32 = 16   /* write fp32 output regardless of `dtype`    */
+};
+enum { FYC_PRED_EPSILON = 0, FYC_PRED_SAMPLE = 1, FYC_PRED_V = 2 };
+
+int32_t fyc_version(void);
+const char* fyc_last_error(void);
+/* 1 if the tcgen05/TMA kernels can run (driver entry point for cuTensorMapEncodeTiled resolved). */
+int32_t fyc_tcgen05_available(void);
+
+/* ---- linear / 1x1 conv / batched matmul ---------------------------------------------------------------
+ * out[b][m, n] = alpha * sum_k A[b][m, k] * W[b][n, k]  (+ epilogue).  Replaces F.linear / 1x1 F.conv2d /
+ * baddbmm call sites: diffusers/models/attention.py:560-569,654-660,672 (q,k,v,out, scores), :733-821 (FF),
+ * animatediff/models/attention.py:182,215 (proj_in/out), resnet.py:286 (shortcut), motion_module.py:128,155.
+ * A: [M, K] lda; W: [N, K] ldw; out: [M, N_out] ldo where N_out = N (or N/2 with FYC_EPI_GEGLU).
+ */
+typedef struct {
+  const void* A; const void* W; void* out;
+  const float* bias;            /* [N] fp32 (FYC_EPI_BIAS) */
+  const void* residual;         /* [M, N_out] ldr, same dtype as out unless residual_f32 */
+  const float* rowbias;         /* [M / rows_per_group, N] fp32 (FYC_EPI_ROWBIAS) */
+  int64_t M, N, K;
+  int64_t lda, ldw, ldo, ldr;
+  int64_t batch, strideA, strideW, strideO;   /* batch >= 1; strides in elements */
+  int64_t rows_per_group;
+  float alpha;
+  int32_t dtype, epilogue, impl;
+} fyc_gemm_args;
+int32_t fyc_gemm(const fyc_gemm_args* a, void* stream);
+
+/* ---- 3x3 convolution as implicit GEMM (NHWC) ----------------------------------------------------------
+ * Replaces InflatedConv3d / nn.Conv2d 3x3 call sites: animatediff/models/resnet.py:19-27,245,270,
+ * unet.py:124,351, Downsample3D resnet.py:184 (stride 2), Upsample3D :155,168 (nearest x2 folded into the
+ * input index), diffusers/models/vae.py:160,205, resnet.py:407,423, Upsample2D :139.
+ * x: [NB, H, W, Cin]; w: [Cout, 3, 3, Cin] (re-packed once from the reference [Cout, Cin, 3, 3]);
+ * out: [NB, Ho, Wo, Cout], Ho = (H*up + 2 - 3)/stride + 1.
+ */
+typedef struct {
+  const void* x; const void* w; void* out;
+  const float* bias; const void* residual; const float* rowbias;
+  int64_t NB, H, W, Cin, Cout;
+  int32_t stride;               /* 1 or 2 */
+  int32_t upsample;             /* 1 or 2: nearest-neighbour upsampling of x before the conv */
+  int64_t images_per_group;     /* rowbias row = image / images_per_group  (= F, frames per clip) */
+  int32_t dtype, epilogue, impl;
+  void* workspace;              /* fyc_conv3x3_workspace_bytes() bytes (stride-2 / upsample on the tcgen05 path) */
+  size_t workspace_bytes;
+} fyc_conv3x3_args;
+size_t fyc_conv3x3_workspace_bytes(const fyc_conv3x3_args* a);
+int32_t fyc_conv3x3(const fyc_conv3x3_args* a, void* stream);
+
+/* ---- normalisation ------------------------------------------------------------------------------------
+ * GroupNorm (+ optional SiLU) over x viewed as [NB, R, C]: statistics per (nb, group) over R rows x C/G
+ * channels.  Cross-frame statistics of ResnetBlock3D (resnet.py:240,263; nn.GroupNorm on the 5-D tensor):
+ * NB = clips, R = F*H*W.  Per-frame statistics (attention.py:178,269; motion_module.py:127,188; VAE): NB =
+ * images, R = H*W.  workspace: fyc_groupnorm_workspace_bytes().
+ */
+size_t fyc_groupnorm_workspace_bytes(int64_t NB, int64_t C, int64_t G);
+int32_t fyc_groupnorm(const void* x, const float* gamma, const float* beta, void* out, int64_t NB, int64_t R,
+                      int64_t C, int64_t G, float eps, int32_t silu, int32_t dtype, void* workspace,
+                      size_t workspace_bytes, void* stream);
+/* LayerNorm over the last dim (attention.py:383,412,418; motion_module.py:261,267), optional sinusoidal
+ * position table added AFTER the norm: out = LN(x) + pe[(row / rows_per_frame) % frames]  (motion_module.py:303,378). */
+int32_t fyc_layernorm(const void* x, const float* gamma, const float* beta, void* out, int64_t M, int64_t C,
+                      float eps, const float* pe, int64_t rows_per_frame, int64_t frames, int32_t dtype,
+                      void* stream);
+
+/* ---- attention ----------------------------------------------------------------------------------------
+ * out[n, i, h*D + :] (=|+=) out_alpha * softmax_j(scale * q[n,i,h] . k[n',j,h]) v[n',j,h],  n' = n / kv_batch_div.
+ * Replaces CrossAttention._attention (diffusers/models/attention.py:649-678) for attn1/attn2 and the two
+ * softmaxes of IPCrossAttention.forward (animatediff/models/attention.py:98-120; second call with
+ * accumulate=1, out_alpha = ip scale).  Never materialises the score matrix.
+ */
+typedef struct {
+  const void* q; const void* k; const void* v; void* out;
+  int64_t batch, heads, Lq, Lk, D;
+  int64_t ldq, ldk, ldv, ldo;            /* row strides in elements */
+  int64_t bsq, bsk, bsv, bso;            /* batch strides in elements */
+  int64_t kv_batch_div;                  /* >= 1: context shared by F consecutive images (attention.py:264) */
+  float scale, out_alpha;
+  int32_t accumulate, dtype, impl;
+} fyc_attention_args;
+int32_t fyc_attention(const fyc_attention_args* a, void* stream);
+
+/* Temporal self-attention over the frame axis (VersatileAttention.forward, motion_module.py:371-464 +
+ * mm_attn_cross.py:148-177): qkv [B, F, HW, 3C] (q | k | v packed per token), out [B, F, HW, C].  The
+ * '(b f) d c -> (b d) f c' regrouping (motion_module.py:376,462) is absorbed into the addressing. */
+int32_t fyc_temporal_attention(const void* qkv, void* out, int64_t B, int64_t F, int64_t HW, int64_t heads,
+                               int64_t D, float scale, int32_t dtype, void* stream);
+/* Row softmax of fp32 scores (VAE AttentionBlock, diffusers/models/attention.py:366), output in `dtype`. */
+int32_t fyc_softmax_rows(const float* scores, void* probs, int64_t rows, int64_t L, int32_t dtype, void* stream);
+
+/* ---- embeddings / glue --------------------------------------------------------------------------------*/
+/* get_timestep_embedding (diffusers/models/embeddings.py:21-61): out[n, dim] fp32; freqs[dim/2] fp32 is
+ * exp(-ln(1e4) k / (half - shift)) computed once on the host. */
+int32_t fyc_timestep_embed(const int64_t* t, const float* freqs, float* out, int64_t n, int64_t dim,
+                           int32_t flip_sin_to_cos, void* stream);
+int32_t fyc_silu(const void* x, void* out, int64_t n, int32_t dtype, void* stream);
+/* GEGLU for the SIMT path: in [M, 2*Hd] (128-col granule interleave) -> out [M, Hd]. */
+int32_t fyc_geglu(const void* in, void* out, int64_t M, int64_t Hd, int32_t dtype, void* stream);
+int32_t fyc_upsample_nearest2x(const void* x, void* out, int64_t NB, int64_t H, int64_t W, int64_t C,
+                               int32_t dtype, void* stream);
+/* torch.cat([a, b], dim=channels) (unet_blocks.py:763,885): a [M, C1], b [M, C2] -> out [M, C1+C2]. */
+int32_t fyc_concat_channels(const void* a, const void* b, void* out, int64_t M, int64_t C1, int64_t C2,
+                            int32_t dtype, void* stream);
+/* fp32 (b, c, f, h, w) <-> dtype [b, f, h, w, c] */
+int32_t fyc_ncfhw_to_nfhwc(const float* in, void* out, int64_t B, int64_t C, int64_t F, int64_t HW,
+                           int32_t dtype, void* stream);
+int32_t fyc_nfhwc_to_ncfhw(const void* in, float* out, int64_t B, int64_t C, int64_t F, int64_t HW,
+                           int32_t dtype, void* stream);
+/* AnimationPipeline.__call__ step prologue (pipeline_animation.py:625-635,693-711): builds the channels-last
+ * UNet input [dup*b, F, H, W, Cin] from latents (b,4,F,H,W) fp32, mask (b,1,1,H,W) fp32 (NULL -> 1 on frame 0)
+ * and first-frame latents (b,4,H,W) fp32 (NULL -> Cin = 4, plain latents). */
+int32_t fyc_build_unet_input(const float* latents, const float* mask, const float* first, void* out, int64_t b,
+                             int64_t F, int64_t HW, int32_t dup, int32_t dtype, void* stream);
+/* CFG combine + DDIMScheduler.step (pipeline_animation.py:763-764 + scheduling_ddim.py:308-349), fp32, exact
+ * reference operation order (no FMA contraction).  pred: [2, n] (uncond, cond) when guidance > 1 else [1, n]. */
+typedef struct {
+  float guidance;                 /* <= 1: no CFG */
+  float sqrt_alpha_t, sqrt_beta_t, sqrt_alpha_prev, dir_coef, noise_coef;
+  int32_t prediction_type, clip_sample;
+} fyc_ddim_coefs;
+int32_t fyc_cfg_ddim_step(const float* pred, const float* sample, const float* noise, float* prev, int64_t n,
+                          const fyc_ddim_coefs* c, void* stream);
+/* decode_latents epilogue (pipeline_animation.py:409-410): x [b*F, HW, 3] -> video (b, 3, F, H, W) fp32,
+ * (x / 2 + 0.5).clamp(0, 1). */
+int32_t fyc_frames_finalize(const void* x, float* video, int64_t b, int64_t F, int64_t HW, int32_t dtype,
+                            void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FYC_H_ */
