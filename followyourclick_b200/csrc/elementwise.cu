@@ -126,13 +126,13 @@ extern "C" int32_t fyc_concat_channels(const void* a, const void* b, void* out, 
 // ---------------------------------------------------------------------------------------------------------
 // fp32 (b, c, f, hw) <-> T [b, f, hw, c].  Used at the UNet boundary (C = 4 / 9) and by tests.
 template <typename T>
-__global__ void ncfhw_to_nfhwc_kernel(const float* __restrict__ in, T* __restrict__ out, int64_t B, int64_t C, int64_t F, int64_t HW) {
+__global__ void ncfhw_to_nfhwc_kernel(const float* __restrict__ in, T* __restrict__ out, int64_t B, int64_t C, int64_t F, int64_t HW, float scale) {
   int64_t total = B * F * HW * C;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t c = i % C; int64_t r = i / C;
     int64_t p = r % HW; r /= HW;
     int64_t f = r % F; int64_t b = r / F;
-    out[i] = from_f<T>(in[((b * C + c) * F + f) * HW + p]);
+    out[i] = from_f<T>(__fmul_rn(in[((b * C + c) * F + f) * HW + p], scale));
   }
 }
 template <typename T>
@@ -145,8 +145,8 @@ __global__ void nfhwc_to_ncfhw_kernel(const T* __restrict__ in, float* __restric
     out[i] = to_f(in[((b * F + f) * HW + p) * C + c]);
   }
 }
-extern "C" int32_t fyc_ncfhw_to_nfhwc(const float* in, void* out, int64_t B, int64_t C, int64_t F, int64_t HW, int32_t dtype, void* stream) {
-  FYC_DISPATCH(dtype, ncfhw_to_nfhwc_kernel<T><<<grid_for(B * C * F * HW, 256), 256, 0, (cudaStream_t)stream>>>(in, (T*)out, B, C, F, HW));
+extern "C" int32_t fyc_ncfhw_to_nfhwc(const float* in, void* out, int64_t B, int64_t C, int64_t F, int64_t HW, float scale, int32_t dtype, void* stream) {
+  FYC_DISPATCH(dtype, ncfhw_to_nfhwc_kernel<T><<<grid_for(B * C * F * HW, 256), 256, 0, (cudaStream_t)stream>>>(in, (T*)out, B, C, F, HW, scale));
   FYC_LAUNCH_CHECK();
   return FYC_OK;
 }

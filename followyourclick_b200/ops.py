@@ -1,0 +1,252 @@
+"""Tensor-level wrappers over the C ABI: PyTorch tensors in, PyTorch tensors out.
+
+PyTorch is used for device memory (caching allocator), streams and nothing else: every FLOP below is executed by
+a kernel of libfyc_sm100a.so.  All tensors must be CUDA, contiguous in the last dimension; activations are either
+all fp32 (strict parity mode) or all bf16 (tensor-core mode).
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+from ._lib import check, dtype_code, lib, ptr, stream_ptr
+
+_impl = L.IMPL_AUTO
+
+
+def set_impl(name):
+    """'auto' (tcgen05 where eligible), 'simt' (CUDA-core kernels only) or 'tc' (fail if not eligible)."""
+    global _impl
+    _impl = {"auto": L.IMPL_AUTO, "simt": L.IMPL_SIMT, "tc": L.IMPL_TC}[name]
+
+
+def get_impl():
+    return {L.IMPL_AUTO: "auto", L.IMPL_SIMT: "simt", L.IMPL_TC: "tc"}[_impl]
+
+
+def _cuda(t, name):
+    if t is None:
+        return
+    if not t.is_cuda:
+        raise L.FycError(f"{name}: tensor must live on a CUDA device (the engine has no CPU path)")
+    if t.stride(-1) != 1:
+        raise L.FycError(f"{name}: last dimension must be contiguous")
+
+
+def _f32vec(t, name):
+    if t is not None and (t.dtype != torch.float32 or not t.is_contiguous()):
+        raise L.FycError(f"{name}: expected a contiguous fp32 tensor")
+
+
+def tc_ok(dtype, M):
+    return _impl != L.IMPL_SIMT and dtype == torch.bfloat16 and M >= 64 and lib().fyc_tcgen05_available() == 1
+
+
+def gemm(A, W, bias=None, residual=None, rowbias=None, rows_per_group=0, alpha=1.0, geglu=False, out_f32=False,
+         out=None, impl=None):
+    """out[M, N] = alpha * A[M, K] @ W[N, K]^T (+bias) (+rowbias[m // rows_per_group]) (+residual); GEGLU halves N.
+    A may be 2-D [M, K] or batched 3-D [B, M, K] with W [B, N, K] (one launch per batch on the tcgen05 path)."""
+    _cuda(A, "gemm.A"); _cuda(W, "gemm.W"); _cuda(residual, "gemm.residual")
+    _f32vec(bias, "gemm.bias"); _f32vec(rowbias, "gemm.rowbias")
+    impl = _impl if impl is None else impl
+    batched = A.dim() == 3
+    if batched:
+        Bn, M, K = A.shape
+        N = W.shape[1]
+        sA, sW, lda, ldw = A.stride(0), W.stride(0), A.stride(1), W.stride(1)
+    else:
+        Bn, (M, K), N = 1, A.shape, W.shape[0]
+        sA = sW = 0
+        lda, ldw = A.stride(0), W.stride(0)
+    assert W.shape[-1] == K and W.dtype == A.dtype
+    fused_geglu = geglu and impl != L.IMPL_SIMT and tc_ok(A.dtype, M)
+    n_out = N // 2 if fused_geglu else N
+    odt = torch.float32 if out_f32 else A.dtype
+    if out is None or (geglu and not fused_geglu):
+        o = torch.empty((Bn, M, n_out) if batched else (M, n_out), dtype=odt, device=A.device)
+    else:
+        o = out
+    epi = (L.EPI_BIAS if bias is not None else 0) | (L.EPI_RESIDUAL if residual is not None else 0) | \
+          (L.EPI_ROWBIAS if rowbias is not None else 0) | (L.EPI_GEGLU if fused_geglu else 0) | (L.EPI_OUT_F32 if out_f32 else 0)
+    a = L.GemmArgs(ptr(A), ptr(W), ptr(o), ptr(bias), ptr(residual), ptr(rowbias), M, N, K, lda, ldw,
+                   o.stride(-2), residual.stride(-2) if residual is not None else 0, Bn, sA, sW,
+                   o.stride(0) if batched else 0, rows_per_group, float(alpha), dtype_code(A.dtype), epi, impl)
+    check(lib().fyc_gemm(C.byref(a), stream_ptr()))
+    if geglu and not fused_geglu:
+        assert not batched
+        g = out if out is not None else torch.empty((M, N // 2), dtype=A.dtype, device=A.device)
+        check(lib().fyc_geglu(ptr(o), ptr(g), M, N // 2, dtype_code(A.dtype), stream_ptr()))
+        return g
+    return o
+
+
+def conv3x3(x, w, bias=None, residual=None, rowbias=None, images_per_group=0, stride=1, upsample=1, out_f32=False, impl=None):
+    """x [NB, H, W, Cin] (NHWC), w [Cout, 3, 3, Cin] -> [NB, Ho, Wo, Cout]; pad 1."""
+    _cuda(x, "conv.x"); _cuda(w, "conv.w"); _cuda(residual, "conv.residual")
+    _f32vec(bias, "conv.bias"); _f32vec(rowbias, "conv.rowbias")
+    assert x.is_contiguous() and w.is_contiguous() and x.dtype == w.dtype
+    impl = _impl if impl is None else impl
+    NB, H, W_, Cin = x.shape
+    Cout = w.shape[0]
+    if upsample == 2 and impl != L.IMPL_SIMT and tc_ok(x.dtype, NB * H * W_):
+        x = upsample_nearest2x(x)            # the tensor-core path reads unit-stride boxes: materialise the upsample
+        NB, H, W_, Cin = x.shape
+        upsample = 1
+    Ho = (H * upsample + 2 - 3) // stride + 1
+    Wo = (W_ * upsample + 2 - 3) // stride + 1
+    out = torch.empty((NB, Ho, Wo, Cout), dtype=torch.float32 if out_f32 else x.dtype, device=x.device)
+    if residual is not None:
+        assert residual.is_contiguous() and residual.shape == out.shape
+    epi = (L.EPI_BIAS if bias is not None else 0) | (L.EPI_RESIDUAL if residual is not None else 0) | \
+          (L.EPI_ROWBIAS if rowbias is not None else 0) | (L.EPI_OUT_F32 if out_f32 else 0)
+    a = L.ConvArgs(ptr(x), ptr(w), ptr(out), ptr(bias), ptr(residual), ptr(rowbias), NB, H, W_, Cin, Cout, stride,
+                   upsample, images_per_group, dtype_code(x.dtype), epi, impl, None, 0)
+    nbytes = lib().fyc_conv3x3_workspace_bytes(C.byref(a))
+    ws = None
+    if nbytes:
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+        a.workspace, a.workspace_bytes = ptr(ws), nbytes
+    check(lib().fyc_conv3x3(C.byref(a), stream_ptr()))
+    return out
+
+
+def groupnorm(x, gamma, beta, groups, eps, silu=False, stat_batches=None):
+    """x [..., C] contiguous; statistics per (stat batch, group) where x is viewed as [stat_batches, R, C]."""
+    _cuda(x, "groupnorm.x"); _f32vec(gamma, "groupnorm.gamma"); _f32vec(beta, "groupnorm.beta")
+    assert x.is_contiguous()
+    Cc = x.shape[-1]
+    NB = x.shape[0] if stat_batches is None else stat_batches
+    R = x.numel() // (NB * Cc)
+    out = torch.empty_like(x)
+    nbytes = lib().fyc_groupnorm_workspace_bytes(NB, Cc, groups)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    check(lib().fyc_groupnorm(ptr(x), ptr(gamma), ptr(beta), ptr(out), NB, R, Cc, groups, float(eps), int(silu),
+                              dtype_code(x.dtype), ptr(ws), nbytes, stream_ptr()))
+    return out
+
+
+def layernorm(x, gamma, beta, eps=1e-5, pe=None, rows_per_frame=0, frames=0):
+    _cuda(x, "layernorm.x"); _f32vec(gamma, "layernorm.gamma"); _f32vec(beta, "layernorm.beta"); _f32vec(pe, "layernorm.pe")
+    assert x.is_contiguous()
+    Cc = x.shape[-1]
+    out = torch.empty_like(x)
+    check(lib().fyc_layernorm(ptr(x), ptr(gamma), ptr(beta), ptr(out), x.numel() // Cc, Cc, float(eps), ptr(pe),
+                              rows_per_frame, frames, dtype_code(x.dtype), stream_ptr()))
+    return out
+
+
+def attention(q, k, v, heads, scale, out=None, out_alpha=1.0, accumulate=False, kv_batch_div=1, impl=None):
+    """q [B, Lq, >=heads*D] / k, v [B', Lk, ...] are (possibly strided) views; head h occupies columns [h*D, (h+1)*D).
+    Returns out [B, Lq, heads*D].  B' = B / kv_batch_div."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        _cuda(t, "attention." + n)
+    B, Lq, _ = q.shape
+    Lk = k.shape[1]
+    if out is None:
+        assert not accumulate
+        assert q.shape[2] % heads == 0
+        out = torch.empty((B, Lq, q.shape[2]), dtype=q.dtype, device=q.device)
+    D = out.shape[2] // heads
+    a = L.AttnArgs(ptr(q), ptr(k), ptr(v), ptr(out), B, heads, Lq, Lk, D, q.stride(1), k.stride(1), v.stride(1),
+                   out.stride(1), q.stride(0), k.stride(0), v.stride(0), out.stride(0), kv_batch_div, float(scale),
+                   float(out_alpha), int(accumulate), dtype_code(q.dtype), _impl if impl is None else impl)
+    check(lib().fyc_attention(C.byref(a), stream_ptr()))
+    return out
+
+
+def temporal_attention(qkv, heads, scale):
+    """qkv [B, F, HW, 3C] -> [B, F, HW, C]; softmax over the F frames of each (clip, pixel, head)."""
+    _cuda(qkv, "temporal_attention.qkv")
+    assert qkv.is_contiguous()
+    B, F, HW, C3 = qkv.shape
+    Cc = C3 // 3
+    out = torch.empty((B, F, HW, Cc), dtype=qkv.dtype, device=qkv.device)
+    check(lib().fyc_temporal_attention(ptr(qkv), ptr(out), B, F, HW, heads, Cc // heads, float(scale),
+                                       dtype_code(qkv.dtype), stream_ptr()))
+    return out
+
+
+def softmax_rows(scores, out_dtype):
+    assert scores.dtype == torch.float32 and scores.is_contiguous()
+    Lk = scores.shape[-1]
+    out = torch.empty(scores.shape, dtype=out_dtype, device=scores.device)
+    check(lib().fyc_softmax_rows(ptr(scores), ptr(out), scores.numel() // Lk, Lk, dtype_code(out_dtype), stream_ptr()))
+    return out
+
+
+def timestep_embed(t, freqs, flip_sin_to_cos):
+    assert t.dtype == torch.int64 and t.is_cuda and freqs.dtype == torch.float32
+    n, dim = t.numel(), 2 * freqs.numel()
+    out = torch.empty((n, dim), dtype=torch.float32, device=t.device)
+    check(lib().fyc_timestep_embed(ptr(t), ptr(freqs), ptr(out), n, dim, int(flip_sin_to_cos), stream_ptr()))
+    return out
+
+
+def silu(x):
+    _cuda(x, "silu.x")
+    out = torch.empty_like(x)
+    check(lib().fyc_silu(ptr(x), ptr(out), x.numel(), dtype_code(x.dtype), stream_ptr()))
+    return out
+
+
+def upsample_nearest2x(x):
+    assert x.is_contiguous()
+    NB, H, W_, Cc = x.shape
+    out = torch.empty((NB, 2 * H, 2 * W_, Cc), dtype=x.dtype, device=x.device)
+    check(lib().fyc_upsample_nearest2x(ptr(x), ptr(out), NB, H, W_, Cc, dtype_code(x.dtype), stream_ptr()))
+    return out
+
+
+def concat_channels(a, b):
+    assert a.is_contiguous() and b.is_contiguous() and a.shape[:-1] == b.shape[:-1] and a.dtype == b.dtype
+    C1, C2 = a.shape[-1], b.shape[-1]
+    out = torch.empty(a.shape[:-1] + (C1 + C2,), dtype=a.dtype, device=a.device)
+    check(lib().fyc_concat_channels(ptr(a), ptr(b), ptr(out), a.numel() // C1, C1, C2, dtype_code(a.dtype), stream_ptr()))
+    return out
+
+
+def ncfhw_to_nfhwc(x, dtype, scale=1.0):
+    """fp32 (b, c, f, h, w) * scale -> dtype [b, f, h, w, c]."""
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.is_cuda
+    b, c, f, h, w = x.shape
+    out = torch.empty((b, f, h, w, c), dtype=dtype, device=x.device)
+    check(lib().fyc_ncfhw_to_nfhwc(ptr(x), ptr(out), b, c, f, h * w, float(scale), dtype_code(dtype), stream_ptr()))
+    return out
+
+
+def nfhwc_to_ncfhw(x):
+    """dtype [b, f, h, w, c] -> fp32 (b, c, f, h, w)."""
+    assert x.is_contiguous() and x.is_cuda
+    b, f, h, w, c = x.shape
+    out = torch.empty((b, c, f, h, w), dtype=torch.float32, device=x.device)
+    check(lib().fyc_nfhwc_to_ncfhw(ptr(x), ptr(out), b, c, f, h * w, dtype_code(x.dtype), stream_ptr()))
+    return out
+
+
+def build_unet_input(latents, mask, first, dup, dtype):
+    """latents (b,4,f,h,w) fp32, mask (b,1,1,h,w) fp32 | None, first (b,4,h,w) fp32 | None -> [dup*b, f, h, w, 9|4]."""
+    assert latents.dtype == torch.float32 and latents.is_contiguous() and latents.is_cuda
+    b, c, f, h, w = latents.shape
+    assert c == 4
+    cin = 9 if first is not None else 4
+    out = torch.empty((dup * b, f, h, w, cin), dtype=dtype, device=latents.device)
+    check(lib().fyc_build_unet_input(ptr(latents), ptr(mask), ptr(first), ptr(out), b, f, h * w, dup, dtype_code(dtype), stream_ptr()))
+    return out
+
+
+def cfg_ddim_step(pred, sample, coefs, noise=None, out=None):
+    """pred fp32 [2, ...] (uncond, cond) if coefs.guidance > 1 else [1, ...]; sample fp32; returns prev sample."""
+    assert pred.dtype == torch.float32 and sample.dtype == torch.float32 and pred.is_contiguous() and sample.is_contiguous()
+    out = torch.empty_like(sample) if out is None else out
+    check(lib().fyc_cfg_ddim_step(ptr(pred), ptr(sample), ptr(noise), ptr(out), sample.numel(), C.byref(coefs), stream_ptr()))
+    return out
+
+
+def frames_finalize(x, b, f):
+    """x [b*f, H, W, 3] -> video (b, 3, f, H, W) fp32 = (x / 2 + 0.5).clamp(0, 1)."""
+    assert x.is_contiguous()
+    _, H, W_, c = x.shape
+    assert c == 3
+    out = torch.empty((b, 3, f, H, W_), dtype=torch.float32, device=x.device)
+    check(lib().fyc_frames_finalize(ptr(x), ptr(out), b, f, H * W_, dtype_code(x.dtype), stream_ptr()))
+    return out

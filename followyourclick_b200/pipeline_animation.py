@@ -1,0 +1,257 @@
+"""AnimationPipeline: reference call surface (animatediff/pipelines/pipeline_animation.py:42-788), engine loop underneath.
+
+``__call__`` accepts the reference's keyword set (``scripts/inference.py:374-395``) and returns ``.videos`` as a CPU fp32
+tensor (b, 3, F, H, W) in [0, 1].  Per DDIM step the engine runs exactly four kinds of work, all libfyc kernels:
+  build 9-channel CFG-duplicated input (1 kernel) -> UNet3D forward -> layout to (2b,4,F,h,w) -> fused CFG+DDIM step.
+The prompt / image encoders are outside the hot path (their outputs are computed once before the loop, :610-612,
+:676-680) and are used as given (any callable with the transformers interface).
+"""
+import inspect
+from dataclasses import dataclass
+from typing import Union
+
+import numpy as np
+import torch
+
+from . import ops
+
+
+@dataclass
+class AnimationPipelineOutput:
+    videos: Union[torch.Tensor, np.ndarray]
+
+
+class _NullBar:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+    def update(self, n=1):
+        pass
+
+
+class AnimationPipeline:
+    _optional_components = []
+
+    def __init__(self, vae, text_encoder, tokenizer, unet, scheduler, image_encoder=None, text_encoder_2=None,
+                 tokenizer_2=None, ip_adapter=None):
+        self.vae, self.text_encoder, self.tokenizer, self.unet, self.scheduler = vae, text_encoder, tokenizer, unet, scheduler
+        self.image_encoder, self.text_encoder_2, self.tokenizer_2, self.ip_adapter = image_encoder, text_encoder_2, tokenizer_2, ip_adapter
+        self.vae_scale_factor = 2 ** (len(self.vae.config.block_out_channels) - 1)
+        self._progress = True
+
+    # ---------------------------------------------------------------- DiffusionPipeline-style plumbing
+    def to(self, device=None, dtype=None):
+        for m in (self.vae, self.unet, self.text_encoder, self.image_encoder, self.text_encoder_2):
+            if m is not None and hasattr(m, "to"):
+                m.to(device) if dtype is None else m.to(device, dtype)
+        return self
+
+    @property
+    def device(self):
+        return self.unet.device
+
+    @property
+    def _execution_device(self):
+        return self.unet.device
+
+    def set_progress_bar_config(self, **kw):
+        self._progress = not kw.get("disable", False)
+
+    def progress_bar(self, iterable=None, total=None):
+        if not self._progress:
+            return _NullBar() if iterable is None else iterable
+        try:
+            from tqdm.auto import tqdm
+        except Exception:       # pragma: no cover
+            return _NullBar() if iterable is None else iterable
+        return tqdm(iterable, total=total) if iterable is not None else tqdm(total=total)
+
+    def enable_vae_slicing(self):
+        self.vae.enable_slicing()
+
+    def disable_vae_slicing(self):
+        self.vae.disable_slicing()
+
+    def enable_sequential_cpu_offload(self, gpu_id=0):
+        raise NotImplementedError("CPU offload is a memory work-around the 180 GB engine does not need")
+
+    # ---------------------------------------------------------------- prompt encoding (outside the hot path)
+    def _encode_prompt(self, prompt, device, num_videos_per_prompt, do_classifier_free_guidance, negative_prompt):
+        """pipeline_animation.py:158-245: CLIP text forward for prompt and negative prompt -> cat([uncond, cond])."""
+        batch_size = len(prompt) if isinstance(prompt, list) else 1
+
+        def encode(text):
+            ti = self.tokenizer(text, padding="max_length", max_length=self.tokenizer.model_max_length, truncation=True,
+                                return_tensors="pt")
+            mask = None
+            cfg = getattr(self.text_encoder, "config", None)
+            if cfg is not None and getattr(cfg, "use_attention_mask", False):
+                mask = ti.attention_mask.to(device)
+            emb = self.text_encoder(ti.input_ids.to(device), attention_mask=mask)[0]
+            bs, seq, _ = emb.shape
+            return emb.repeat(1, num_videos_per_prompt, 1).view(bs * num_videos_per_prompt, seq, -1)
+
+        text_embeddings = encode(prompt)
+        if do_classifier_free_guidance:
+            if negative_prompt is None:
+                uncond_tokens = [""] * batch_size
+            elif isinstance(negative_prompt, str):
+                uncond_tokens = [negative_prompt]
+            elif batch_size != len(negative_prompt):
+                raise ValueError(f"`negative_prompt`: {negative_prompt} has batch size {len(negative_prompt)}, but `prompt`:"
+                                 f" {prompt} has batch size {batch_size}.")
+            else:
+                uncond_tokens = negative_prompt
+            text_embeddings = torch.cat([encode(uncond_tokens), text_embeddings])
+        return text_embeddings
+
+    def check_inputs(self, prompt, height, width, callback_steps):
+        if not isinstance(prompt, str) and not isinstance(prompt, list):
+            raise ValueError(f"`prompt` has to be of type `str` or `list` but is {type(prompt)}")
+        if height % 8 != 0 or width % 8 != 0:
+            raise ValueError(f"`height` and `width` have to be divisible by 8 but are {height} and {width}.")
+        if (callback_steps is None) or (callback_steps is not None and (not isinstance(callback_steps, int) or callback_steps <= 0)):
+            raise ValueError(f"`callback_steps` has to be a positive integer but is {callback_steps} of type {type(callback_steps)}.")
+
+    def prepare_extra_step_kwargs(self, generator, eta):
+        kw = {}
+        params = set(inspect.signature(self.scheduler.step).parameters.keys())
+        if "eta" in params:
+            kw["eta"] = eta
+        if "generator" in params:
+            kw["generator"] = generator
+        return kw
+
+    def prepare_latents(self, batch_size, num_channels_latents, video_length, height, width, dtype, device, generator,
+                        latents=None, use_interpolate_noise=False, **unused):
+        """pipeline_animation.py:448-537 (init_latents / residual-noise branches are not used by scripts/inference.py)."""
+        shape = (batch_size, num_channels_latents, video_length, height // self.vae_scale_factor, width // self.vae_scale_factor)
+        if isinstance(generator, list) and len(generator) != batch_size:
+            raise ValueError(f"You have passed a list of generators of length {len(generator)}, but requested an effective batch"
+                             f" size of {batch_size}. Make sure the batch size matches the length of the generators.")
+        if latents is None:
+            if isinstance(generator, list):
+                latents = torch.cat([torch.randn(shape, generator=g, device=device, dtype=torch.float32) for g in generator], dim=0)
+            else:
+                latents = torch.randn(shape, generator=generator, device=device, dtype=torch.float32)
+                if use_interpolate_noise:
+                    latents = latents[:, :, :1].repeat(1, 1, shape[2], 1, 1)
+        else:
+            if tuple(latents.shape) != shape:
+                raise ValueError(f"Unexpected latents shape, got {latents.shape}, expected {shape}")
+            latents = latents.to(device=device, dtype=torch.float32)
+        return (latents * self.scheduler.init_noise_sigma).contiguous()
+
+    # ---------------------------------------------------------------- decode (hot path, after the loop)
+    @torch.no_grad()
+    def decode_latents_device(self, latents):
+        """latents (b, 4, F, h, w) fp32 on device -> video (b, 3, F, H, W) fp32 on device, (x/2+0.5).clamp(0,1)."""
+        b, c, f, h, w = latents.shape
+        z = ops.ncfhw_to_nfhwc(latents.to(torch.float32).contiguous(), self.vae.dtype, scale=1 / 0.18215).view(b * f, h, w, c)
+        frames = self.vae.decode_nhwc(z)
+        return ops.frames_finalize(frames, b, f)
+
+    def decode_latents(self, latents):
+        """pipeline_animation.py:400-413: returns a numpy array (b, 3, F, H, W) fp32 (device -> host boundary)."""
+        return self.decode_latents_device(latents.to(self.device)).cpu().float().numpy()
+
+    # ---------------------------------------------------------------- the denoising loop
+    @torch.no_grad()
+    def denoise(self, latents, text_embeddings, num_inference_steps, guidance_scale, first_image_latents=None,
+                first_images_mask=None, use_first_frame_mask_condition_concat=False, fps_tensor=None, flow_control=None,
+                use_fps_condition=False, use_ip_cross_attention=False, image_clip_feat_pair=None,
+                use_camera_motion_condition=False, camera_movement_type=None, eta=0.0, generator=None, callback=None,
+                callback_steps=1, progress=False):
+        """pipeline_animation.py:686-773 on the engine.  latents fp32 (b,4,F,h,w) on device; returns final latents."""
+        dev = self.unet.device
+        do_cfg = guidance_scale > 1.0
+        dup = 2 if do_cfg else 1
+        sched, unet = self.scheduler, self.unet
+        sched.set_timesteps(num_inference_steps, device=dev)
+        t_host = list(sched._timesteps_host)
+        t_dev = sched.timesteps
+
+        def as_dev(v):
+            if v is None:
+                return None
+            v = torch.as_tensor(v).reshape(-1).to(dev)
+            return torch.cat([v] * dup) if do_cfg else v
+
+        fps_d, flow_d, cam_d = as_dev(fps_tensor), as_dev(flow_control), as_dev(camera_movement_type)
+        mask = first = None
+        if use_first_frame_mask_condition_concat:
+            first = first_image_latents.to(device=dev, dtype=torch.float32).contiguous()
+            if first_images_mask is not None:
+                mask = first_images_mask[:, :, 0].to(device=dev, dtype=torch.float32).contiguous()     # :632-635 (frame 0, clamp in-kernel)
+        latents = latents.to(device=dev, dtype=torch.float32).contiguous()
+        text_embeddings = text_embeddings.to(dev)
+        bar = self.progress_bar(total=num_inference_steps) if progress else _NullBar()
+        with bar as pb:
+            for i, t in enumerate(t_host):
+                x = ops.build_unet_input(latents, mask, first, dup, unet.dtype)
+                y = unet.forward_nfhwc(x, t_dev[i], text_embeddings, fps_tensor=fps_d, flow_control=flow_d,
+                                       reference_images_clip_feat=image_clip_feat_pair,
+                                       camera_movement_type_tensor=cam_d, use_ip_cross_attention=use_ip_cross_attention,
+                                       use_camera_motion_condition=use_camera_motion_condition,
+                                       use_fps_condition=use_fps_condition)
+                pred = ops.nfhwc_to_ncfhw(y)
+                latents = sched.step_cfg(pred, t, latents, guidance_scale if do_cfg else 1.0, eta=eta, generator=generator)
+                pb.update()
+                if callback is not None and i % callback_steps == 0:
+                    callback(i, t, latents)
+        return latents
+
+    @torch.no_grad()
+    def __call__(self, prompt, video_length, height=None, width=None, num_inference_steps=50, guidance_scale=7.5,
+                 negative_prompt=None, num_videos_per_prompt=1, eta=0.0, generator=None, latents=None, output_type="tensor",
+                 return_dict=True, callback=None, callback_steps=1, use_first_frame_condition=False,
+                 use_first_frame_condition_concat=False, use_first_frame_mask_condition_concat=False,
+                 use_first_frame_mask_condition_concat_image_partial_mask=None, first_image_latents=None,
+                 use_first_image_as_init_latents=False, video_scale=0, use_ip_cross_attention=False, condition_images=None,
+                 use_uncond_images=False, use_camera_motion_condition=False, camera_movement_type=None,
+                 use_text_encoder_2=False, use_uncond_text_2=False, use_fps_condition=False, fps_tensor=None,
+                 use_interpolate_noise=False, first_images_mask=None, flow_control=None, **kwargs):
+        if use_first_frame_condition or use_first_frame_condition_concat or use_text_encoder_2 or use_first_image_as_init_latents \
+                or use_first_frame_mask_condition_concat_image_partial_mask is not None:
+            raise NotImplementedError("option outside the scripts/inference.py path (SURVEY 8f)")
+        if video_scale > 0:
+            raise NotImplementedError("video_scale > 0 (per-frame guidance branch, pipeline_animation.py:738-761) is SURVEY 8f row 3")
+        height = height or self.unet.config.sample_size * self.vae_scale_factor
+        width = width or self.unet.config.sample_size * self.vae_scale_factor
+        self.check_inputs(prompt, height, width, callback_steps)
+        batch_size = 1
+        if latents is not None:
+            batch_size = latents.shape[0]
+        if isinstance(prompt, list):
+            batch_size = len(prompt)
+        device = self._execution_device
+        do_cfg = guidance_scale > 1.0
+        prompt = prompt if isinstance(prompt, list) else [prompt] * batch_size
+        if negative_prompt is not None:
+            negative_prompt = negative_prompt if isinstance(negative_prompt, list) else [negative_prompt] * batch_size
+        text_embeddings = self._encode_prompt(prompt, device, num_videos_per_prompt, do_cfg, negative_prompt)
+        latents = self.prepare_latents(batch_size * num_videos_per_prompt, self.unet.in_channels, video_length, height, width,
+                                       torch.float32, device, generator, latents, use_interpolate_noise=use_interpolate_noise)
+        clip_pair = None
+        if use_ip_cross_attention:
+            cond, uncond = self.ip_adapter.get_image_clip_feat(input_image=condition_images)       # :676-680
+            if use_uncond_images:
+                cond = uncond.clone()
+            clip_pair = torch.cat([uncond, cond]) if do_cfg else cond
+        latents = self.denoise(latents, text_embeddings, num_inference_steps, guidance_scale,
+                               first_image_latents=first_image_latents, first_images_mask=first_images_mask,
+                               use_first_frame_mask_condition_concat=use_first_frame_mask_condition_concat,
+                               fps_tensor=fps_tensor, flow_control=flow_control, use_fps_condition=use_fps_condition,
+                               use_ip_cross_attention=use_ip_cross_attention, image_clip_feat_pair=clip_pair,
+                               use_camera_motion_condition=use_camera_motion_condition, camera_movement_type=camera_movement_type,
+                               eta=eta, generator=generator if not isinstance(generator, list) else None,
+                               callback=callback, callback_steps=callback_steps, progress=self._progress)
+        video = self.decode_latents(latents)
+        if output_type == "tensor":
+            video = torch.from_numpy(video)
+        if not return_dict:
+            return video
+        return AnimationPipelineOutput(videos=video)

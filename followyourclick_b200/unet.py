@@ -1,0 +1,506 @@
+"""UNet3DConditionModel: reference call surface (animatediff/models/unet.py:27-726), CUDA engine underneath.
+
+Same constructor kwargs, same state-dict keys, same ``forward`` signature and ``.sample`` output as
+the reference class, so ``scripts/inference.py`` and ``AnimationPipeline`` can use it unchanged.  The forward pass is
+not an nn.Module graph: activations live as channels-last tokens ``[B*F, H, W, C]`` in bf16 (tensor-core mode) or
+fp32 (strict mode) and every operator is a libfyc_sm100a kernel (followyourclick_b200.ops):
+
+  ResnetBlock3D  (resnet.py:296-342)   GN(cross-frame)+SiLU -> conv3x3 [+bias +time-emb row bias] -> GN+SiLU ->
+                                       conv3x3 [+bias +residual | 1x1 shortcut]
+  Transformer3DModel / BasicTransformerBlock (attention.py:217-308,489-564)
+                                       GN -> proj_in -> LN -> fused qkv GEMM -> flash attention -> out GEMM[+res] ->
+                                       LN -> q GEMM -> cross attention (text [+IP second softmax]) -> out GEMM[+res] ->
+                                       LN -> GEGLU GEMM (fused epilogue) -> GEMM[+res] -> proj_out[+res]
+  VanillaTemporalModule (motion_module.py:51-283)
+                                       GN -> proj_in -> 2x [LN(+PE) -> qkv GEMM -> temporal attention (strided over F,
+                                       no transposes) -> out GEMM[+res]] -> LN -> GEGLU FF -> proj_out[+res]
+"""
+import json
+import math
+import os
+from collections import OrderedDict
+from dataclasses import dataclass
+
+import torch
+
+from . import ops
+from .modeling import FrozenDict, ParamTreeModel, geglu_interleave
+
+
+@dataclass
+class UNet3DConditionOutput:
+    sample: torch.Tensor
+
+
+def _as_tuple(v, n):
+    return tuple(v) if isinstance(v, (tuple, list)) else (v,) * n
+
+
+def unet_param_spec(cfg):
+    """{state-dict key: shape} for the reference architecture described by ``cfg`` (the key contract of SURVEY App. E)."""
+    spec = OrderedDict()
+    boc = tuple(cfg["block_out_channels"])
+    n = len(boc)
+    temb = boc[0] * 4
+    xd = cfg["cross_attention_dim"]
+    mm = cfg["motion_module_kwargs"]
+    cin = cfg["in_channels"]
+    if cfg["use_first_frame_condition_concat"]:
+        cin = cfg["in_channels"] * 2
+    elif cfg["use_first_frame_mask_condition_concat"]:
+        cin = cfg["in_channels"] * 2 + 1
+
+    def lin(p, o, i, bias=True):
+        spec[p + ".weight"] = (o, i)
+        if bias:
+            spec[p + ".bias"] = (o,)
+
+    def conv(p, o, i, k):
+        spec[p + ".weight"] = (o, i, k, k)
+        spec[p + ".bias"] = (o,)
+
+    def norm(p, c):
+        spec[p + ".weight"] = (c,)
+        spec[p + ".bias"] = (c,)
+
+    def temb_mlp(p):
+        lin(p + ".linear_1", temb, boc[0])
+        lin(p + ".linear_2", temb, temb)
+
+    def resnet(p, i, o):
+        norm(p + ".norm1", i); conv(p + ".conv1", o, i, 3); lin(p + ".time_emb_proj", o, temb)
+        norm(p + ".norm2", o); conv(p + ".conv2", o, o, 3)
+        if i != o:
+            conv(p + ".conv_shortcut", o, i, 1)
+
+    def attn(p, c, kv_dim, ip=False):
+        lin(p + ".to_q", c, c, False); lin(p + ".to_k", c, kv_dim, False); lin(p + ".to_v", c, kv_dim, False)
+        lin(p + ".to_out.0", c, c)
+        if ip:
+            lin(p + ".to_k_ip", c, kv_dim, False); lin(p + ".to_v_ip", c, kv_dim, False)
+
+    def ff(p, c):
+        lin(p + ".net.0.proj", 8 * c, c); lin(p + ".net.2", c, 4 * c)
+
+    def transformer(p, c):
+        norm(p + ".norm", c); conv(p + ".proj_in", c, c, 1)
+        q = p + ".transformer_blocks.0"
+        attn(q + ".attn1", c, c); norm(q + ".norm1", c)
+        attn(q + ".attn2", c, xd, cfg["use_ip_cross_attention"]); norm(q + ".norm2", c)
+        ff(q + ".ff", c); norm(q + ".norm3", c)
+        conv(p + ".proj_out", c, c, 1)
+
+    def motion(p, c):
+        p = p + ".temporal_transformer"
+        norm(p + ".norm", c); lin(p + ".proj_in", c, c)
+        for b in range(mm["num_transformer_block"]):
+            q = p + f".transformer_blocks.{b}"
+            for j, _ in enumerate(mm["attention_block_types"]):
+                a = q + f".attention_blocks.{j}"
+                attn(a, c, c)
+                if mm.get("temporal_position_encoding", False):
+                    spec[a + ".pos_encoder.pe"] = (1, mm["temporal_position_encoding_max_len"], c)
+                if mm.get("add_temporal_lora", False):
+                    for nm in ("to_q", "to_k", "to_v", "to_out"):
+                        lin(a + f".{nm}_lora.down", mm["rank"], c, False); lin(a + f".{nm}_lora.up", c, mm["rank"], False)
+            for j, _ in enumerate(mm["attention_block_types"]):
+                norm(q + f".norms.{j}", c)
+            ff(q + ".ff", c); norm(q + ".ff_norm", c)
+        lin(p + ".proj_out", c, c)
+
+    def has_motion(level, decoder):
+        on = cfg["use_motion_module"] and (2 ** level) in tuple(cfg["motion_module_resolutions"])
+        return on and (decoder or not cfg["motion_module_decoder_only"])
+
+    conv("conv_in", boc[0], cin, 3)
+    temb_mlp("time_embedding")
+    if cfg["use_camera_motion_condition"]:
+        temb_mlp("camera_motion_embedding")
+    if cfg["use_fps_condition"]:
+        temb_mlp("fps_embedding"); temb_mlp("motion_embedding")
+    out_c = boc[0]
+    for i in range(n):
+        in_c, out_c = out_c, boc[i]
+        p = f"down_blocks.{i}"
+        for j in range(cfg["layers_per_block"]):
+            resnet(f"{p}.resnets.{j}", in_c if j == 0 else out_c, out_c)
+            if i < n - 1:
+                transformer(f"{p}.attentions.{j}", out_c)
+            if has_motion(i, False):
+                motion(f"{p}.motion_modules.{j}", out_c)
+        if i < n - 1:
+            conv(f"{p}.downsamplers.0.conv", out_c, out_c, 3)
+    resnet("mid_block.resnets.0", boc[-1], boc[-1]); transformer("mid_block.attentions.0", boc[-1])
+    if cfg["use_motion_module"] and cfg["motion_module_mid_block"]:
+        motion("mid_block.motion_modules.0", boc[-1])
+    resnet("mid_block.resnets.1", boc[-1], boc[-1])
+    rev = boc[::-1]
+    out_c = rev[0]
+    for i in range(n):
+        prev, out_c, in_c = out_c, rev[i], rev[min(i + 1, n - 1)]
+        p = f"up_blocks.{i}"
+        nl = cfg["layers_per_block"] + 1
+        for j in range(nl):
+            skip = in_c if j == nl - 1 else out_c
+            resnet(f"{p}.resnets.{j}", (prev if j == 0 else out_c) + skip, out_c)
+            if i > 0:
+                transformer(f"{p}.attentions.{j}", out_c)
+            if has_motion(n - 1 - i, True):
+                motion(f"{p}.motion_modules.{j}", out_c)
+        if i < n - 1:
+            conv(f"{p}.upsamplers.0.conv", out_c, out_c, 3)
+    norm("conv_norm_out", boc[0]); conv("conv_out", cfg["out_channels"], boc[0], 3)
+    return spec
+
+
+def sinusoidal_pe(max_len, d_model):
+    """motion_module.py:295-299 (same torch ops, so the buffer is bit-identical to the reference's)."""
+    position = torch.arange(max_len).unsqueeze(1)
+    div_term = torch.exp(torch.arange(0, d_model, 2) * (-math.log(10000.0) / d_model))
+    pe = torch.zeros(1, max_len, d_model)
+    pe[0, :, 0::2] = torch.sin(position * div_term)
+    pe[0, :, 1::2] = torch.cos(position * div_term)
+    return pe
+
+
+class ImageProjModel(ParamTreeModel):
+    """ip_adapter/my_ip_adapter.py:28-45: Linear(clip_dim -> T*D) + LayerNorm(D); forward runs on the engine."""
+
+    def __init__(self, cross_attention_dim=1024, clip_embeddings_dim=1024, clip_extra_context_tokens=4):
+        super().__init__()
+        self.cross_attention_dim, self.clip_extra_context_tokens = cross_attention_dim, clip_extra_context_tokens
+        self._build_tree(OrderedDict([("proj.weight", (clip_extra_context_tokens * cross_attention_dim, clip_embeddings_dim)),
+                                      ("proj.bias", (clip_extra_context_tokens * cross_attention_dim,)),
+                                      ("norm.weight", (cross_attention_dim,)), ("norm.bias", (cross_attention_dim,))]))
+
+    def forward(self, image_embeds):
+        x = image_embeds.float().contiguous()
+        y = ops.gemm(x, self._p("proj.weight").detach(), bias=self._p("proj.bias").detach())
+        y = ops.layernorm(y.view(-1, self.cross_attention_dim), self._p("norm.weight").detach(), self._p("norm.bias").detach())
+        return y.view(x.shape[0], self.clip_extra_context_tokens, self.cross_attention_dim)
+
+
+class UNet3DConditionModel(ParamTreeModel):
+    _supports_gradient_checkpointing = True
+
+    def __init__(self, sample_size=None, in_channels=4, out_channels=4, center_input_sample=False, flip_sin_to_cos=True,
+                 freq_shift=0,
+                 down_block_types=("CrossAttnDownBlock3D", "CrossAttnDownBlock3D", "CrossAttnDownBlock3D", "DownBlock3D"),
+                 mid_block_type="UNetMidBlock3DCrossAttn",
+                 up_block_types=("UpBlock3D", "CrossAttnUpBlock3D", "CrossAttnUpBlock3D", "CrossAttnUpBlock3D"),
+                 only_cross_attention=False, block_out_channels=(320, 640, 1280, 1280), layers_per_block=2,
+                 downsample_padding=1, mid_block_scale_factor=1, act_fn="silu", norm_num_groups=32, norm_eps=1e-5,
+                 cross_attention_dim=1280, attention_head_dim=8, dual_cross_attention=False, use_linear_projection=False,
+                 class_embed_type=None, num_class_embeds=None, upcast_attention=False, resnet_time_scale_shift="default",
+                 use_motion_module=False, motion_module_resolutions=(1, 2, 4, 8), motion_module_mid_block=False,
+                 motion_module_decoder_only=False, motion_module_type=None, motion_module_kwargs=None,
+                 unet_use_cross_frame_attention=None, unet_use_temporal_attention=None, use_pseudo_conv3d=False,
+                 use_first_frame_condition_concat=False, image_condition_dim=1024, use_ip_cross_attention=False, scale=1.0,
+                 num_tokens=4, use_camera_motion_condition=False, use_text_encoder_2=False, text_encoder_2_dim=4096,
+                 use_inflated_groupnorm=False, use_fps_condition=False, use_temporal_conv=False,
+                 use_first_frame_mask_condition_concat=False, **unused):
+        super().__init__()
+        kw = {k: v for k, v in locals().items() if k not in ("self", "unused", "__class__")}
+        kw["motion_module_kwargs"] = dict(motion_module_kwargs or {})
+        unsupported = dict(center_input_sample=False, only_cross_attention=False, dual_cross_attention=False,
+                           use_linear_projection=False, class_embed_type=None, num_class_embeds=None,
+                           upcast_attention=False, resnet_time_scale_shift="default", use_pseudo_conv3d=False,
+                           use_text_encoder_2=False, use_temporal_conv=False, downsample_padding=1,
+                           mid_block_scale_factor=1, act_fn="silu")
+        for k, v in unsupported.items():
+            if kw[k] != v:
+                raise NotImplementedError(f"UNet3DConditionModel: {k}={kw[k]!r} is outside the shipped inference configs")
+        if unet_use_cross_frame_attention or unet_use_temporal_attention:
+            raise NotImplementedError("unet_use_cross_frame_attention / unet_use_temporal_attention are off in every shipped config")
+        if tuple(down_block_types) != ("CrossAttnDownBlock3D",) * (len(block_out_channels) - 1) + ("DownBlock3D",):
+            raise NotImplementedError(f"down_block_types {down_block_types}")
+        if use_motion_module and motion_module_type != "Vanilla":
+            raise ValueError(f"unknown motion_module_type {motion_module_type}")
+        mm = dict(num_attention_heads=8, num_transformer_block=2, attention_block_types=("Temporal_Self", "Temporal_Self"),
+                  cross_frame_attention_mode=None, temporal_position_encoding=False, temporal_position_encoding_max_len=24,
+                  temporal_attention_dim_div=1, zero_initialize=True, add_temporal_lora=False, rank=4,
+                  use_rope_postion_encoding=False)
+        mm.update(kw["motion_module_kwargs"])
+        if mm["temporal_attention_dim_div"] != 1 or mm["use_rope_postion_encoding"] or any(
+                t != "Temporal_Self" for t in mm["attention_block_types"]):
+            raise NotImplementedError("motion module variant outside the shipped configs")
+        self._mm = mm
+        self.config = FrozenDict(dict(kw, _class_name="UNet3DConditionModel", _diffusers_version="0.11.1"))
+        self.sample_size = sample_size
+        self.in_channels = in_channels
+        self.image_proj_model = None
+        cfg = dict(kw, motion_module_kwargs=mm)
+        self._cfg = cfg
+        spec = unet_param_spec(cfg)
+        buffers = {k: sinusoidal_pe(s[1], s[2]) for k, s in spec.items() if k.endswith(".pos_encoder.pe")}
+        self._build_tree(spec, buffers)
+        self._heads = _as_tuple(attention_head_dim, len(block_out_channels))
+        self.num_upsamplers = len(block_out_channels) - 1
+
+    # ------------------------------------------------------------------------------------------ construction
+    @classmethod
+    def from_config(cls, config, **kwargs):
+        cfg = {k: v for k, v in dict(config).items() if not k.startswith("_")}
+        cfg.update(kwargs)
+        return cls(**cfg)
+
+    @classmethod
+    def from_pretrained_2d(cls, pretrained_model_path, subfolder=None, unet_additional_kwargs=None):
+        """animatediff/models/unet.py:674-726: SD-1.5 2-D UNet folder (config.json + diffusion_pytorch_model.bin)
+        inflated to the 3-D model; conv_in zero-extended to 9 input channels when a concat condition is on."""
+        unet_additional_kwargs = dict(unet_additional_kwargs or {})
+        if subfolder is not None:
+            pretrained_model_path = os.path.join(pretrained_model_path, subfolder)
+        config_file = os.path.join(pretrained_model_path, "config.json")
+        if not os.path.isfile(config_file):
+            raise RuntimeError(f"{config_file} does not exist")
+        with open(config_file) as f:
+            config = json.load(f)
+        config["down_block_types"] = ["CrossAttnDownBlock3D"] * 3 + ["DownBlock3D"]
+        config["up_block_types"] = ["UpBlock3D"] + ["CrossAttnUpBlock3D"] * 3
+        model = cls.from_config(config, **unet_additional_kwargs)
+        model_file = os.path.join(pretrained_model_path, "diffusion_pytorch_model.bin")
+        if not os.path.isfile(model_file):
+            raise RuntimeError(f"{model_file} does not exist")
+        state_dict = torch.load(model_file, map_location="cpu")
+        if unet_additional_kwargs.get("use_first_frame_condition_concat") or unet_additional_kwargs.get("use_first_frame_mask_condition_concat"):
+            w = torch.zeros_like(model._p("conv_in.weight"))
+            w[:, :4] = state_dict["conv_in.weight"]
+            state_dict["conv_in.weight"] = w
+        m, u = model.load_state_dict(state_dict, strict=False)
+        print(f"### missing keys: {len(m)}; \n### unexpected keys: {len(u)};")
+        return model
+
+    # ------------------------------------------------------------------------------------------ packed weights
+    def _fw(self, key):
+        """fp32 weight (time-embedding MLPs always run in fp32)"""
+        return self._cached(("fw", key), lambda: self._p(key).detach().float().contiguous())
+
+    def _cat_w(self, name, keys, lora=None):
+        def make():
+            ws = []
+            for i, k in enumerate(keys):
+                w = self._p(k).detach().float()
+                if lora is not None and self._has(lora[i] + ".down.weight"):      # motion_module.py:389-456, scale 1.0
+                    w = w + self._p(lora[i] + ".up.weight").detach().float() @ self._p(lora[i] + ".down.weight").detach().float()
+                ws.append(w)
+            return torch.cat(ws, dim=0).to(self._compute_dtype).contiguous()
+        return self._cached(("cat", name), make)
+
+    def _geglu(self, p):
+        def make():
+            w, b = geglu_interleave(self._p(p + ".net.0.proj.weight").detach().float(), self._p(p + ".net.0.proj.bias").detach().float())
+            return w.to(self._compute_dtype).contiguous(), b
+        return self._cached(("geglu", p), make)
+
+    def _freqs(self):
+        def make():
+            half = self._cfg["block_out_channels"][0] // 2
+            exponent = -math.log(10000) * torch.arange(half, dtype=torch.float32) / (half - self._cfg["freq_shift"])
+            return torch.exp(exponent).to(self.device)          # embeddings.py:39-44, evaluated on the host like the reference
+        return self._cached(("freqs",), make)
+
+    # ------------------------------------------------------------------------------------------ blocks
+    def _gn(self, p, x, B, silu, per_frame, eps=None, groups=None):
+        eps = self._cfg["norm_eps"] if eps is None else eps
+        g = self._cfg["norm_num_groups"] if groups is None else groups
+        nb = x.shape[0] if (per_frame or self._cfg["use_inflated_groupnorm"]) else B
+        return ops.groupnorm(x, self._f(p + ".weight"), self._f(p + ".bias"), g, eps, silu=silu, stat_batches=nb)
+
+    def _resnet(self, p, x, semb, B, F):
+        NB, H, W, Cin = x.shape
+        temb = ops.gemm(semb, self._fw(p + ".time_emb_proj.weight"), bias=self._f(p + ".time_emb_proj.bias"))   # [B, Cout] fp32
+        h = self._gn(p + ".norm1", x, B, True, False)
+        h = ops.conv3x3(h, self._conv_w(p + ".conv1.weight"), bias=self._f(p + ".conv1.bias"), rowbias=temb, images_per_group=F)
+        h = self._gn(p + ".norm2", h, B, True, False)
+        if self._has(p + ".conv_shortcut.weight"):
+            res = ops.gemm(x.view(-1, Cin), self._w1x1(p + ".conv_shortcut.weight"), bias=self._f(p + ".conv_shortcut.bias"))
+            res = res.view(NB, H, W, -1)
+        else:
+            res = x
+        return ops.conv3x3(h, self._conv_w(p + ".conv2.weight"), bias=self._f(p + ".conv2.bias"), residual=res)
+
+    def _ff(self, p, tok, n):
+        w1, b1 = self._geglu(p)
+        h = ops.gemm(n, w1, bias=b1, geglu=True)
+        return ops.gemm(h, self._w(p + ".net.2.weight"), bias=self._f(p + ".net.2.bias"), residual=tok)
+
+    def _transformer(self, p, x, ctx, heads, F):
+        NB, H, W, C = x.shape
+        M, HW, d = NB * H * W, H * W, C // heads
+        res = x.view(M, C)
+        h = self._gn(p + ".norm", x, None, False, True, eps=1e-6)
+        tok = ops.gemm(h.view(M, C), self._w1x1(p + ".proj_in.weight"), bias=self._f(p + ".proj_in.bias"))
+        q = p + ".transformer_blocks.0"
+        # self attention (attention.py:507)
+        n1 = ops.layernorm(tok, self._f(q + ".norm1.weight"), self._f(q + ".norm1.bias"))
+        qkv = ops.gemm(n1, self._cat_w(q + ".attn1", [q + ".attn1.to_q.weight", q + ".attn1.to_k.weight", q + ".attn1.to_v.weight"]))
+        qkv = qkv.view(NB, HW, 3 * C)
+        o = ops.attention(qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:], heads, d ** -0.5)
+        tok = ops.gemm(o.view(M, C), self._w(q + ".attn1.to_out.0.weight"), bias=self._f(q + ".attn1.to_out.0.bias"), residual=tok)
+        # cross attention (attention.py:516-521; IPCrossAttention.forward :49-127)
+        n2 = ops.layernorm(tok, self._f(q + ".norm2.weight"), self._f(q + ".norm2.bias"))
+        qx = ops.gemm(n2, self._w(q + ".attn2.to_q.weight")).view(NB, HW, C)
+        Bc, L, xd = ctx.shape
+        kv = ops.gemm(ctx.view(Bc * L, xd), self._cat_w(q + ".attn2", [q + ".attn2.to_k.weight", q + ".attn2.to_v.weight"])).view(Bc, L, 2 * C)
+        if self._cfg["use_ip_cross_attention"]:
+            T = self._cfg["num_tokens"]
+            # reference quirk (animatediff/models/attention.py:43): without xformers the IP scale replaces d^-1/2
+            sc = d ** -0.5 if self._xformers_semantics else float(self._cfg["scale"])
+            o = ops.attention(qx, kv[:, :L - T, :C], kv[:, :L - T, C:], heads, sc, kv_batch_div=F)
+            kvi = ops.gemm(ctx.view(Bc * L, xd), self._cat_w(q + ".attn2ip", [q + ".attn2.to_k_ip.weight", q + ".attn2.to_v_ip.weight"])).view(Bc, L, 2 * C)
+            ops.attention(qx, kvi[:, L - T:, :C], kvi[:, L - T:, C:], heads, sc, out=o, out_alpha=float(self._cfg["scale"]),
+                          accumulate=True, kv_batch_div=F)
+        else:
+            o = ops.attention(qx, kv[:, :, :C], kv[:, :, C:], heads, d ** -0.5, kv_batch_div=F)
+        tok = ops.gemm(o.view(M, C), self._w(q + ".attn2.to_out.0.weight"), bias=self._f(q + ".attn2.to_out.0.bias"), residual=tok)
+        # feed forward (attention.py:563)
+        n3 = ops.layernorm(tok, self._f(q + ".norm3.weight"), self._f(q + ".norm3.bias"))
+        tok = self._ff(q + ".ff", tok, n3)
+        out = ops.gemm(tok, self._w1x1(p + ".proj_out.weight"), bias=self._f(p + ".proj_out.bias"), residual=res)
+        return out.view(NB, H, W, C)
+
+    def _motion(self, p, x, B, F):
+        p = p + ".temporal_transformer"
+        mm = self._mm
+        NB, H, W, C = x.shape
+        M, HW, heads = NB * H * W, H * W, mm["num_attention_heads"]
+        d = C // heads
+        res = x.view(M, C)
+        h = self._gn(p + ".norm", x, None, False, True, eps=1e-6, groups=32)
+        tok = ops.gemm(h.view(M, C), self._w(p + ".proj_in.weight"), bias=self._f(p + ".proj_in.bias"))
+        for b in range(mm["num_transformer_block"]):
+            q = p + f".transformer_blocks.{b}"
+            for j in range(len(mm["attention_block_types"])):
+                a = q + f".attention_blocks.{j}"
+                pe = None
+                if self._has(a + ".pos_encoder.pe"):
+                    if F > self._p(a + ".pos_encoder.pe").shape[1]:
+                        raise ValueError(f"video_length {F} exceeds temporal_position_encoding_max_len")
+                    pe = self._cached(("pe", a), lambda a=a: self._p(a + ".pos_encoder.pe").detach()[0].float().contiguous())
+                n = ops.layernorm(tok, self._f(q + f".norms.{j}.weight"), self._f(q + f".norms.{j}.bias"), pe=pe,
+                                  rows_per_frame=HW, frames=F)
+                names = ["to_q", "to_k", "to_v"]
+                wqkv = self._cat_w(a, [a + f".{nm}.weight" for nm in names], lora=[a + f".{nm}_lora" for nm in names])
+                qkv = ops.gemm(n, wqkv).view(B, F, HW, 3 * C)
+                o = ops.temporal_attention(qkv, heads, d ** -0.5)
+                wo = self._cat_w(a + ".out", [a + ".to_out.0.weight"], lora=[a + ".to_out_lora"])
+                tok = ops.gemm(o.view(M, C), wo, bias=self._f(a + ".to_out.0.bias"), residual=tok)
+            n = ops.layernorm(tok, self._f(q + ".ff_norm.weight"), self._f(q + ".ff_norm.bias"))
+            tok = self._ff(q + ".ff", tok, n)
+        out = ops.gemm(tok, self._w(p + ".proj_out.weight"), bias=self._f(p + ".proj_out.bias"), residual=res)
+        return out.view(NB, H, W, C)
+
+    # ------------------------------------------------------------------------------------------ forward
+    def _embed(self, name, values, B, residual=None):
+        dev = self.device
+        v = torch.as_tensor(values)
+        v = (v.reshape(1) if v.dim() == 0 else v.reshape(-1)).to(device=dev, dtype=torch.int64).expand(B).contiguous()
+        s = ops.timestep_embed(v, self._freqs(), self._cfg["flip_sin_to_cos"])
+        h = ops.silu(ops.gemm(s, self._fw(name + ".linear_1.weight"), bias=self._f(name + ".linear_1.bias")))
+        return ops.gemm(h, self._fw(name + ".linear_2.weight"), bias=self._f(name + ".linear_2.bias"), residual=residual)
+
+    def _to_compute(self, t):
+        """fp32 tensor of any shape -> contiguous compute-dtype copy (conversion kernel of the engine)."""
+        t = t.to(device=self.device, dtype=torch.float32).contiguous()
+        if self._compute_dtype == torch.float32:
+            return t
+        return ops.ncfhw_to_nfhwc(t.view(1, 1, 1, 1, -1), self._compute_dtype).view(t.shape)
+
+    def forward_nfhwc(self, x, timestep, encoder_hidden_states, fps_tensor=None, flow_control=None,
+                      reference_images_clip_feat=None, camera_movement_type_tensor=None, use_ip_cross_attention=False,
+                      use_camera_motion_condition=False, use_fps_condition=False, use_first_frame_condition_concat=False):
+        """Engine entry: x [B, F, H, W, Cin] channels-last in the compute dtype -> fp32 [B, F, H, W, out_channels]."""
+        if not x.is_cuda:
+            raise RuntimeError("UNet3DConditionModel runs only on CUDA (B200); the CPU path is the reference/oracle")
+        cfg = self._cfg
+        B, F, H, W, Cin = x.shape
+        x = x.reshape(B * F, H, W, Cin)
+        boc = tuple(cfg["block_out_channels"])
+        n = len(boc)
+        emb = self._embed("time_embedding", timestep, B)
+        if use_camera_motion_condition:
+            emb = self._embed("camera_motion_embedding", camera_movement_type_tensor, B, residual=emb)
+        if use_fps_condition:
+            emb = self._embed("fps_embedding", fps_tensor, B, residual=emb)
+            emb = self._embed("motion_embedding", flow_control, B, residual=emb)
+        semb = ops.silu(emb)                                     # every resnet applies SiLU to emb first (resnet.py:307)
+        ctx = self._to_compute(encoder_hidden_states)
+        if use_ip_cross_attention:
+            ipm = self.image_proj_model
+            if ipm is None:
+                raise RuntimeError("use_ip_cross_attention=True but unet.image_proj_model is not set (scripts/inference.py:166)")
+            tokens = ipm(reference_images_clip_feat.to(self.device))
+            tokens = self._to_compute(tokens.float())
+            ctx = ops.concat_channels(ctx.view(B, -1), tokens.view(B, -1)).view(B, -1, ctx.shape[-1])   # unet.py:592-594
+        if use_first_frame_condition_concat:
+            w_in = self._cached(("cin_half",), lambda: (self._conv_w("conv_in.weight") * 0.5).contiguous())
+            b_in = self._cached(("bin_half",), lambda: self._f("conv_in.bias") * 0.5)
+        else:
+            w_in, b_in = self._conv_w("conv_in.weight"), self._f("conv_in.bias")
+        x = ops.conv3x3(x, w_in, bias=b_in)
+
+        def motion_on(level, decoder):
+            on = cfg["use_motion_module"] and (2 ** level) in tuple(cfg["motion_module_resolutions"])
+            return on and (decoder or not cfg["motion_module_decoder_only"])
+
+        skips = [x]
+        for i in range(n):
+            p = f"down_blocks.{i}"
+            for j in range(cfg["layers_per_block"]):
+                x = self._resnet(f"{p}.resnets.{j}", x, semb, B, F)
+                if i < n - 1:
+                    x = self._transformer(f"{p}.attentions.{j}", x, ctx, self._heads[i], F)
+                if motion_on(i, False):
+                    x = self._motion(f"{p}.motion_modules.{j}", x, B, F)
+                skips.append(x)
+            if i < n - 1:
+                x = ops.conv3x3(x, self._conv_w(f"{p}.downsamplers.0.conv.weight"), bias=self._f(f"{p}.downsamplers.0.conv.bias"), stride=2)
+                skips.append(x)
+        x = self._resnet("mid_block.resnets.0", x, semb, B, F)
+        x = self._transformer("mid_block.attentions.0", x, ctx, self._heads[-1], F)
+        if cfg["use_motion_module"] and cfg["motion_module_mid_block"]:
+            x = self._motion("mid_block.motion_modules.0", x, B, F)
+        x = self._resnet("mid_block.resnets.1", x, semb, B, F)
+        for i in range(n):
+            p = f"up_blocks.{i}"
+            lvl = n - 1 - i
+            for j in range(cfg["layers_per_block"] + 1):
+                x = ops.concat_channels(x, skips.pop())
+                x = self._resnet(f"{p}.resnets.{j}", x, semb, B, F)
+                if i > 0:
+                    x = self._transformer(f"{p}.attentions.{j}", x, ctx, self._heads[lvl], F)
+                if motion_on(lvl, True):
+                    x = self._motion(f"{p}.motion_modules.{j}", x, B, F)
+            if i < n - 1:
+                x = ops.conv3x3(x, self._conv_w(f"{p}.upsamplers.0.conv.weight"), bias=self._f(f"{p}.upsamplers.0.conv.bias"), upsample=2)
+        x = self._gn("conv_norm_out", x, B, True, False)
+        y = ops.conv3x3(x, self._conv_w("conv_out.weight"), bias=self._f("conv_out.bias"), out_f32=True)
+        return y.view(B, F, H, W, -1)
+
+    @torch.no_grad()
+    def forward(self, sample, timestep, encoder_hidden_states, class_labels=None, attention_mask=None, return_dict=True,
+                use_first_frame_condition=False, use_first_frame_condition_concat=False, use_ip_cross_attention=False,
+                reference_images_latent=None, reference_images_clip_feat=None, use_camera_motion_condition=False,
+                camera_movement_type_tensor=None, use_image_concat_training=False, use_text_encoder_2=False,
+                encoder_hidden_states_2=None, use_fps_condition=False, fps_tensor=None, first_images_mask=None,
+                flow_control=None):
+        """Same signature/semantics as animatediff/models/unet.py:422-672 (sample: (b, c, f, h, w))."""
+        if use_first_frame_condition or use_text_encoder_2 or class_labels is not None or attention_mask is not None:
+            raise NotImplementedError("forward option outside the shipped inference path")
+        x = sample.to(device=self.device, dtype=torch.float32)
+        if use_first_frame_condition_concat and reference_images_latent is not None:          # unet.py:578-583
+            first = reference_images_latent.to(x).unsqueeze(2).expand(-1, -1, x.shape[2], -1, -1)
+            x = torch.cat((x, first), dim=1)
+        x = ops.ncfhw_to_nfhwc(x.contiguous(), self._compute_dtype)
+        y = self.forward_nfhwc(x, timestep, encoder_hidden_states, fps_tensor=fps_tensor, flow_control=flow_control,
+                               reference_images_clip_feat=reference_images_clip_feat,
+                               camera_movement_type_tensor=camera_movement_type_tensor,
+                               use_ip_cross_attention=use_ip_cross_attention,
+                               use_camera_motion_condition=use_camera_motion_condition,
+                               use_fps_condition=use_fps_condition,
+                               use_first_frame_condition_concat=use_first_frame_condition_concat)
+        out = ops.nfhwc_to_ncfhw(y)
+        if not return_dict:
+            return (out,)
+        return UNet3DConditionOutput(sample=out)

@@ -1,0 +1,184 @@
+"""AutoencoderKL: reference call surface (diffusers/models/vae.py:500-638), CUDA engine underneath.
+
+Round-1 scope is the decoder half: ``decode(z).sample`` and the batched ``decode_frames`` used by
+``AnimationPipeline.decode_latents``.  All frames of a clip are decoded in ONE batch (the reference loops batch-1
+calls, pipeline_animation.py:405-408); GroupNorm statistics are per image so the result is identical.
+The mid-block attention (one 512-wide head over H*W tokens, softmax in fp32 - diffusers/models/attention.py:331-379)
+is three tensor-core GEMMs (QK^T with fp32 scores, PV on V^T) around an fp32 row-softmax kernel.
+The encoder (``encode``) is a "next" row: its parameters are part of the state dict so checkpoints load,
+but calling it raises.
+"""
+from collections import OrderedDict
+from dataclasses import dataclass
+
+import torch
+
+from . import ops
+from .modeling import FrozenDict, ParamTreeModel
+
+
+@dataclass
+class DecoderOutput:
+    sample: torch.Tensor
+
+
+def vae_param_spec(cfg):
+    spec = OrderedDict()
+    boc = tuple(cfg["block_out_channels"])
+    lc = cfg["latent_channels"]
+    lpb = cfg["layers_per_block"]
+
+    def conv(p, o, i, k):
+        spec[p + ".weight"] = (o, i, k, k); spec[p + ".bias"] = (o,)
+
+    def norm(p, c):
+        spec[p + ".weight"] = (c,); spec[p + ".bias"] = (c,)
+
+    def lin(p, o, i):
+        spec[p + ".weight"] = (o, i); spec[p + ".bias"] = (o,)
+
+    def resnet(p, i, o):
+        norm(p + ".norm1", i); conv(p + ".conv1", o, i, 3); norm(p + ".norm2", o); conv(p + ".conv2", o, o, 3)
+        if i != o:
+            conv(p + ".conv_shortcut", o, i, 1)
+
+    def mid(p, c):
+        for nm in ("group_norm",):
+            norm(p + ".attentions.0." + nm, c)
+        for nm in ("query", "key", "value", "proj_attn"):
+            lin(p + ".attentions.0." + nm, c, c)
+        resnet(p + ".resnets.0", c, c); resnet(p + ".resnets.1", c, c)
+
+    conv("encoder.conv_in", boc[0], cfg["in_channels"], 3)
+    out_c = boc[0]
+    for i in range(len(boc)):
+        in_c, out_c = out_c, boc[i]
+        for j in range(lpb):
+            resnet(f"encoder.down_blocks.{i}.resnets.{j}", in_c if j == 0 else out_c, out_c)
+        if i < len(boc) - 1:
+            conv(f"encoder.down_blocks.{i}.downsamplers.0.conv", out_c, out_c, 3)
+    mid("encoder.mid_block", boc[-1])
+    norm("encoder.conv_norm_out", boc[-1]); conv("encoder.conv_out", 2 * lc, boc[-1], 3)
+    conv("decoder.conv_in", boc[-1], lc, 3)
+    rev = boc[::-1]
+    out_c = rev[0]
+    for i in range(len(boc)):
+        prev, out_c = out_c, rev[i]
+        for j in range(lpb + 1):
+            resnet(f"decoder.up_blocks.{i}.resnets.{j}", prev if j == 0 else out_c, out_c)
+        if i < len(boc) - 1:
+            conv(f"decoder.up_blocks.{i}.upsamplers.0.conv", out_c, out_c, 3)
+    mid("decoder.mid_block", boc[-1])
+    norm("decoder.conv_norm_out", boc[0]); conv("decoder.conv_out", cfg["out_channels"], boc[0], 3)
+    conv("quant_conv", 2 * lc, 2 * lc, 1); conv("post_quant_conv", lc, lc, 1)
+    return spec
+
+
+class AutoencoderKL(ParamTreeModel):
+    def __init__(self, in_channels=3, out_channels=3, down_block_types=("DownEncoderBlock2D",),
+                 up_block_types=("UpDecoderBlock2D",), block_out_channels=(64,), layers_per_block=1, act_fn="silu",
+                 latent_channels=4, norm_num_groups=32, sample_size=32, **unused):
+        super().__init__()
+        kw = dict(in_channels=in_channels, out_channels=out_channels, down_block_types=tuple(down_block_types),
+                  up_block_types=tuple(up_block_types), block_out_channels=tuple(block_out_channels),
+                  layers_per_block=layers_per_block, act_fn=act_fn, latent_channels=latent_channels,
+                  norm_num_groups=norm_num_groups, sample_size=sample_size)
+        if act_fn != "silu":
+            raise NotImplementedError(act_fn)
+        self.config = FrozenDict(dict(kw, _class_name="AutoencoderKL", _diffusers_version="0.11.1"))
+        self._cfg = kw
+        self.use_slicing = False
+        self._build_tree(vae_param_spec(kw))
+
+    @classmethod
+    def from_config(cls, config, **kwargs):
+        cfg = {k: v for k, v in dict(config).items() if not k.startswith("_")}
+        cfg.update(kwargs)
+        return cls(**cfg)
+
+    @classmethod
+    def from_pretrained(cls, path, subfolder=None, **kw):
+        import json, os
+        if subfolder is not None:
+            path = os.path.join(path, subfolder)
+        with open(os.path.join(path, "config.json")) as f:
+            model = cls.from_config(json.load(f))
+        sd_file = os.path.join(path, "diffusion_pytorch_model.bin")
+        model.load_state_dict(torch.load(sd_file, map_location="cpu"), strict=False)
+        return model
+
+    def enable_slicing(self):
+        self.use_slicing = True      # frames are independent either way; kept for API compatibility
+
+    def disable_slicing(self):
+        self.use_slicing = False
+
+    def encode(self, x, return_dict=True):
+        raise NotImplementedError("AutoencoderKL.encode (first-frame conditioning prep) is SURVEY 8f row 1 - not built yet")
+
+    # ------------------------------------------------------------------------------------------ decoder engine
+    def _gn(self, p, x, silu):
+        return ops.groupnorm(x, self._f(p + ".weight"), self._f(p + ".bias"), self._cfg["norm_num_groups"], 1e-6, silu=silu)
+
+    def _resnet(self, p, x):
+        NB, H, W, Cin = x.shape
+        h = self._gn(p + ".norm1", x, True)
+        h = ops.conv3x3(h, self._conv_w(p + ".conv1.weight"), bias=self._f(p + ".conv1.bias"))
+        h = self._gn(p + ".norm2", h, True)
+        res = x
+        if self._has(p + ".conv_shortcut.weight"):
+            res = ops.gemm(x.view(-1, Cin), self._w1x1(p + ".conv_shortcut.weight"), bias=self._f(p + ".conv_shortcut.bias")).view(NB, H, W, -1)
+        return ops.conv3x3(h, self._conv_w(p + ".conv2.weight"), bias=self._f(p + ".conv2.bias"), residual=res)
+
+    def _attn(self, p, x):
+        NB, H, W, C = x.shape
+        HW = H * W
+        t = self._gn(p + ".group_norm", x, False).view(NB * HW, C)
+        q = ops.gemm(t, self._w(p + ".query.weight"), bias=self._f(p + ".query.bias")).view(NB, HW, C)
+        k = ops.gemm(t, self._w(p + ".key.weight"), bias=self._f(p + ".key.bias")).view(NB, HW, C)
+        scores = ops.gemm(q, k, alpha=C ** -0.5, out_f32=True)                         # [NB, HW, HW] fp32
+        probs = ops.softmax_rows(scores, x.dtype)
+        del scores
+        # V^T[n] = Wv @ t[n]^T (bias folded into the next GEMM: softmax rows sum to 1, so P (V + 1 b^T) = P V + b^T)
+        wv = self._w(p + ".value.weight")
+        vt = ops.gemm(wv.unsqueeze(0).expand(NB, C, C), t.view(NB, HW, C))            # [NB, C, HW]
+        o = ops.gemm(probs, vt, bias=self._f(p + ".value.bias"))                       # [NB, HW, C]
+        out = ops.gemm(o.view(NB * HW, C), self._w(p + ".proj_attn.weight"), bias=self._f(p + ".proj_attn.bias"),
+                       residual=x.view(NB * HW, C))
+        return out.view(NB, H, W, C)
+
+    def decode_nhwc(self, z):
+        """z [N, h, w, latent] channels-last in the compute dtype -> [N, 8h, 8w, 3] (compute dtype)."""
+        if not z.is_cuda:
+            raise RuntimeError("AutoencoderKL.decode runs only on CUDA (B200); the CPU path is the reference/oracle")
+        NB, H, W, lc = z.shape
+        boc = self._cfg["block_out_channels"]
+        x = ops.gemm(z.reshape(-1, lc), self._w1x1("post_quant_conv.weight"), bias=self._f("post_quant_conv.bias")).view(NB, H, W, lc)
+        x = ops.conv3x3(x, self._conv_w("decoder.conv_in.weight"), bias=self._f("decoder.conv_in.bias"))
+        x = self._resnet("decoder.mid_block.resnets.0", x)
+        x = self._attn("decoder.mid_block.attentions.0", x)
+        x = self._resnet("decoder.mid_block.resnets.1", x)
+        for i in range(len(boc)):
+            for j in range(self._cfg["layers_per_block"] + 1):
+                x = self._resnet(f"decoder.up_blocks.{i}.resnets.{j}", x)
+            if i < len(boc) - 1:
+                p = f"decoder.up_blocks.{i}.upsamplers.0.conv"
+                x = ops.conv3x3(x, self._conv_w(p + ".weight"), bias=self._f(p + ".bias"), upsample=2)
+        x = self._gn("decoder.conv_norm_out", x, True)
+        return ops.conv3x3(x, self._conv_w("decoder.conv_out.weight"), bias=self._f("decoder.conv_out.bias"))
+
+    @torch.no_grad()
+    def decode(self, z, return_dict=True):
+        """diffusers/models/vae.py:600-610: z (n, 4, h, w) -> .sample (n, 3, 8h, 8w) fp32."""
+        z = z.to(device=self.device, dtype=torch.float32).contiguous()
+        n, c, h, w = z.shape
+        zz = ops.ncfhw_to_nfhwc(z.view(n, c, 1, h, w), self._compute_dtype).view(n, h, w, c)
+        y = self.decode_nhwc(zz)
+        out = ops.nfhwc_to_ncfhw(y.view(n, 1, y.shape[1], y.shape[2], y.shape[3]))
+        out = out.view(n, y.shape[3], y.shape[1], y.shape[2])
+        if not return_dict:
+            return (out,)
+        return DecoderOutput(sample=out)
+
+    def forward(self, *a, **kw):
+        raise NotImplementedError("AutoencoderKL.forward (encode+decode) needs the encoder: SURVEY 8f row 1")

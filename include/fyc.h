@@ -140,8 +140,9 @@ int32_t fyc_upsample_nearest2x(const void* x, void* out, int64_t NB, int64_t H, 
 /* torch.cat([a, b], dim=channels) (unet_blocks.py:763,885): a [M, C1], b [M, C2] -> out [M, C1+C2]. */
 int32_t fyc_concat_channels(const void* a, const void* b, void* out, int64_t M, int64_t C1, int64_t C2,
                             int32_t dtype, void* stream);
-/* fp32 (b, c, f, h, w) <-> dtype [b, f, h, w, c] */
-int32_t fyc_ncfhw_to_nfhwc(const float* in, void* out, int64_t B, int64_t C, int64_t F, int64_t HW,
+/* fp32 (b, c, f, h, w) <-> dtype [b, f, h, w, c]; the forward direction multiplies by `scale` in fp32 first
+ * (1/0.18215 latent scaling of decode_latents, pipeline_animation.py:402). */
+int32_t fyc_ncfhw_to_nfhwc(const float* in, void* out, int64_t B, int64_t C, int64_t F, int64_t HW, float scale,
                            int32_t dtype, void* stream);
 int32_t fyc_nfhwc_to_ncfhw(const void* in, float* out, int64_t B, int64_t C, int64_t F, int64_t HW,
                            int32_t dtype, void* stream);

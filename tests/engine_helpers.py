@@ -1,0 +1,157 @@
+"""Shared helpers for the GPU parity tests, smoke() and bench.py's checker legs.
+
+Build the product models at "mini" size with the deterministic synthetic state dict, run them on cuda:0 and run the
+CPU oracle on the same inputs.  (Imports oracle/: test infrastructure only.)
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from followyourclick_b200 import AnimationPipeline, AutoencoderKL, DDIMScheduler, ImageProjModel, UNet3DConditionModel  # noqa: E402
+from followyourclick_b200.synth import synth_clip_inputs, synth_state_dict  # noqa: E402
+from oracle import ref_pipeline, ref_unet, ref_vae  # noqa: E402
+from tests.cfgs import (CLIP_DIM, MINI_VAE, SCHED_V, mini_unet_oracle_cfg, mini_unet_ref_kwargs, unet_inputs)  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def golden(name):
+    return np.load(os.path.join(GOLD, name))
+
+
+def load_synth(model, seed=0):
+    sd = model.state_dict()
+    new = synth_state_dict({k: tuple(v.shape) for k, v in sd.items()}, seed)
+    missing, unexpected = model.load_state_dict(new, strict=False)
+    assert not unexpected and all(k.endswith(".pe") for k in missing), (missing, unexpected)
+    return {k: v.detach().clone().cpu() for k, v in model.state_dict().items()}
+
+
+def make_unet(variant, dtype=torch.float32, device="cuda"):
+    kw = mini_unet_ref_kwargs(variant)
+    unet = UNet3DConditionModel(**kw)
+    if kw.get("use_ip_cross_attention"):
+        unet.image_proj_model = ImageProjModel(cross_attention_dim=768, clip_embeddings_dim=CLIP_DIM,
+                                               clip_extra_context_tokens=kw["num_tokens"])
+    sd = load_synth(unet)
+    if device is not None:
+        unet.to(device)
+        unet.to(dtype)
+    return unet, sd
+
+
+def make_vae(dtype=torch.float32, device="cuda", cfg=MINI_VAE):
+    vae = AutoencoderKL(in_channels=3, out_channels=3, down_block_types=("DownEncoderBlock2D",) * 4,
+                        up_block_types=("UpDecoderBlock2D",) * 4, block_out_channels=cfg["block_out_channels"],
+                        layers_per_block=cfg["layers_per_block"], latent_channels=4, norm_num_groups=32)
+    sd = load_synth(vae)
+    if device is not None:
+        vae.to(device)
+        vae.to(dtype)
+    return vae, sd
+
+
+def unet_forward_kwargs(variant, inp, device):
+    ocfg = mini_unet_oracle_cfg(variant)
+    mv = lambda t: None if t is None else t.to(device)
+    return dict(encoder_hidden_states=mv(inp["ctx"]), use_ip_cross_attention=ocfg["use_ip_cross_attention"],
+                reference_images_clip_feat=mv(inp.get("clip")), use_camera_motion_condition=ocfg["use_camera_motion_condition"],
+                camera_movement_type_tensor=mv(inp.get("camera")), use_fps_condition=ocfg["use_fps_condition"],
+                fps_tensor=mv(inp.get("fps")), flow_control=mv(inp.get("flow")))
+
+
+def stats(a, b):
+    """error summary of a (test) against b (reference)"""
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    d = (a - b)
+    return dict(maxabs=float(d.abs().max()), rel_l2=float(d.norm() / (b.norm() + 1e-12)), ref_max=float(b.abs().max()),
+                finite=bool(torch.isfinite(a).all()))
+
+
+def run_unet_case(variant, dtype, against="golden"):
+    unet, sd = make_unet(variant, dtype)
+    inp = unet_inputs(variant)
+    out = unet(inp["sample"].cuda(), inp["timestep"], **unet_forward_kwargs(variant, inp, "cuda")).sample
+    torch.cuda.synchronize()
+    if against == "golden":
+        ref = torch.from_numpy(golden(f"unet_{variant}.npz")["out"])
+    else:
+        ref = ref_unet.unet3d_forward(sd, mini_unet_oracle_cfg(variant), inp["sample"], inp["timestep"], inp["ctx"],
+                                      fps_tensor=inp.get("fps"), flow_control=inp.get("flow"),
+                                      reference_images_clip_feat=inp.get("clip"), camera_movement_type_tensor=inp.get("camera"))
+    return stats(out, ref)
+
+
+def run_vae_case(dtype):
+    vae, sd = make_vae(dtype)
+    g = golden("vae.npz")
+    out = vae.decode(torch.from_numpy(g["z"]).cuda()).sample
+    torch.cuda.synchronize()
+    return stats(out, torch.from_numpy(g["out"]))
+
+
+class FakeTokenizer:
+    model_max_length = 77
+
+    def __call__(self, prompt, **kw):
+        n = len(prompt) if isinstance(prompt, list) else 1
+        ids = torch.zeros(n, 77, dtype=torch.long)
+        return type("Tok", (), dict(input_ids=ids, attention_mask=torch.ones_like(ids)))()
+
+
+class FakeTextEncoder(torch.nn.Module):
+    """Seeded embeddings stand in for CLIP (outside the hot path): cond for the prompt call, uncond for the negative."""
+
+    def __init__(self, emb):
+        super().__init__()
+        self.emb, self.calls, self.config = emb, 0, type("Cfg", (), {})()
+
+    def forward(self, ids, attention_mask=None):
+        i = self.calls
+        self.calls += 1
+        e = self.emb[1:2] if i % 2 == 0 else self.emb[0:1]
+        return (e.to(ids.device),)
+
+
+def make_pipeline(dtype, variant="base", vae_cfg=MINI_VAE, device="cuda", clip_inputs=None):
+    unet, usd = make_unet(variant, dtype, device)
+    vae, vsd = make_vae(dtype, device, vae_cfg)
+    ci = clip_inputs if clip_inputs is not None else synth_clip_inputs(1, 4, 8, 8)
+    sched = DDIMScheduler(**{k: v for k, v in SCHED_V.items()})
+    pipe = AnimationPipeline(vae=vae, text_encoder=FakeTextEncoder(ci["text_embeddings"]), tokenizer=FakeTokenizer(),
+                             unet=unet, scheduler=sched)
+    pipe.set_progress_bar_config(disable=True)
+    return pipe, ci, usd, vsd
+
+
+def pipeline_call(pipe, ci, F, h, w, steps, gs):
+    pipe.text_encoder.calls = 0
+    return pipe("p", negative_prompt="n", video_length=F, height=h * 8, width=w * 8, num_inference_steps=steps,
+                guidance_scale=gs, latents=ci["latents"].clone(), use_first_frame_mask_condition_concat=True,
+                first_image_latents=ci["first_image_latents"], use_fps_condition=True, fps_tensor=torch.tensor([2]),
+                flow_control=torch.tensor([4]), first_images_mask=ci["first_images_mask"]).videos
+
+
+def run_pipeline_case(dtype, steps=3, against="oracle"):
+    """cfg1-style plumbing at mini size: F=4, 8x8 latents, CFG 8.0, mask/first-frame concat, fps/flow condition."""
+    F, h, w, gs = 4, 8, 8, 8.0
+    pipe, ci, usd, vsd = make_pipeline(dtype)
+    video = pipeline_call(pipe, ci, F, h, w, steps, gs)
+    if against == "golden":
+        assert steps == 3
+        ref = torch.from_numpy(golden("pipeline.npz")["video"])
+    else:
+        lat = ref_pipeline.denoise(usd, mini_unet_oracle_cfg("base"), SCHED_V, ci["latents"], ci["text_embeddings"], steps, gs,
+                                   first_image_latents=ci["first_image_latents"], first_images_mask=ci["first_images_mask"],
+                                   fps_tensor=torch.tensor([2]), flow_control=torch.tensor([4]))
+        ref = ref_vae.decode_latents(vsd, MINI_VAE, lat)
+    s = stats(video, ref)
+    mse = float(((video.float() - ref) ** 2).mean())
+    return dict(video_maxabs=s["maxabs"], video_rel_l2=s["rel_l2"], psnr=float(10 * np.log10(1.0 / max(mse, 1e-20))),
+                shape=tuple(video.shape), finite=s["finite"])

@@ -1,0 +1,279 @@
+"""Per-kernel parity (GPU): every C-ABI entry point against a plain PyTorch fp32 reference of the same op.
+
+Tolerances: fp32 kernels - rel-L2 <= 2e-5 (fp32 re-association only); bf16 storage with fp32 accumulation - rel-L2 <=
+1.5e-2 against the fp32 reference fed the same bf16-rounded inputs (output rounding 2^-9 + operand rounding);
+integer/elementwise fp32 glue (DDIM step, layout) - bit exact.
+"""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+F32_TOL = 2e-5
+BF16_TOL = 1.5e-2
+
+
+def rel(a, b):
+    a, b = a.float(), b.float()
+    return float((a - b).norm() / (b.norm() + 1e-12))
+
+
+def rnd(shape, seed, dtype=torch.float32, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(dtype).cuda()
+
+
+def tol(dtype):
+    return F32_TOL if dtype == torch.float32 else BF16_TOL
+
+
+MODES = [(torch.float32, "simt"), (torch.bfloat16, "simt"), (torch.bfloat16, "tc")]
+
+
+@pytest.fixture(autouse=True)
+def _impl(cuda):
+    from followyourclick_b200 import ops
+    yield
+    ops.set_impl("auto")
+
+
+@pytest.mark.parametrize("dtype,impl", MODES)
+@pytest.mark.parametrize("M,N,K", [(256, 320, 320), (300, 160, 64), (4096, 960, 320), (154, 640, 768), (128, 2560, 320),
+                                   (2, 1280, 320), (1000, 48, 72)])
+def test_gemm_bias_residual(dtype, impl, M, N, K):
+    from followyourclick_b200 import ops
+    if impl == "tc" and (M < 64 or N % 16 or K % 8):
+        pytest.skip("shape not eligible for the tcgen05 path")
+    ops.set_impl(impl)
+    A, W = rnd((M, K), 1, dtype), rnd((N, K), 2, dtype, K ** -0.5)
+    bias, res = rnd((N,), 3), rnd((M, N), 4, dtype)
+    out = ops.gemm(A, W, bias=bias, residual=res, alpha=0.5)
+    ref = 0.5 * (A.float() @ W.float().t()) + bias + res.float()
+    assert out.dtype == dtype and rel(out, ref) < tol(dtype), rel(out, ref)
+
+
+@pytest.mark.parametrize("dtype,impl", MODES)
+def test_gemm_rowbias_and_f32_out(dtype, impl):
+    from followyourclick_b200 import ops
+    ops.set_impl(impl)
+    M, N, K, rpg = 512, 320, 128, 128
+    A, W, rb = rnd((M, K), 1, dtype), rnd((N, K), 2, dtype, K ** -0.5), rnd((M // rpg, N), 3)
+    out = ops.gemm(A, W, rowbias=rb, rows_per_group=rpg, out_f32=True)
+    ref = A.float() @ W.float().t() + rb.repeat_interleave(rpg, dim=0)
+    assert out.dtype == torch.float32 and rel(out, ref) < (F32_TOL if dtype == torch.float32 else 4e-3)
+
+
+@pytest.mark.parametrize("dtype,impl", MODES)
+def test_gemm_geglu(dtype, impl):
+    from followyourclick_b200 import ops
+    from followyourclick_b200.modeling import geglu_interleave
+    ops.set_impl(impl)
+    M, C = 384, 160
+    x, w, b = rnd((M, C), 1, dtype), rnd((8 * C, C), 2, torch.float32, C ** -0.5), rnd((8 * C,), 3)
+    wi, bi = geglu_interleave(w, b)
+    out = ops.gemm(x, wi.to(dtype).contiguous(), bias=bi.contiguous(), geglu=True)
+    h = x.float() @ w.to(dtype).float().t() + b
+    a, g = h.chunk(2, dim=-1)
+    ref = a * F.gelu(g)
+    assert out.shape == (M, 4 * C) and rel(out, ref) < tol(dtype), rel(out, ref)
+
+
+@pytest.mark.parametrize("dtype,impl", MODES)
+def test_gemm_batched_scores_and_shared_A(dtype, impl):
+    from followyourclick_b200 import ops
+    ops.set_impl(impl)
+    NB, HW, C = 3, 256, 128
+    q, k = rnd((NB, HW, C), 1, dtype), rnd((NB, HW, C), 2, dtype)
+    s = ops.gemm(q, k, alpha=C ** -0.5, out_f32=True)
+    ref = torch.einsum("bik,bjk->bij", q.float(), k.float()) * C ** -0.5
+    assert rel(s, ref) < (F32_TOL if dtype == torch.float32 else 4e-3)
+    w = rnd((C, C), 3, dtype, C ** -0.5)
+    vt = ops.gemm(w.unsqueeze(0).expand(NB, C, C), k)            # [NB, C, HW] = W @ k[n]^T
+    assert rel(vt, torch.einsum("ck,bjk->bcj", w.float(), k.float())) < tol(dtype)
+
+
+@pytest.mark.parametrize("dtype,impl", MODES)
+@pytest.mark.parametrize("NB,H,W,Cin,Cout,stride,up", [(4, 16, 16, 64, 32, 1, 1), (2, 32, 32, 160, 160, 1, 1), (8, 8, 8, 320, 640, 1, 1),
+                                                        (2, 16, 16, 64, 64, 2, 1), (2, 8, 8, 64, 48, 1, 2), (2, 16, 16, 9, 32, 1, 1),
+                                                        (2, 16, 16, 32, 4, 1, 1), (1, 64, 64, 128, 128, 1, 1), (4, 12, 12, 64, 64, 1, 1)])
+def test_conv3x3(dtype, impl, NB, H, W, Cin, Cout, stride, up):
+    from followyourclick_b200 import ops
+    if impl == "tc" and (Cin % 8 or Cout % 16):
+        pytest.skip("shape not eligible for the tcgen05 path")
+    ops.set_impl("auto" if impl == "tc" else impl)       # 'auto' so that ineligible patch shapes fall back instead of failing
+    x = rnd((NB, H, W, Cin), 1, dtype)
+    w = rnd((Cout, Cin, 3, 3), 2, torch.float32, (9 * Cin) ** -0.5)
+    bias, temb = rnd((Cout,), 3), rnd((NB // 2 if NB > 1 else 1, Cout), 4)
+    ipg = 2 if NB > 1 else 1
+    wp = w.permute(0, 2, 3, 1).to(dtype).contiguous()
+    Ho, Wo = (H * up + 2 - 3) // stride + 1, (W * up + 2 - 3) // stride + 1
+    res = rnd((NB, Ho, Wo, Cout), 5, dtype)
+    out = ops.conv3x3(x, wp, bias=bias, residual=res, rowbias=temb, images_per_group=ipg, stride=stride, upsample=up)
+    xr = x.float().permute(0, 3, 1, 2)
+    if up == 2:
+        xr = F.interpolate(xr, scale_factor=2.0, mode="nearest")
+    ref = F.conv2d(xr, w.to(dtype).float(), bias, stride=stride, padding=1)
+    ref = ref + temb.repeat_interleave(ipg, dim=0)[:, :, None, None]
+    ref = ref.permute(0, 2, 3, 1) + res.float()
+    assert out.shape == ref.shape and rel(out, ref) < tol(dtype), rel(out, ref)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("NB,R,C,G,stat", [(2, 4 * 64, 160, 32, 2), (8, 64, 160, 32, 8), (2, 1024, 1920, 32, 2), (4, 16, 128, 32, 4),
+                                            (3, 100, 36, 4, 3)])
+@pytest.mark.parametrize("silu", [False, True])
+def test_groupnorm(cuda, dtype, NB, R, C, G, stat, silu):
+    from followyourclick_b200 import ops
+    x = (rnd((NB, R, C), 1) * 2 + 3).to(dtype)
+    gamma, beta = rnd((C,), 2) + 1, rnd((C,), 3)
+    out = ops.groupnorm(x, gamma, beta, G, 1e-5, silu=silu, stat_batches=stat)
+    ref = F.group_norm(x.float().permute(0, 2, 1), G, gamma, beta, 1e-5)
+    ref = (F.silu(ref) if silu else ref).permute(0, 2, 1)
+    assert rel(out, ref) < (1e-5 if dtype == torch.float32 else 6e-3), rel(out, ref)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("C", [160, 320, 640, 1280, 768])
+def test_layernorm_with_pe(cuda, dtype, C):
+    from followyourclick_b200 import ops
+    Fr, HW = 4, 16
+    x = (rnd((2 * Fr * HW, C), 1) * 1.5 + 0.5).to(dtype)
+    gamma, beta, pe = rnd((C,), 2) + 1, rnd((C,), 3), rnd((24, C), 4)
+    out = ops.layernorm(x, gamma, beta)
+    ref = F.layer_norm(x.float(), (C,), gamma, beta, 1e-5)
+    assert rel(out, ref) < (1e-5 if dtype == torch.float32 else 6e-3)
+    out = ops.layernorm(x, gamma, beta, pe=pe, rows_per_frame=HW, frames=Fr)
+    ref2 = (ref.view(2, Fr, HW, C) + pe[:Fr].view(1, Fr, 1, C)).view(-1, C)
+    assert rel(out, ref2) < (1e-5 if dtype == torch.float32 else 6e-3)
+
+
+def _mha_ref(q, k, v, heads, scale):
+    B, Lq, C = q.shape
+    d = C // heads
+    qh = q.float().view(B, Lq, heads, d).transpose(1, 2)
+    kh = k.float().view(k.shape[0], -1, heads, d).transpose(1, 2)
+    vh = v.float().view(v.shape[0], -1, heads, d).transpose(1, 2)
+    s = (qh @ kh.transpose(-1, -2) * scale).softmax(-1)
+    return (s @ vh).transpose(1, 2).reshape(B, Lq, C)
+
+
+@pytest.mark.parametrize("dtype,impl", MODES)
+@pytest.mark.parametrize("heads,D,Lq,Lk", [(4, 40, 256, 256), (2, 80, 100, 77), (2, 160, 64, 64), (4, 40, 70, 81), (8, 40, 1024, 1024),
+                                           (2, 160, 16, 4)])
+def test_attention_self_and_cross(dtype, impl, heads, D, Lq, Lk):
+    from followyourclick_b200 import ops
+    ops.set_impl(impl)
+    B, C = 4, heads * D
+    qkv = rnd((B, Lq, 3 * C), 1, dtype)
+    kv = rnd((B // 2, Lk, 2 * C), 2, dtype)
+    scale = D ** -0.5
+    if Lq == Lk:   # self attention on the fused qkv buffer (strided views)
+        out = ops.attention(qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:], heads, scale)
+        ref = _mha_ref(qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:], heads, scale)
+        assert rel(out, ref) < tol(dtype), rel(out, ref)
+    # cross attention: context shared by 2 consecutive batch entries, then an accumulated second pass (IP adapter)
+    q = qkv[:, :, :C]
+    out = ops.attention(q, kv[:, :, :C], kv[:, :, C:], heads, scale, kv_batch_div=2)
+    kk, vv = kv[:, :, :C].repeat_interleave(2, 0), kv[:, :, C:].repeat_interleave(2, 0)
+    ref = _mha_ref(q, kk, vv, heads, scale)
+    assert rel(out, ref) < tol(dtype), rel(out, ref)
+    T = 4
+    ops.attention(q, kv[:, Lk - T:, :C], kv[:, Lk - T:, C:], heads, scale, out=out, out_alpha=0.7, accumulate=True, kv_batch_div=2)
+    ref2 = ref + 0.7 * _mha_ref(q, kk[:, Lk - T:], vv[:, Lk - T:], heads, scale)
+    assert rel(out, ref2) < tol(dtype) * 1.5, rel(out, ref2)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,Fr,HW,heads,D", [(2, 4, 64, 4, 40), (2, 16, 16, 8, 40), (1, 8, 16, 4, 80), (2, 16, 4, 8, 160), (1, 24, 9, 2, 40),
+                                             (1, 32, 4, 4, 160)])
+def test_temporal_attention(cuda, dtype, B, Fr, HW, heads, D):
+    from followyourclick_b200 import ops
+    C = heads * D
+    qkv = rnd((B, Fr, HW, 3 * C), 1, dtype)
+    out = ops.temporal_attention(qkv, heads, D ** -0.5)
+    t = qkv.float().permute(0, 2, 1, 3).reshape(B * HW, Fr, 3 * C)          # (b d) f c
+    ref = _mha_ref(t[:, :, :C], t[:, :, C:2 * C], t[:, :, 2 * C:], heads, D ** -0.5)
+    ref = ref.view(B, HW, Fr, C).permute(0, 2, 1, 3)
+    assert rel(out, ref) < tol(dtype), rel(out, ref)
+
+
+def test_softmax_rows_and_misc(cuda):
+    from followyourclick_b200 import ops
+    s = rnd((64, 300), 1) * 4
+    assert rel(ops.softmax_rows(s, torch.float32), s.softmax(-1)) < 1e-6
+    assert rel(ops.softmax_rows(s, torch.bfloat16), s.softmax(-1)) < 5e-3
+    x = rnd((3, 5, 7, 16), 2)
+    assert torch.equal(ops.upsample_nearest2x(x), x.repeat_interleave(2, 1).repeat_interleave(2, 2))
+    xb = x.bfloat16()
+    assert torch.equal(ops.upsample_nearest2x(xb), xb.repeat_interleave(2, 1).repeat_interleave(2, 2))
+    a, b = rnd((10, 24), 3), rnd((10, 40), 4)
+    assert torch.equal(ops.concat_channels(a, b), torch.cat([a, b], -1))
+    assert torch.equal(ops.concat_channels(a.bfloat16(), b.bfloat16()), torch.cat([a, b], -1).bfloat16())
+    assert rel(ops.silu(a), F.silu(a)) < 1e-6
+    v = rnd((2, 4, 3, 5, 6), 5)
+    nf = ops.ncfhw_to_nfhwc(v, torch.float32)
+    assert torch.equal(nf, v.permute(0, 2, 3, 4, 1).contiguous())
+    assert torch.equal(ops.nfhwc_to_ncfhw(nf), v)
+    assert torch.equal(ops.ncfhw_to_nfhwc(v, torch.float32, scale=1 / 0.18215), (1 / 0.18215 * v).permute(0, 2, 3, 4, 1).contiguous())
+
+
+def test_timestep_embed_matches_reference_formula(cuda):
+    from followyourclick_b200 import ops
+    dim, half = 320, 160
+    t = torch.tensor([961, 501, 1, 2, 4], dtype=torch.int64)
+    exponent = -math.log(10000) * torch.arange(half, dtype=torch.float32) / half
+    freqs = torch.exp(exponent)
+    emb = t[:, None].float() * freqs[None]
+    ref = torch.cat([torch.cos(emb), torch.sin(emb)], -1)        # flip_sin_to_cos=True
+    out = ops.timestep_embed(t.cuda(), freqs.cuda(), True)
+    assert float((out.cpu() - ref).abs().max()) < 2e-6
+
+
+def test_build_unet_input_and_finalize(cuda):
+    from followyourclick_b200 import ops
+    from oracle.ref_pipeline import build_unet_input
+    b, f, h, w = 2, 3, 4, 5
+    lat, first = rnd((b, 4, f, h, w), 1), rnd((b, 4, h, w), 2)
+    mask = (rnd((b, 1, 1, h, w), 3) * 2)
+    ref = build_unet_input(lat.cpu(), first.cpu(), mask.cpu(), True).permute(0, 2, 3, 4, 1)
+    out = ops.build_unet_input(lat, mask[:, :, 0].contiguous(), first, 2, torch.float32)
+    assert torch.equal(out.cpu(), ref.contiguous())
+    ref0 = build_unet_input(lat.cpu(), first.cpu(), None, True).permute(0, 2, 3, 4, 1)
+    assert torch.equal(ops.build_unet_input(lat, None, first, 2, torch.float32).cpu(), ref0.contiguous())
+    assert torch.equal(ops.build_unet_input(lat, None, None, 1, torch.float32), lat.permute(0, 2, 3, 4, 1).contiguous())
+    x = rnd((b * f, 8, 8, 3), 4) * 2
+    vid = ops.frames_finalize(x, b, f)
+    refv = (x.view(b, f, 8, 8, 3).permute(0, 4, 1, 2, 3) / 2 + 0.5).clamp(0, 1)
+    assert torch.equal(vid, refv.contiguous())
+
+
+def test_cfg_ddim_step_bit_exact_vs_golden(cuda):
+    """DDIMScheduler.step against the reference-generated fixture, bit for bit (both prediction types, eta > 0)."""
+    import numpy as np
+    from followyourclick_b200 import DDIMScheduler
+    from tests.cfgs import SCHED_EPS, SCHED_V
+    from tests.engine_helpers import golden
+    g = golden("ddim.npz")
+    for name, cfg in (("v", SCHED_V), ("eps", SCHED_EPS)):
+        sch = DDIMScheduler(**cfg)
+        x, v = torch.from_numpy(g[f"{name}_x"]).cuda(), torch.from_numpy(g[f"{name}_v"]).cuda()
+        for n in (4, 25, 50):
+            sch.set_timesteps(n, device="cuda")
+            assert np.array_equal(sch.timesteps.cpu().numpy(), g[f"{name}_timesteps_{n}"])
+            ts = sch._timesteps_host
+            for t in (ts[0], ts[len(ts) // 2], ts[-1]):
+                out = sch.step(v, t, x).prev_sample
+                assert np.array_equal(out.cpu().numpy(), g[f"{name}_step_{n}_{t}"]), (name, n, t)
+        sch.set_timesteps(25, device="cuda")
+        out = sch.step(v, 481, x, eta=0.5, variance_noise=torch.from_numpy(g[f"{name}_noise"]).cuda()).prev_sample
+        assert np.array_equal(out.cpu().numpy(), g[f"{name}_step_eta0.5_25_481"])
+    # fused CFG: u + s (c - u) then step == two-stage reference arithmetic
+    sch = DDIMScheduler(**SCHED_V)
+    sch.set_timesteps(25, device="cuda")
+    u, c, x = rnd((1, 4, 4, 8, 8), 1), rnd((1, 4, 4, 8, 8), 2), rnd((1, 4, 4, 8, 8), 3)
+    fused = sch.step_cfg(torch.cat([u, c]), 481, x, 8.0)
+    two = sch.step(u + 8.0 * (c - u), 481, x).prev_sample
+    assert torch.equal(fused, two)
