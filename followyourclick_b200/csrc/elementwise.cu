@@ -269,18 +269,16 @@ __global__ void softmax_rows_kernel(const float* __restrict__ s, T* __restrict__
   m = warp_max(m);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
   __syncthreads();
-  m = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : -INFINITY;
+  m = (threadIdx.x & 31) < (blockDim.x >> 5) ? red[threadIdx.x & 31] : -INFINITY;   // every warp reduces the 8 partials
   m = warp_max(m);
-  m = __shfl_sync(0xffffffffu, m, 0);
   __syncthreads();
   float sum = 0.f;
   for (int64_t j = threadIdx.x; j < L; j += blockDim.x) sum += expf(row[j] - m);
   sum = warp_sum(sum);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
   __syncthreads();
-  sum = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+  sum = (threadIdx.x & 31) < (blockDim.x >> 5) ? red[threadIdx.x & 31] : 0.f;
   sum = warp_sum(sum);
-  sum = __shfl_sync(0xffffffffu, sum, 0);
   float inv = 1.0f / sum;
   for (int64_t j = threadIdx.x; j < L; j += blockDim.x) out[j] = from_f<T>(expf(row[j] - m) * inv);
 }

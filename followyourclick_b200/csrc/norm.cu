@@ -4,18 +4,19 @@
 #include "common.cuh"
 
 // ---------------------------------------------------------------------------------------------------------
-// stats: x viewed as [NB, R, C]; grid (chunks, NB); each CTA reduces rows [r0, r1) for all channels.
+// stats: x viewed as [NB, R, C]; grid (chunks, NB); each CTA reduces rows [r0, r1) for all channels and writes ONE
+// partial (sum, sumsq) per group.  No atomics anywhere: the per-thread channel sums are combined through shared
+// memory in a fixed order and the per-CTA partials are summed in chunk order by gn_finalize_kernel, so the
+// statistics (and therefore the whole engine) are bit-reproducible run to run.
 template <typename T, int V>
-__global__ void __launch_bounds__(256) gn_stats_kernel(const T* __restrict__ x, double* __restrict__ sums, int64_t R,
+__global__ void __launch_bounds__(256) gn_stats_kernel(const T* __restrict__ x, float2* __restrict__ partials, int64_t R,
                                                        int C, int G, int64_t rows_per_cta) {
-  extern __shared__ float s_acc[];   // [2 * G]
+  extern __shared__ float s_ch[];   // [RY][C][2]
   const int cpg = C / G;
   const int cvn = C / V;
   const int TX = cvn < 256 ? cvn : 256;
   const int RY = 256 / TX;
   const int tx = threadIdx.x % TX, ry = threadIdx.x / TX;
-  for (int i = threadIdx.x; i < 2 * G; i += 256) s_acc[i] = 0.f;
-  __syncthreads();
   const int64_t nb = blockIdx.y;
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
   const int64_t r1 = (r0 + rows_per_cta < R) ? r0 + rows_per_cta : R;
@@ -33,41 +34,47 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const T* __restrict__ x, 
 #pragma unroll
         for (int e = 0; e < V; ++e) { s[e] += f[e]; q[e] = fmaf(f[e], f[e], q[e]); }
       }
-      // flush: consecutive channels mostly share a group -> merge before the shared atomics
-      int g_prev = (cv * V) / cpg;
-      float as = 0.f, aq = 0.f;
 #pragma unroll
       for (int e = 0; e < V; ++e) {
-        int g = (cv * V + e) / cpg;
-        if (g != g_prev) {
-          atomicAdd(&s_acc[2 * g_prev], as); atomicAdd(&s_acc[2 * g_prev + 1], aq);
-          as = 0.f; aq = 0.f; g_prev = g;
-        }
-        as += s[e]; aq += q[e];
+        s_ch[((size_t)ry * C + cv * V + e) * 2] = s[e];
+        s_ch[((size_t)ry * C + cv * V + e) * 2 + 1] = q[e];
       }
-      atomicAdd(&s_acc[2 * g_prev], as); atomicAdd(&s_acc[2 * g_prev + 1], aq);
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 2 * G; i += 256) atomicAdd(&sums[nb * 2 * G + i], (double)s_acc[i]);
+  for (int g = threadIdx.x; g < G; g += 256) {
+    float as = 0.f, aq = 0.f;
+    for (int y = 0; y < RY; ++y)
+      for (int c = g * cpg; c < (g + 1) * cpg; ++c) { as += s_ch[((size_t)y * C + c) * 2]; aq += s_ch[((size_t)y * C + c) * 2 + 1]; }
+    partials[((int64_t)nb * gridDim.x + blockIdx.x) * G + g] = make_float2(as, aq);
+  }
 }
 
-// finalize: per (nb, c): scale = rstd * gamma, shift = beta - mean * scale   (same form as ATen's CPU kernel)
-__global__ void gn_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, float* __restrict__ scale, float* __restrict__ shift,
-                                   int64_t NB, int C, int G, double count, float eps) {
-  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= NB * C) return;
-  int c = (int)(i % C);
-  int64_t nb = i / C;
-  int g = c / (C / G);
-  double mean = sums[(nb * G + g) * 2] / count;
-  double var = sums[(nb * G + g) * 2 + 1] / count - mean * mean;
-  if (var < 0) var = 0;
-  float rstd = (float)(1.0 / sqrt(var + (double)eps));
-  float sc = rstd * gamma[c];
-  scale[i] = sc;
-  shift[i] = beta[c] - (float)mean * sc;
+// finalize: one CTA per nb.  mean/rstd per group from the chunk partials (fp64, fixed order), then per channel
+// scale = rstd * gamma, shift = beta - mean * scale   (same form as ATen's CPU kernel)
+__global__ void __launch_bounds__(256) gn_finalize_kernel(const float2* __restrict__ partials, int chunks,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          float* __restrict__ scale, float* __restrict__ shift, int C, int G,
+                                                          double count, float eps) {
+  extern __shared__ float s_stat[];   // [G][2] mean, rstd
+  const int64_t nb = blockIdx.x;
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    double s = 0.0, q = 0.0;
+    for (int k = 0; k < chunks; ++k) { float2 p = partials[(nb * chunks + k) * G + g]; s += (double)p.x; q += (double)p.y; }
+    double mean = s / count;
+    double var = q / count - mean * mean;
+    if (var < 0) var = 0;
+    s_stat[2 * g] = (float)mean;
+    s_stat[2 * g + 1] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  const int cpg = C / G;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    int g = c / cpg;
+    float sc = s_stat[2 * g + 1] * gamma[c];
+    scale[nb * C + c] = sc;
+    shift[nb * C + c] = beta[c] - s_stat[2 * g] * sc;
+  }
 }
 
 template <typename T, int V, bool SILU>
@@ -96,29 +103,36 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ x, 
   }
 }
 
+static int64_t gn_max_chunks(int64_t NB) { return ((int64_t)fyc_sm_count() * 4 + NB - 1) / NB + 1; }
+
 extern "C" size_t fyc_groupnorm_workspace_bytes(int64_t NB, int64_t C, int64_t G) {
-  return (size_t)(NB * G * 2 * sizeof(double) + NB * C * 2 * sizeof(float));
+  return (size_t)(NB * gn_max_chunks(NB) * G * sizeof(float2) + NB * C * 2 * sizeof(float));
 }
 
 template <typename T, int V>
 static int32_t groupnorm_impl(const T* x, const float* gamma, const float* beta, T* out, int64_t NB, int64_t R, int C,
                               int G, float eps, int silu, void* ws, cudaStream_t st) {
-  double* sums = (double*)ws;
-  float* scale = (float*)(sums + NB * G * 2);
+  float2* partials = (float2*)ws;
+  float* scale = (float*)(partials + NB * gn_max_chunks(NB) * G);
   float* shift = scale + NB * C;
-  FYC_CUDA(cudaMemsetAsync(sums, 0, NB * G * 2 * sizeof(double), st));
   const int cvn = C / V;
   const int TX = cvn < 256 ? cvn : 256;
   const int RY = 256 / TX;
-  int64_t target = ((int64_t)fyc_sm_count() * 4 + NB - 1) / NB;          // CTAs per nb
+  int64_t target = gn_max_chunks(NB) - 1;                                 // CTAs per nb
   int64_t rows_per_cta = ceil_div64(R, target);
   if (rows_per_cta < 4 * RY) rows_per_cta = 4 * RY;
   rows_per_cta = ceil_div64(rows_per_cta, RY) * RY;
-  dim3 grid((unsigned)ceil_div64(R, rows_per_cta), (unsigned)NB);
-  gn_stats_kernel<T, V><<<grid, 256, 2 * G * sizeof(float), st>>>(x, sums, R, C, G, rows_per_cta);
+  const int chunks = (int)ceil_div64(R, rows_per_cta);
+  FYC_CHECK(chunks <= gn_max_chunks(NB), "groupnorm: internal chunk count");
+  const size_t smem = (size_t)RY * C * 2 * sizeof(float);
+  FYC_CHECK(smem <= 200 * 1024, "groupnorm: C=%d too large", C);
+  auto kern = gn_stats_kernel<T, V>;
+  if (smem > 48 * 1024) FYC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)chunks, (unsigned)NB);
+  kern<<<grid, 256, smem, st>>>(x, partials, R, C, G, rows_per_cta);
   FYC_LAUNCH_CHECK();
-  gn_finalize_kernel<<<(unsigned)ceil_div64(NB * C, 256), 256, 0, st>>>(sums, gamma, beta, scale, shift, NB, C, G,
-                                                                         (double)R * (C / G), eps);
+  gn_finalize_kernel<<<(unsigned)NB, 256, 2 * G * sizeof(float), st>>>(partials, chunks, gamma, beta, scale, shift, C, G,
+                                                                        (double)R * (C / G), eps);
   FYC_LAUNCH_CHECK();
   int64_t total_vec = NB * R * cvn;
   int64_t blocks = ceil_div64(total_vec, 256);

@@ -12,6 +12,45 @@ from . import _lib as L
 from ._lib import check, dtype_code, lib, ptr, stream_ptr
 
 _impl = L.IMPL_AUTO
+_prof = None      # list of (family, algorithmic_flops, algorithmic_bytes, start_event, end_event) while profiling
+
+
+class profile:
+    """Context manager: record a CUDA-event pair around every C-ABI call (bench.py's live per-kernel timing)."""
+
+    def __enter__(self):
+        global _prof
+        _prof = []
+        self.records = _prof
+        return self
+
+    def __exit__(self, *a):
+        global _prof
+        _prof = None
+        torch.cuda.synchronize()
+        self.summary = {}
+        for fam, fl, by, e0, e1 in self.records:
+            d = self.summary.setdefault(fam, dict(ms=0.0, flops=0.0, bytes=0.0, launches=0))
+            d["ms"] += e0.elapsed_time(e1); d["flops"] += fl; d["bytes"] += by; d["launches"] += 1
+        return False
+
+
+class _rec:
+    def __init__(self, fam, flops=0.0, nbytes=0.0):
+        self.a = (fam, float(flops), float(nbytes))
+
+    def __enter__(self):
+        if _prof is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *a):
+        if _prof is not None:
+            self.e1.record()
+            _prof.append(self.a + (self.e0, self.e1))
+        return False
 
 
 def set_impl(name):
@@ -71,7 +110,9 @@ def gemm(A, W, bias=None, residual=None, rowbias=None, rows_per_group=0, alpha=1
     a = L.GemmArgs(ptr(A), ptr(W), ptr(o), ptr(bias), ptr(residual), ptr(rowbias), M, N, K, lda, ldw,
                    o.stride(-2), residual.stride(-2) if residual is not None else 0, Bn, sA, sW,
                    o.stride(0) if batched else 0, rows_per_group, float(alpha), dtype_code(A.dtype), epi, impl)
-    check(lib().fyc_gemm(C.byref(a), stream_ptr()))
+    fam = "gemm_tc" if (impl != L.IMPL_SIMT and tc_ok(A.dtype, M) and N % 16 == 0 and K % 8 == 0) else "gemm_simt"
+    with _rec(fam, 2.0 * Bn * M * N * K, A.element_size() * Bn * (M * K + N * K + M * n_out)):
+        check(lib().fyc_gemm(C.byref(a), stream_ptr()))
     if geglu and not fused_geglu:
         assert not batched
         g = out if out is not None else torch.empty((M, N // 2), dtype=A.dtype, device=A.device)
@@ -106,7 +147,9 @@ def conv3x3(x, w, bias=None, residual=None, rowbias=None, images_per_group=0, st
     if nbytes:
         ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
         a.workspace, a.workspace_bytes = ptr(ws), nbytes
-    check(lib().fyc_conv3x3(C.byref(a), stream_ptr()))
+    fam = "conv_tc" if (impl != L.IMPL_SIMT and tc_ok(x.dtype, NB * Ho * Wo) and Cin % 8 == 0 and Cout % 16 == 0) else "conv_simt"
+    with _rec(fam, 2.0 * NB * Ho * Wo * Cout * 9 * Cin, x.element_size() * (x.numel() + w.numel() + out.numel())):
+        check(lib().fyc_conv3x3(C.byref(a), stream_ptr()))
     return out
 
 
@@ -120,8 +163,9 @@ def groupnorm(x, gamma, beta, groups, eps, silu=False, stat_batches=None):
     out = torch.empty_like(x)
     nbytes = lib().fyc_groupnorm_workspace_bytes(NB, Cc, groups)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
-    check(lib().fyc_groupnorm(ptr(x), ptr(gamma), ptr(beta), ptr(out), NB, R, Cc, groups, float(eps), int(silu),
-                              dtype_code(x.dtype), ptr(ws), nbytes, stream_ptr()))
+    with _rec("groupnorm", 0, 3 * x.numel() * x.element_size()):
+        check(lib().fyc_groupnorm(ptr(x), ptr(gamma), ptr(beta), ptr(out), NB, R, Cc, groups, float(eps), int(silu),
+                                  dtype_code(x.dtype), ptr(ws), nbytes, stream_ptr()))
     return out
 
 
@@ -130,8 +174,9 @@ def layernorm(x, gamma, beta, eps=1e-5, pe=None, rows_per_frame=0, frames=0):
     assert x.is_contiguous()
     Cc = x.shape[-1]
     out = torch.empty_like(x)
-    check(lib().fyc_layernorm(ptr(x), ptr(gamma), ptr(beta), ptr(out), x.numel() // Cc, Cc, float(eps), ptr(pe),
-                              rows_per_frame, frames, dtype_code(x.dtype), stream_ptr()))
+    with _rec("layernorm", 0, 2 * x.numel() * x.element_size()):
+        check(lib().fyc_layernorm(ptr(x), ptr(gamma), ptr(beta), ptr(out), x.numel() // Cc, Cc, float(eps), ptr(pe),
+                                  rows_per_frame, frames, dtype_code(x.dtype), stream_ptr()))
     return out
 
 
@@ -150,7 +195,8 @@ def attention(q, k, v, heads, scale, out=None, out_alpha=1.0, accumulate=False, 
     a = L.AttnArgs(ptr(q), ptr(k), ptr(v), ptr(out), B, heads, Lq, Lk, D, q.stride(1), k.stride(1), v.stride(1),
                    out.stride(1), q.stride(0), k.stride(0), v.stride(0), out.stride(0), kv_batch_div, float(scale),
                    float(out_alpha), int(accumulate), dtype_code(q.dtype), _impl if impl is None else impl)
-    check(lib().fyc_attention(C.byref(a), stream_ptr()))
+    with _rec("attention", 4.0 * B * heads * Lq * Lk * D, q.element_size() * (2 * B * Lq * heads * D + 2 * (B // kv_batch_div) * Lk * heads * D)):
+        check(lib().fyc_attention(C.byref(a), stream_ptr()))
     return out
 
 
@@ -161,8 +207,9 @@ def temporal_attention(qkv, heads, scale):
     B, F, HW, C3 = qkv.shape
     Cc = C3 // 3
     out = torch.empty((B, F, HW, Cc), dtype=qkv.dtype, device=qkv.device)
-    check(lib().fyc_temporal_attention(ptr(qkv), ptr(out), B, F, HW, heads, Cc // heads, float(scale),
-                                       dtype_code(qkv.dtype), stream_ptr()))
+    with _rec("temporal_attention", 4.0 * B * HW * heads * F * F * (Cc // heads), (qkv.numel() + out.numel()) * qkv.element_size()):
+        check(lib().fyc_temporal_attention(ptr(qkv), ptr(out), B, F, HW, heads, Cc // heads, float(scale),
+                                           dtype_code(qkv.dtype), stream_ptr()))
     return out
 
 

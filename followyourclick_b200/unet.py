@@ -400,6 +400,12 @@ class UNet3DConditionModel(ParamTreeModel):
         h = ops.silu(ops.gemm(s, self._fw(name + ".linear_1.weight"), bias=self._f(name + ".linear_1.bias")))
         return ops.gemm(h, self._fw(name + ".linear_2.weight"), bias=self._f(name + ".linear_2.bias"), residual=residual)
 
+    _taps = None    # set to a dict to record named intermediate activations (debug / layer-wise parity)
+
+    def _tap(self, name, x):
+        if self._taps is not None:
+            self._taps[name] = x.detach().float().cpu()
+
     def _to_compute(self, t):
         """fp32 tensor of any shape -> contiguous compute-dtype copy (conversion kernel of the engine)."""
         t = t.to(device=self.device, dtype=torch.float32).contiguous()
@@ -439,6 +445,7 @@ class UNet3DConditionModel(ParamTreeModel):
         else:
             w_in, b_in = self._conv_w("conv_in.weight"), self._f("conv_in.bias")
         x = ops.conv3x3(x, w_in, bias=b_in)
+        self._tap("conv_in", x)
 
         def motion_on(level, decoder):
             on = cfg["use_motion_module"] and (2 ** level) in tuple(cfg["motion_module_resolutions"])
@@ -457,11 +464,13 @@ class UNet3DConditionModel(ParamTreeModel):
             if i < n - 1:
                 x = ops.conv3x3(x, self._conv_w(f"{p}.downsamplers.0.conv.weight"), bias=self._f(f"{p}.downsamplers.0.conv.bias"), stride=2)
                 skips.append(x)
+            self._tap(f"down{i}", x)
         x = self._resnet("mid_block.resnets.0", x, semb, B, F)
         x = self._transformer("mid_block.attentions.0", x, ctx, self._heads[-1], F)
         if cfg["use_motion_module"] and cfg["motion_module_mid_block"]:
             x = self._motion("mid_block.motion_modules.0", x, B, F)
         x = self._resnet("mid_block.resnets.1", x, semb, B, F)
+        self._tap("mid", x)
         for i in range(n):
             p = f"up_blocks.{i}"
             lvl = n - 1 - i
@@ -474,6 +483,7 @@ class UNet3DConditionModel(ParamTreeModel):
                     x = self._motion(f"{p}.motion_modules.{j}", x, B, F)
             if i < n - 1:
                 x = ops.conv3x3(x, self._conv_w(f"{p}.upsamplers.0.conv.weight"), bias=self._f(f"{p}.upsamplers.0.conv.bias"), upsample=2)
+            self._tap(f"up{i}", x)
         x = self._gn("conv_norm_out", x, B, True, False)
         y = ops.conv3x3(x, self._conv_w("conv_out.weight"), bias=self._f("conv_out.bias"), out_f32=True)
         return y.view(B, F, H, W, -1)
