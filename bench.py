@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""Headline benchmark: frames/sec of the FollowYourClick denoising hot path on B200.
+
+  python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+One "step" = one complete clip on every GPU: BASELINE.json configs[1] (cfg2): 512x512, 16 frames, 25 DDIM steps
+(UNet3D forward with CFG pair + fused CFG/DDIM step) followed by AutoencoderKL.decode of all frames; at N > 1 each
+rank runs its own clip (weak scaling, one clip per GPU) and the decoded frames are all-gathered once (NCCL).
+Weights are synthetic (random-init SD-1.5 + motion-module architecture, 1.28 B params; no checkpoints offline).
+
+The JSON line (rank 0) carries: value (device-resident inputs, CUDA-event timed, max over ranks), e2e (public
+AnimationPipeline.__call__ with HOST inputs/outputs inside the timed region), roofline (live per-kernel CUDA-event
+timing of the dominant tcgen05 GEMM/conv kernel against MEASURED_PEAKS.json), cpu_baseline (the CPU oracle port timed
+on this box's host cores on a bounded sample) and clocks sampled with nvidia-smi during the timed region.
+`--impl reference` times the reference algorithm's CPU port (oracle/) instead - /root/reference is not on the GPU box.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "frames/sec (64x64x16f latent, 25 DDIM steps)"
+TFLOP_PER_FRAME = 57.8          # (25 x 35.35 + 16 x 2.515) / 16
+UNET_TFLOP = {"cfg1": 4.08, "cfg2": 35.35}
+VAE_TFLOP = {32: 0.622, 64: 2.515}
+WORKLOADS = {
+    "cfg2": dict(F=16, h=64, w=64, steps=25, guidance=8.0,
+                 desc="cfg2: 512x512, 16 frames, 25 DDIM steps, CFG 8.0, mask/first-frame concat + fps/flow condition, "
+                      "SD-1.5 UNet3D + 20 motion modules (1.28 B params) + KL-f8 VAE decode of all frames"),
+    "mini": dict(F=4, h=16, w=16, steps=3, guidance=8.0, desc="mini (development only; not a valid bench line)"),
+}
+
+
+def unet_kwargs(mini=False):
+    mm = dict(num_attention_heads=4 if mini else 8, num_transformer_block=1, attention_block_types=("Temporal_Self", "Temporal_Self"),
+              temporal_position_encoding=True, temporal_position_encoding_max_len=24, temporal_attention_dim_div=1)
+    kw = dict(sample_size=64, in_channels=4, out_channels=4, cross_attention_dim=768, attention_head_dim=4 if mini else 8,
+              use_motion_module=True, motion_module_resolutions=(1, 2, 4, 8), unet_use_cross_frame_attention=False,
+              unet_use_temporal_attention=False, motion_module_type="Vanilla", use_fps_condition=True,
+              use_first_frame_mask_condition_concat=True, motion_module_kwargs=mm)
+    if mini:
+        kw.update(block_out_channels=(160, 320, 640, 640), layers_per_block=1)
+    return kw
+
+
+def vae_kwargs(mini=False):
+    return dict(in_channels=3, out_channels=3, down_block_types=("DownEncoderBlock2D",) * 4, up_block_types=("UpDecoderBlock2D",) * 4,
+                block_out_channels=(32, 64, 128, 128) if mini else (128, 256, 512, 512), layers_per_block=1 if mini else 2,
+                latent_channels=4, norm_num_groups=32)
+
+
+SCHED = dict(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, beta_schedule="linear", steps_offset=1,
+             clip_sample=False, prediction_type="v_prediction", rescale_betas_zero_snr=True)
+
+
+class _Tok:
+    model_max_length = 77
+
+    def __call__(self, prompt, **kw):
+        n = len(prompt) if isinstance(prompt, list) else 1
+        ids = torch.zeros(n, 77, dtype=torch.long)
+        return type("T", (), dict(input_ids=ids, attention_mask=torch.ones_like(ids)))()
+
+
+class _TextEnc(torch.nn.Module):
+    """CLIP stand-in (outside the hot path): returns seeded embeddings kept in pinned HOST memory."""
+
+    def __init__(self, emb):
+        super().__init__()
+        self.emb, self.calls, self.config = emb, 0, type("C", (), {})()
+
+    def forward(self, ids, attention_mask=None):
+        self.calls += 1
+        e = self.emb[1:2] if self.calls % 2 == 1 else self.emb[0:1]
+        return (e.to(ids.device, non_blocking=True),)
+
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.lines, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(index),
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.lines:
+            if ts < t0 or ts > t1:
+                continue
+            p = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(p[0])); mx = float(p[1])
+            except Exception:
+                continue
+            for n, v in zip(names, p[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(tflops=d.get("bf16_tflops_sustained", 1429.0), hbm=d.get("hbm_gbs", 6585.8), src="measured (MEASURED_PEAKS.json, sustained)")
+    return dict(tflops=1400.0, hbm=6650.0, src="fallback (B200_PROFILING.md)")
+
+
+# ------------------------------------------------------------------------------------------------ CPU reference arm
+def cpu_reference_sample(threads, repeats=1):
+    """Time the reference algorithm's CPU port (oracle/, pinned to the reference by tests/golden) on a bounded sample:
+    one full-size (1.28 B param) UNet3D forward at cfg1 shape (B=2 CFG pair, F=8, 32x32 latent; 4.08 TFLOP) + one
+    256x256 frame VAE decode (0.622 TFLOP), fp32, all host threads; extrapolated to cfg2 by algorithmic FLOPs."""
+    from followyourclick_b200.synth import synth_state_dict
+    from followyourclick_b200.unet import sinusoidal_pe, unet_param_spec
+    from followyourclick_b200.vae import vae_param_spec
+    from oracle import ref_unet, ref_vae
+    torch.set_num_threads(threads)
+    ocfg = ref_unet.default_unet_config()
+    spec = unet_param_spec(dict(ocfg, use_first_frame_condition_concat=False))
+    usd = synth_state_dict(spec)
+    for k, s in spec.items():
+        if k.endswith(".pos_encoder.pe"):
+            usd[k] = sinusoidal_pe(s[1], s[2])
+    vcfg = ref_vae.default_vae_config()
+    vsd = synth_state_dict(vae_param_spec(dict(vcfg, in_channels=3)))
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 9, 8, 32, 32, generator=g)
+    ctx = torch.randn(2, 77, 768, generator=g)
+    z = torch.randn(1, 4, 32, 32, generator=g)
+    tu, tv = [], []
+    with torch.no_grad():
+        for _ in range(repeats):
+            t0 = time.time()
+            ref_unet.unet3d_forward(usd, ocfg, x, torch.tensor(501), ctx, fps_tensor=torch.tensor([2, 2]), flow_control=torch.tensor([4, 4]))
+            tu.append(time.time() - t0)
+            t0 = time.time()
+            ref_vae.vae_decode(vsd, vcfg, z)
+            tv.append(time.time() - t0)
+    t_u, t_v = min(tu), min(tv)
+    t_clip = 25 * t_u * UNET_TFLOP["cfg2"] / UNET_TFLOP["cfg1"] + 16 * t_v * VAE_TFLOP[64] / VAE_TFLOP[32]
+    return dict(fps=16.0 / t_clip, t_unet_cfg1=t_u, t_vae_256=t_v, sample_s=t_u + t_v)
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    t0 = time.time()
+    # K timed "steps" are K repetitions of the bounded sample (best-of); W warm-ups are skipped on purpose: a CPU sample
+    # costs ~15-60 s and the first repetition already runs on warm weights (generated just before).
+    r = cpu_reference_sample(cores, repeats=max(1, min(args.steps, 2)))
+    wl = WORKLOADS["cfg2"]
+    sample = "1 UNet3D fwd (1.28B params, B=2,F=8,32x32 latent, 4.08 TFLOP) + 1 VAE frame decode 256x256 (0.622 TFLOP), fp32 " \
+             "oracle port on all host threads; extrapolated to cfg2 by algorithmic FLOPs (x8.66 UNet, x4.04 VAE)"
+    line = dict(metric=METRIC, value=r["fps"], unit="frames/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=r["sample_s"] * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                data="synthetic", impl="reference", config=dict(workload=wl["desc"]),
+                cpu_baseline=dict(value=r["fps"], unit="frames/s", cores=cores, kind="port", sample=sample),
+                e2e=dict(value=r["fps"], unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0, wall_s=time.time() - t0)
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=list(WORKLOADS))
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "f32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ddim-steps", type=int, default=0, help="override the workload's 25 DDIM steps (profiling only: the line is marked invalid)")
+    args = ap.parse_args()
+    rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        return run_reference_arm(args, rank)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path (use --impl reference for the CPU arm)")
+
+    from followyourclick_b200 import AnimationPipeline, AutoencoderKL, DDIMScheduler, UNet3DConditionModel, _lib, ops
+    from followyourclick_b200.distributed import gather_frames, init_from_env
+    from followyourclick_b200.synth import synth_on_device_
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = init_from_env() if world > 1 else None
+    wl = WORKLOADS[args.workload]
+    mini = args.workload == "mini"
+    dt = torch.bfloat16 if args.dtype == "bf16" else torch.float32
+    unet = UNet3DConditionModel(**unet_kwargs(mini)).to(dev).to(dt)
+    vae = AutoencoderKL(**vae_kwargs(mini)).to(dev).to(dt)
+    synth_on_device_(unet, seed=0)
+    synth_on_device_(vae, seed=1)
+    F, h, w, nsteps, gs = wl["F"], wl["h"], wl["w"], args.ddim_steps or wl["steps"], wl["guidance"]
+    g = torch.Generator().manual_seed(1234 + rank)
+    host = dict(latents=torch.randn(1, 4, F, h, w, generator=g).pin_memory(),
+                first=torch.randn(1, 4, h, w, generator=g).pin_memory(),
+                text=torch.randn(2, 77, 768, generator=g).pin_memory())
+    mask = torch.zeros(1, 1, 1, h, w)
+    mask[..., h // 4:3 * h // 4, w // 4:3 * w // 4] = 1
+    host["mask"] = mask.pin_memory()
+    pipe = AnimationPipeline(vae=vae, text_encoder=_TextEnc(host["text"]), tokenizer=_Tok(), unet=unet, scheduler=DDIMScheduler(**SCHED))
+    pipe.set_progress_bar_config(disable=True)
+    devin = {k: v.to(dev) for k, v in host.items()}
+    fps_t, flow_t = torch.tensor([2]), torch.tensor([4])
+
+    def step_resident():
+        lat = pipe.denoise(devin["latents"], devin["text"], nsteps, gs, first_image_latents=devin["first"],
+                           first_images_mask=devin["mask"], use_first_frame_mask_condition_concat=True, fps_tensor=fps_t,
+                           flow_control=flow_t, use_fps_condition=True)
+        video = pipe.decode_latents_device(lat)
+        if dist is not None:
+            video = gather_frames(video)
+        return video
+
+    def step_e2e():
+        pipe.text_encoder.calls = 0
+        return pipe("p", negative_prompt="n", video_length=F, height=h * 8, width=w * 8, num_inference_steps=nsteps,
+                    guidance_scale=gs, latents=host["latents"], use_first_frame_mask_condition_concat=True,
+                    first_image_latents=host["first"], use_fps_condition=True, fps_tensor=fps_t, flow_control=flow_t,
+                    first_images_mask=host["mask"]).videos
+
+    def barrier():
+        if dist is not None:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0, t0 = _lib.launch_count, time.time()
+        e0.record()
+        for _ in range(k):
+            out = fn()
+        e1.record()
+        barrier()
+        t1 = time.time()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            tt = torch.tensor([ms], device=dev)
+            torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+            ms = float(tt)
+        return ms, _lib.launch_count - l0, t0, t1, out
+
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms, launches, t0, t1, video = timed(step_resident, args.steps)
+    clocks = sampler.stop(t0, t1) if sampler else None
+    assert bool(torch.isfinite(video).all()), "non-finite frames"
+    fps = world * F * args.steps / (ms / 1e3)
+
+    step_e2e()
+    ms_e2e, _, _, _, vid = timed(step_e2e, args.steps)
+    fps_e2e = world * F * args.steps / (ms_e2e / 1e3)
+    h2d = sum(host[k].numel() * 4 for k in ("latents", "first", "text", "mask"))
+    d2h = vid.numel() * 4
+
+    roof = None
+    if rank == 0:
+        # live per-kernel timing: CUDA-event pair around every C-ABI call of one UNet forward + decode (separate pass,
+        # so the headline numbers above are not perturbed); dominant kernel = gemm_tc_kernel (linear + implicit conv)
+        x = ops.build_unet_input(devin["latents"], devin["mask"][:, :, 0].contiguous(), devin["first"], 2, dt)
+        targs = dict(fps_tensor=torch.tensor([2, 2], device=dev), flow_control=torch.tensor([4, 4], device=dev), use_fps_condition=True)
+        with ops.profile() as prof:
+            unet.forward_nfhwc(x, torch.tensor(501, device=dev), devin["text"].to(dev), **targs)
+        pk = peaks()
+        tc = [prof.summary.get(k, dict(ms=0, flops=0, launches=0)) for k in ("gemm_tc", "conv_tc")]
+        tc_ms, tc_fl, tc_n = sum(d["ms"] for d in tc), sum(d["flops"] for d in tc), sum(d["launches"] for d in tc)
+        total_ms = sum(d["ms"] for d in prof.summary.values())
+        ach = tc_fl / (tc_ms * 1e-3) / 1e12 if tc_ms else 0.0
+        roof = dict(bound="tensor", kernel="gemm_tc_kernel (tcgen05 GEMM + implicit-GEMM conv3x3)", achieved=ach, peak=pk["tflops"],
+                    unit="TFLOP/s", frac=ach / pk["tflops"], traffic=None, peak_source=pk["src"], launches_per_unet_forward=tc_n,
+                    avg_launch_ms=tc_ms / max(tc_n, 1), share_of_unet_forward=tc_ms / max(total_ms, 1e-9),
+                    algorithmic_tflop_per_unet_forward=tc_fl / 1e12,
+                    step_frac=(fps / world) * TFLOP_PER_FRAME / pk["tflops"] if not mini else None,
+                    families={k: dict(ms=round(v["ms"], 3), launches=v["launches"],
+                                      tflops=round(v["flops"] / (v["ms"] * 1e9), 1) if v["ms"] else 0.0,
+                                      gbs=round(v["bytes"] / (v["ms"] * 1e6), 1) if v["ms"] else 0.0) for k, v in prof.summary.items()})
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        r = cpu_reference_sample(cores)
+        cpu = dict(value=r["fps"], unit="frames/s", cores=cores, kind="port",
+                   sample=f"1 UNet3D fwd at cfg1 shape ({r['t_unet_cfg1']:.1f} s) + 1 VAE frame 256x256 ({r['t_vae_256']:.1f} s), fp32 "
+                          "oracle port, all host threads; extrapolated to cfg2 by algorithmic FLOPs")
+    if rank == 0:
+        line = dict(metric=METRIC, value=fps, unit="frames/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                    dtype="bf16" if dt == torch.bfloat16 else "f32", data="synthetic",
+                    config=dict(workload=wl["desc"], clips_per_gpu=1, parallelism=f"clip-per-gpu x{world}, 1 all_gather of frames",
+                                l2="working set (2.6 GB weights + >1 GB activations per step) >> 126 MB L2; no flush needed"),
+                    clocks=clocks, e2e=dict(value=fps_e2e, unit="frames/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                                            ms_per_step=ms_e2e / args.steps),
+                    gpu_launches=launches, roofline=roof, cpu_baseline=cpu)
+        if args.ddim_steps and args.ddim_steps != wl["steps"]:
+            line["invalid"] = f"profiling run with {args.ddim_steps} DDIM steps instead of {wl['steps']}"
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -5,9 +5,10 @@ procedurally generated weights.  Values depend only on (key name, shape, seed), 
 construction order, so the reference model (in the build container), the CPU oracle and the CUDA
 engine can all be loaded with the *same* state dict without shipping it.
 
-Scaling keeps activations O(1) through the network and keeps attention softmaxes peaky enough that
-key-ordering / masking bugs are visible (uniform softmaxes would hide them):
-  * >=2-D ``*.weight``: N(0, 1/fan_in); ``to_q`` / ``to_k`` / ``query`` / ``key`` get gain 2
+Scaling keeps activations O(1) through the network with attention logits of unit scale (std ~1: non-uniform
+softmaxes, so key-ordering / masking bugs are visible, yet well conditioned - with logit std ~4 the random network
+amplifies a 1e-4 input perturbation 12x and bf16 rounding to ~9 % at the output, measured in tests/diag_bf16.py):
+  * >=2-D ``*.weight``: N(0, 1/fan_in)
   * 1-D ``*.weight`` (norm gains): 1 + 0.1 N(0,1);  ``*.bias``: 0.05 N(0,1)
   * ``*.pos_encoder.pe`` buffers are left untouched (they are a formula, motion_module.py:295-299)
   * zero-initialised reference tensors (motion proj_out, fps/motion embedding linear_2) are drawn
@@ -18,7 +19,7 @@ import zlib
 
 import torch
 
-_QK_GAIN = 2.0
+_QK_GAIN = 1.0
 
 
 def synth_tensor(key, shape, seed=0):
@@ -78,3 +79,23 @@ def synth_clip_inputs(b, f, h, w, seed=1234, ctx_len=77, ctx_dim=768, clip_dim=N
         out["image_clip_feat"] = rn((b, clip_dim), seed + 3)
         out["uncond_image_clip_feat"] = torch.zeros(b, clip_dim, dtype=dtype)
     return out
+
+
+def synth_on_device_(module, seed=0):
+    """Fast on-device variant for the benchmark (values differ from the CPU generator; same distributions).  Used where
+    only timing matters: drawing 1.28 B normals on the host takes tens of seconds."""
+    dev = next(module.parameters()).device
+    g = torch.Generator(device=dev).manual_seed(seed)
+    for k, p in module.state_dict(keep_vars=True).items():
+        if k.endswith(".pe"):
+            continue
+        x = torch.randn(p.shape, generator=g, device=dev, dtype=torch.float32)
+        if k.endswith(".bias"):
+            p.data = 0.05 * x
+        elif p.dim() == 1:
+            p.data = 1.0 + 0.1 * x
+        else:
+            p.data = x * (p[0].numel() ** -0.5)
+    if hasattr(module, "_invalidate"):
+        module._invalidate()
+    return module
