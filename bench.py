@@ -173,6 +173,7 @@ def run_reference_arm(args, rank):
     t0 = time.time()
     # K timed "steps" are K repetitions of the bounded sample (best-of); W warm-ups are skipped on purpose: a CPU sample
     # costs ~15-60 s and the first repetition already runs on warm weights (generated just before).
+    cores = min(cores, 32)      # the fp32 ATen CPU kernels slow down beyond ~32 threads on this shape (measured: 128 thr 4x slower)
     r = cpu_reference_sample(cores, repeats=max(1, min(args.steps, 2)))
     wl = WORKLOADS["cfg2"]
     sample = "1 UNet3D fwd (1.28B params, B=2,F=8,32x32 latent, 4.08 TFLOP) + 1 VAE frame decode 256x256 (0.622 TFLOP), fp32 " \
@@ -271,7 +272,11 @@ def main():
     for _ in range(args.warmup):
         step_resident()
     sampler = ClockSampler(local) if rank == 0 else None
+    if os.environ.get("FYC_CUPROF"):            # ncu --profile-from-start off: capture only the timed region
+        torch.cuda.profiler.start()
     ms, launches, t0, t1, video = timed(step_resident, args.steps)
+    if os.environ.get("FYC_CUPROF"):
+        torch.cuda.profiler.stop()
     clocks = sampler.stop(t0, t1) if sampler else None
     assert bool(torch.isfinite(video).all()), "non-finite frames"
     fps = world * F * args.steps / (ms / 1e3)
@@ -305,7 +310,7 @@ def main():
                                       gbs=round(v["bytes"] / (v["ms"] * 1e6), 1) if v["ms"] else 0.0) for k, v in prof.summary.items()})
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
+        cores = min(os.cpu_count() or 1, 32)     # more threads are slower for these fp32 CPU kernels (measured)
         r = cpu_reference_sample(cores)
         cpu = dict(value=r["fps"], unit="frames/s", cores=cores, kind="port",
                    sample=f"1 UNet3D fwd at cfg1 shape ({r['t_unet_cfg1']:.1f} s) + 1 VAE frame 256x256 ({r['t_vae_256']:.1f} s), fp32 "

@@ -99,6 +99,8 @@ template <> struct Vec4<float> {
 };
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
+// bf16-storage paths: 2-ulp intrinsics are far below the 2^-9 output rounding
+__device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 // exact-erf GELU (F.gelu default; diffusers/models/attention.py:815)
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 

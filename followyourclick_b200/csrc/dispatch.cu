@@ -12,6 +12,10 @@ int32_t fyc_space_to_planes(const void* x, void* out, int64_t NB, int64_t H, int
 int32_t fyc_attention_simt(const fyc_attention_args* a, cudaStream_t st);
 int32_t fyc_attention_mma(const fyc_attention_args* a, cudaStream_t st);
 bool fyc_attention_mma_eligible(const fyc_attention_args* a);
+bool fyc_gemv_eligible(const fyc_gemm_args* g);
+int32_t fyc_gemv(const fyc_gemm_args* g, cudaStream_t st);
+bool fyc_conv_small_n_eligible(const fyc_conv3x3_args* c);
+int32_t fyc_conv_small_n(const fyc_conv3x3_args* c, cudaStream_t st);
 
 extern "C" int32_t fyc_gemm(const fyc_gemm_args* g, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
@@ -24,6 +28,7 @@ extern "C" int32_t fyc_gemm(const fyc_gemm_args* g, void* stream) {
   FYC_CHECK(!(g->epilogue & FYC_EPI_OUT_F32) || g->dtype == FYC_BF16 || g->dtype == FYC_F32, "gemm: bad dtype");
   if (g->impl == FYC_IMPL_TCGEN05) return fyc_gemm_tc(g, st);
   if (g->impl == FYC_IMPL_AUTO && fyc_gemm_tc_eligible(g)) return fyc_gemm_tc(g, st);
+  if (g->impl == FYC_IMPL_AUTO && fyc_gemv_eligible(g)) return fyc_gemv(g, st);
   return fyc_gemm_simt(g, st);
 }
 
@@ -46,6 +51,7 @@ extern "C" int32_t fyc_conv3x3(const fyc_conv3x3_args* c, void* stream) {
     tc = false;
   }
   FYC_CHECK(tc || c->impl != FYC_IMPL_TCGEN05, "conv3x3: tcgen05 path requested but shape not eligible");
+  if (!tc && c->impl == FYC_IMPL_AUTO && fyc_conv_small_n_eligible(c)) return fyc_conv_small_n(c, st);
   if (!tc) return fyc_conv3x3_simt(c, st);
   if (c->stride == 2) {
     int32_t rc = fyc_space_to_planes(c->x, c->workspace, c->NB, c->H, c->W, c->Cin, st);

@@ -162,7 +162,7 @@ extern "C" int32_t fyc_nfhwc_to_ncfhw(const void* in, float* out, int64_t B, int
 template <typename T>
 __global__ void build_unet_input_kernel(const float* __restrict__ lat, const float* __restrict__ mask,
                                         const float* __restrict__ first, T* __restrict__ out, int64_t b, int64_t F,
-                                        int64_t HW, int dup, int concat) {
+                                        int64_t HW, int dup, int concat, int c_pad) {
   int Cin = concat ? 9 : 4;
   int64_t total = b * F * HW;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -178,16 +178,18 @@ __global__ void build_unet_input_kernel(const float* __restrict__ lat, const flo
       for (int c = 0; c < 4; ++c) v[5 + c] = (f == 0) ? first[(bi * 4 + c) * HW + p] : 0.f;
     }
     for (int d = 0; d < dup; ++d) {
-      T* o = out + (((d * b + bi) * F + f) * HW + p) * Cin;
+      T* o = out + (((d * b + bi) * F + f) * HW + p) * c_pad;
       for (int c = 0; c < Cin; ++c) o[c] = from_f<T>(v[c]);
+      for (int c = Cin; c < c_pad; ++c) o[c] = from_f<T>(0.f);
     }
   }
 }
 extern "C" int32_t fyc_build_unet_input(const float* latents, const float* mask, const float* first, void* out, int64_t b,
-                                        int64_t F, int64_t HW, int32_t dup, int32_t dtype, void* stream) {
+                                        int64_t F, int64_t HW, int32_t dup, int32_t c_pad, int32_t dtype, void* stream) {
   FYC_CHECK(dup == 1 || dup == 2, "build_unet_input: dup must be 1 or 2");
   int concat = first != nullptr;
-  FYC_DISPATCH(dtype, build_unet_input_kernel<T><<<grid_for(b * F * HW, 256), 256, 0, (cudaStream_t)stream>>>(latents, mask, first, (T*)out, b, F, HW, dup, concat));
+  FYC_CHECK(c_pad >= (concat ? 9 : 4) && c_pad <= 64, "build_unet_input: c_pad=%d", c_pad);
+  FYC_DISPATCH(dtype, build_unet_input_kernel<T><<<grid_for(b * F * HW, 256), 256, 0, (cudaStream_t)stream>>>(latents, mask, first, (T*)out, b, F, HW, dup, concat, c_pad));
   FYC_LAUNCH_CHECK();
   return FYC_OK;
 }

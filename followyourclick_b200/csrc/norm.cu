@@ -26,7 +26,22 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const T* __restrict__ x, 
       float s[V], q[V];
 #pragma unroll
       for (int e = 0; e < V; ++e) { s[e] = 0.f; q[e] = 0.f; }
-      for (int64_t r = r0 + ry; r < r1; r += RY) {
+      int64_t r = r0 + ry;
+      for (; r + 3 * RY < r1; r += 4 * RY) {      // 4 independent 16-byte loads in flight per thread
+        float f[4][8];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const T* src = base + (r + (int64_t)u * RY) * C + cv * V;
+          if constexpr (V == 8) Vec8<T>::load(src, f[u]);
+          else if constexpr (V == 4) Vec4<T>::load(src, f[u]);
+          else f[u][0] = to_f(*src);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int e = 0; e < V; ++e) { s[e] += f[u][e]; q[e] = fmaf(f[u][e], f[u][e], q[e]); }
+      }
+      for (; r < r1; r += RY) {
         float f[8];
         if constexpr (V == 8) Vec8<T>::load(base + r * C + cv * V, f);
         else if constexpr (V == 4) Vec4<T>::load(base + r * C + cv * V, f);
@@ -82,24 +97,36 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ x, 
                                                        const float* __restrict__ shift, T* __restrict__ out, int64_t R,
                                                        int C, int64_t total_vec) {
   const int cvn = C / V;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total_vec; i += (int64_t)gridDim.x * blockDim.x) {
-    int cv = (int)(i % cvn);
-    int64_t row = i / cvn;
-    int64_t nb = row / R;
-    const float* sc = scale + nb * C + cv * V;
-    const float* sh = shift + nb * C + cv * V;
-    float f[8];
-    if constexpr (V == 8) Vec8<T>::load(x + i * V, f);
-    else if constexpr (V == 4) Vec4<T>::load(x + i * V, f);
-    else f[0] = to_f(x[i]);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  constexpr int U = 4;     // vectors in flight per thread
+  for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < total_vec; i0 += stride * U) {
+    float f[U][8];
 #pragma unroll
-    for (int e = 0; e < V; ++e) {
-      float y = fmaf(f[e], sc[e], sh[e]);
-      f[e] = SILU ? silu_f(y) : y;
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < total_vec) {
+        if constexpr (V == 8) Vec8<T>::load(x + i * V, f[u]);
+        else if constexpr (V == 4) Vec4<T>::load(x + i * V, f[u]);
+        else f[u][0] = to_f(x[i]);
+      }
     }
-    if constexpr (V == 8) Vec8<T>::store(out + i * V, f);
-    else if constexpr (V == 4) Vec4<T>::store(out + i * V, f);
-    else out[i] = from_f<T>(f[0]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i >= total_vec) break;
+      const int cv = (int)(i % cvn);
+      const int64_t nb = (i / cvn) / R;
+      const float* sc = scale + nb * C + cv * V;
+      const float* sh = shift + nb * C + cv * V;
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        float y = fmaf(f[u][e], __ldg(sc + e), __ldg(sh + e));
+        f[u][e] = SILU ? (sizeof(T) == 2 ? silu_fast(y) : silu_f(y)) : y;
+      }
+      if constexpr (V == 8) Vec8<T>::store(out + i * V, f[u]);
+      else if constexpr (V == 4) Vec4<T>::store(out + i * V, f[u]);
+      else out[i] = from_f<T>(f[u][0]);
+    }
   }
 }
 

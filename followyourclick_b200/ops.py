@@ -270,14 +270,17 @@ def nfhwc_to_ncfhw(x):
     return out
 
 
-def build_unet_input(latents, mask, first, dup, dtype):
+def build_unet_input(latents, mask, first, dup, dtype, c_pad=None, out=None):
     """latents (b,4,f,h,w) fp32, mask (b,1,1,h,w) fp32 | None, first (b,4,h,w) fp32 | None -> [dup*b, f, h, w, 9|4]."""
     assert latents.dtype == torch.float32 and latents.is_contiguous() and latents.is_cuda
     b, c, f, h, w = latents.shape
     assert c == 4
     cin = 9 if first is not None else 4
-    out = torch.empty((dup * b, f, h, w, cin), dtype=dtype, device=latents.device)
-    check(lib().fyc_build_unet_input(ptr(latents), ptr(mask), ptr(first), ptr(out), b, f, h * w, dup, dtype_code(dtype), stream_ptr()))
+    c_pad = cin if c_pad is None else c_pad
+    if out is None:
+        out = torch.empty((dup * b, f, h, w, c_pad), dtype=dtype, device=latents.device)
+    assert out.shape == (dup * b, f, h, w, c_pad) and out.dtype == dtype and out.is_contiguous()
+    check(lib().fyc_build_unet_input(ptr(latents), ptr(mask), ptr(first), ptr(out), b, f, h * w, dup, c_pad, dtype_code(dtype), stream_ptr()))
     return out
 
 

@@ -13,7 +13,7 @@ from typing import Union
 import numpy as np
 import torch
 
-from . import ops
+from . import _lib, ops
 
 
 @dataclass
@@ -32,8 +32,49 @@ class _NullBar:
         pass
 
 
+class _GraphedUNetStep:
+    """One UNet3D forward (+ layout change of the prediction) captured as a CUDA graph.  Shapes are static per clip
+    configuration, so the ~700 kernel launches of a forward are replayed with one call; inputs live in static buffers
+    (x: channels-last UNet input, t: timestep, text / fps / flow / camera / clip features)."""
+
+    def __init__(self, unet, x_shape, text, fps, flow, cam, clip, flags):
+        dev = unet.device
+        self.version = unet._pack_version
+        self.x = torch.zeros(x_shape, dtype=unet.dtype, device=dev)
+        self.t = torch.zeros((), dtype=torch.int64, device=dev)
+        self.text = text.to(dev).float().contiguous().clone()
+        cl = lambda v: None if v is None else v.to(dev).contiguous().clone()
+        self.fps, self.flow, self.cam, self.clip = cl(fps), cl(flow), cl(cam), cl(clip)
+        self.flags = flags
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):           # warm-up outside capture: packs weights, sets kernel attributes
+            for _ in range(2):
+                self._run(unet)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = _lib.launch_count
+        with torch.cuda.graph(self.graph):
+            self.pred = self._run(unet)
+        self.n_calls = _lib.launch_count - n0      # kernel-launching C-ABI calls replayed by one graph launch
+
+    def _run(self, unet):
+        y = unet.forward_nfhwc(self.x, self.t, self.text, fps_tensor=self.fps, flow_control=self.flow,
+                               reference_images_clip_feat=self.clip, camera_movement_type_tensor=self.cam, **self.flags)
+        return ops.nfhwc_to_ncfhw(y)
+
+    def load(self, text, fps, flow, cam, clip):
+        self.text.copy_(text)
+        for dst, src in ((self.fps, fps), (self.flow, flow), (self.cam, cam), (self.clip, clip)):
+            if dst is not None:
+                dst.copy_(src)
+
+
 class AnimationPipeline:
     _optional_components = []
+    use_cuda_graph = True          # replay one captured UNet forward per DDIM step (set False to launch kernel by kernel)
 
     def __init__(self, vae, text_encoder, tokenizer, unet, scheduler, image_encoder=None, text_encoder_2=None,
                  tokenizer_2=None, ip_adapter=None):
@@ -188,16 +229,35 @@ class AnimationPipeline:
                 mask = first_images_mask[:, :, 0].to(device=dev, dtype=torch.float32).contiguous()     # :632-635 (frame 0, clamp in-kernel)
         latents = latents.to(device=dev, dtype=torch.float32).contiguous()
         text_embeddings = text_embeddings.to(dev)
+        c_pad = unet.input_channel_pad() if hasattr(unet, "input_channel_pad") else None
         bar = self.progress_bar(total=num_inference_steps) if progress else _NullBar()
+        flags = dict(use_ip_cross_attention=use_ip_cross_attention, use_camera_motion_condition=use_camera_motion_condition,
+                     use_fps_condition=use_fps_condition)
+        clip_d = None if image_clip_feat_pair is None else image_clip_feat_pair.to(dev)
+        graphed = None
+        if self.use_cuda_graph and hasattr(unet, "forward_nfhwc"):
+            b, _, f, h, w = latents.shape
+            cin = c_pad if c_pad is not None else (9 if first is not None else 4)
+            key = (dup * b, f, h, w, cin, unet.dtype, tuple(sorted(flags.items())), tuple(text_embeddings.shape),
+                   None if clip_d is None else tuple(clip_d.shape))
+            cache = self.__dict__.setdefault("_graph_cache", {})
+            graphed = cache.get(key)
+            if graphed is None or graphed.version != unet._pack_version:
+                graphed = cache[key] = _GraphedUNetStep(unet, (dup * b, f, h, w, cin), text_embeddings, fps_d, flow_d, cam_d, clip_d, flags)
+            graphed.load(text_embeddings, fps_d, flow_d, cam_d, clip_d)
         with bar as pb:
             for i, t in enumerate(t_host):
-                x = ops.build_unet_input(latents, mask, first, dup, unet.dtype)
-                y = unet.forward_nfhwc(x, t_dev[i], text_embeddings, fps_tensor=fps_d, flow_control=flow_d,
-                                       reference_images_clip_feat=image_clip_feat_pair,
-                                       camera_movement_type_tensor=cam_d, use_ip_cross_attention=use_ip_cross_attention,
-                                       use_camera_motion_condition=use_camera_motion_condition,
-                                       use_fps_condition=use_fps_condition)
-                pred = ops.nfhwc_to_ncfhw(y)
+                if graphed is not None:
+                    ops.build_unet_input(latents, mask, first, dup, unet.dtype, c_pad=c_pad, out=graphed.x)
+                    graphed.t.copy_(t_dev[i])
+                    graphed.graph.replay()
+                    _lib.launch_count += graphed.n_calls
+                    pred = graphed.pred
+                else:
+                    x = ops.build_unet_input(latents, mask, first, dup, unet.dtype, c_pad=c_pad)
+                    y = unet.forward_nfhwc(x, t_dev[i], text_embeddings, fps_tensor=fps_d, flow_control=flow_d,
+                                           reference_images_clip_feat=clip_d, camera_movement_type_tensor=cam_d, **flags)
+                    pred = ops.nfhwc_to_ncfhw(y)
                 latents = sched.step_cfg(pred, t, latents, guidance_scale if do_cfg else 1.0, eta=eta, generator=generator)
                 pb.update()
                 if callback is not None and i % callback_steps == 0:

@@ -400,6 +400,15 @@ class UNet3DConditionModel(ParamTreeModel):
         h = ops.silu(ops.gemm(s, self._fw(name + ".linear_1.weight"), bias=self._f(name + ".linear_1.bias")))
         return ops.gemm(h, self._fw(name + ".linear_2.weight"), bias=self._f(name + ".linear_2.bias"), residual=residual)
 
+    def input_channel_pad(self):
+        """Channel count the engine wants for its channels-last input: 16 (zero padded) in tensor-core mode so the stem
+        conv runs on tcgen05, else the model's true input channels."""
+        w = self._p("conv_in.weight")
+        cin = w.shape[1]
+        if self._compute_dtype == torch.bfloat16 and cin % 8 != 0 and cin <= 16 and ops.tc_ok(torch.bfloat16, 1 << 20):
+            return 16
+        return cin
+
     _taps = None    # set to a dict to record named intermediate activations (debug / layer-wise parity)
 
     def _tap(self, name, x):
@@ -444,6 +453,14 @@ class UNet3DConditionModel(ParamTreeModel):
             b_in = self._cached(("bin_half",), lambda: self._f("conv_in.bias") * 0.5)
         else:
             w_in, b_in = self._conv_w("conv_in.weight"), self._f("conv_in.bias")
+        if Cin > w_in.shape[-1]:
+            # channel-padded input (ops.build_unet_input(c_pad=16)): zero-extend the filter so the 9-channel stem takes
+            # the tcgen05 path (TMA needs 16-byte channel rows); the padded channels multiply zeros.
+            def pad(w=w_in, c=Cin):
+                wp = torch.zeros(w.shape[:-1] + (c,), dtype=w.dtype, device=w.device)
+                wp[..., :w.shape[-1]] = w
+                return wp
+            w_in = self._cached(("cin_pad", Cin, bool(use_first_frame_condition_concat)), pad)
         x = ops.conv3x3(x, w_in, bias=b_in)
         self._tap("conv_in", x)
 

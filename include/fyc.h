@@ -148,9 +148,10 @@ int32_t fyc_nfhwc_to_ncfhw(const void* in, float* out, int64_t B, int64_t C, int
                            int32_t dtype, void* stream);
 /* AnimationPipeline.__call__ step prologue (pipeline_animation.py:625-635,693-711): builds the channels-last
  * UNet input [dup*b, F, H, W, Cin] from latents (b,4,F,H,W) fp32, mask (b,1,1,H,W) fp32 (NULL -> 1 on frame 0)
- * and first-frame latents (b,4,H,W) fp32 (NULL -> Cin = 4, plain latents). */
+ * and first-frame latents (b,4,H,W) fp32 (NULL -> Cin = 4, plain latents).  c_pad >= Cin: channels Cin..c_pad-1 are
+ * written as zeros (lets the 9-channel stem run on the tensor-core path with a 16-channel, zero-extended filter). */
 int32_t fyc_build_unet_input(const float* latents, const float* mask, const float* first, void* out, int64_t b,
-                             int64_t F, int64_t HW, int32_t dup, int32_t dtype, void* stream);
+                             int64_t F, int64_t HW, int32_t dup, int32_t c_pad, int32_t dtype, void* stream);
 /* CFG combine + DDIMScheduler.step (pipeline_animation.py:763-764 + scheduling_ddim.py:308-349), fp32, exact
  * reference operation order (no FMA contraction).  pred: [2, n] (uncond, cond) when guidance > 1 else [1, n]. */
 typedef struct {
