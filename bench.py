@@ -228,7 +228,9 @@ def main():
     host["mask"] = mask.pin_memory()
     pipe = AnimationPipeline(vae=vae, text_encoder=_TextEnc(host["text"]), tokenizer=_Tok(), unet=unet, scheduler=DDIMScheduler(**SCHED))
     pipe.set_progress_bar_config(disable=True)
-    devin = {k: v.to(dev) for k, v in host.items()}
+    if os.environ.get("FYC_NO_GRAPH"):          # kernel-by-kernel launches (ncu launch lists)
+        pipe.use_cuda_graph = False
+    devin ={k: v.to(dev) for k, v in host.items()}
     fps_t, flow_t = torch.tensor([2]), torch.tensor([4])
 
     def step_resident():

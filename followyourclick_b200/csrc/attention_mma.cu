@@ -38,12 +38,18 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 }
 
 // copy a [64 x DP] tile (rows row0.., valid while < L, columns < D; everything else zero) into smem
-template <int D, int DP, int LDS>
+template <int D, int DP, int LDS, bool ONES_COL = false>
 __device__ __forceinline__ void load_tile(bf16* dst, const bf16* src, int64_t ld, int64_t row0, int64_t L, int tid) {
   constexpr int CH = DP / 8;
   for (int i = tid; i < 64 * CH; i += NTHR) {
     int r = i / CH, c = (i % CH) * 8;
     bool ok = (row0 + r < L) && (c < D);
+    if (ONES_COL && c == D) {
+      // V padding chunk: [1, 0, 0, ...] for valid keys (row sum via the PV MMA), zeros for keys past the end
+      uint4 v = make_uint4((row0 + r < L) ? 0x00003F80u : 0u, 0u, 0u, 0u);     // bf16(1.0) = 0x3F80 in the low half
+      *reinterpret_cast<uint4*>(dst + r * LDS + c) = v;
+      continue;
+    }
     const bf16* s = ok ? src + (row0 + r) * ld + c : src;
     cp_async16(dst + r * LDS + c, s, ok ? 16 : 0);
   }
@@ -54,6 +60,7 @@ __global__ void __launch_bounds__(NTHR) attention_mma_kernel(fyc_attention_args 
   constexpr int LDS = DP + 8;          // padded row stride: ldmatrix row addresses hit distinct bank groups
   constexpr int KS = DP / 16;          // k-steps of QK^T
   constexpr int NO = DP / 8;           // n-tiles of the output
+  constexpr bool ONES = DP > D;        // V's first padding column (col D) holds ones -> O[:, D] accumulates the softmax row sum
   extern __shared__ __align__(16) unsigned char smem_raw[];
   bf16* sQ = reinterpret_cast<bf16*>(smem_raw);
   bf16* sK = sQ + 64 * LDS;            // [2][64][LDS]
@@ -70,7 +77,7 @@ __global__ void __launch_bounds__(NTHR) attention_mma_kernel(fyc_attention_args 
 
   load_tile<D, DP, LDS>(sQ, qg, a.ldq, q0, a.Lq, tid);
   load_tile<D, DP, LDS>(sK, kg, a.ldk, 0, a.Lk, tid);
-  load_tile<D, DP, LDS>(sV, vg, a.ldv, 0, a.Lk, tid);
+  load_tile<D, DP, LDS, (DP > D)>(sV, vg, a.ldv, 0, a.Lk, tid);
   cp_async_commit();
 
   uint32_t qf[KS][4];
@@ -78,13 +85,13 @@ __global__ void __launch_bounds__(NTHR) attention_mma_kernel(fyc_attention_args 
 #pragma unroll
   for (int i = 0; i < NO; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;   // rows g and g+8 of this warp's 16-row slab
-  const float sl2 = a.scale * 1.4426950408889634f;             // fold log2(e): p = 2^(s*sl2 - m)
+  const float sl2 = a.scale * 1.4426950408889634f;             // fold log2(e): p = 2^((s - m) * sl2)
 
   for (int kt = 0; kt < nkt; ++kt) {
     const int buf = kt & 1;
     if (kt + 1 < nkt) {
       load_tile<D, DP, LDS>(sK + (buf ^ 1) * 64 * LDS, kg, a.ldk, (int64_t)(kt + 1) * BKV, a.Lk, tid);
-      load_tile<D, DP, LDS>(sV + (buf ^ 1) * 64 * LDS, vg, a.ldv, (int64_t)(kt + 1) * BKV, a.Lk, tid);
+      load_tile<D, DP, LDS, (DP > D)>(sV + (buf ^ 1) * 64 * LDS, vg, a.ldv, (int64_t)(kt + 1) * BKV, a.Lk, tid);
       cp_async_commit();
       cp_async_wait<1>();
     } else {
@@ -113,36 +120,45 @@ __global__ void __launch_bounds__(NTHR) attention_mma_kernel(fyc_attention_args 
         mma_bf16(s[2 * jp + 1], qf[ks], b[2], b[3]);
       }
     }
-    // ---- mask + online softmax (rows g, g+8; this thread holds cols 8j + 2t, +1)
-    const int64_t kbase = (int64_t)kt * BKV;
-    float mx0 = -INFINITY, mx1 = -INFINITY;
+    // ---- online softmax on the raw scores (rows g, g+8; this thread holds cols 8j + 2t, +1).
+    // Instruction diet (the kernel is issue-bound, profiles/round1): the logit scale is folded into one FFMA per
+    // element (p = 2^(s*sl2 - m*sl2)), masking runs only on the last, ragged KV tile, and for D < DP the row sum comes
+    // out of the PV MMA itself through a column of ones planted in V's padding (col D) - no per-element FADD.
+    if (kt == nkt - 1 && (a.Lk & (BKV - 1))) {
+      const int64_t kbase = (int64_t)kt * BKV;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+          if (kbase + 8 * j + 2 * t + e >= a.Lk) { s[j][e] = -INFINITY; s[j][2 + e] = -INFINITY; }
+    }
+    float mx0 = s[0][0], mx1 = s[0][2];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        bool ok = kbase + 8 * j + 2 * t + e < a.Lk;
-        s[j][e] = ok ? s[j][e] * sl2 : -INFINITY;
-        s[j][2 + e] = ok ? s[j][2 + e] * sl2 : -INFINITY;
-        mx0 = fmaxf(mx0, s[j][e]); mx1 = fmaxf(mx1, s[j][2 + e]);
-      }
+      mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
     }
     mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-    const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
-    const float c0 = (m0 == -INFINITY) ? 0.f : exp2f(m0 - mn0), c1 = (m1 == -INFINITY) ? 0.f : exp2f(m1 - mn1);
+    const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);           // running maxima of the RAW scores (scale > 0)
+    const float c0 = (m0 == -INFINITY) ? 0.f : exp2f((m0 - mn0) * sl2), c1 = (m1 == -INFINITY) ? 0.f : exp2f((m1 - mn1) * sl2);
     m0 = mn0; m1 = mn1;
+    const float nb0 = -mn0 * sl2, nb1 = -mn1 * sl2;
     float rs0 = 0.f, rs1 = 0.f;
     uint32_t pf[4][4];   // P as A fragments: k-step kk covers keys 16kk..16kk+15 = n-tiles 2kk, 2kk+1
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float p0 = exp2f(s[j][0] - mn0), p1 = exp2f(s[j][1] - mn0), p2 = exp2f(s[j][2] - mn1), p3 = exp2f(s[j][3] - mn1);
-      rs0 += p0 + p1; rs1 += p2 + p3;
+      float p0 = exp2f(fmaf(s[j][0], sl2, nb0)), p1 = exp2f(fmaf(s[j][1], sl2, nb0));
+      float p2 = exp2f(fmaf(s[j][2], sl2, nb1)), p3 = exp2f(fmaf(s[j][3], sl2, nb1));
+      if constexpr (!ONES) { rs0 += p0 + p1; rs1 += p2 + p3; }
       pf[j >> 1][(j & 1) * 2 + 0] = pack_bf16(p0, p1);
       pf[j >> 1][(j & 1) * 2 + 1] = pack_bf16(p2, p3);
     }
-    rs0 += __shfl_xor_sync(0xffffffffu, rs0, 1); rs0 += __shfl_xor_sync(0xffffffffu, rs0, 2);
-    rs1 += __shfl_xor_sync(0xffffffffu, rs1, 1); rs1 += __shfl_xor_sync(0xffffffffu, rs1, 2);
-    l0 = l0 * c0 + rs0; l1 = l1 * c1 + rs1;
+    if constexpr (!ONES) {
+      rs0 += __shfl_xor_sync(0xffffffffu, rs0, 1); rs0 += __shfl_xor_sync(0xffffffffu, rs0, 2);
+      rs1 += __shfl_xor_sync(0xffffffffu, rs1, 1); rs1 += __shfl_xor_sync(0xffffffffu, rs1, 2);
+      l0 = l0 * c0 + rs0; l1 = l1 * c1 + rs1;
+    }
 #pragma unroll
     for (int i = 0; i < NO; ++i) { o[i][0] *= c0; o[i][1] *= c0; o[i][2] *= c1; o[i][3] *= c1; }
     // ---- O += P V
@@ -160,6 +176,11 @@ __global__ void __launch_bounds__(NTHR) attention_mma_kernel(fyc_attention_args 
     __syncthreads();
   }
   // ---- epilogue: O / l * out_alpha (+ existing out)
+  if constexpr (ONES) {   // column D of O is sum_j P_ij: lives in n-tile D/8, element 0/2 of the lane with 2t == D % 8
+    constexpr int NTL = D / 8, SRC = (D % 8) / 2;
+    l0 = __shfl_sync(0xffffffffu, o[NTL][0], (lane & ~3) | SRC);
+    l1 = __shfl_sync(0xffffffffu, o[NTL][2], (lane & ~3) | SRC);
+  }
   const float i0 = a.out_alpha / l0, i1 = a.out_alpha / l1;
   bf16* og = (bf16*)a.out + n * a.bso + h * D;
   const int64_t r0 = q0 + w * 16 + g, r1 = r0 + 8;

@@ -243,11 +243,16 @@ int32_t fyc_attention_simt(const fyc_attention_args* a, cudaStream_t st) {
   FYC_CHECK(false, "attention: unknown dtype %d", a->dtype);
 }
 
+bool fyc_temporal_mma_eligible(int64_t F, int64_t D, int64_t heads, int32_t dtype, const void* qkv, const void* out);
+int32_t fyc_temporal_attention_mma(const void* qkv, void* out, int64_t B, int64_t F, int64_t HW, int64_t heads, int64_t D, float scale,
+                                   cudaStream_t st);
+
 extern "C" int32_t fyc_temporal_attention(const void* qkv, void* out, int64_t B, int64_t F, int64_t HW, int64_t heads,
                                           int64_t D, float scale, int32_t dtype, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   FYC_CHECK(F >= 1 && F <= 32, "temporal_attention: F=%lld must be in [1, 32]", (long long)F);
   FYC_CHECK(D % 4 == 0, "temporal_attention: head dim %lld must be a multiple of 4", (long long)D);
+  if (fyc_temporal_mma_eligible(F, D, heads, dtype, qkv, out)) return fyc_temporal_attention_mma(qkv, out, B, F, HW, heads, D, scale, st);
 #define FYC_TA(T)                                                                                             \
   if (F <= 4) return launch_temporal<T, 4>((const T*)qkv, (T*)out, B, (int)F, HW, (int)heads, (int)D, scale, st);   \
   if (F <= 8) return launch_temporal<T, 8>((const T*)qkv, (T*)out, B, (int)F, HW, (int)heads, (int)D, scale, st);   \

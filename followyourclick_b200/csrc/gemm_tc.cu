@@ -7,7 +7,7 @@
 //                                   slab) into a 4-stage 128B-swizzled shared-memory ring, mbarrier expect_tx
 //   warp 1 (1 lane)  MMA issuer   : tcgen05.mma.cta_group::1.kind::f16  128 x BN x 16, bf16 x bf16 -> fp32 in TMEM,
 //                                   tcgen05.commit releases smem stages / publishes the accumulator
-//   warps 2..5       epilogue     : tcgen05.ld (32x32b) TMEM -> registers, fused bias / time-embedding row bias /
+//   warps 2..9       epilogue     : tcgen05.ld (32x32b) TMEM -> registers, fused bias / time-embedding row bias /
 //                                   residual / GEGLU / alpha, vectorised global stores; double-buffered TMEM
 //                                   accumulators (2 x 256 columns) overlap the epilogue with the next tile's MMAs.
 // The 3x3 convolution never builds an im2col matrix: for each filter tap the producer loads the SAME 4-D box shifted
@@ -28,7 +28,7 @@ constexpr int A_BYTES = BM * BK * 2;           // 16 KB
 constexpr int B_BYTES = MAX_BN * BK * 2;       // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;          // TMA warp, MMA warp, 8 epilogue warps (2 per TMEM lane quarter)
 
 struct TcParams {
   // problem
@@ -108,6 +108,21 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// split TMEM load: issue now, wait later (the wait names the registers so their uses cannot be hoisted above it)
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait(uint32_t* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :: "memory");
+}
+
 // shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor)
 __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
   uint64_t d = 0;
@@ -142,7 +157,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 128); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {   // TMEM: all 512 columns (2 accumulator stages x 256); this warp also frees them
@@ -210,6 +225,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   } else {
     // ================================================================== epilogue (warps 2..5)
     const int quarter = warp & 3;                      // TMEM lane quarter this warp may access
+    const int egroup = (warp - 2) >> 2;                // 0: warps 2-5, 1: warps 6-9 (same rows, other half of the columns)
     const int r = quarter * 32 + lane;                 // row of the tile handled by this thread
     int acc = 0; uint32_t aphase = 0;
     const bool geglu = (p.flags & FYC_EPI_GEGLU) != 0;
@@ -231,51 +247,66 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int n0 = n_blk * p.BN;
       const float* rb = (p.flags & FYC_EPI_ROWBIAS) ? p.rowbias + (row_ok ? pix / p.rows_per_group : 0) * p.N : nullptr;
       if (!geglu) {
-        for (int c = 0; c < p.BN; c += 16) {
+        // this warp's share of the tile columns: 16-column chunks [cb, ce); the two warps of a lane quarter split them
+        const int nch = p.BN >> 4, half = (nch + 1) >> 1;
+        const int cb = egroup ? half : 0, ce = egroup ? nch : half;
+        auto process = [&](const uint32_t* r, int ch) {
+          const int n = n0 + ch * 16;
+          if (!(row_ok && n < p.N)) return;     // N is a multiple of 16 on this path
           float v[16];
-          tmem_ld16(taddr + c, v);
-          const int n = n0 + c;
-          if (row_ok && n < p.N) {     // N is a multiple of 16 on this path
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] *= p.alpha;
-            if (p.flags & FYC_EPI_BIAS) {
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
+          if (p.flags & FYC_EPI_BIAS) {
 #pragma unroll
-              for (int i = 0; i < 16; i += 4) {
-                float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + i));
-                v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
-              }
+            for (int i = 0; i < 16; i += 4) {
+              float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + i));
+              v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
             }
-            if (rb) {
+          }
+          if (rb) {
 #pragma unroll
-              for (int i = 0; i < 16; i += 4) {
-                float4 b = __ldg(reinterpret_cast<const float4*>(rb + n + i));
-                v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
-              }
+            for (int i = 0; i < 16; i += 4) {
+              float4 b = __ldg(reinterpret_cast<const float4*>(rb + n + i));
+              v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
             }
-            if (p.flags & FYC_EPI_RESIDUAL) {
-              float f[16];
-              if (out_f32) {
-                Vec8<float>::load(reinterpret_cast<const float*>(p.residual) + pix * p.ldr + n, f);
-                Vec8<float>::load(reinterpret_cast<const float*>(p.residual) + pix * p.ldr + n + 8, f + 8);
-              } else {
-                Vec8<bf16>::load(reinterpret_cast<const bf16*>(p.residual) + pix * p.ldr + n, f);
-                Vec8<bf16>::load(reinterpret_cast<const bf16*>(p.residual) + pix * p.ldr + n + 8, f + 8);
-              }
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] += f[i];
-            }
+          }
+          if (p.flags & FYC_EPI_RESIDUAL) {
+            float f[16];
             if (out_f32) {
-              float* o = reinterpret_cast<float*>(p.out) + pix * p.ldo + n;
-              Vec8<float>::store(o, v); Vec8<float>::store(o + 8, v + 8);
+              Vec8<float>::load(reinterpret_cast<const float*>(p.residual) + pix * p.ldr + n, f);
+              Vec8<float>::load(reinterpret_cast<const float*>(p.residual) + pix * p.ldr + n + 8, f + 8);
             } else {
-              bf16* o = reinterpret_cast<bf16*>(p.out) + pix * p.ldo + n;
-              Vec8<bf16>::store(o, v); Vec8<bf16>::store(o + 8, v + 8);
+              Vec8<bf16>::load(reinterpret_cast<const bf16*>(p.residual) + pix * p.ldr + n, f);
+              Vec8<bf16>::load(reinterpret_cast<const bf16*>(p.residual) + pix * p.ldr + n + 8, f + 8);
             }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] += f[i];
+          }
+          if (out_f32) {
+            float* o = reinterpret_cast<float*>(p.out) + pix * p.ldo + n;
+            Vec8<float>::store(o, v); Vec8<float>::store(o + 8, v + 8);
+          } else {
+            bf16* o = reinterpret_cast<bf16*>(p.out) + pix * p.ldo + n;
+            Vec8<bf16>::store(o, v); Vec8<bf16>::store(o + 8, v + 8);
+          }
+        };
+        // software-pipelined TMEM reads: chunk c+1 is in flight while chunk c goes through the epilogue math/stores
+        uint32_t ra[16], rc[16];
+        if (cb < ce) tmem_ld16_issue(taddr + cb * 16, ra);
+        for (int ch = cb; ch < ce; ch += 2) {
+          tmem_ld_wait(ra);
+          if (ch + 1 < ce) tmem_ld16_issue(taddr + (ch + 1) * 16, rc);
+          process(ra, ch);
+          if (ch + 1 < ce) {
+            tmem_ld_wait(rc);
+            if (ch + 2 < ce) tmem_ld16_issue(taddr + (ch + 2) * 16, ra);
+            process(rc, ch + 1);
           }
         }
       } else {
-        // GEGLU: columns [0,128) of the tile are `a`, [128,256) the matching `gate` (weight rows pre-interleaved)
-        for (int c = 0; c < 128; c += 16) {
+        // GEGLU: columns [0,128) of the tile are `a`, [128,256) the matching `gate` (weight rows pre-interleaved);
+        // epilogue group 0 takes a-columns [0,64), group 1 [64,128)
+        for (int c = egroup * 64; c < egroup * 64 + 64; c += 16) {
           float a[16], g[16];
           tmem_ld16(taddr + c, a);
           tmem_ld16(taddr + 128 + c, g);

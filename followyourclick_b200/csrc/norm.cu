@@ -118,9 +118,21 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ x, 
       const int64_t nb = (i / cvn) / R;
       const float* sc = scale + nb * C + cv * V;
       const float* sh = shift + nb * C + cv * V;
+      float scv[V], shv[V];
+      if constexpr (V >= 4) {     // 16-byte parameter loads (scalar loads saturated the LSU queue: lg_throttle)
+#pragma unroll
+        for (int e = 0; e < V; e += 4) {
+          float4 a = __ldg(reinterpret_cast<const float4*>(sc + e));
+          float4 b = __ldg(reinterpret_cast<const float4*>(sh + e));
+          scv[e] = a.x; scv[e + 1] = a.y; scv[e + 2] = a.z; scv[e + 3] = a.w;
+          shv[e] = b.x; shv[e + 1] = b.y; shv[e + 2] = b.z; shv[e + 3] = b.w;
+        }
+      } else {
+        scv[0] = __ldg(sc); shv[0] = __ldg(sh);
+      }
 #pragma unroll
       for (int e = 0; e < V; ++e) {
-        float y = fmaf(f[u][e], __ldg(sc + e), __ldg(sh + e));
+        float y = fmaf(f[u][e], scv[e], shv[e]);
         f[u][e] = SILU ? (sizeof(T) == 2 ? silu_fast(y) : silu_f(y)) : y;
       }
       if constexpr (V == 8) Vec8<T>::store(out + i * V, f[u]);
@@ -131,16 +143,17 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ x, 
 }
 
 static int64_t gn_max_chunks(int64_t NB) { return ((int64_t)fyc_sm_count() * 4 + NB - 1) / NB + 1; }
+static int64_t gn_partials(int64_t NB, int64_t G) { return (NB * gn_max_chunks(NB) * G + 1) / 2 * 2; }   // even: keeps scale/shift 16-byte aligned
 
 extern "C" size_t fyc_groupnorm_workspace_bytes(int64_t NB, int64_t C, int64_t G) {
-  return (size_t)(NB * gn_max_chunks(NB) * G * sizeof(float2) + NB * C * 2 * sizeof(float));
+  return (size_t)(gn_partials(NB, G) * sizeof(float2) + NB * C * 2 * sizeof(float));
 }
 
 template <typename T, int V>
 static int32_t groupnorm_impl(const T* x, const float* gamma, const float* beta, T* out, int64_t NB, int64_t R, int C,
                               int G, float eps, int silu, void* ws, cudaStream_t st) {
   float2* partials = (float2*)ws;
-  float* scale = (float*)(partials + NB * gn_max_chunks(NB) * G);
+  float* scale = (float*)(partials + gn_partials(NB, G));
   float* shift = scale + NB * C;
   const int cvn = C / V;
   const int TX = cvn < 256 ? cvn : 256;
@@ -228,13 +241,24 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const T* __restrict__ x,
   for (int i = 0; i < NV; ++i) {
     int cv = lane + 32 * i;
     if (cv < cvn) {
-      float o[V];
+      float o[V], gm[V], bt[V];
+      // 16-byte parameter loads (scalar loads here saturated the LSU queue: lg_throttle in profiles/round1)
 #pragma unroll
-      for (int e = 0; e < V; ++e) {
-        int c = cv * V + e;
-        float y = (v[i][e] - mean) * rstd * gamma[c] + beta[c];
-        o[e] = per ? y + per[c] : y;
+      for (int e = 0; e < V; e += 4) {
+        float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + cv * V + e));
+        float4 b4 = __ldg(reinterpret_cast<const float4*>(beta + cv * V + e));
+        gm[e] = g4.x; gm[e + 1] = g4.y; gm[e + 2] = g4.z; gm[e + 3] = g4.w;
+        bt[e] = b4.x; bt[e + 1] = b4.y; bt[e + 2] = b4.z; bt[e + 3] = b4.w;
       }
+      if (per) {
+#pragma unroll
+        for (int e = 0; e < V; e += 4) {
+          float4 p4 = __ldg(reinterpret_cast<const float4*>(per + cv * V + e));
+          bt[e] += p4.x; bt[e + 1] += p4.y; bt[e + 2] += p4.z; bt[e + 3] += p4.w;
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < V; ++e) o[e] = (v[i][e] - mean) * rstd * gm[e] + bt[e];
       if constexpr (V == 8) Vec8<T>::store(orow + cv * V, o); else Vec4<T>::store(orow + cv * V, o);
     }
   }
