@@ -73,14 +73,20 @@ __global__ void __launch_bounds__(256) gn_finalize_kernel(const float2* __restri
                                                           double count, float eps) {
   extern __shared__ float s_stat[];   // [G][2] mean, rstd
   const int64_t nb = blockIdx.x;
-  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+  // one warp per group: lanes stride over the chunk partials, then a fixed-shape shuffle tree (deterministic)
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int g = wid; g < G; g += nw) {
     double s = 0.0, q = 0.0;
-    for (int k = 0; k < chunks; ++k) { float2 p = partials[(nb * chunks + k) * G + g]; s += (double)p.x; q += (double)p.y; }
-    double mean = s / count;
-    double var = q / count - mean * mean;
-    if (var < 0) var = 0;
-    s_stat[2 * g] = (float)mean;
-    s_stat[2 * g + 1] = (float)(1.0 / sqrt(var + (double)eps));
+    for (int k = lane; k < chunks; k += 32) { float2 p = partials[(nb * chunks + k) * G + g]; s += (double)p.x; q += (double)p.y; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+    if (lane == 0) {
+      double mean = s / count;
+      double var = q / count - mean * mean;
+      if (var < 0) var = 0;
+      s_stat[2 * g] = (float)mean;
+      s_stat[2 * g + 1] = (float)(1.0 / sqrt(var + (double)eps));
+    }
   }
   __syncthreads();
   const int cpg = C / G;
