@@ -1,0 +1,418 @@
+// Spatial self-attention on 5th-gen tensor cores (tcgen05) for the long-sequence, small-head case that dominates the
+// UNet (level 0: 4096 tokens, 8 heads x 40 dims, 256 (image, head) problems per forward, 5 forwards-worth per step).
+//
+// One CTA = 128 query rows of one (image, head).  Per 128-key tile:
+//   MMA warp      S = Q K^T       tcgen05.mma 128 x 128 x 64 (head dim zero-padded to 64 by the projection GEMM), fp32 S in TMEM
+//   softmax warps tcgen05.ld one S row per thread (128 fp32 registers), running max with lazy rescale (O is touched only when
+//                 the max grows by > 2^8), p = ex2(s * scale*log2e - m), row sum; P (bf16) written to shared memory in the
+//                 128B-swizzled K-major layout the tensor core reads; O rescaled in TMEM with tcgen05.ld/st when needed
+//   MMA warp      O += P V        tcgen05.mma 128 x 48 x 128 with V^T (keys contiguous) as the K-major B operand, fp32 O in TMEM
+// S is double-buffered in TMEM and P in shared memory, so QK^T of tile j+1 overlaps the softmax of tile j; K and V^T tiles
+// arrive through two 2-stage TMA rings.  The score matrix never exists outside TMEM/registers.
+// Operand prerequisites (prepared by the host side once per layer call, see unet.py::_transformer):
+//   q, k : [NB, L, heads * 64] bf16 (zero columns 40..63 per head come for free from zero rows in the packed projection weight)
+//   v^T  : [NB, heads * D, L] bf16 (fyc_transpose_tokens)
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int BQ = 128, BKV = 128, DPAD = 64, DV = 48;        // DV: PV accumulator columns (D = 40 padded to a UMMA N multiple of 16)
+constexpr int Q_BYTES = BQ * DPAD * 2;                         // 16 KB
+constexpr int K_BYTES = BKV * DPAD * 2;                        // 16 KB per stage
+constexpr int VBOX_BYTES = DV * 64 * 2;                        // 6 KB: one box = 48 rows (d) x 64 keys
+constexpr int V_BYTES = 2 * VBOX_BYTES;                        // 12 KB per stage (keys 0-63 | 64-127)
+constexpr int PHALF_BYTES = BQ * 64 * 2;                       // 16 KB: 128 rows x 64 keys
+constexpr int P_BYTES = 2 * PHALF_BYTES;                       // 32 KB per buffer
+constexpr int OFF_K = Q_BYTES, OFF_V = OFF_K + 2 * K_BYTES, OFF_P = OFF_V + 2 * V_BYTES, OFF_BAR = OFF_P + 2 * P_BYTES;
+constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+constexpr int NTHREADS = 192;
+constexpr int TM_S0 = 0, TM_S1 = 128, TM_O = 256;              // TMEM column map
+
+struct AttnTcParams {
+  bf16* out; int64_t ldo, bso;      // out[n, token, h*D + d]
+  int L, heads, D;
+  float scale_log2e, out_alpha;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra.uni WAIT_DONE;\n\t"
+      "bra.uni WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ uint64_t sw128_desc(uint32_t saddr) {     // K-major, SWIZZLE_128B, 8-row groups 1024 B apart
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                    const __grid_constant__ CUtensorMap map_vt, const AttnTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024 - (raw & 1023)) & 1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* q_full = bars;            // [1]
+  uint64_t* k_full = bars + 1;        // [2]
+  uint64_t* k_empty = bars + 3;       // [2]
+  uint64_t* v_full = bars + 5;        // [2]
+  uint64_t* v_empty = bars + 7;       // [2]
+  uint64_t* s_full = bars + 9;        // [2]
+  uint64_t* s_empty = bars + 11;      // [2]
+  uint64_t* p_full = bars + 13;       // [2]
+  uint64_t* p_empty = bars + 15;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
+  const int T = p.L / BKV;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_q)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_k)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_vt)) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
+      mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 128); mbar_init(&p_full[i], 128); mbar_init(&p_empty[i], 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================================================== TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(q_full, Q_BYTES);
+      tma_load_4d(&map_q, q_full, smem, 0, qt * BQ, h, n);
+      for (int j = 0; j < T; ++j) {
+        const int st = j & 1; const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&k_empty[st], ph ^ 1);
+        mbar_expect_tx(&k_full[st], K_BYTES);
+        tma_load_4d(&map_k, &k_full[st], smem + OFF_K + st * K_BYTES, 0, j * BKV, h, n);
+        mbar_wait(&v_empty[st], ph ^ 1);
+        mbar_expect_tx(&v_full[st], V_BYTES);
+        uint8_t* sv = smem + OFF_V + st * V_BYTES;
+        tma_load_3d(&map_vt, &v_full[st], sv, j * BKV, h * p.D, n);
+        tma_load_3d(&map_vt, &v_full[st], sv + VBOX_BYTES, j * BKV + 64, h * p.D, n);
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BKV >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
+      const uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(DV >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
+      const uint64_t q_desc = sw128_desc(smem_u32(smem));
+      auto issue_s = [&](int j) {
+        const int b = j & 1; const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&k_full[b], ph);
+        mbar_wait(&s_empty[b], ph ^ 1);
+        tc_fence_after();
+        const uint64_t k_desc = sw128_desc(smem_u32(smem + OFF_K + b * K_BYTES));
+#pragma unroll
+        for (int kk = 0; kk < DPAD / 16; ++kk)
+          umma(tmem_base + (b ? TM_S1 : TM_S0), q_desc + 2 * kk, k_desc + 2 * kk, idesc_s, kk > 0 ? 1u : 0u);
+        tc_commit(&k_empty[b]);
+        tc_commit(&s_full[b]);
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      for (int j = 0; j < T; ++j) {
+        if (j + 1 < T) issue_s(j + 1);
+        const int b = j & 1; const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&v_full[b], ph);
+        mbar_wait(&p_full[b], ph);
+        tc_fence_after();
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const uint64_t a_desc = sw128_desc(smem_u32(smem + OFF_P + b * P_BYTES + hh * PHALF_BYTES));
+          const uint64_t b_desc = sw128_desc(smem_u32(smem + OFF_V + b * V_BYTES + hh * VBOX_BYTES));
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma(tmem_base + TM_O, a_desc + 2 * kk, b_desc + 2 * kk, idesc_o, (j > 0 || hh > 0 || kk > 0) ? 1u : 0u);
+        }
+        tc_commit(&v_empty[b]);
+        tc_commit(&p_empty[b]);
+      }
+    }
+  } else {
+    // ================================================================== softmax / correction / epilogue (warps 2..5)
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;                       // query row of the tile owned by this thread
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    const float sl2 = p.scale_log2e;
+    float m_used = -INFINITY, l = 0.f;
+    for (int j = 0; j < T; ++j) {
+      const int b = j & 1; const uint32_t ph = (j >> 1) & 1;
+      mbar_wait(&s_full[b], ph);
+      tc_fence_after();
+      uint32_t sr[128];
+      const uint32_t s_addr = tmem_base + lane_base + (b ? TM_S1 : TM_S0);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld32(s_addr + c * 32, sr + c * 32);
+      tmem_wait_ld();
+      tc_fence_before();
+      mbar_arrive(&s_empty[b]);                               // S_b may be overwritten by tile j+2
+      float mt = __uint_as_float(sr[0]);
+#pragma unroll
+      for (int i = 1; i < 128; ++i) mt = fmaxf(mt, __uint_as_float(sr[i]));
+      // lazy rescale: keep the stale maximum unless it would let p exceed 2^8 (bf16/fp32 have the range to absorb it)
+      float factor = 1.0f;
+      bool need = false;
+      if (j == 0) {
+        m_used = mt;
+      } else if ((mt - m_used) * sl2 > 8.0f) {
+        factor = ex2((m_used - mt) * sl2);
+        m_used = mt;
+        need = true;
+      }
+      l *= factor;
+      const float nb = -m_used * sl2;
+      mbar_wait(&p_empty[b], ph ^ 1);                         // P_b free (PV of tile j-2 retired)
+      uint8_t* prow = smem + OFF_P + b * P_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {                          // 16 chunks of 8 keys = 16 bytes of bf16
+        float e[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { e[i] = ex2(fmaf(__uint_as_float(sr[c * 8 + i]), sl2, nb)); sum += e[i]; }
+        uint4 v;
+        __nv_bfloat162 t0 = __floats2bfloat162_rn(e[0], e[1]), t1 = __floats2bfloat162_rn(e[2], e[3]);
+        __nv_bfloat162 t2 = __floats2bfloat162_rn(e[4], e[5]), t3 = __floats2bfloat162_rn(e[6], e[7]);
+        v.x = *reinterpret_cast<uint32_t*>(&t0); v.y = *reinterpret_cast<uint32_t*>(&t1);
+        v.z = *reinterpret_cast<uint32_t*>(&t2); v.w = *reinterpret_cast<uint32_t*>(&t3);
+        const int half = c >> 3, cc = c & 7;                  // 64-key half tile, 16-byte chunk inside the 128-byte row
+        *reinterpret_cast<uint4*>(prow + half * PHALF_BYTES + ((cc ^ (r & 7)) << 4)) = v;
+      }
+      l += sum;
+      if (__any_sync(0xffffffffu, need)) {
+        // O must be quiescent: PV of tile j-1 retired (its commit completes p_empty[b^1] for that tile's phase)
+        mbar_wait(&p_empty[b ^ 1], ((j - 1) >> 1) & 1);
+        tc_fence_after();
+        const uint32_t o_addr = tmem_base + lane_base + TM_O;
+#pragma unroll
+        for (int c = 0; c < DV / 16; ++c) {
+          uint32_t orr[16];
+          tmem_ld16(o_addr + c * 16, orr);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) orr[i] = __float_as_uint(__uint_as_float(orr[i]) * factor);
+          tmem_st16(o_addr + c * 16, orr);
+        }
+        tmem_wait_st();
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // P (generic-proxy stores) -> visible to the tensor core
+      tc_fence_before();
+      mbar_arrive(&p_full[b]);
+    }
+    // ---- epilogue: O / l
+    mbar_wait(&p_empty[(T - 1) & 1], ((T - 1) >> 1) & 1);
+    tc_fence_after();
+    const float inv = p.out_alpha / l;
+    bf16* orow = p.out + (int64_t)n * p.bso + ((int64_t)qt * BQ + r) * p.ldo + h * p.D;
+    const uint32_t o_addr = tmem_base + lane_base + TM_O;
+#pragma unroll
+    for (int c = 0; c < DV / 16; ++c) {
+      uint32_t orr[16];
+      tmem_ld16(o_addr + c * 16, orr);
+      tmem_wait_ld();
+      float f[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(orr[i]) * inv;
+      if (c * 16 + 8 <= p.D) Vec8<bf16>::store(orow + c * 16, f);
+      if (c * 16 + 16 <= p.D) Vec8<bf16>::store(orow + c * 16 + 8, f + 8);
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// [NB, L, ld] (columns col0 .. col0+C) -> [NB, C, L]   (V -> V^T so that keys are the contiguous, K-major dimension of PV)
+__global__ void __launch_bounds__(256) transpose_tokens_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int L, int C,
+                                                               int64_t ld, int64_t col0) {
+  __shared__ bf16 tile[64][66];
+  const int n = blockIdx.z, t0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+  const bf16* src = in + (int64_t)n * L * ld + col0;
+  for (int i = threadIdx.x; i < 64 * 32; i += 256) {        // 64 tokens x 32 channel pairs
+    int t = i >> 5, cp = (i & 31) * 2;
+    __nv_bfloat162 v = __floats2bfloat162_rn(0.f, 0.f);
+    if (t0 + t < L && c0 + cp < C) v = *reinterpret_cast<const __nv_bfloat162*>(src + (int64_t)(t0 + t) * ld + c0 + cp);
+    tile[t][cp] = v.x; tile[t][cp + 1] = v.y;
+  }
+  __syncthreads();
+  bf16* dst = out + (int64_t)n * C * L;
+  for (int i = threadIdx.x; i < 64 * 32; i += 256) {        // 64 channels x 32 token pairs
+    int c = i >> 5, tp = (i & 31) * 2;
+    if (c0 + c < C && t0 + tp < L) {
+      __nv_bfloat162 v;
+      v.x = tile[tp][c]; v.y = tile[tp + 1][c];
+      *reinterpret_cast<__nv_bfloat162*>(dst + (int64_t)(c0 + c) * L + t0 + tp) = v;
+    }
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    else
+      (void)cudaGetLastError();
+  }
+  return fn;
+}
+int32_t make_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides, const uint32_t* box) {
+  EncodeTiledFn fn = encode_fn();
+  FYC_CHECK(fn != nullptr, "attention(tcgen05): cuTensorMapEncodeTiled unavailable");
+  cuuint64_t gd[5], gs[4]; cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides[i];
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  FYC_CHECK(r == CUDA_SUCCESS, "attention(tcgen05): cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return FYC_OK;
+}
+
+}  // namespace
+
+extern "C" int32_t fyc_transpose_tokens(const void* in, void* out, int64_t NB, int64_t L, int64_t C, int64_t ld, int64_t col0,
+                                        void* stream) {
+  FYC_CHECK(C % 2 == 0 && L % 2 == 0 && ld % 2 == 0 && col0 % 2 == 0 && NB < 65536, "transpose_tokens: even sizes required");
+  dim3 grid((unsigned)ceil_div64(L, 64), (unsigned)ceil_div64(C, 64), (unsigned)NB);
+  transpose_tokens_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)in, (bf16*)out, (int)L, (int)C, ld, col0);
+  FYC_LAUNCH_CHECK();
+  return FYC_OK;
+}
+
+// qk: [NB, L, ldqk] bf16 with q head h at columns [q_col0 + 64h, +64) and k head h at [k_col0 + 64h, +64) (cols D..63 zero);
+// vt: [NB, heads*D, L]; out: [NB, L, ldo] (head h at columns [h*D, (h+1)*D)).
+extern "C" int32_t fyc_self_attention_tc(const void* qk, int64_t ldqk, int64_t q_col0, int64_t k_col0, const void* vt, void* out,
+                                         int64_t ldo, int64_t NB, int64_t heads, int64_t L, int64_t D, float scale, void* stream) {
+  FYC_CHECK(D == 40, "self_attention_tc: built for head dim 40 (got %lld)", (long long)D);
+  FYC_CHECK(L % 128 == 0 && L >= 128, "self_attention_tc: sequence length %lld must be a multiple of 128", (long long)L);
+  FYC_CHECK(ldqk % 8 == 0 && q_col0 % 8 == 0 && k_col0 % 8 == 0 && ldo % 8 == 0, "self_attention_tc: 16-byte alignment");
+  FYC_CHECK((((uintptr_t)qk | (uintptr_t)vt | (uintptr_t)out) & 15) == 0, "self_attention_tc: pointers must be 16-byte aligned");
+  FYC_CHECK(NB < 65536 && heads < 65536, "self_attention_tc: grid too large");
+  CUtensorMap mq, mk, mv;
+  {
+    uint64_t dims[4] = {64, (uint64_t)L, (uint64_t)heads, (uint64_t)NB};
+    uint64_t str[3] = {(uint64_t)ldqk * 2, 128, (uint64_t)L * ldqk * 2};
+    uint32_t box[4] = {64, 128, 1, 1};
+    int32_t rc = make_map(&mq, (const bf16*)qk + q_col0, 4, dims, str, box);
+    if (rc) return rc;
+    rc = make_map(&mk, (const bf16*)qk + k_col0, 4, dims, str, box);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)L, (uint64_t)(heads * D), (uint64_t)NB};
+    uint64_t str[2] = {(uint64_t)L * 2, (uint64_t)L * heads * D * 2};
+    uint32_t box[3] = {64, (uint32_t)DV, 1};
+    int32_t rc = make_map(&mv, vt, 3, dims, str, box);
+    if (rc) return rc;
+  }
+  static bool attr = false;
+  if (!attr) {
+    FYC_CUDA(cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr = true;
+  }
+  AttnTcParams p;
+  p.out = (bf16*)out; p.ldo = ldo; p.bso = L * ldo; p.L = (int)L; p.heads = (int)heads; p.D = (int)D;
+  p.scale_log2e = scale * 1.4426950408889634f; p.out_alpha = 1.0f;
+  dim3 grid((unsigned)(L / BQ), (unsigned)heads, (unsigned)NB);
+  attention_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(mq, mk, mv, p);
+  FYC_LAUNCH_CHECK();
+  return FYC_OK;
+}

@@ -24,6 +24,11 @@ __device__ __forceinline__ void mma16816(float* c, const uint32_t* a, uint32_t b
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
@@ -94,7 +99,7 @@ __global__ void __launch_bounds__(256) temporal_attention_mma_kernel(const bf16*
     uint32_t pf[KK][4];
 #pragma unroll
     for (int j = 0; j < NT; ++j) {
-      float p0 = exp2f(s[j][0] - mx0), p1 = exp2f(s[j][1] - mx0), p2 = exp2f(s[j][2] - mx1), p3 = exp2f(s[j][3] - mx1);
+      float p0 = ex2_approx(s[j][0] - mx0), p1 = ex2_approx(s[j][1] - mx0), p2 = ex2_approx(s[j][2] - mx1), p3 = ex2_approx(s[j][3] - mx1);
       l0 += p0 + p1; l1 += p2 + p3;
       pf[j >> 1][(j & 1) * 2] = pack2(p0, p1);
       pf[j >> 1][(j & 1) * 2 + 1] = pack2(p2, p3);

@@ -12,6 +12,7 @@ from . import _lib as L
 from ._lib import check, dtype_code, lib, ptr, stream_ptr
 
 _impl = L.IMPL_AUTO
+L_SIMT = L.IMPL_SIMT
 _prof = None      # list of (family, algorithmic_flops, algorithmic_bytes, start_event, end_event) while profiling
 
 
@@ -197,6 +198,30 @@ def attention(q, k, v, heads, scale, out=None, out_alpha=1.0, accumulate=False, 
                    float(out_alpha), int(accumulate), dtype_code(q.dtype), _impl if impl is None else impl)
     with _rec("attention", 4.0 * B * heads * Lq * Lk * D, q.element_size() * (2 * B * Lq * heads * D + 2 * (B // kv_batch_div) * Lk * heads * D)):
         check(lib().fyc_attention(C.byref(a), stream_ptr()))
+    return out
+
+
+def transpose_tokens(x, col0, C):
+    """x [NB, L, ld] (bf16) -> columns [col0, col0+C) transposed per batch entry: [NB, C, L]."""
+    assert x.dtype == torch.bfloat16 and x.dim() == 3 and x.stride(2) == 1 and x.stride(0) == x.shape[1] * x.stride(1)
+    NB, L, _ = x.shape
+    out = torch.empty((NB, C, L), dtype=x.dtype, device=x.device)
+    with _rec("transpose", 0, 2 * NB * L * C * 2):
+        check(lib().fyc_transpose_tokens(ptr(x), ptr(out), NB, L, C, x.stride(1), col0, stream_ptr()))
+    return out
+
+
+def self_attention_tc_ok(dtype, L, D):
+    return _impl != L_SIMT and dtype == torch.bfloat16 and D == 40 and L % 128 == 0 and lib().fyc_tcgen05_available() == 1
+
+
+def self_attention_tc(qk, q_col0, k_col0, vt, heads, D, scale):
+    """tcgen05 self-attention: qk [NB, L, ld] with 64-wide zero-padded q/k heads, vt [NB, heads*D, L] -> [NB, L, heads*D]."""
+    NB, L, _ = qk.shape
+    out = torch.empty((NB, L, heads * D), dtype=qk.dtype, device=qk.device)
+    with _rec("attention_tc", 4.0 * NB * heads * L * L * D, qk.element_size() * (4 * NB * L * heads * D)):
+        check(lib().fyc_self_attention_tc(ptr(qk), qk.stride(1), q_col0, k_col0, ptr(vt), ptr(out), out.stride(1), NB, heads, L, D,
+                                          float(scale), stream_ptr()))
     return out
 
 

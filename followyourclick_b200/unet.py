@@ -287,6 +287,18 @@ class UNet3DConditionModel(ParamTreeModel):
             return torch.cat(ws, dim=0).to(self._compute_dtype).contiguous()
         return self._cached(("cat", name), make)
 
+    def _qkv_padded(self, p, heads, d, pad=64):
+        """[Wq (heads x 64 rows, rows d..63 of every head zero) ; Wk (same) ; Wv] for the tcgen05 attention kernel."""
+        def make():
+            def padded(w):
+                C = w.shape[1]
+                wp = torch.zeros(heads, pad, C, dtype=torch.float32, device=w.device)
+                wp[:, :d] = w.detach().float().view(heads, d, C)
+                return wp.view(heads * pad, C)
+            ws = [padded(self._p(p + ".to_q.weight")), padded(self._p(p + ".to_k.weight")), self._p(p + ".to_v.weight").detach().float()]
+            return torch.cat(ws, dim=0).to(self._compute_dtype).contiguous()
+        return self._cached(("qkvpad", p), make)
+
     def _geglu(self, p):
         def make():
             w, b = geglu_interleave(self._p(p + ".net.0.proj.weight").detach().float(), self._p(p + ".net.0.proj.bias").detach().float())
@@ -334,9 +346,15 @@ class UNet3DConditionModel(ParamTreeModel):
         q = p + ".transformer_blocks.0"
         # self attention (attention.py:507)
         n1 = ops.layernorm(tok, self._f(q + ".norm1.weight"), self._f(q + ".norm1.bias"))
-        qkv = ops.gemm(n1, self._cat_w(q + ".attn1", [q + ".attn1.to_q.weight", q + ".attn1.to_k.weight", q + ".attn1.to_v.weight"]))
-        qkv = qkv.view(NB, HW, 3 * C)
-        o = ops.attention(qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:], heads, d ** -0.5)
+        if ops.self_attention_tc_ok(tok.dtype, HW, d):
+            # tcgen05 path: q/k heads zero-padded to 64 columns by the packed weight, V transposed per image (keys contiguous)
+            qkv = ops.gemm(n1, self._qkv_padded(q + ".attn1", heads, d)).view(NB, HW, 2 * heads * 64 + C)
+            vt = ops.transpose_tokens(qkv, 2 * heads * 64, C)
+            o = ops.self_attention_tc(qkv, 0, heads * 64, vt, heads, d, d ** -0.5)
+        else:
+            qkv = ops.gemm(n1, self._cat_w(q + ".attn1", [q + ".attn1.to_q.weight", q + ".attn1.to_k.weight", q + ".attn1.to_v.weight"]))
+            qkv = qkv.view(NB, HW, 3 * C)
+            o = ops.attention(qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:], heads, d ** -0.5)
         tok = ops.gemm(o.view(M, C), self._w(q + ".attn1.to_out.0.weight"), bias=self._f(q + ".attn1.to_out.0.bias"), residual=tok)
         # cross attention (attention.py:516-521; IPCrossAttention.forward :49-127)
         n2 = ops.layernorm(tok, self._f(q + ".norm2.weight"), self._f(q + ".norm2.bias"))

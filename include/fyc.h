@@ -124,6 +124,16 @@ int32_t fyc_attention(const fyc_attention_args* a, void* stream);
  * '(b f) d c -> (b d) f c' regrouping (motion_module.py:376,462) is absorbed into the addressing. */
 int32_t fyc_temporal_attention(const void* qkv, void* out, int64_t B, int64_t F, int64_t HW, int64_t heads,
                                int64_t D, float scale, int32_t dtype, void* stream);
+/* Spatial self-attention on tcgen05 tensor cores (S, O accumulators in TMEM) for head dim 40, L % 128 == 0 - the level-0
+ * attn1 of the UNet (diffusers/models/attention.py:649-678 via animatediff/models/attention.py:507).  qk: [NB, L, ldqk]
+ * bf16, q head h at columns [q_col0 + 64h, +64), k head h at [k_col0 + 64h, +64), columns D..63 of each head ZERO (zero
+ * rows in the packed projection weight); vt: [NB, heads*D, L] (V transposed per image, fyc_transpose_tokens);
+ * out: [NB, L, ldo], head h at columns [h*D, (h+1)*D). */
+int32_t fyc_self_attention_tc(const void* qk, int64_t ldqk, int64_t q_col0, int64_t k_col0, const void* vt, void* out,
+                              int64_t ldo, int64_t NB, int64_t heads, int64_t L, int64_t D, float scale, void* stream);
+/* in [NB, L, ld] columns [col0, col0 + C) (bf16) -> out [NB, C, L] */
+int32_t fyc_transpose_tokens(const void* in, void* out, int64_t NB, int64_t L, int64_t C, int64_t ld, int64_t col0,
+                             void* stream);
 /* Row softmax of fp32 scores (VAE AttentionBlock, diffusers/models/attention.py:366), output in `dtype`. */
 int32_t fyc_softmax_rows(const float* scores, void* probs, int64_t rows, int64_t L, int32_t dtype, void* stream);
 

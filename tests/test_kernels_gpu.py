@@ -200,6 +200,33 @@ def test_temporal_attention(cuda, dtype, B, Fr, HW, heads, D):
     assert rel(out, ref) < tol(dtype), rel(out, ref)
 
 
+@pytest.mark.parametrize("L,heads,NB,gain", [(128, 2, 2, 1.0), (256, 4, 3, 1.0), (1024, 8, 2, 1.0), (512, 2, 1, 3.0)])
+def test_self_attention_tcgen05(cuda, L, heads, NB, gain):
+    """tcgen05 attention (S/O in TMEM) against the fp32 reference; gain 3 produces logits large enough to exercise the
+    lazy O-rescale path (running max growing by more than 2^8 between key tiles)."""
+    from followyourclick_b200 import ops
+    if not ops.self_attention_tc_ok(torch.bfloat16, L, 40):
+        pytest.skip("tcgen05 path unavailable")
+    D, C = 40, heads * 40
+    q = rnd((NB, L, heads, D), 1, torch.bfloat16, gain)
+    k = rnd((NB, L, heads, D), 2, torch.bfloat16, gain)
+    v = rnd((NB, L, C), 3, torch.bfloat16)
+    if gain > 1:   # make the maximum grow along the key axis so later tiles raise the running max
+        k = (k.float() * torch.linspace(0.2, 1.5, L, device="cuda").view(1, L, 1, 1)).bfloat16()
+    qk = torch.zeros(NB, L, 2 * heads * 64 + C, dtype=torch.bfloat16, device="cuda")
+    qk[:, :, :heads * 64].view(NB, L, heads, 64)[..., :D] = q
+    qk[:, :, heads * 64:2 * heads * 64].view(NB, L, heads, 64)[..., :D] = k
+    qk[:, :, 2 * heads * 64:] = v
+    vt = ops.transpose_tokens(qk, 2 * heads * 64, C)
+    assert torch.equal(vt, v.transpose(1, 2).contiguous())
+    out = ops.self_attention_tc(qk, 0, heads * 64, vt, heads, D, D ** -0.5)
+    ref = _mha_ref(q.reshape(NB, L, C), k.reshape(NB, L, C), v, heads, D ** -0.5)
+    assert rel(out, ref) < BF16_TOL, rel(out, ref)
+    # agreement with the mma.sync flash kernel on the same operands
+    o2 = ops.attention(q.reshape(NB, L, C), k.reshape(NB, L, C), v, heads, D ** -0.5)
+    assert rel(out, o2) < BF16_TOL
+
+
 def test_softmax_rows_and_misc(cuda):
     from followyourclick_b200 import ops
     s = rnd((64, 300), 1) * 4
