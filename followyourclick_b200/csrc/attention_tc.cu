@@ -313,6 +313,215 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Two query tiles per CTA ("ping-pong"): 256 query rows, two softmax warpgroups (warps 2-5 -> rows 0-127, warps 6-9 -> rows
+// 128-255), each with its own S / O accumulators in TMEM and its own P buffer.  With one softmax warp per scheduler the
+// single-tile kernel above is bound by that warp's serial instruction stream (2230 clk per 128x128 tile, measured); two warps
+// per scheduler overlap each other's MUFU / FMA / shared-memory latencies, and every K / V^T tile is loaded once for 256 rows.
+constexpr int G2_THREADS = 320;
+constexpr int G2_OFF_K = 2 * Q_BYTES, G2_OFF_V = G2_OFF_K + 2 * K_BYTES, G2_OFF_P = G2_OFF_V + 2 * V_BYTES;
+constexpr int G2_OFF_BAR = G2_OFF_P + 2 * P_BYTES, G2_SMEM_BYTES = G2_OFF_BAR + 256 + 1024;
+constexpr int G2_TM_S = 0 /* +128 g */, G2_TM_O = 256 /* +64 g */;
+
+__global__ void __launch_bounds__(G2_THREADS, 1)
+attention_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                     const __grid_constant__ CUtensorMap map_vt, const AttnTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024 - (raw & 1023)) & 1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G2_OFF_BAR);
+  uint64_t* q_full = bars;            // [1]
+  uint64_t* k_full = bars + 1;        // [2]
+  uint64_t* k_empty = bars + 3;       // [2]
+  uint64_t* v_full = bars + 5;        // [2]
+  uint64_t* v_empty = bars + 7;       // [2]
+  uint64_t* s_full = bars + 9;        // [2] per group
+  uint64_t* s_empty = bars + 11;      // [2]
+  uint64_t* p_full = bars + 13;       // [2]
+  uint64_t* p_empty = bars + 15;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
+  const int T = p.L / BKV;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_q)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_k)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_vt)) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
+      mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 128); mbar_init(&p_full[i], 128); mbar_init(&p_empty[i], 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================================================== TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(q_full, 2 * Q_BYTES);
+      tma_load_4d(&map_q, q_full, smem, 0, qt * 2 * BQ, h, n);
+      tma_load_4d(&map_q, q_full, smem + Q_BYTES, 0, qt * 2 * BQ + BQ, h, n);
+      for (int j = 0; j < T; ++j) {
+        const int st = j & 1; const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&k_empty[st], ph ^ 1);
+        mbar_expect_tx(&k_full[st], K_BYTES);
+        tma_load_4d(&map_k, &k_full[st], smem + G2_OFF_K + st * K_BYTES, 0, j * BKV, h, n);
+        mbar_wait(&v_empty[st], ph ^ 1);
+        mbar_expect_tx(&v_full[st], V_BYTES);
+        uint8_t* sv = smem + G2_OFF_V + st * V_BYTES;
+        tma_load_3d(&map_vt, &v_full[st], sv, j * BKV, h * p.D, n);
+        tma_load_3d(&map_vt, &v_full[st], sv + VBOX_BYTES, j * BKV + 64, h * p.D, n);
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BKV >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
+      const uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(DV >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
+      auto issue_s = [&](int j) {           // S_g(j) = Q_g K_j^T for both groups
+        const int st = j & 1; const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&k_full[st], ph);
+        const uint64_t k_desc = sw128_desc(smem_u32(smem + G2_OFF_K + st * K_BYTES));
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          mbar_wait(&s_empty[g], (uint32_t)((j & 1) ^ 1));
+          tc_fence_after();
+          const uint64_t q_desc = sw128_desc(smem_u32(smem + g * Q_BYTES));
+#pragma unroll
+          for (int kk = 0; kk < DPAD / 16; ++kk)
+            umma(tmem_base + G2_TM_S + g * 128, q_desc + 2 * kk, k_desc + 2 * kk, idesc_s, kk > 0 ? 1u : 0u);
+          tc_commit(&s_full[g]);
+        }
+        tc_commit(&k_empty[st]);
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      for (int j = 0; j < T; ++j) {
+        if (j + 1 < T) issue_s(j + 1);
+        const int st = j & 1; const uint32_t ph = (j >> 1) & 1;
+        mbar_wait(&v_full[st], ph);
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          mbar_wait(&p_full[g], (uint32_t)(j & 1));
+          tc_fence_after();
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const uint64_t a_desc = sw128_desc(smem_u32(smem + G2_OFF_P + g * P_BYTES + hh * PHALF_BYTES));
+            const uint64_t b_desc = sw128_desc(smem_u32(smem + G2_OFF_V + st * V_BYTES + hh * VBOX_BYTES));
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma(tmem_base + G2_TM_O + g * 64, a_desc + 2 * kk, b_desc + 2 * kk, idesc_o, (j > 0 || hh > 0 || kk > 0) ? 1u : 0u);
+          }
+          tc_commit(&p_empty[g]);
+        }
+        tc_commit(&v_empty[st]);
+      }
+    }
+  } else {
+    // ================================================================== softmax / correction / epilogue (group g = warps 2-5 | 6-9)
+    const int g = (warp - 2) >> 2;
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    const float sl2 = p.scale_log2e;
+    float m_used = -INFINITY, l = 0.f;
+    const uint32_t s_addr = tmem_base + lane_base + G2_TM_S + g * 128;
+    const uint32_t o_addr = tmem_base + lane_base + G2_TM_O + g * 64;
+    for (int j = 0; j < T; ++j) {
+      const uint32_t par = (uint32_t)(j & 1);
+      mbar_wait(&s_full[g], par);
+      tc_fence_after();
+      uint32_t sr[128];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld32(s_addr + c * 32, sr + c * 32);
+      tmem_wait_ld();
+      tc_fence_before();
+      mbar_arrive(&s_empty[g]);                               // S_g may be overwritten by tile j+1
+      float mt = __uint_as_float(sr[0]);
+#pragma unroll
+      for (int i = 1; i < 128; ++i) mt = fmaxf(mt, __uint_as_float(sr[i]));
+      float factor = 1.0f;
+      bool need = false;
+      if (j == 0) {
+        m_used = mt;
+      } else if ((mt - m_used) * sl2 > 8.0f) {
+        factor = ex2((m_used - mt) * sl2);
+        m_used = mt;
+        need = true;
+      }
+      l *= factor;
+      const float nb = -m_used * sl2;
+      mbar_wait(&p_empty[g], par ^ 1);                        // PV_g(j-1) retired: P_g is free and O_g is quiescent
+      uint8_t* prow = smem + G2_OFF_P + g * P_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        float e[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { e[i] = ex2(fmaf(__uint_as_float(sr[c * 8 + i]), sl2, nb)); sum += e[i]; }
+        uint4 v;
+        __nv_bfloat162 t0 = __floats2bfloat162_rn(e[0], e[1]), t1 = __floats2bfloat162_rn(e[2], e[3]);
+        __nv_bfloat162 t2 = __floats2bfloat162_rn(e[4], e[5]), t3 = __floats2bfloat162_rn(e[6], e[7]);
+        v.x = *reinterpret_cast<uint32_t*>(&t0); v.y = *reinterpret_cast<uint32_t*>(&t1);
+        v.z = *reinterpret_cast<uint32_t*>(&t2); v.w = *reinterpret_cast<uint32_t*>(&t3);
+        const int half = c >> 3, cc = c & 7;
+        *reinterpret_cast<uint4*>(prow + half * PHALF_BYTES + ((cc ^ (r & 7)) << 4)) = v;
+      }
+      l += sum;
+      if (__any_sync(0xffffffffu, need)) {
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < DV / 16; ++c) {
+          uint32_t orr[16];
+          tmem_ld16(o_addr + c * 16, orr);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) orr[i] = __float_as_uint(__uint_as_float(orr[i]) * factor);
+          tmem_st16(o_addr + c * 16, orr);
+        }
+        tmem_wait_st();
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      tc_fence_before();
+      mbar_arrive(&p_full[g]);
+    }
+    mbar_wait(&p_empty[g], (uint32_t)((T - 1) & 1));
+    tc_fence_after();
+    const float inv = p.out_alpha / l;
+    bf16* orow = p.out + (int64_t)n * p.bso + ((int64_t)qt * 2 * BQ + g * BQ + r) * p.ldo + h * p.D;
+#pragma unroll
+    for (int c = 0; c < DV / 16; ++c) {
+      uint32_t orr[16];
+      tmem_ld16(o_addr + c * 16, orr);
+      tmem_wait_ld();
+      float f[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(orr[i]) * inv;
+      if (c * 16 + 8 <= p.D) Vec8<bf16>::store(orow + c * 16, f);
+      if (c * 16 + 16 <= p.D) Vec8<bf16>::store(orow + c * 16 + 8, f + 8);
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
 // [NB, L, ld] (columns col0 .. col0+C) -> [NB, C, L]   (V -> V^T so that keys are the contiguous, K-major dimension of PV)
 __global__ void __launch_bounds__(256) transpose_tokens_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int L, int C,
                                                                int64_t ld, int64_t col0) {
@@ -411,6 +620,17 @@ extern "C" int32_t fyc_self_attention_tc(const void* qk, int64_t ldqk, int64_t q
   AttnTcParams p;
   p.out = (bf16*)out; p.ldo = ldo; p.bso = L * ldo; p.L = (int)L; p.heads = (int)heads; p.D = (int)D;
   p.scale_log2e = scale * 1.4426950408889634f; p.out_alpha = 1.0f;
+  if (L % (2 * BQ) == 0) {       // two query tiles per CTA (ping-pong softmax warpgroups)
+    static bool attr2 = false;
+    if (!attr2) {
+      FYC_CUDA(cudaFuncSetAttribute(attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES));
+      attr2 = true;
+    }
+    dim3 grid2((unsigned)(L / (2 * BQ)), (unsigned)heads, (unsigned)NB);
+    attention_tc2_kernel<<<grid2, G2_THREADS, G2_SMEM_BYTES, (cudaStream_t)stream>>>(mq, mk, mv, p);
+    FYC_LAUNCH_CHECK();
+    return FYC_OK;
+  }
   dim3 grid((unsigned)(L / BQ), (unsigned)heads, (unsigned)NB);
   attention_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(mq, mk, mv, p);
   FYC_LAUNCH_CHECK();

@@ -104,6 +104,23 @@ __device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f 
 // exact-erf GELU (F.gelu default; diffusers/models/attention.py:815)
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
+// exact-erf GELU evaluated with Abramowitz-Stegun 7.1.26 (|erf error| <= 1.5e-7): one rcp + one ex2 + 7 FMAs instead of
+// erff()'s ~30 instructions; used where the result is rounded to bf16 (2^-9) anyway (tcgen05 GEGLU epilogue).
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * z * 1.4426950408889634f));
+  const float erf_abs = 1.0f - poly * e;
+  const float erfv = copysignf(erf_abs, x);
+  return 0.5f * x * (1.0f + erfv);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -13,6 +13,7 @@ from ._lib import check, dtype_code, lib, ptr, stream_ptr
 
 _impl = L.IMPL_AUTO
 L_SIMT = L.IMPL_SIMT
+_prof_shapes = False   # per-shape family names in the profile (diagnostics)
 _prof = None      # list of (family, algorithmic_flops, algorithmic_bytes, start_event, end_event) while profiling
 
 
@@ -112,6 +113,8 @@ def gemm(A, W, bias=None, residual=None, rowbias=None, rows_per_group=0, alpha=1
                    o.stride(-2), residual.stride(-2) if residual is not None else 0, Bn, sA, sW,
                    o.stride(0) if batched else 0, rows_per_group, float(alpha), dtype_code(A.dtype), epi, impl)
     fam = "gemm_tc" if (impl != L.IMPL_SIMT and tc_ok(A.dtype, M) and N % 16 == 0 and K % 8 == 0) else "gemm_simt"
+    if _prof_shapes:
+        fam += f"[{Bn}x{M}x{N}x{K}{'g' if fused_geglu else ''}{'r' if residual is not None else ''}]"
     with _rec(fam, 2.0 * Bn * M * N * K, A.element_size() * Bn * (M * K + N * K + M * n_out)):
         check(lib().fyc_gemm(C.byref(a), stream_ptr()))
     if geglu and not fused_geglu:
@@ -149,6 +152,8 @@ def conv3x3(x, w, bias=None, residual=None, rowbias=None, images_per_group=0, st
         ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
         a.workspace, a.workspace_bytes = ptr(ws), nbytes
     fam = "conv_tc" if (impl != L.IMPL_SIMT and tc_ok(x.dtype, NB * Ho * Wo) and Cin % 8 == 0 and Cout % 16 == 0) else "conv_simt"
+    if _prof_shapes:
+        fam += f"[{NB}x{Ho}x{Wo} {Cin}->{Cout} s{stride}]"
     with _rec(fam, 2.0 * NB * Ho * Wo * Cout * 9 * Cin, x.element_size() * (x.numel() + w.numel() + out.numel())):
         check(lib().fyc_conv3x3(C.byref(a), stream_ptr()))
     return out

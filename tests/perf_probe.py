@@ -49,6 +49,14 @@ def main():
     for fam, d in sorted(prof.summary.items(), key=lambda kv: -kv[1]["ms"]):
         print(f"   {fam:20s} {d['ms']:8.2f} ms {100*d['ms']/tot:5.1f}%  launches {d['launches']:4d}  {d['flops']/d['ms']/1e9 if d['ms'] else 0:8.1f} TFLOP/s  {d['bytes']/d['ms']/1e6 if d['ms'] else 0:8.1f} GB/s")
     print("   sum of event times", tot)
+    if os.environ.get("SHAPES"):
+        ops._prof_shapes = True
+        with ops.profile() as prof2: run()
+        ops._prof_shapes = False
+        rows = sorted(prof2.summary.items(), key=lambda kv: -kv[1]["ms"])
+        for fam, d in rows[:45]:
+            if d["flops"]:
+                print(f"   {fam:46s} {d['ms']:7.3f} ms x{d['launches']:3d}  {d['flops']/d['ms']/1e9:7.1f} TFLOP/s  {d['bytes']/d['ms']/1e6:7.1f} GB/s(alg)")
     # VAE decode of F frames
     vae = AutoencoderKL(in_channels=3, out_channels=3, down_block_types=("DownEncoderBlock2D",) * 4, up_block_types=("UpDecoderBlock2D",) * 4,
                         block_out_channels=(128, 256, 512, 512), layers_per_block=2, latent_channels=4, norm_num_groups=32).to("cuda").to(torch.bfloat16)
