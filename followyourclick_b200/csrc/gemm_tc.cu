@@ -27,7 +27,9 @@ constexpr int MAX_BN = 256;
 constexpr int A_BYTES = BM * BK * 2;           // 16 KB
 constexpr int B_BYTES = MAX_BN * BK * 2;       // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int STAGING_BYTES = 8 * 4096;         // per epilogue warp: 32 rows x 128 B (64 bf16 columns), 128B-swizzled
+constexpr int OFF_STAGING = STAGES * STAGE_BYTES + 256;
+constexpr int SMEM_BYTES = OFF_STAGING + STAGING_BYTES + 1024 /*align slack*/;
 constexpr int NUM_THREADS = 320;          // TMA warp, MMA warp, 8 epilogue warps (2 per TMEM lane quarter)
 
 struct TcParams {
@@ -140,7 +142,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024 - (raw & 1023)) & 1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);     // 256 B reserved; staging follows
   uint64_t* full = bars;                  // [STAGES]
   uint64_t* empty = bars + STAGES;        // [STAGES]
   uint64_t* tfull = bars + 2 * STAGES;    // [2]
@@ -227,6 +229,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int quarter = warp & 3;                      // TMEM lane quarter this warp may access
     const int egroup = (warp - 2) >> 2;                // 0: warps 2-5, 1: warps 6-9 (same rows, other half of the columns)
     const int r = quarter * 32 + lane;                 // row of the tile handled by this thread
+    uint8_t* stage = smem + OFF_STAGING + (warp - 2) * 4096;
     int acc = 0; uint32_t aphase = 0;
     const bool geglu = (p.flags & FYC_EPI_GEGLU) != 0;
     const bool out_f32 = (p.flags & FYC_EPI_OUT_F32) != 0;
@@ -242,121 +245,139 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int64_t pix = ((int64_t)img * p.Ho + oh) * p.Wo + ow;
       const bool row_ok = (ow < p.Wo) && (oh < p.Ho) && (pix < p.M);
       const int n0 = n_blk * p.BN;
-      // this warp's share of the tile columns: 16-column chunks [cb, ce); the two warps of a lane quarter split them
-      const int nch = p.BN >> 4, half = (nch + 1) >> 1;
-      const int cb = egroup ? half : 0, ce = egroup ? nch : half;
-      // Residual prefetch: the (bf16) residual row segments of up to RPF chunks are requested BEFORE waiting for the
-      // accumulator, so their HBM/L2 latency hides behind the tile's main loop instead of stalling every chunk
-      // (the K = 320 GEMMs with a residual ran at 274 TFLOP/s vs 458 without one, profiles/round1).
-      constexpr int RPF = 5;
-      uint4 resv[RPF][2];
-      const bool res_bf16 = (p.flags & FYC_EPI_RESIDUAL) && !out_f32 && !geglu;
-      if (res_bf16 && row_ok) {
-        const bf16* rrow = reinterpret_cast<const bf16*>(p.residual) + pix * p.ldr + n0;
-#pragma unroll
-        for (int i = 0; i < RPF; ++i) {
-          const int ch = cb + i;
-          if (ch < ce && n0 + ch * 16 < p.N) {
-            resv[i][0] = __ldg(reinterpret_cast<const uint4*>(rrow + ch * 16));
-            resv[i][1] = __ldg(reinterpret_cast<const uint4*>(rrow + ch * 16 + 8));
-          }
-        }
-      }
       mbar_wait(&tfull[acc], aphase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * MAX_BN;
       const float* rb = (p.flags & FYC_EPI_ROWBIAS) ? p.rowbias + (row_ok ? pix / p.rows_per_group : 0) * p.N : nullptr;
-      if (!geglu) {
-        auto process = [&](const uint32_t* r, int ch, uint4 u0, uint4 u1, bool pref) {
-          const int n = n0 + ch * 16;
-          if (!(row_ok && n < p.N)) return;     // N is a multiple of 16 on this path
+      if (out_f32) {
+        // fp32 output (attention scores of the VAE mid block): direct per-thread stores, 16-column chunks split between
+        // the two warps of a lane quarter
+        const int nch = p.BN >> 4, half = (nch + 1) >> 1;
+        const int cb = egroup ? half : 0, ce = egroup ? nch : half;
+        for (int ch = cb; ch < ce; ++ch) {
           float v[16];
+          tmem_ld16(taddr + ch * 16, v);
+          const int n = n0 + ch * 16;
+          if (row_ok && n < p.N) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) * p.alpha;
-          if (p.flags & FYC_EPI_BIAS) {
+            for (int i = 0; i < 16; ++i) v[i] *= p.alpha;
+            if (p.flags & FYC_EPI_BIAS) {
 #pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-              float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + i));
-              v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+              for (int i = 0; i < 16; i += 4) {
+                float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + i));
+                v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+              }
             }
-          }
-          if (rb) {
+            if (rb) {
 #pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-              float4 b = __ldg(reinterpret_cast<const float4*>(rb + n + i));
-              v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+              for (int i = 0; i < 16; i += 4) {
+                float4 b = __ldg(reinterpret_cast<const float4*>(rb + n + i));
+                v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+              }
             }
-          }
-          if (p.flags & FYC_EPI_RESIDUAL) {
-            float f[16];
-            if (out_f32) {
+            if (p.flags & FYC_EPI_RESIDUAL) {
+              float f[16];
               Vec8<float>::load(reinterpret_cast<const float*>(p.residual) + pix * p.ldr + n, f);
               Vec8<float>::load(reinterpret_cast<const float*>(p.residual) + pix * p.ldr + n + 8, f + 8);
-            } else {
-              if (!pref) {
-                u0 = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.residual) + pix * p.ldr + n));
-                u1 = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.residual) + pix * p.ldr + n + 8));
-              }
-              const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&u0);
-              const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&u1);
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                float2 a = __bfloat1622float2(h0[i]), b = __bfloat1622float2(h1[i]);
-                f[2 * i] = a.x; f[2 * i + 1] = a.y; f[8 + 2 * i] = b.x; f[8 + 2 * i + 1] = b.y;
-              }
+              for (int i = 0; i < 16; ++i) v[i] += f[i];
             }
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] += f[i];
-          }
-          if (out_f32) {
             float* o = reinterpret_cast<float*>(p.out) + pix * p.ldo + n;
             Vec8<float>::store(o, v); Vec8<float>::store(o + 8, v + 8);
-          } else {
-            bf16* o = reinterpret_cast<bf16*>(p.out) + pix * p.ldo + n;
-            Vec8<bf16>::store(o, v); Vec8<bf16>::store(o + 8, v + 8);
-          }
-        };
-        // software-pipelined TMEM reads: chunk c+1 is in flight while chunk c goes through the epilogue math/stores.
-        // The loop is fully unrolled over the (at most 8) chunks of this warp so resv[] stays in registers.
-        uint32_t ra[16], rc[16];
-        const uint4 z4 = make_uint4(0, 0, 0, 0);
-        if (cb < ce) tmem_ld16_issue(taddr + cb * 16, ra);
-#pragma unroll
-        for (int i = 0; i < 8; i += 2) {
-          const int ch = cb + i;
-          if (ch < ce) {
-            tmem_ld_wait(ra);
-            if (ch + 1 < ce) tmem_ld16_issue(taddr + (ch + 1) * 16, rc);
-            process(ra, ch, i < RPF ? resv[i < RPF ? i : 0][0] : z4, i < RPF ? resv[i < RPF ? i : 0][1] : z4, res_bf16 && i < RPF);
-            if (ch + 1 < ce) {
-              tmem_ld_wait(rc);
-              if (ch + 2 < ce) tmem_ld16_issue(taddr + (ch + 2) * 16, ra);
-              process(rc, ch + 1, (i + 1) < RPF ? resv[(i + 1) < RPF ? i + 1 : 0][0] : z4,
-                      (i + 1) < RPF ? resv[(i + 1) < RPF ? i + 1 : 0][1] : z4, res_bf16 && (i + 1) < RPF);
-            }
           }
         }
       } else {
-        // GEGLU: columns [0,128) of the tile are `a`, [128,256) the matching `gate` (weight rows pre-interleaved);
-        // epilogue group 0 takes a-columns [0,64), group 1 [64,128)
-        for (int c = egroup * 64; c < egroup * 64 + 64; c += 16) {
-          float a[16], g[16];
-          tmem_ld16(taddr + c, a);
-          tmem_ld16(taddr + 128 + c, g);
-          if (row_ok) {
-            const int n = n0 + c;
+        // bf16 output, coalesced through a per-warp shared-memory staging tile (32 rows x 64 columns, 128B-swizzled):
+        // thread = row for the TMEM read and the epilogue math, but global memory is touched with 8 lanes per row
+        // (8 x 16 B = one full 128-byte line per row segment).  The direct thread-per-row stores of the first version
+        // issued 32 half-sector requests per instruction and capped the K = 320 GEMMs at ~450 TFLOP/s (profiles/round1).
+        const int out_cols = geglu ? 128 : p.BN;
+        const int n_out0 = geglu ? n_blk * 128 : n0;
+        const int n_lim = geglu ? p.N_out : p.N;
+        const int NG = (out_cols + 63) >> 6;
+        const uint32_t okmask = __ballot_sync(0xffffffffu, row_ok);
+        const int sub = lane >> 3, ch8 = lane & 7;           // coalesced phase: 4 rows per pass, 8 x 16-byte chunks per row
+        for (int gi = egroup; gi < NG; gi += 2) {
+          const int c0 = gi * 64;
+          const int width = (out_cols - c0) < 64 ? (out_cols - c0) : 64;
+          // (1) residual tile -> staging (coalesced)
+          if (p.flags & FYC_EPI_RESIDUAL) {
 #pragma unroll
-            for (int i = 0; i < 16; i += 4) {
-              float4 ba = __ldg(reinterpret_cast<const float4*>(p.bias + n + i));
-              float4 bg = __ldg(reinterpret_cast<const float4*>(p.bias + n + 128 + i));
-              a[i] += ba.x; a[i + 1] += ba.y; a[i + 2] += ba.z; a[i + 3] += ba.w;
-              g[i] += bg.x; g[i + 1] += bg.y; g[i + 2] += bg.z; g[i + 3] += bg.w;
+            for (int itp = 0; itp < 8; ++itp) {
+              const int rl = itp * 4 + sub;
+              const int64_t pl = __shfl_sync(0xffffffffu, pix, rl);
+              const int n = n_out0 + c0 + ch8 * 8;
+              if (((okmask >> rl) & 1u) && ch8 * 8 < width && n < n_lim) {
+                uint4 u = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.residual) + pl * p.ldr + n));
+                *reinterpret_cast<uint4*>(stage + rl * 128 + ((ch8 ^ (rl & 7)) << 4)) = u;
+              }
             }
-#pragma unroll
-            for (int i = 0; i < 16; ++i) a[i] *= gelu_erf_fast(g[i]);
-            bf16* o = reinterpret_cast<bf16*>(p.out) + pix * p.ldo + n_blk * 128 + c;
-            Vec8<bf16>::store(o, a); Vec8<bf16>::store(o + 8, a + 8);
+            __syncwarp();
           }
+          // (2) own row: TMEM -> registers -> epilogue math -> staging
+          for (int k = 0; k < (width >> 4); ++k) {
+            float v[16];
+            const int n = n_out0 + c0 + k * 16;
+            if (!geglu) {
+              tmem_ld16(taddr + c0 + k * 16, v);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] *= p.alpha;
+              if (n < n_lim) {
+                if (p.flags & FYC_EPI_BIAS) {
+#pragma unroll
+                  for (int i = 0; i < 16; i += 4) {
+                    float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + i));
+                    v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+                  }
+                }
+                if (rb) {
+#pragma unroll
+                  for (int i = 0; i < 16; i += 4) {
+                    float4 b = __ldg(reinterpret_cast<const float4*>(rb + n + i));
+                    v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
+                  }
+                }
+              }
+            } else {
+              float g[16];
+              tmem_ld16(taddr + c0 + k * 16, v);
+              tmem_ld16(taddr + 128 + c0 + k * 16, g);
+              const int nb = n0 + c0 + k * 16;             // packed (interleaved) bias index of the `a` columns
+#pragma unroll
+              for (int i = 0; i < 16; i += 4) {
+                float4 ba = __ldg(reinterpret_cast<const float4*>(p.bias + nb + i));
+                float4 bg = __ldg(reinterpret_cast<const float4*>(p.bias + nb + 128 + i));
+                v[i] += ba.x; v[i + 1] += ba.y; v[i + 2] += ba.z; v[i + 3] += ba.w;
+                g[i] += bg.x; g[i + 1] += bg.y; g[i + 2] += bg.z; g[i + 3] += bg.w;
+              }
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] *= gelu_erf_fast(g[i]);
+            }
+            uint8_t* srow = stage + lane * 128;
+            const int s0 = ((2 * k) ^ (lane & 7)) << 4, s1 = ((2 * k + 1) ^ (lane & 7)) << 4;
+            if (p.flags & FYC_EPI_RESIDUAL) {
+              float f[16];
+              Vec8<bf16>::load(reinterpret_cast<const bf16*>(srow + s0), f);
+              Vec8<bf16>::load(reinterpret_cast<const bf16*>(srow + s1), f + 8);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] += f[i];
+            }
+            Vec8<bf16>::store(reinterpret_cast<bf16*>(srow + s0), v);
+            Vec8<bf16>::store(reinterpret_cast<bf16*>(srow + s1), v + 8);
+          }
+          __syncwarp();
+          // (3) staging -> global (coalesced: 8 lanes cover one 128-byte row segment)
+#pragma unroll
+          for (int itp = 0; itp < 8; ++itp) {
+            const int rl = itp * 4 + sub;
+            const int64_t pl = __shfl_sync(0xffffffffu, pix, rl);
+            const int n = n_out0 + c0 + ch8 * 8;
+            if (((okmask >> rl) & 1u) && ch8 * 8 < width && n < n_lim) {
+              uint4 u = *reinterpret_cast<const uint4*>(stage + rl * 128 + ((ch8 ^ (rl & 7)) << 4));
+              *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + pl * p.ldo + n) = u;
+            }
+          }
+          __syncwarp();
         }
       }
       tcgen05_fence_before();
