@@ -47,6 +47,7 @@ struct TcParams {
   int64_t ldo, ldr, rows_per_group;
   float alpha;
   int flags;
+  long long* debug;          // optional [gridDim.x][8] cycle counters (FYC_TC_DEBUG diagnostics), else nullptr
 };
 
 // ---------------------------------------------------------------------------------------------- PTX wrappers
@@ -125,6 +126,26 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t* r) {
                :: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+// wait for the TMEM loads; naming the registers as in/out operands keeps their uses below the wait
+__device__ __forceinline__ void tmem_ld_wait32(uint32_t* r) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+                 "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]),
+                 "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]),
+                 "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :: "memory");
+}
+
 // shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor)
 __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
   uint64_t d = 0;
@@ -175,6 +196,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ================================================================== TMA producer
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
+      long long dbg_wait = 0; const long long dbg_t0 = clock64();
       const uint32_t tx_bytes = A_BYTES + (uint32_t)p.BN * BK * 2;
       for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int n_blk = (int)(tile % p.n_tiles);
@@ -185,7 +207,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int ow0 = wt * p.bw, oh0 = ht * p.bh, img0 = it * p.bn;
         for (int tap = 0; tap < p.taps; ++tap) {
           for (int cb = 0; cb < p.cin_blocks; ++cb) {
+            const long long tw0 = clock64();
             mbar_wait(&empty[stage], phase ^ 1);
+            dbg_wait += clock64() - tw0;
             uint8_t* sa = smem + stage * STAGE_BYTES;
             mbar_expect_tx(&full[stage], tx_bytes);
             tma_load_4d(&map_a, &full[stage], sa, cb * BK, ow0 + p.tap_dx[tap], oh0 + p.tap_dy[tap], img0 + p.tap_img[tap]);
@@ -194,6 +218,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
         }
       }
+      if (p.debug) { p.debug[blockIdx.x * 8 + 0] = dbg_wait; p.debug[blockIdx.x * 8 + 1] = clock64() - dbg_t0; }
     }
   } else if (warp == 1) {
     // ================================================================== MMA issuer
@@ -202,12 +227,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t aphase = 0;
+      long long dbg_wfull = 0, dbg_wtempty = 0; const long long dbg_t0 = clock64();
       for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        long long tw0 = clock64();
         mbar_wait(&tempty[acc], aphase ^ 1);
+        dbg_wtempty += clock64() - tw0;
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * MAX_BN;
         for (int k = 0; k < k_iters; ++k) {
+          tw0 = clock64();
           mbar_wait(&full[stage], phase);
+          dbg_wfull += clock64() - tw0;
           tcgen05_fence_after();
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           const uint64_t a_desc = make_sw128_desc(sa);
@@ -223,6 +253,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         if (++acc == 2) { acc = 0; aphase ^= 1; }
       }
+      if (p.debug) { p.debug[blockIdx.x * 8 + 2] = dbg_wfull; p.debug[blockIdx.x * 8 + 3] = dbg_wtempty; p.debug[blockIdx.x * 8 + 4] = clock64() - dbg_t0; }
     }
   } else {
     // ================================================================== epilogue (warps 2..5)
@@ -230,6 +261,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int egroup = (warp - 2) >> 2;                // 0: warps 2-5, 1: warps 6-9 (same rows, other half of the columns)
     const int r = quarter * 32 + lane;                 // row of the tile handled by this thread
     uint8_t* stage = smem + OFF_STAGING + (warp - 2) * 4096;
+    long long dbg_epi = 0, dbg_wtfull = 0;
     int acc = 0; uint32_t aphase = 0;
     const bool geglu = (p.flags & FYC_EPI_GEGLU) != 0;
     const bool out_f32 = (p.flags & FYC_EPI_OUT_F32) != 0;
@@ -245,7 +277,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int64_t pix = ((int64_t)img * p.Ho + oh) * p.Wo + ow;
       const bool row_ok = (ow < p.Wo) && (oh < p.Ho) && (pix < p.M);
       const int n0 = n_blk * p.BN;
+      const long long te0 = clock64();
       mbar_wait(&tfull[acc], aphase);
+      const long long te1 = clock64();
+      dbg_wtfull += te1 - te0;
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * MAX_BN;
       const float* rb = (p.flags & FYC_EPI_ROWBIAS) ? p.rowbias + (row_ok ? pix / p.rows_per_group : 0) * p.N : nullptr;
@@ -286,104 +321,123 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             Vec8<float>::store(o, v); Vec8<float>::store(o + 8, v + 8);
           }
         }
-      } else {
-        // bf16 output, coalesced through a per-warp shared-memory staging tile (32 rows x 64 columns, 128B-swizzled):
-        // thread = row for the TMEM read and the epilogue math, but global memory is touched with 8 lanes per row
-        // (8 x 16 B = one full 128-byte line per row segment).  The direct thread-per-row stores of the first version
-        // issued 32 half-sector requests per instruction and capped the K = 320 GEMMs at ~450 TFLOP/s (profiles/round1).
-        const int out_cols = geglu ? 128 : p.BN;
-        const int n_out0 = geglu ? n_blk * 128 : n0;
-        const int n_lim = geglu ? p.N_out : p.N;
-        const int NG = (out_cols + 63) >> 6;
+      } else if (!geglu) {
+        // bf16 output, plain epilogue.  Two phases per 32-column group, through a per-warp 4 KB fp32 staging tile
+        // (32 rows x 32 columns, 16-byte chunks XOR-swizzled by row):
+        //   P2  thread = row   : one tcgen05.ld.x32, alpha, 8 conflict-free 16-byte stores       (pure TMEM -> smem transpose)
+        //   P3  4 lanes = row  : lane owns 8 fixed columns -> bias lives in 8 registers, the residual is read and the output
+        //                        written as 64-byte row segments (8 rows per instruction), single bf16 rounding at the end.
+        // The first version (thread-per-row global I/O, per-chunk waits) left the MMA warp waiting on the epilogue for
+        // 50-70 % of the kernel on the K = 320 GEMMs (tests/diag_gemm.py counters).
+        const int NG = (p.BN + 31) >> 5;
         const uint32_t okmask = __ballot_sync(0xffffffffu, row_ok);
-        const int sub = lane >> 3, ch8 = lane & 7;           // coalesced phase: 4 rows per pass, 8 x 16-byte chunks per row
+        const int rgrp = (int)(row_ok ? pix / p.rows_per_group : 0);
+        const int rip = lane >> 2, q = lane & 3;             // P3: row within a pass of 8, 8-column quarter of the 32-column group
         for (int gi = egroup; gi < NG; gi += 2) {
-          const int c0 = gi * 64;
-          const int width = (out_cols - c0) < 64 ? (out_cols - c0) : 64;
-          // (1) residual tile -> staging (coalesced)
-          if (p.flags & FYC_EPI_RESIDUAL) {
+          const int c0 = gi * 32;
+          // ---- P2
+          uint32_t rr[32];
+          tmem_ld32(taddr + c0, rr);
+          tmem_ld_wait32(rr);
+          uint8_t* srow = stage + lane * 128;
 #pragma unroll
-            for (int itp = 0; itp < 8; ++itp) {
-              const int rl = itp * 4 + sub;
-              const int64_t pl = __shfl_sync(0xffffffffu, pix, rl);
-              const int n = n_out0 + c0 + ch8 * 8;
-              if (((okmask >> rl) & 1u) && ch8 * 8 < width && n < n_lim) {
-                uint4 u = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.residual) + pl * p.ldr + n));
-                *reinterpret_cast<uint4*>(stage + rl * 128 + ((ch8 ^ (rl & 7)) << 4)) = u;
-              }
-            }
-            __syncwarp();
-          }
-          // (2) own row: TMEM -> registers -> epilogue math -> staging
-          for (int k = 0; k < (width >> 4); ++k) {
-            float v[16];
-            const int n = n_out0 + c0 + k * 16;
-            if (!geglu) {
-              tmem_ld16(taddr + c0 + k * 16, v);
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] *= p.alpha;
-              if (n < n_lim) {
-                if (p.flags & FYC_EPI_BIAS) {
-#pragma unroll
-                  for (int i = 0; i < 16; i += 4) {
-                    float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n + i));
-                    v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
-                  }
-                }
-                if (rb) {
-#pragma unroll
-                  for (int i = 0; i < 16; i += 4) {
-                    float4 b = __ldg(reinterpret_cast<const float4*>(rb + n + i));
-                    v[i] += b.x; v[i + 1] += b.y; v[i + 2] += b.z; v[i + 3] += b.w;
-                  }
-                }
-              }
-            } else {
-              float g[16];
-              tmem_ld16(taddr + c0 + k * 16, v);
-              tmem_ld16(taddr + 128 + c0 + k * 16, g);
-              const int nb = n0 + c0 + k * 16;             // packed (interleaved) bias index of the `a` columns
-#pragma unroll
-              for (int i = 0; i < 16; i += 4) {
-                float4 ba = __ldg(reinterpret_cast<const float4*>(p.bias + nb + i));
-                float4 bg = __ldg(reinterpret_cast<const float4*>(p.bias + nb + 128 + i));
-                v[i] += ba.x; v[i + 1] += ba.y; v[i + 2] += ba.z; v[i + 3] += ba.w;
-                g[i] += bg.x; g[i + 1] += bg.y; g[i + 2] += bg.z; g[i + 3] += bg.w;
-              }
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] *= gelu_erf_fast(g[i]);
-            }
-            uint8_t* srow = stage + lane * 128;
-            const int s0 = ((2 * k) ^ (lane & 7)) << 4, s1 = ((2 * k + 1) ^ (lane & 7)) << 4;
-            if (p.flags & FYC_EPI_RESIDUAL) {
-              float f[16];
-              Vec8<bf16>::load(reinterpret_cast<const bf16*>(srow + s0), f);
-              Vec8<bf16>::load(reinterpret_cast<const bf16*>(srow + s1), f + 8);
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] += f[i];
-            }
-            Vec8<bf16>::store(reinterpret_cast<bf16*>(srow + s0), v);
-            Vec8<bf16>::store(reinterpret_cast<bf16*>(srow + s1), v + 8);
+          for (int c = 0; c < 8; ++c) {
+            float4 v = make_float4(__uint_as_float(rr[4 * c]) * p.alpha, __uint_as_float(rr[4 * c + 1]) * p.alpha,
+                                   __uint_as_float(rr[4 * c + 2]) * p.alpha, __uint_as_float(rr[4 * c + 3]) * p.alpha);
+            *reinterpret_cast<float4*>(srow + ((c ^ (lane & 7)) << 4)) = v;
           }
           __syncwarp();
-          // (3) staging -> global (coalesced: 8 lanes cover one 128-byte row segment)
+          // ---- P3
+          const int n = n0 + c0 + q * 8;
+          const bool col_ok = (c0 + q * 8 < p.BN) && (n < p.N);
+          float bias8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          if ((p.flags & FYC_EPI_BIAS) && col_ok) {
+            float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n)), b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
+            bias8[0] = b0.x; bias8[1] = b0.y; bias8[2] = b0.z; bias8[3] = b0.w; bias8[4] = b1.x; bias8[5] = b1.y; bias8[6] = b1.z; bias8[7] = b1.w;
+          }
+          int64_t pl[4]; bool ok[4]; uint4 res[4]; int rg[4];
 #pragma unroll
-          for (int itp = 0; itp < 8; ++itp) {
-            const int rl = itp * 4 + sub;
-            const int64_t pl = __shfl_sync(0xffffffffu, pix, rl);
-            const int n = n_out0 + c0 + ch8 * 8;
-            if (((okmask >> rl) & 1u) && ch8 * 8 < width && n < n_lim) {
-              uint4 u = *reinterpret_cast<const uint4*>(stage + rl * 128 + ((ch8 ^ (rl & 7)) << 4));
-              *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + pl * p.ldo + n) = u;
+          for (int ps = 0; ps < 4; ++ps) {
+            const int rl = ps * 8 + rip;
+            pl[ps] = __shfl_sync(0xffffffffu, pix, rl);
+            rg[ps] = __shfl_sync(0xffffffffu, rgrp, rl);
+            ok[ps] = ((okmask >> rl) & 1u) && col_ok;
+            res[ps] = make_uint4(0, 0, 0, 0);
+            if ((p.flags & FYC_EPI_RESIDUAL) && ok[ps])
+              res[ps] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.residual) + pl[ps] * p.ldr + n));
+          }
+#pragma unroll
+          for (int ps = 0; ps < 4; ++ps) {
+            const int rl = ps * 8 + rip;
+            const uint8_t* sr = stage + rl * 128;
+            float4 x0 = *reinterpret_cast<const float4*>(sr + (((2 * q) ^ (rl & 7)) << 4));
+            float4 x1 = *reinterpret_cast<const float4*>(sr + (((2 * q + 1) ^ (rl & 7)) << 4));
+            float v[8] = {x0.x + bias8[0], x0.y + bias8[1], x0.z + bias8[2], x0.w + bias8[3],
+                          x1.x + bias8[4], x1.y + bias8[5], x1.z + bias8[6], x1.w + bias8[7]};
+            if ((p.flags & FYC_EPI_ROWBIAS) && ok[ps]) {
+              const float* rbp = p.rowbias + (int64_t)rg[ps] * p.N + n;
+              float4 r0 = __ldg(reinterpret_cast<const float4*>(rbp)), r1 = __ldg(reinterpret_cast<const float4*>(rbp + 4));
+              v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w; v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
             }
+            if (p.flags & FYC_EPI_RESIDUAL) {
+              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&res[ps]);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) { float2 t = __bfloat1622float2(h[i]); v[2 * i] += t.x; v[2 * i + 1] += t.y; }
+            }
+            if (ok[ps]) Vec8<bf16>::store(reinterpret_cast<bf16*>(p.out) + pl[ps] * p.ldo + n, v);
           }
           __syncwarp();
         }
+      } else {
+        // GEGLU: columns [0,128) of the tile are `a`, [128,256) the matching `gate` (weight rows pre-interleaved).  Thread = row
+        // for the math (bias + a * gelu(gate) in fp32, one bf16 rounding), 32 `a` + 32 gate columns per TMEM round trip; the
+        // bf16 results go through a 32 x 64 staging tile so that global stores cover full 128-byte row segments.
+        const uint32_t okmask = __ballot_sync(0xffffffffu, row_ok);
+        const int sub = lane >> 3, ch8 = lane & 7;
+        const int c0 = egroup * 64;                            // this warp's 64 output columns of the tile
+        uint8_t* srow = stage + lane * 128;
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          uint32_t ar[32], gr[32];
+          tmem_ld32(taddr + c0 + hh * 32, ar);
+          tmem_ld32(taddr + 128 + c0 + hh * 32, gr);
+          tmem_ld_wait32(ar);
+          tmem_ld_wait32(gr);
+          const int nb = n0 + c0 + hh * 32;                    // packed (interleaved) bias index of the `a` columns
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {                        // 8 output columns = one 16-byte chunk of bf16
+            float o[8];
+#pragma unroll
+            for (int i = 0; i < 8; i += 4) {
+              float4 ba = __ldg(reinterpret_cast<const float4*>(p.bias + nb + c * 8 + i));
+              float4 bg = __ldg(reinterpret_cast<const float4*>(p.bias + nb + 128 + c * 8 + i));
+              const float av[4] = {ba.x, ba.y, ba.z, ba.w}, gv[4] = {bg.x, bg.y, bg.z, bg.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                o[i + e] = (__uint_as_float(ar[c * 8 + i + e]) + av[e]) * gelu_erf_fast(__uint_as_float(gr[c * 8 + i + e]) + gv[e]);
+            }
+            Vec8<bf16>::store(reinterpret_cast<bf16*>(srow + (((hh * 4 + c) ^ (lane & 7)) << 4)), o);
+          }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int itp = 0; itp < 8; ++itp) {
+          const int rl = itp * 4 + sub;
+          const int64_t pl = __shfl_sync(0xffffffffu, pix, rl);
+          const int n = n_blk * 128 + c0 + ch8 * 8;
+          if (((okmask >> rl) & 1u) && n < p.N_out) {
+            uint4 u = *reinterpret_cast<const uint4*>(stage + rl * 128 + ((ch8 ^ (rl & 7)) << 4));
+            *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + pl * p.ldo + n) = u;
+          }
+        }
+        __syncwarp();
       }
       tcgen05_fence_before();
       mbar_arrive(&tempty[acc]);
+      dbg_epi += clock64() - te1;
       if (++acc == 2) { acc = 0; aphase ^= 1; }
     }
+    if (p.debug && lane == 0 && (warp == 2 || warp == 6)) { p.debug[blockIdx.x * 8 + 5 + (warp == 6)] = dbg_epi; if (warp == 2) p.debug[blockIdx.x * 8 + 7] = dbg_wtfull; }
   }
   __syncwarp();
   tcgen05_fence_before();
@@ -453,7 +507,10 @@ int pick_bn(int64_t N, bool geglu) {
   return 256;                           // ragged last tile (guarded stores)
 }
 
-int32_t launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, const TcParams& p, cudaStream_t st) {
+long long* g_tc_debug = nullptr;
+
+int32_t launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, TcParams p, cudaStream_t st) {
+  p.debug = g_tc_debug;
   static bool attr_set = false;
   if (!attr_set) {
     FYC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -467,6 +524,9 @@ int32_t launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, const TcParams& 
 }
 
 }  // namespace
+
+// diagnostics only (not part of include/fyc.h): per-CTA cycle counters of the next launches are written to buf[grid][8]
+extern "C" void fyc_debug_tc_counters(long long* buf) { g_tc_debug = buf; }
 
 extern "C" int32_t fyc_tcgen05_available(void) { return get_encode_fn() != nullptr ? 1 : 0; }
 
