@@ -2,7 +2,7 @@
 //
 //   out[p, n] = epilogue( alpha * sum_{tap, c} X[pixel(p) + (dy,dx)(tap), c] * W[n, tap, c] )
 //
-// One persistent CTA per SM, 6 warps, warp-specialised:
+// One persistent CTA per SM, 10 warps, warp-specialised:
 //   warp 0 (1 lane)  TMA producer : cp.async.bulk.tensor (4-D box for the activation patch, 3-D box for the weight
 //                                   slab) into a 4-stage 128B-swizzled shared-memory ring, mbarrier expect_tx
 //   warp 1 (1 lane)  MMA issuer   : tcgen05.mma.cta_group::1.kind::f16  128 x BN x 16, bf16 x bf16 -> fp32 in TMEM,
@@ -157,6 +157,153 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
   return d;
 }
 
+// ---------------------------------------------------------------------------------------------- plain bf16 epilogue
+// Two phases per 32-column group of the accumulator, through a per-warp 4 KB fp32 staging tile (32 rows x 32 columns,
+// 16-byte chunks XOR-swizzled by row):
+//   P2  thread = row   : one tcgen05.ld.x32, alpha, 8 conflict-free 16-byte stores          (pure TMEM -> smem transpose)
+//   P3  4 lanes = row  : lane owns 8 fixed columns; bias / row bias / residual arrive in registers that were loaded one
+//                        group AHEAD (across tile boundaries too), the output leaves as 64-byte row segments, 8 rows per
+//                        instruction, with a single bf16 rounding.
+// Why the prefetch: with 226 KB of shared memory the L1 is nearly gone, so every bias / residual load is an L2 round trip
+// (~700 clk).  Issued at their point of use these loads made a 32-column group cost ~1800 clk and left the MMA warp
+// waiting on tmem-empty for half of the kernel on the K = 320 GEMMs (profiles/round1_gemm_epilogue.md).
+struct EpiRows {
+  int pix[4];                 // output pixel (row of out / residual) of tile row ps*8 + rip; < 2^31 (checked at launch)
+  int rgu;                    // the warp's common row-bias group, or -1 when its 32 rows straddle two groups
+  uint32_t ok;                // bit ps: the row exists
+  int n0;                     // first column of the tile
+};
+struct EpiPrefetch { float4 b0, b1, r0, r1; uint4 res[4]; };
+
+__device__ __forceinline__ void epi_rows(const TcParams& p, int64_t tile, const int* wl, const int* hl, const int* il, EpiRows& t) {
+  const uint32_t tl = (uint32_t)tile;
+  const uint32_t n_blk = tl % (uint32_t)p.n_tiles, m_blk = tl / (uint32_t)p.n_tiles;
+  const uint32_t wt = m_blk % (uint32_t)p.w_tiles, m2 = m_blk / (uint32_t)p.w_tiles;
+  const uint32_t ht = m2 % (uint32_t)p.h_tiles, it = m2 / (uint32_t)p.h_tiles;
+  t.n0 = (int)n_blk * p.BN;
+  t.ok = 0; t.rgu = -1;
+  int mn = 0x7fffffff, mx = -1;
+#pragma unroll
+  for (int ps = 0; ps < 4; ++ps) {
+    const int ow = (int)wt * p.bw + wl[ps], oh = (int)ht * p.bh + hl[ps], img = (int)it * p.bn + il[ps];
+    const int64_t pix = ((int64_t)img * p.Ho + oh) * p.Wo + ow;
+    const bool ok = (ow < p.Wo) && (oh < p.Ho) && (pix < p.M);
+    t.ok |= (ok ? 1u : 0u) << ps;
+    t.pix[ps] = ok ? (int)pix : 0;
+    if ((p.flags & FYC_EPI_ROWBIAS) && ok) {
+      const int rg = (int)((uint32_t)pix / (uint32_t)p.rows_per_group);
+      mn = min(mn, rg); mx = max(mx, rg);
+    }
+  }
+  if (p.flags & FYC_EPI_ROWBIAS) {
+    mn = __reduce_min_sync(0xffffffffu, mn); mx = __reduce_max_sync(0xffffffffu, mx);
+    t.rgu = (mn == mx) ? mn : -1;
+  }
+}
+
+__device__ __forceinline__ void epi_prefetch(const TcParams& p, const EpiRows& t, int g, int q, EpiPrefetch& f) {
+  const int c = g * 32 + q * 8, n = t.n0 + c;
+  const bool col_ok = (c < p.BN) && (n < p.N);
+  f.b0 = f.b1 = f.r0 = f.r1 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if ((p.flags & FYC_EPI_BIAS) && col_ok) {
+    f.b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+    f.b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
+  }
+  if ((p.flags & FYC_EPI_ROWBIAS) && col_ok && t.rgu >= 0) {
+    const float* rbp = p.rowbias + (int64_t)t.rgu * p.N + n;
+    f.r0 = __ldg(reinterpret_cast<const float4*>(rbp));
+    f.r1 = __ldg(reinterpret_cast<const float4*>(rbp + 4));
+  }
+#pragma unroll
+  for (int ps = 0; ps < 4; ++ps) {
+    f.res[ps] = make_uint4(0, 0, 0, 0);
+    if ((p.flags & FYC_EPI_RESIDUAL) && col_ok && ((t.ok >> ps) & 1u))
+      f.res[ps] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.residual) + (int64_t)t.pix[ps] * p.ldr + n));
+  }
+}
+
+__device__ __forceinline__ void epilogue_plain(const TcParams& p, uint8_t* stage, uint64_t* tfull, uint64_t* tempty, uint32_t tmem_base,
+                                               int warp, int lane, int64_t num_tiles) {
+  const int quarter = warp & 3, egroup = (warp - 2) >> 2;
+  const int rip = lane >> 2, q = lane & 3;
+  const int NG = (p.BN + 31) >> 5;
+  int wl[4], hl[4], il[4];
+#pragma unroll
+  for (int ps = 0; ps < 4; ++ps) {
+    const int r = quarter * 32 + ps * 8 + rip;
+    wl[ps] = r % p.bw; hl[ps] = (r / p.bw) % p.bh; il[ps] = r / (p.bw * p.bh);
+  }
+  long long dbg_epi = 0;
+  int acc = 0; uint32_t aphase = 0;
+  int eg = egroup;                                  // the column half alternates per tile: NG is odd for N = 320 (3 + 2 groups)
+  EpiRows cur, nxt;
+  EpiPrefetch pf;
+  int64_t tile = blockIdx.x;
+  if (tile < num_tiles) { epi_rows(p, tile, wl, hl, il, cur); epi_prefetch(p, cur, eg, q, pf); }
+  nxt = cur;
+  for (; tile < num_tiles; tile += gridDim.x) {
+    mbar_wait(&tfull[acc], aphase);
+    const long long te1 = clock64();
+    tcgen05_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * MAX_BN;
+    const int64_t next_tile = tile + gridDim.x;
+    if (eg >= NG && next_tile < num_tiles) { epi_rows(p, next_tile, wl, hl, il, nxt); epi_prefetch(p, nxt, eg ^ 1, q, pf); }
+    for (int gi = eg; gi < NG; gi += 2) {
+      // ---- P2
+      uint32_t rr[32];
+      tmem_ld32(taddr + gi * 32, rr);
+      // ---- prefetch of the group after this one while the TMEM load is in flight
+      EpiPrefetch pn = pf;
+      if (gi + 2 < NG) epi_prefetch(p, cur, gi + 2, q, pn);
+      else if (next_tile < num_tiles) { epi_rows(p, next_tile, wl, hl, il, nxt); epi_prefetch(p, nxt, eg ^ 1, q, pn); }
+      tmem_ld_wait32(rr);
+      uint8_t* srow = stage + lane * 128;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float4 v = make_float4(__uint_as_float(rr[4 * c]) * p.alpha, __uint_as_float(rr[4 * c + 1]) * p.alpha,
+                               __uint_as_float(rr[4 * c + 2]) * p.alpha, __uint_as_float(rr[4 * c + 3]) * p.alpha);
+        *reinterpret_cast<float4*>(srow + ((c ^ (lane & 7)) << 4)) = v;
+      }
+      __syncwarp();
+      // ---- P3
+      const int c0 = gi * 32 + q * 8;
+      const bool col_ok = (c0 < p.BN) && (cur.n0 + c0 < p.N);
+      const float bias8[8] = {pf.b0.x + pf.r0.x, pf.b0.y + pf.r0.y, pf.b0.z + pf.r0.z, pf.b0.w + pf.r0.w,
+                              pf.b1.x + pf.r1.x, pf.b1.y + pf.r1.y, pf.b1.z + pf.r1.z, pf.b1.w + pf.r1.w};
+#pragma unroll
+      for (int ps = 0; ps < 4; ++ps) {
+        const int rl = ps * 8 + rip;
+        const uint8_t* sr = stage + rl * 128;
+        const float4 x0 = *reinterpret_cast<const float4*>(sr + (((2 * q) ^ (rl & 7)) << 4));
+        const float4 x1 = *reinterpret_cast<const float4*>(sr + (((2 * q + 1) ^ (rl & 7)) << 4));
+        float v[8] = {x0.x + bias8[0], x0.y + bias8[1], x0.z + bias8[2], x0.w + bias8[3],
+                      x1.x + bias8[4], x1.y + bias8[5], x1.z + bias8[6], x1.w + bias8[7]};
+        const bool ok = ((cur.ok >> ps) & 1u) && col_ok;
+        if ((p.flags & FYC_EPI_ROWBIAS) && cur.rgu < 0 && ok) {          // rare: the warp's rows straddle two row-bias groups
+          const float* rbp = p.rowbias + (int64_t)((uint32_t)cur.pix[ps] / (uint32_t)p.rows_per_group) * p.N + cur.n0 + c0;
+          const float4 r0 = __ldg(reinterpret_cast<const float4*>(rbp)), r1 = __ldg(reinterpret_cast<const float4*>(rbp + 4));
+          v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w; v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
+        }
+        if (p.flags & FYC_EPI_RESIDUAL) {
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pf.res[ps]);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { float2 t = __bfloat1622float2(h[i]); v[2 * i] += t.x; v[2 * i + 1] += t.y; }
+        }
+        if (ok) Vec8<bf16>::store(reinterpret_cast<bf16*>(p.out) + (int64_t)cur.pix[ps] * p.ldo + cur.n0 + c0, v);
+      }
+      __syncwarp();
+      pf = pn;
+    }
+    tcgen05_fence_before();
+    mbar_arrive(&tempty[acc]);
+    dbg_epi += clock64() - te1;
+    if (++acc == 2) { acc = 0; aphase ^= 1; }
+    cur = nxt;
+    eg ^= 1;
+  }
+  if (p.debug && lane == 0 && (warp == 2 || warp == 6)) p.debug[blockIdx.x * 8 + 5 + (warp == 6)] = dbg_epi;
+}
+
 // ---------------------------------------------------------------------------------------------- kernel
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const TcParams p) {
@@ -218,7 +365,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
         }
       }
-      if (p.debug) { p.debug[blockIdx.x * 8 + 0] = dbg_wait; p.debug[blockIdx.x * 8 + 1] = clock64() - dbg_t0; }
+      (void)dbg_wait; (void)dbg_t0;
     }
   } else if (warp == 1) {
     // ================================================================== MMA issuer
@@ -256,16 +403,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       if (p.debug) { p.debug[blockIdx.x * 8 + 2] = dbg_wfull; p.debug[blockIdx.x * 8 + 3] = dbg_wtempty; p.debug[blockIdx.x * 8 + 4] = clock64() - dbg_t0; }
     }
   } else {
-    // ================================================================== epilogue (warps 2..5)
+    // ================================================================== epilogue (warps 2..9)
     const int quarter = warp & 3;                      // TMEM lane quarter this warp may access
     const int egroup = (warp - 2) >> 2;                // 0: warps 2-5, 1: warps 6-9 (same rows, other half of the columns)
     const int r = quarter * 32 + lane;                 // row of the tile handled by this thread
     uint8_t* stage = smem + OFF_STAGING + (warp - 2) * 4096;
-    long long dbg_epi = 0, dbg_wtfull = 0;
+    long long dbg_epi = 0;
     int acc = 0; uint32_t aphase = 0;
     const bool geglu = (p.flags & FYC_EPI_GEGLU) != 0;
     const bool out_f32 = (p.flags & FYC_EPI_OUT_F32) != 0;
-    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    if (!geglu && !out_f32) epilogue_plain(p, stage, tfull, tempty, tmem_base, warp, lane, num_tiles);
+    else for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int n_blk = (int)(tile % p.n_tiles);
       const int64_t m_blk = tile / p.n_tiles;
       const int wt = (int)(m_blk % p.w_tiles);
@@ -277,10 +425,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int64_t pix = ((int64_t)img * p.Ho + oh) * p.Wo + ow;
       const bool row_ok = (ow < p.Wo) && (oh < p.Ho) && (pix < p.M);
       const int n0 = n_blk * p.BN;
-      const long long te0 = clock64();
       mbar_wait(&tfull[acc], aphase);
       const long long te1 = clock64();
-      dbg_wtfull += te1 - te0;
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * MAX_BN;
       const float* rb = (p.flags & FYC_EPI_ROWBIAS) ? p.rowbias + (row_ok ? pix / p.rows_per_group : 0) * p.N : nullptr;
@@ -320,73 +466,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             float* o = reinterpret_cast<float*>(p.out) + pix * p.ldo + n;
             Vec8<float>::store(o, v); Vec8<float>::store(o + 8, v + 8);
           }
-        }
-      } else if (!geglu) {
-        // bf16 output, plain epilogue.  Two phases per 32-column group, through a per-warp 4 KB fp32 staging tile
-        // (32 rows x 32 columns, 16-byte chunks XOR-swizzled by row):
-        //   P2  thread = row   : one tcgen05.ld.x32, alpha, 8 conflict-free 16-byte stores       (pure TMEM -> smem transpose)
-        //   P3  4 lanes = row  : lane owns 8 fixed columns -> bias lives in 8 registers, the residual is read and the output
-        //                        written as 64-byte row segments (8 rows per instruction), single bf16 rounding at the end.
-        // The first version (thread-per-row global I/O, per-chunk waits) left the MMA warp waiting on the epilogue for
-        // 50-70 % of the kernel on the K = 320 GEMMs (tests/diag_gemm.py counters).
-        const int NG = (p.BN + 31) >> 5;
-        const uint32_t okmask = __ballot_sync(0xffffffffu, row_ok);
-        const int rgrp = (int)(row_ok ? pix / p.rows_per_group : 0);
-        const int rip = lane >> 2, q = lane & 3;             // P3: row within a pass of 8, 8-column quarter of the 32-column group
-        for (int gi = egroup; gi < NG; gi += 2) {
-          const int c0 = gi * 32;
-          // ---- P2
-          uint32_t rr[32];
-          tmem_ld32(taddr + c0, rr);
-          tmem_ld_wait32(rr);
-          uint8_t* srow = stage + lane * 128;
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            float4 v = make_float4(__uint_as_float(rr[4 * c]) * p.alpha, __uint_as_float(rr[4 * c + 1]) * p.alpha,
-                                   __uint_as_float(rr[4 * c + 2]) * p.alpha, __uint_as_float(rr[4 * c + 3]) * p.alpha);
-            *reinterpret_cast<float4*>(srow + ((c ^ (lane & 7)) << 4)) = v;
-          }
-          __syncwarp();
-          // ---- P3
-          const int n = n0 + c0 + q * 8;
-          const bool col_ok = (c0 + q * 8 < p.BN) && (n < p.N);
-          float bias8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-          if ((p.flags & FYC_EPI_BIAS) && col_ok) {
-            float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n)), b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
-            bias8[0] = b0.x; bias8[1] = b0.y; bias8[2] = b0.z; bias8[3] = b0.w; bias8[4] = b1.x; bias8[5] = b1.y; bias8[6] = b1.z; bias8[7] = b1.w;
-          }
-          int64_t pl[4]; bool ok[4]; uint4 res[4]; int rg[4];
-#pragma unroll
-          for (int ps = 0; ps < 4; ++ps) {
-            const int rl = ps * 8 + rip;
-            pl[ps] = __shfl_sync(0xffffffffu, pix, rl);
-            rg[ps] = __shfl_sync(0xffffffffu, rgrp, rl);
-            ok[ps] = ((okmask >> rl) & 1u) && col_ok;
-            res[ps] = make_uint4(0, 0, 0, 0);
-            if ((p.flags & FYC_EPI_RESIDUAL) && ok[ps])
-              res[ps] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.residual) + pl[ps] * p.ldr + n));
-          }
-#pragma unroll
-          for (int ps = 0; ps < 4; ++ps) {
-            const int rl = ps * 8 + rip;
-            const uint8_t* sr = stage + rl * 128;
-            float4 x0 = *reinterpret_cast<const float4*>(sr + (((2 * q) ^ (rl & 7)) << 4));
-            float4 x1 = *reinterpret_cast<const float4*>(sr + (((2 * q + 1) ^ (rl & 7)) << 4));
-            float v[8] = {x0.x + bias8[0], x0.y + bias8[1], x0.z + bias8[2], x0.w + bias8[3],
-                          x1.x + bias8[4], x1.y + bias8[5], x1.z + bias8[6], x1.w + bias8[7]};
-            if ((p.flags & FYC_EPI_ROWBIAS) && ok[ps]) {
-              const float* rbp = p.rowbias + (int64_t)rg[ps] * p.N + n;
-              float4 r0 = __ldg(reinterpret_cast<const float4*>(rbp)), r1 = __ldg(reinterpret_cast<const float4*>(rbp + 4));
-              v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w; v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
-            }
-            if (p.flags & FYC_EPI_RESIDUAL) {
-              const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&res[ps]);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) { float2 t = __bfloat1622float2(h[i]); v[2 * i] += t.x; v[2 * i + 1] += t.y; }
-            }
-            if (ok[ps]) Vec8<bf16>::store(reinterpret_cast<bf16*>(p.out) + pl[ps] * p.ldo + n, v);
-          }
-          __syncwarp();
         }
       } else {
         // GEGLU: columns [0,128) of the tile are `a`, [128,256) the matching `gate` (weight rows pre-interleaved).  Thread = row
@@ -437,7 +516,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       dbg_epi += clock64() - te1;
       if (++acc == 2) { acc = 0; aphase ^= 1; }
     }
-    if (p.debug && lane == 0 && (warp == 2 || warp == 6)) { p.debug[blockIdx.x * 8 + 5 + (warp == 6)] = dbg_epi; if (warp == 2) p.debug[blockIdx.x * 8 + 7] = dbg_wtfull; }
+    if (p.debug && (geglu || out_f32) && lane == 0 && (warp == 2 || warp == 6)) p.debug[blockIdx.x * 8 + 5 + (warp == 6)] = dbg_epi;
   }
   __syncwarp();
   tcgen05_fence_before();
@@ -517,6 +596,7 @@ int32_t launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, TcParams p, cuda
     attr_set = true;
   }
   int64_t tiles = p.m_tiles * p.n_tiles;
+  FYC_CHECK(tiles < (1ll << 31) && p.M < (1ll << 31) && p.rows_per_group < (1ll << 31), "tcgen05 GEMM: problem exceeds the 32-bit tile index range");
   int grid = (int)(tiles < fyc_sm_count() ? tiles : fyc_sm_count());
   gemm_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mw, p);
   FYC_LAUNCH_CHECK();

@@ -18,5 +18,5 @@ for (M, N, K, res, geglu) in [(131072, 320, 320, False, False), (131072, 320, 32
     us = e0.elapsed_time(e1) * 100
     dbg.zero_(); lib.fyc_debug_tc_counters(dbg.data_ptr()); ops.gemm(A, W, bias=bias, residual=R, geglu=geglu); torch.cuda.synchronize(); lib.fyc_debug_tc_counters(None)
     d = dbg.view(148, 8).double().mean(0).tolist()
-    print(f"M={M} N={N} K={K} res={res} geglu={geglu}: {us:.1f} us  {2*M*N*K/us/1e6:.0f} TFLOP/s | producer wait-empty {d[0]:.0f} / total {d[1]:.0f} | "
-          f"mma wait-full {d[2]:.0f} wait-tempty {d[3]:.0f} / total {d[4]:.0f} | epi busy w2 {d[5]:.0f} w6 {d[6]:.0f}, wait-tfull {d[7]:.0f} clk")
+    print(f"M={M} N={N} K={K} res={res} geglu={geglu}: {us:.1f} us  {2*M*N*K/us/1e6:.0f} TFLOP/s | "
+          f"mma wait-full {d[2]:.0f} wait-tempty {d[3]:.0f} / total {d[4]:.0f} | epi busy w2 {d[5]:.0f} w6 {d[6]:.0f} clk")

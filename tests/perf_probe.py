@@ -54,8 +54,8 @@ def main():
         with ops.profile() as prof2: run()
         ops._prof_shapes = False
         rows = sorted(prof2.summary.items(), key=lambda kv: -kv[1]["ms"])
-        for fam, d in rows[:45]:
-            if d["flops"]:
+        for fam, d in rows[:70]:
+            if d["ms"]:
                 print(f"   {fam:46s} {d['ms']:7.3f} ms x{d['launches']:3d}  {d['flops']/d['ms']/1e9:7.1f} TFLOP/s  {d['bytes']/d['ms']/1e6:7.1f} GB/s(alg)")
     # VAE decode of F frames
     vae = AutoencoderKL(in_channels=3, out_channels=3, down_block_types=("DownEncoderBlock2D",) * 4, up_block_types=("UpDecoderBlock2D",) * 4,
