@@ -27,9 +27,12 @@ constexpr int MAX_BN = 256;
 constexpr int A_BYTES = BM * BK * 2;           // 16 KB
 constexpr int B_BYTES = MAX_BN * BK * 2;       // 32 KB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int MAX_STAGES = 8;                   // barrier slots; the W-resident mode runs up to 8 A-only stages
+constexpr int RING_BYTES = STAGES * STAGE_BYTES;                // 192 KB operand ring (or W slab + A ring)
 constexpr int STAGING_BYTES = 8 * 4096;         // per epilogue warp: 32 rows x 128 B (64 bf16 columns), 128B-swizzled
-constexpr int OFF_STAGING = STAGES * STAGE_BYTES + 256;
-constexpr int SMEM_BYTES = OFF_STAGING + STAGING_BYTES + 1024 /*align slack*/;
+constexpr int OFF_STAGING = RING_BYTES + 256;
+constexpr int OFF_BIAS = OFF_STAGING + STAGING_BYTES;           // GEGLU: 2 x 256 fp32 bias values of the current / next tile
+constexpr int SMEM_BYTES = OFF_BIAS + 2048;                     // dynamic smem is declared 1024-aligned (checked in the kernel)
 constexpr int NUM_THREADS = 320;          // TMA warp, MMA warp, 8 epilogue warps (2 per TMEM lane quarter)
 
 struct TcParams {
@@ -47,6 +50,10 @@ struct TcParams {
   int64_t ldo, ldr, rows_per_group;
   float alpha;
   int flags;
+  // W-resident mode (small K): the CTA keeps its whole BN x K weight slab in shared memory and only streams A
+  int resident, a_stages;
+  // gridDim.x as mixed-radix digits (n, w, h, image tiles): tile coordinates advance by addition, not by four divisions per tile
+  int dg_n, dg_w, dg_h, dg_i;
   long long* debug;          // optional [gridDim.x][8] cycle counters (FYC_TC_DEBUG diagnostics), else nullptr
 };
 
@@ -111,21 +118,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// split TMEM load: issue now, wait later (the wait names the registers so their uses cannot be hoisted above it)
-__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld_wait(uint32_t* r) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;"
-               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
-                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
-               :: "memory");
-}
-
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -157,41 +149,64 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
   return d;
 }
 
+// ---------------------------------------------------------------------------------------------- tile coordinates
+struct TileCoord { int n, w, h, i; };   // n block; patch column / row / image-group of the 128-pixel m block
+__device__ __forceinline__ TileCoord tile_coord(const TcParams& p, uint32_t tile) {
+  TileCoord c;
+  c.n = (int)(tile % (uint32_t)p.n_tiles);
+  const uint32_t m_blk = tile / (uint32_t)p.n_tiles;
+  c.w = (int)(m_blk % (uint32_t)p.w_tiles);
+  const uint32_t m2 = m_blk / (uint32_t)p.w_tiles;
+  c.h = (int)(m2 % (uint32_t)p.h_tiles);
+  c.i = (int)(m2 / (uint32_t)p.h_tiles);
+  return c;
+}
+// tile += gridDim.x
+__device__ __forceinline__ void tile_advance(const TcParams& p, TileCoord& c) {
+  c.n += p.dg_n; int cy = c.n >= p.n_tiles ? 1 : 0; c.n -= cy ? p.n_tiles : 0;
+  c.w += p.dg_w + cy; cy = c.w >= p.w_tiles ? 1 : 0; c.w -= cy ? p.w_tiles : 0;
+  c.h += p.dg_h + cy; cy = c.h >= p.h_tiles ? 1 : 0; c.h -= cy ? p.h_tiles : 0;
+  c.i += p.dg_i + cy;
+}
+
 // ---------------------------------------------------------------------------------------------- plain bf16 epilogue
 // Two phases per 32-column group of the accumulator, through a per-warp 4 KB fp32 staging tile (32 rows x 32 columns,
 // 16-byte chunks XOR-swizzled by row):
-//   P2  thread = row   : one tcgen05.ld.x32, alpha, 8 conflict-free 16-byte stores          (pure TMEM -> smem transpose)
-//   P3  4 lanes = row  : lane owns 8 fixed columns; bias / row bias / residual arrive in registers that were loaded one
-//                        group AHEAD (across tile boundaries too), the output leaves as 64-byte row segments, 8 rows per
-//                        instruction, with a single bf16 rounding.
-// Why the prefetch: with 226 KB of shared memory the L1 is nearly gone, so every bias / residual load is an L2 round trip
-// (~700 clk).  Issued at their point of use these loads made a 32-column group cost ~1800 clk and left the MMA warp
-// waiting on tmem-empty for half of the kernel on the K = 320 GEMMs (profiles/round1_gemm_epilogue.md).
+//   P2  thread = row   : one tcgen05.ld.x32 and 8 conflict-free 16-byte shared stores          (pure TMEM -> smem transpose)
+//   P3  4 lanes = row  : lane owns 8 fixed columns; alpha and bias are one FFMA, bias / row bias / residual arrive in
+//                        registers that were loaded one group AHEAD (across tile boundaries too), the output leaves as
+//                        64-byte row segments, 8 rows per instruction, with a single bf16 rounding.
+// Why: with 226 KB of shared memory the L1 is nearly gone, so every bias / residual load is an L2 round trip (~700 clk),
+// and with two epilogue warps per scheduler there is no one to hide it - issued at their point of use these loads made a
+// 32-column group cost ~1800 clk and left the MMA warp waiting on tmem-empty for half of the K = 320 GEMMs.  The phase
+// is also instruction-bound (8 warps share the 4 schedulers with nobody else), so addresses are 32-bit offsets in 16-byte
+// units computed once per tile, not 64-bit pixel * ld products per store.
 struct EpiRows {
-  int pix[4];                 // output pixel (row of out / residual) of tile row ps*8 + rip; < 2^31 (checked at launch)
+  uint32_t oo[4], ro[4];      // (row ps*8+rip, column n0 + q*8) of out / residual, in 16-byte units (< 2^32, checked at launch)
   int rgu;                    // the warp's common row-bias group, or -1 when its 32 rows straddle two groups
   uint32_t ok;                // bit ps: the row exists
   int n0;                     // first column of the tile
 };
-struct EpiPrefetch { float4 b0, b1, r0, r1; uint4 res[4]; };
+struct EpiPrefetch { float4 b0, b1; uint4 res[4]; };
 
-__device__ __forceinline__ void epi_rows(const TcParams& p, int64_t tile, const int* wl, const int* hl, const int* il, EpiRows& t) {
-  const uint32_t tl = (uint32_t)tile;
-  const uint32_t n_blk = tl % (uint32_t)p.n_tiles, m_blk = tl / (uint32_t)p.n_tiles;
-  const uint32_t wt = m_blk % (uint32_t)p.w_tiles, m2 = m_blk / (uint32_t)p.w_tiles;
-  const uint32_t ht = m2 % (uint32_t)p.h_tiles, it = m2 / (uint32_t)p.h_tiles;
+__device__ __forceinline__ void epi_rows(const TcParams& p, const TileCoord& tc, const uint32_t* whi, int q, EpiRows& t) {
+  const int n_blk = tc.n, wt = tc.w, ht = tc.h, it = tc.i;
   t.n0 = (int)n_blk * p.BN;
   t.ok = 0; t.rgu = -1;
+  const uint32_t cq = (uint32_t)(t.n0 + q * 8) >> 3, ldo8 = (uint32_t)(p.ldo >> 3), ldr8 = (uint32_t)(p.ldr >> 3);
   int mn = 0x7fffffff, mx = -1;
 #pragma unroll
   for (int ps = 0; ps < 4; ++ps) {
-    const int ow = (int)wt * p.bw + wl[ps], oh = (int)ht * p.bh + hl[ps], img = (int)it * p.bn + il[ps];
+    const int ow = (int)wt * p.bw + (int)(whi[ps] & 1023u), oh = (int)ht * p.bh + (int)((whi[ps] >> 10) & 1023u);
+    const int img = (int)it * p.bn + (int)(whi[ps] >> 20);
     const int64_t pix = ((int64_t)img * p.Ho + oh) * p.Wo + ow;
     const bool ok = (ow < p.Wo) && (oh < p.Ho) && (pix < p.M);
     t.ok |= (ok ? 1u : 0u) << ps;
-    t.pix[ps] = ok ? (int)pix : 0;
+    const uint32_t px = ok ? (uint32_t)pix : 0u;
+    t.oo[ps] = px * ldo8 + cq;
+    t.ro[ps] = px * ldr8 + cq;
     if ((p.flags & FYC_EPI_ROWBIAS) && ok) {
-      const int rg = (int)((uint32_t)pix / (uint32_t)p.rows_per_group);
+      const int rg = (int)(px / (uint32_t)p.rows_per_group);
       mn = min(mn, rg); mx = max(mx, rg);
     }
   }
@@ -201,24 +216,22 @@ __device__ __forceinline__ void epi_rows(const TcParams& p, int64_t tile, const 
   }
 }
 
+// loads for 32-column group g of tile t: bias (+ the warp-uniform row bias) of this lane's 8 columns, residual of its 4 rows
 __device__ __forceinline__ void epi_prefetch(const TcParams& p, const EpiRows& t, int g, int q, EpiPrefetch& f) {
   const int c = g * 32 + q * 8, n = t.n0 + c;
   const bool col_ok = (c < p.BN) && (n < p.N);
-  f.b0 = f.b1 = f.r0 = f.r1 = make_float4(0.f, 0.f, 0.f, 0.f);
+  f.b0 = f.b1 = make_float4(0.f, 0.f, 0.f, 0.f);
   if ((p.flags & FYC_EPI_BIAS) && col_ok) {
     f.b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
     f.b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
   }
-  if ((p.flags & FYC_EPI_ROWBIAS) && col_ok && t.rgu >= 0) {
-    const float* rbp = p.rowbias + (int64_t)t.rgu * p.N + n;
-    f.r0 = __ldg(reinterpret_cast<const float4*>(rbp));
-    f.r1 = __ldg(reinterpret_cast<const float4*>(rbp + 4));
-  }
+  if (p.flags & FYC_EPI_RESIDUAL) {
+    const uint4* rbase = reinterpret_cast<const uint4*>(p.residual);
 #pragma unroll
-  for (int ps = 0; ps < 4; ++ps) {
-    f.res[ps] = make_uint4(0, 0, 0, 0);
-    if ((p.flags & FYC_EPI_RESIDUAL) && col_ok && ((t.ok >> ps) & 1u))
-      f.res[ps] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.residual) + (int64_t)t.pix[ps] * p.ldr + n));
+    for (int ps = 0; ps < 4; ++ps) {
+      f.res[ps] = make_uint4(0, 0, 0, 0);
+      if (col_ok && ((t.ok >> ps) & 1u)) f.res[ps] = __ldg(rbase + (t.ro[ps] + (uint32_t)g * 4u));
+    }
   }
 }
 
@@ -227,76 +240,128 @@ __device__ __forceinline__ void epilogue_plain(const TcParams& p, uint8_t* stage
   const int quarter = warp & 3, egroup = (warp - 2) >> 2;
   const int rip = lane >> 2, q = lane & 3;
   const int NG = (p.BN + 31) >> 5;
-  int wl[4], hl[4], il[4];
+  const float alpha = p.alpha;
+  uint32_t whi[4];                                  // (w, h, image) of this lane's 4 rows inside the 128-pixel patch, 10 bits each
 #pragma unroll
   for (int ps = 0; ps < 4; ++ps) {
     const int r = quarter * 32 + ps * 8 + rip;
-    wl[ps] = r % p.bw; hl[ps] = (r / p.bw) % p.bh; il[ps] = r / (p.bw * p.bh);
+    whi[ps] = (uint32_t)(r % p.bw) | ((uint32_t)((r / p.bw) % p.bh) << 10) | ((uint32_t)(r / (p.bw * p.bh)) << 20);
   }
+  // staging addresses: P2 writes row `lane`, P3 reads rows ps*8 + rip (row & 7 == rip for every ps)
+  uint8_t* const srow = stage + lane * 128;
+  const int sw = lane & 7;
+  const uint8_t* const prow = stage + rip * 128;
+  const int px0 = ((2 * q) ^ rip) << 4, px1 = ((2 * q + 1) ^ rip) << 4;
+  uint4* const obase = reinterpret_cast<uint4*>(p.out);
   long long dbg_epi = 0;
   int acc = 0; uint32_t aphase = 0;
   int eg = egroup;                                  // the column half alternates per tile: NG is odd for N = 320 (3 + 2 groups)
   EpiRows cur, nxt;
   EpiPrefetch pf;
   int64_t tile = blockIdx.x;
-  if (tile < num_tiles) { epi_rows(p, tile, wl, hl, il, cur); epi_prefetch(p, cur, eg, q, pf); }
+  TileCoord tcn = tile_coord(p, (uint32_t)tile);     // coordinates of the NEXT tile to be decoded
+  if (tile < num_tiles) { epi_rows(p, tcn, whi, q, cur); epi_prefetch(p, cur, eg, q, pf); }
   nxt = cur;
   for (; tile < num_tiles; tile += gridDim.x) {
     mbar_wait(&tfull[acc], aphase);
-    const long long te1 = clock64();
+    const long long te1 = p.debug ? clock64() : 0;
     tcgen05_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * MAX_BN;
     const int64_t next_tile = tile + gridDim.x;
-    if (eg >= NG && next_tile < num_tiles) { epi_rows(p, next_tile, wl, hl, il, nxt); epi_prefetch(p, nxt, eg ^ 1, q, pf); }
+    tile_advance(p, tcn);
+    if (next_tile < num_tiles) {
+      epi_rows(p, tcn, whi, q, nxt);
+      if (p.flags & FYC_EPI_RESIDUAL) {             // pull the next tile's residual rows into L2 a whole tile ahead: lane q takes its
+        const int g = (eg ^ 1) + 2 * q;             // q-th group, so one instruction per row covers all of this warp's groups
+        if (g < NG && nxt.n0 + g * 32 < p.N) {
+#pragma unroll
+          for (int ps = 0; ps < 4; ++ps)
+            if ((nxt.ok >> ps) & 1u) {
+              const uint4* ptr = reinterpret_cast<const uint4*>(p.residual) + (nxt.ro[ps] - (uint32_t)q + (uint32_t)g * 4u);
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(ptr));
+            }
+        }
+      }
+    } else nxt.ok = 0;                               // nothing follows: the prefetch below degenerates to (valid) bias loads
+    if (eg >= NG) epi_prefetch(p, nxt, eg ^ 1, q, pf);
     for (int gi = eg; gi < NG; gi += 2) {
       // ---- P2
       uint32_t rr[32];
       tmem_ld32(taddr + gi * 32, rr);
-      // ---- prefetch of the group after this one while the TMEM load is in flight
-      EpiPrefetch pn = pf;
-      if (gi + 2 < NG) epi_prefetch(p, cur, gi + 2, q, pn);
-      else if (next_tile < num_tiles) { epi_rows(p, next_tile, wl, hl, il, nxt); epi_prefetch(p, nxt, eg ^ 1, q, pn); }
-      tmem_ld_wait32(rr);
-      uint8_t* srow = stage + lane * 128;
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        float4 v = make_float4(__uint_as_float(rr[4 * c]) * p.alpha, __uint_as_float(rr[4 * c + 1]) * p.alpha,
-                               __uint_as_float(rr[4 * c + 2]) * p.alpha, __uint_as_float(rr[4 * c + 3]) * p.alpha);
-        *reinterpret_cast<float4*>(srow + ((c ^ (lane & 7)) << 4)) = v;
+      // ---- prefetch of the group after this one (possibly the next tile's first) while the TMEM load is in flight
+      EpiPrefetch pn;
+      {
+        const bool last = gi + 2 >= NG;
+        EpiRows src = cur;
+        if (last) src = nxt;
+        epi_prefetch(p, src, last ? (eg ^ 1) : gi + 2, q, pn);
       }
+      tmem_ld_wait32(rr);
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<uint4*>(srow + ((c ^ sw) << 4)) = make_uint4(rr[4 * c], rr[4 * c + 1], rr[4 * c + 2], rr[4 * c + 3]);
       __syncwarp();
       // ---- P3
       const int c0 = gi * 32 + q * 8;
       const bool col_ok = (c0 < p.BN) && (cur.n0 + c0 < p.N);
-      const float bias8[8] = {pf.b0.x + pf.r0.x, pf.b0.y + pf.r0.y, pf.b0.z + pf.r0.z, pf.b0.w + pf.r0.w,
-                              pf.b1.x + pf.r1.x, pf.b1.y + pf.r1.y, pf.b1.z + pf.r1.z, pf.b1.w + pf.r1.w};
+      const uint32_t g4 = (uint32_t)gi * 4u;
+      float a_eff = alpha;
+      if (p.flags & FYC_EPI_ROWBIAS) {
+        if (cur.rgu >= 0) {                                // the 32 rows share one row-bias vector (the usual case)
+          if (col_ok) {
+            const float* rbp = p.rowbias + (int64_t)cur.rgu * p.N + cur.n0 + c0;
+            const float4 r0 = __ldg(reinterpret_cast<const float4*>(rbp)), r1 = __ldg(reinterpret_cast<const float4*>(rbp + 4));
+            pf.b0.x += r0.x; pf.b0.y += r0.y; pf.b0.z += r0.z; pf.b0.w += r0.w;
+            pf.b1.x += r1.x; pf.b1.y += r1.y; pf.b1.z += r1.z; pf.b1.w += r1.w;
+          }
+        } else {                                           // rare: rows straddle two groups - fold alpha and the row bias into the staged tile
+#pragma unroll
+          for (int ps = 0; ps < 4; ++ps) {
+            if (!(((cur.ok >> ps) & 1u) && col_ok)) continue;
+            const uint32_t pix = (uint32_t)((((uint64_t)cur.oo[ps] << 3) - (uint32_t)(cur.n0 + q * 8)) / (uint64_t)p.ldo);
+            const float* rbp = p.rowbias + (int64_t)(pix / (uint32_t)p.rows_per_group) * p.N + cur.n0 + c0;
+            const float4 r0 = __ldg(reinterpret_cast<const float4*>(rbp)), r1 = __ldg(reinterpret_cast<const float4*>(rbp + 4));
+            float4* s0 = reinterpret_cast<float4*>(const_cast<uint8_t*>(prow) + ps * 1024 + px0);
+            float4* s1 = reinterpret_cast<float4*>(const_cast<uint8_t*>(prow) + ps * 1024 + px1);
+            float4 x0 = *s0, x1 = *s1;
+            x0.x = fmaf(x0.x, alpha, r0.x); x0.y = fmaf(x0.y, alpha, r0.y); x0.z = fmaf(x0.z, alpha, r0.z); x0.w = fmaf(x0.w, alpha, r0.w);
+            x1.x = fmaf(x1.x, alpha, r1.x); x1.y = fmaf(x1.y, alpha, r1.y); x1.z = fmaf(x1.z, alpha, r1.z); x1.w = fmaf(x1.w, alpha, r1.w);
+            *s0 = x0; *s1 = x1;
+          }
+          a_eff = 1.0f;
+        }
+      }
+      float4 xs[4][2];
 #pragma unroll
       for (int ps = 0; ps < 4; ++ps) {
-        const int rl = ps * 8 + rip;
-        const uint8_t* sr = stage + rl * 128;
-        const float4 x0 = *reinterpret_cast<const float4*>(sr + (((2 * q) ^ (rl & 7)) << 4));
-        const float4 x1 = *reinterpret_cast<const float4*>(sr + (((2 * q + 1) ^ (rl & 7)) << 4));
-        float v[8] = {x0.x + bias8[0], x0.y + bias8[1], x0.z + bias8[2], x0.w + bias8[3],
-                      x1.x + bias8[4], x1.y + bias8[5], x1.z + bias8[6], x1.w + bias8[7]};
-        const bool ok = ((cur.ok >> ps) & 1u) && col_ok;
-        if ((p.flags & FYC_EPI_ROWBIAS) && cur.rgu < 0 && ok) {          // rare: the warp's rows straddle two row-bias groups
-          const float* rbp = p.rowbias + (int64_t)((uint32_t)cur.pix[ps] / (uint32_t)p.rows_per_group) * p.N + cur.n0 + c0;
-          const float4 r0 = __ldg(reinterpret_cast<const float4*>(rbp)), r1 = __ldg(reinterpret_cast<const float4*>(rbp + 4));
-          v[0] += r0.x; v[1] += r0.y; v[2] += r0.z; v[3] += r0.w; v[4] += r1.x; v[5] += r1.y; v[6] += r1.z; v[7] += r1.w;
-        }
-        if (p.flags & FYC_EPI_RESIDUAL) {
-          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&pf.res[ps]);
+        xs[ps][0] = *reinterpret_cast<const float4*>(prow + ps * 1024 + px0);
+        xs[ps][1] = *reinterpret_cast<const float4*>(prow + ps * 1024 + px1);
+      }
 #pragma unroll
-          for (int i = 0; i < 4; ++i) { float2 t = __bfloat1622float2(h[i]); v[2 * i] += t.x; v[2 * i + 1] += t.y; }
+      for (int ps = 0; ps < 4; ++ps) {
+        const float4 x0 = xs[ps][0], x1 = xs[ps][1];
+        float v[8] = {fmaf(x0.x, a_eff, pf.b0.x), fmaf(x0.y, a_eff, pf.b0.y), fmaf(x0.z, a_eff, pf.b0.z), fmaf(x0.w, a_eff, pf.b0.w),
+                      fmaf(x1.x, a_eff, pf.b1.x), fmaf(x1.y, a_eff, pf.b1.y), fmaf(x1.z, a_eff, pf.b1.z), fmaf(x1.w, a_eff, pf.b1.w)};
+        if (p.flags & FYC_EPI_RESIDUAL) {
+          const uint32_t u[4] = {pf.res[ps].x, pf.res[ps].y, pf.res[ps].z, pf.res[ps].w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) { v[2 * i] += __uint_as_float(u[i] << 16); v[2 * i + 1] += __uint_as_float(u[i] & 0xffff0000u); }
         }
-        if (ok) Vec8<bf16>::store(reinterpret_cast<bf16*>(p.out) + (int64_t)cur.pix[ps] * p.ldo + cur.n0 + c0, v);
+        if (((cur.ok >> ps) & 1u) && col_ok) {
+          uint4 o;
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]), h1 = __floats2bfloat162_rn(v[2], v[3]);
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(v[4], v[5]), h3 = __floats2bfloat162_rn(v[6], v[7]);
+          o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
+          o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
+          obase[cur.oo[ps] + g4] = o;
+        }
       }
       __syncwarp();
       pf = pn;
     }
     tcgen05_fence_before();
     mbar_arrive(&tempty[acc]);
-    dbg_epi += clock64() - te1;
+    if (p.debug) dbg_epi += clock64() - te1;
     if (++acc == 2) { acc = 0; aphase ^= 1; }
     cur = nxt;
     eg ^= 1;
@@ -304,18 +369,106 @@ __device__ __forceinline__ void epilogue_plain(const TcParams& p, uint8_t* stage
   if (p.debug && lane == 0 && (warp == 2 || warp == 6)) p.debug[blockIdx.x * 8 + 5 + (warp == 6)] = dbg_epi;
 }
 
+// ---------------------------------------------------------------------------------------------- GEGLU epilogue
+// Columns [0,128) of the tile are `a`, [128,256) the matching `gate` (weight rows pre-interleaved per 128 outputs).
+// Thread = row for the math (bias + a * gelu(gate) in fp32, one bf16 rounding), 32 `a` + 32 gate columns per TMEM round
+// trip; the bf16 results go through a 32 x 64 staging tile so that global stores cover full 128-byte row segments.
+// The 256 bias values of a tile are fetched one tile ahead (one register per epilogue thread), parked in shared memory
+// and read back as broadcast LDS.128 - as global loads at their point of use they were an L2 round trip per chunk.
+__device__ __forceinline__ void epilogue_geglu(const TcParams& p, uint8_t* stage, float* sbias, uint64_t* tfull, uint64_t* tempty,
+                                               uint32_t tmem_base, int warp, int lane, int64_t num_tiles) {
+  const int quarter = warp & 3, egroup = (warp - 2) >> 2;
+  const int r = quarter * 32 + lane;
+  const int wl = r % p.bw, hl = (r / p.bw) % p.bh, il = r / (p.bw * p.bh);
+  const int et = (warp - 2) * 32 + lane;                 // 0..255: the bias element this thread carries
+  const int sub = lane >> 3, ch8 = lane & 7;
+  const int c0 = egroup * 64;                            // this warp's 64 output columns of the tile
+  uint8_t* const srow = stage + lane * 128;
+  uint4* const obase = reinterpret_cast<uint4*>(p.out);
+  const uint32_t ldo8 = (uint32_t)(p.ldo >> 3);
+  long long dbg_epi = 0;
+  int acc = 0; uint32_t aphase = 0;
+  int64_t tile = blockIdx.x;
+  float bnext = 0.f;
+  TileCoord tc = tile_coord(p, (uint32_t)tile);
+  if (tile < num_tiles) bnext = __ldg(p.bias + tc.n * 256 + et);
+  for (; tile < num_tiles; tile += gridDim.x) {
+    const int n_blk = tc.n;
+    const int ow = tc.w * p.bw + wl, oh = tc.h * p.bh + hl, img = tc.i * p.bn + il;
+    const int64_t pix = ((int64_t)img * p.Ho + oh) * p.Wo + ow;
+    const bool row_ok = (ow < p.Wo) && (oh < p.Ho) && (pix < p.M);
+    const uint32_t rowoff = row_ok ? (uint32_t)pix * ldo8 : 0u;
+    const uint32_t okmask = __ballot_sync(0xffffffffu, row_ok);
+    float* const sb = sbias + acc * 256;
+    sb[et] = bnext;
+    const int64_t next_tile = tile + gridDim.x;
+    tile_advance(p, tc);                                   // tc now describes next_tile; n_blk / ow / oh / img above are this tile's
+    if (next_tile < num_tiles) bnext = __ldg(p.bias + tc.n * 256 + et);
+    asm volatile("bar.sync 1, 256;" ::: "memory");       // the 8 epilogue warps: bias of this tile visible, previous reads done
+    mbar_wait(&tfull[acc], aphase);
+    const long long te1 = p.debug ? clock64() : 0;
+    tcgen05_fence_after();
+    const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * MAX_BN;
+#pragma unroll
+    for (int hh = 0; hh < 2; ++hh) {
+      uint32_t ar[32], gr[32];
+      tmem_ld32(taddr + c0 + hh * 32, ar);
+      tmem_ld32(taddr + 128 + c0 + hh * 32, gr);
+      tmem_ld_wait32(ar);
+      tmem_ld_wait32(gr);
+      const float* ba_p = sb + c0 + hh * 32;                // packed (interleaved) bias of the `a` columns; gate = +128
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {                          // 8 output columns = one 16-byte chunk of bf16
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; i += 4) {
+          const float4 ba = *reinterpret_cast<const float4*>(ba_p + c * 8 + i);
+          const float4 bg = *reinterpret_cast<const float4*>(ba_p + 128 + c * 8 + i);
+          const float av[4] = {ba.x, ba.y, ba.z, ba.w}, gv[4] = {bg.x, bg.y, bg.z, bg.w};
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            o[i + e] = (__uint_as_float(ar[c * 8 + i + e]) + av[e]) * gelu_erf_fast(__uint_as_float(gr[c * 8 + i + e]) + gv[e]);
+        }
+        Vec8<bf16>::store(reinterpret_cast<bf16*>(srow + (((hh * 4 + c) ^ (lane & 7)) << 4)), o);
+      }
+    }
+    __syncwarp();
+    const uint32_t ncol8 = (uint32_t)(n_blk * 128 + c0 + ch8 * 8) >> 3;
+    const bool col_ok = (int)(n_blk * 128) + c0 + ch8 * 8 < p.N_out;
+#pragma unroll
+    for (int itp = 0; itp < 8; ++itp) {
+      const int rl = itp * 4 + sub;
+      const uint32_t pl = __shfl_sync(0xffffffffu, rowoff, rl);
+      if (((okmask >> rl) & 1u) && col_ok)
+        obase[pl + ncol8] = *reinterpret_cast<const uint4*>(stage + rl * 128 + ((ch8 ^ (rl & 7)) << 4));
+    }
+    __syncwarp();
+    tcgen05_fence_before();
+    mbar_arrive(&tempty[acc]);
+    if (p.debug) dbg_epi += clock64() - te1;
+    if (++acc == 2) { acc = 0; aphase ^= 1; }
+  }
+  if (p.debug && lane == 0 && (warp == 2 || warp == 6)) p.debug[blockIdx.x * 8 + 5 + (warp == 6)] = dbg_epi;
+}
+
 // ---------------------------------------------------------------------------------------------- kernel
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const TcParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw = smem_u32(smem_raw);
-  uint8_t* smem = smem_raw + ((1024 - (raw & 1023)) & 1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);     // 256 B reserved; staging follows
-  uint64_t* full = bars;                  // [STAGES]
-  uint64_t* empty = bars + STAGES;        // [STAGES]
-  uint64_t* tfull = bars + 2 * STAGES;    // [2]
-  uint64_t* tempty = bars + 2 * STAGES + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if (smem_u32(smem) & 1023u) __trap();   // SWIZZLE_128B operands need 1024-byte alignment
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + RING_BYTES);     // 256 B reserved; staging follows
+  uint64_t* full = bars;                       // [MAX_STAGES]
+  uint64_t* empty = bars + MAX_STAGES;         // [MAX_STAGES]
+  uint64_t* tfull = bars + 2 * MAX_STAGES;     // [2]
+  uint64_t* tempty = bars + 2 * MAX_STAGES + 2;
+  uint64_t* wbar = bars + 2 * MAX_STAGES + 4;  // W-resident mode: the weight slab has landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 5);
+  // operand ring: [A 16 KB | W 32 KB] x 4 stages, or (resident) [W slab k_iters x BN x 128 B][A 16 KB x a_stages]
+  const int nstages = p.resident ? p.a_stages : STAGES;
+  const uint32_t slab_kb = (uint32_t)p.BN * (BK * 2);
+  const uint32_t a_base = p.resident ? (uint32_t)(p.taps * p.cin_blocks) * slab_kb : 0u;
+  const uint32_t a_stride = p.resident ? (uint32_t)A_BYTES : (uint32_t)STAGE_BYTES;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t num_tiles = p.m_tiles * p.n_tiles;
@@ -326,8 +479,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 256); }
+    mbar_init(wbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {   // TMEM: all 512 columns (2 accumulator stages x 256); this warp also frees them
@@ -343,8 +497,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ================================================================== TMA producer
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      long long dbg_wait = 0; const long long dbg_t0 = clock64();
-      const uint32_t tx_bytes = A_BYTES + (uint32_t)p.BN * BK * 2;
+      const uint32_t tx_bytes = p.resident ? (uint32_t)A_BYTES : A_BYTES + slab_kb;
+      if (p.resident) {   // grid % n_tiles == 0, so this CTA's n block never changes: load its weight slab once
+        const int n_blk = (int)(blockIdx.x % p.n_tiles);
+        mbar_expect_tx(wbar, (uint32_t)k_iters * slab_kb);
+        for (int k = 0; k < k_iters; ++k)
+          tma_load_3d(&map_w, wbar, smem + (uint32_t)k * slab_kb, (k % p.cin_blocks) * BK, k / p.cin_blocks, n_blk * p.BN);
+      }
       for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int n_blk = (int)(tile % p.n_tiles);
         const int64_t m_blk = tile / p.n_tiles;
@@ -354,18 +513,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int ow0 = wt * p.bw, oh0 = ht * p.bh, img0 = it * p.bn;
         for (int tap = 0; tap < p.taps; ++tap) {
           for (int cb = 0; cb < p.cin_blocks; ++cb) {
-            const long long tw0 = clock64();
             mbar_wait(&empty[stage], phase ^ 1);
-            dbg_wait += clock64() - tw0;
-            uint8_t* sa = smem + stage * STAGE_BYTES;
+            uint8_t* sa = smem + a_base + (uint32_t)stage * a_stride;
             mbar_expect_tx(&full[stage], tx_bytes);
             tma_load_4d(&map_a, &full[stage], sa, cb * BK, ow0 + p.tap_dx[tap], oh0 + p.tap_dy[tap], img0 + p.tap_img[tap]);
-            tma_load_3d(&map_w, &full[stage], sa + A_BYTES, cb * BK, tap, n_blk * p.BN);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            if (!p.resident) tma_load_3d(&map_w, &full[stage], sa + A_BYTES, cb * BK, tap, n_blk * p.BN);
+            if (++stage == nstages) { stage = 0; phase ^= 1; }
           }
         }
       }
-      (void)dbg_wait; (void)dbg_t0;
     }
   } else if (warp == 1) {
     // ================================================================== MMA issuer
@@ -375,6 +531,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t aphase = 0;
       long long dbg_wfull = 0, dbg_wtempty = 0; const long long dbg_t0 = clock64();
+      if (p.resident) mbar_wait(wbar, 0);
       for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         long long tw0 = clock64();
         mbar_wait(&tempty[acc], aphase ^ 1);
@@ -386,9 +543,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           mbar_wait(&full[stage], phase);
           dbg_wfull += clock64() - tw0;
           tcgen05_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint32_t sa = smem_u32(smem + a_base + (uint32_t)stage * a_stride);
           const uint64_t a_desc = make_sw128_desc(sa);
-          const uint64_t b_desc = make_sw128_desc(sa + A_BYTES);
+          const uint64_t b_desc = make_sw128_desc(p.resident ? smem_u32(smem) + (uint32_t)k * slab_kb : sa + A_BYTES);
 #pragma unroll
           for (int kk = 0; kk < BK / 16; ++kk) {
             // advance 16 elements (32 B) along K inside the 128B swizzle atom: +2 in the (addr >> 4) field
@@ -396,7 +553,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
           tcgen05_commit(&empty[stage]);                     // frees the smem stage when these MMAs retire
           if (k == k_iters - 1) tcgen05_commit(&tfull[acc]); // accumulator complete
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
         if (++acc == 2) { acc = 0; aphase ^= 1; }
       }
@@ -412,7 +569,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     int acc = 0; uint32_t aphase = 0;
     const bool geglu = (p.flags & FYC_EPI_GEGLU) != 0;
     const bool out_f32 = (p.flags & FYC_EPI_OUT_F32) != 0;
-    if (!geglu && !out_f32) epilogue_plain(p, stage, tfull, tempty, tmem_base, warp, lane, num_tiles);
+    if (geglu) epilogue_geglu(p, stage, reinterpret_cast<float*>(smem + OFF_BIAS), tfull, tempty, tmem_base, warp, lane, num_tiles);
+    else if (!out_f32) epilogue_plain(p, stage, tfull, tempty, tmem_base, warp, lane, num_tiles);
     else for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int n_blk = (int)(tile % p.n_tiles);
       const int64_t m_blk = tile / p.n_tiles;
@@ -467,56 +625,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             Vec8<float>::store(o, v); Vec8<float>::store(o + 8, v + 8);
           }
         }
-      } else {
-        // GEGLU: columns [0,128) of the tile are `a`, [128,256) the matching `gate` (weight rows pre-interleaved).  Thread = row
-        // for the math (bias + a * gelu(gate) in fp32, one bf16 rounding), 32 `a` + 32 gate columns per TMEM round trip; the
-        // bf16 results go through a 32 x 64 staging tile so that global stores cover full 128-byte row segments.
-        const uint32_t okmask = __ballot_sync(0xffffffffu, row_ok);
-        const int sub = lane >> 3, ch8 = lane & 7;
-        const int c0 = egroup * 64;                            // this warp's 64 output columns of the tile
-        uint8_t* srow = stage + lane * 128;
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          uint32_t ar[32], gr[32];
-          tmem_ld32(taddr + c0 + hh * 32, ar);
-          tmem_ld32(taddr + 128 + c0 + hh * 32, gr);
-          tmem_ld_wait32(ar);
-          tmem_ld_wait32(gr);
-          const int nb = n0 + c0 + hh * 32;                    // packed (interleaved) bias index of the `a` columns
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {                        // 8 output columns = one 16-byte chunk of bf16
-            float o[8];
-#pragma unroll
-            for (int i = 0; i < 8; i += 4) {
-              float4 ba = __ldg(reinterpret_cast<const float4*>(p.bias + nb + c * 8 + i));
-              float4 bg = __ldg(reinterpret_cast<const float4*>(p.bias + nb + 128 + c * 8 + i));
-              const float av[4] = {ba.x, ba.y, ba.z, ba.w}, gv[4] = {bg.x, bg.y, bg.z, bg.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e)
-                o[i + e] = (__uint_as_float(ar[c * 8 + i + e]) + av[e]) * gelu_erf_fast(__uint_as_float(gr[c * 8 + i + e]) + gv[e]);
-            }
-            Vec8<bf16>::store(reinterpret_cast<bf16*>(srow + (((hh * 4 + c) ^ (lane & 7)) << 4)), o);
-          }
-        }
-        __syncwarp();
-#pragma unroll
-        for (int itp = 0; itp < 8; ++itp) {
-          const int rl = itp * 4 + sub;
-          const int64_t pl = __shfl_sync(0xffffffffu, pix, rl);
-          const int n = n_blk * 128 + c0 + ch8 * 8;
-          if (((okmask >> rl) & 1u) && n < p.N_out) {
-            uint4 u = *reinterpret_cast<const uint4*>(stage + rl * 128 + ((ch8 ^ (rl & 7)) << 4));
-            *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + pl * p.ldo + n) = u;
-          }
-        }
-        __syncwarp();
       }
       tcgen05_fence_before();
       mbar_arrive(&tempty[acc]);
       dbg_epi += clock64() - te1;
       if (++acc == 2) { acc = 0; aphase ^= 1; }
     }
-    if (p.debug && (geglu || out_f32) && lane == 0 && (warp == 2 || warp == 6)) p.debug[blockIdx.x * 8 + 5 + (warp == 6)] = dbg_epi;
+    if (p.debug && out_f32 && lane == 0 && (warp == 2 || warp == 6)) p.debug[blockIdx.x * 8 + 5 + (warp == 6)] = dbg_epi;
   }
   __syncwarp();
   tcgen05_fence_before();
@@ -586,9 +701,56 @@ int pick_bn(int64_t N, bool geglu) {
   return 256;                           // ragged last tile (guarded stores)
 }
 
+// Tile width, operand-staging mode and grid for one launch.
+//  * default: the largest BN <= 256 dividing N (fewest re-reads of the A tiles through L2);
+//  * few rounds of tiles per SM (small M): BN that minimises rounds x (BN + fixed cost) - a 2.2-round launch at BN = 256 runs as
+//    3 full rounds, the same problem at BN = 144 as 4 rounds of 56 % the length (ragged last N tile is zero-filled by TMA and
+//    guarded in the epilogue);
+//  * small K (k_iters x BN x 128 B <= 128 KB) and many tiles per CTA: W-resident - the grid is rounded down to a multiple of
+//    n_tiles so a CTA's n block is fixed, its weight slab is loaded once, and the ring streams only A (L2 -> SM traffic per tile
+//    drops from (128 + BN) x K to 128 x K elements; the K = 320 GEMMs were bound by it).
+void choose_tiles(TcParams& p, int* grid_out) {
+  const int sms = fyc_sm_count();
+  const bool geglu = (p.flags & FYC_EPI_GEGLU) != 0;
+  const int k_iters = p.taps * p.cin_blocks;
+  p.resident = 0; p.a_stages = STAGES;
+  p.BN = pick_bn(p.N, geglu);
+  p.n_tiles = (int)ceil_div64(p.N, p.BN);
+  int64_t tiles = p.m_tiles * p.n_tiles;
+  if (!geglu) {
+    // W-resident candidate
+    int rbn = 0;
+    for (int bn = 256; bn >= 128; bn -= 16)
+      if (p.N % bn == 0 && (int64_t)k_iters * bn * 128 <= RING_BYTES - 4 * A_BYTES) { rbn = bn; break; }
+    if (rbn) {
+      const int nt = p.N / rbn;
+      const int grid = (sms / nt) * nt;
+      if (nt <= sms && grid * 16 >= sms * 15 && p.m_tiles * nt >= (int64_t)grid * 4) {
+        p.resident = 1; p.BN = rbn; p.n_tiles = nt;
+        int st = (int)((RING_BYTES - (int64_t)k_iters * rbn * 128) / A_BYTES);
+        p.a_stages = st > MAX_STAGES ? MAX_STAGES : st;
+        *grid_out = grid;
+        return;
+      }
+    }
+    const int64_t rounds0 = ceil_div64(tiles, sms);
+    if (rounds0 < 8) {
+      int64_t best = rounds0 * (p.BN + 32);
+      for (int bn = 256; bn >= 64; bn -= 16) {
+        if (bn > p.N) continue;
+        const int64_t nt = ceil_div64(p.N, bn);
+        const int64_t cost = ceil_div64(p.m_tiles * nt, sms) * (bn + 32) ;
+        if (cost < best) { best = cost; p.BN = bn; p.n_tiles = (int)nt; }
+      }
+      tiles = p.m_tiles * p.n_tiles;
+    }
+  }
+  *grid_out = (int)(tiles < sms ? tiles : sms);
+}
+
 long long* g_tc_debug = nullptr;
 
-int32_t launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, TcParams p, cudaStream_t st) {
+int32_t launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, TcParams p, int grid, cudaStream_t st) {
   p.debug = g_tc_debug;
   static bool attr_set = false;
   if (!attr_set) {
@@ -597,7 +759,16 @@ int32_t launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, TcParams p, cuda
   }
   int64_t tiles = p.m_tiles * p.n_tiles;
   FYC_CHECK(tiles < (1ll << 31) && p.M < (1ll << 31) && p.rows_per_group < (1ll << 31), "tcgen05 GEMM: problem exceeds the 32-bit tile index range");
-  int grid = (int)(tiles < fyc_sm_count() ? tiles : fyc_sm_count());
+  FYC_CHECK(p.M * (p.ldo / 8) + p.ldo / 8 < (1ll << 32) && p.M * (p.ldr / 8) + p.ldr / 8 < (1ll << 32),
+            "tcgen05 GEMM: output larger than 64 GB is not addressable by the epilogue");
+  if (grid > tiles) grid = (int)tiles;
+  {
+    int64_t g = grid;
+    p.dg_n = (int)(g % p.n_tiles); g /= p.n_tiles;
+    p.dg_w = (int)(g % p.w_tiles); g /= p.w_tiles;
+    p.dg_h = (int)(g % p.h_tiles); g /= p.h_tiles;
+    p.dg_i = (int)g;
+  }
   gemm_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mw, p);
   FYC_LAUNCH_CHECK();
   return FYC_OK;
@@ -645,9 +816,11 @@ int32_t fyc_gemm_tc(const fyc_gemm_args* g, cudaStream_t st) {
     TcParams p{};
     p.M = g->M; p.N = (int)g->N; p.N_out = geglu ? (int)g->N / 2 : (int)g->N;
     p.taps = 1; p.cin_blocks = (int)ceil_div64(g->K, BK);
-    p.BN = pick_bn(g->N, geglu); p.n_tiles = (int)ceil_div64(g->N, p.BN);
     p.bw = BM; p.bh = 1; p.bn = 1; p.Wo = (int)g->M; p.Ho = 1;
     p.w_tiles = (int)ceil_div64(g->M, BM); p.h_tiles = 1; p.m_tiles = p.w_tiles;
+    p.flags = g->epilogue;
+    int grid = 0;
+    choose_tiles(p, &grid);
     p.tap_dy[0] = p.tap_dx[0] = p.tap_img[0] = 0;
     {
       uint64_t dims[3] = {(uint64_t)g->K, 1, (uint64_t)g->N};
@@ -661,7 +834,7 @@ int32_t fyc_gemm_tc(const fyc_gemm_args* g, cudaStream_t st) {
     p.residual = g->residual ? (f32 ? (const void*)((const float*)g->residual + b * g->strideO) : (const void*)((const bf16*)g->residual + b * g->strideO)) : nullptr;
     p.out = f32 ? (void*)((float*)g->out + b * g->strideO) : (void*)((bf16*)g->out + b * g->strideO);
     p.ldo = g->ldo; p.ldr = g->ldr; p.alpha = g->alpha; p.flags = g->epilogue;
-    int32_t rc = launch_tc(ma, mw, p, st);
+    int32_t rc = launch_tc(ma, mw, p, grid, st);
     if (rc) return rc;
   }
   return FYC_OK;
@@ -700,9 +873,11 @@ int32_t fyc_conv3x3_tc(const fyc_conv3x3_args* c, const void* x_planes, cudaStre
   pick_patch(c->NB, Ho, Wo, &p.bw, &p.bh, &p.bn);
   p.M = c->NB * Ho * Wo; p.N = (int)c->Cout; p.N_out = p.N;
   p.taps = 9; p.cin_blocks = (int)ceil_div64(c->Cin, BK);
-  p.BN = pick_bn(c->Cout, false); p.n_tiles = (int)ceil_div64(c->Cout, p.BN);
   p.Wo = (int)Wo; p.Ho = (int)Ho; p.w_tiles = (int)(Wo / p.bw); p.h_tiles = (int)(Ho / p.bh);
   p.m_tiles = (int64_t)p.w_tiles * p.h_tiles * (c->NB / p.bn);
+  p.flags = c->epilogue;
+  int grid = 0;
+  choose_tiles(p, &grid);
   CUtensorMap ma, mw;
   const void* xa = c->x;
   uint64_t imgs = (uint64_t)c->NB;
@@ -734,7 +909,7 @@ int32_t fyc_conv3x3_tc(const fyc_conv3x3_args* c, const void* x_planes, cudaStre
   p.rows_per_group = (c->images_per_group > 0 ? c->images_per_group : 1) * Ho * Wo;
   p.ldo = c->Cout; p.ldr = c->Cout; p.alpha = 1.0f; p.flags = c->epilogue;
   (void)f32;
-  return launch_tc(ma, mw, p, st);
+  return launch_tc(ma, mw, p, grid, st);
 }
 
 int32_t fyc_space_to_planes(const void* x, void* out, int64_t NB, int64_t H, int64_t W, int64_t C, cudaStream_t st) {

@@ -6,7 +6,9 @@ from followyourclick_b200 import ops, _lib
 lib = _lib.lib()
 lib.fyc_debug_tc_counters.argtypes = [ctypes.c_void_p]
 dbg = torch.zeros(148 * 8, dtype=torch.int64, device="cuda")
-for (M, N, K, res, geglu) in [(131072, 320, 320, False, False), (131072, 320, 320, True, False), (131072, 2560, 320, False, True), (32768, 640, 640, True, False), (8192, 10240, 1280, False, True)]:
+SHAPES = [(131072, 320, 320, False, False), (131072, 320, 320, True, False), (131072, 2560, 320, False, True), (32768, 640, 640, True, False), (8192, 10240, 1280, False, True)]
+if os.environ.get('SHAPE'): SHAPES = [SHAPES[int(os.environ['SHAPE'])]]
+for (M, N, K, res, geglu) in SHAPES:
     A = torch.randn(M, K, device="cuda").bfloat16(); W = (torch.randn(N, K, device="cuda") * K ** -0.5).bfloat16()
     bias = torch.randn(N, device="cuda"); R = torch.randn(M, N, device="cuda").bfloat16() if res else None
     for _ in range(3): ops.gemm(A, W, bias=bias, residual=R, geglu=geglu)
