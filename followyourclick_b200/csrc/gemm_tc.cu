@@ -52,6 +52,9 @@ struct TcParams {
   int flags;
   // W-resident mode (small K): the CTA keeps its whole BN x K weight slab in shared memory and only streams A
   int resident, a_stages;
+  // CTA-pair mode (tcgen05 cta_group::2): a cluster of two CTAs computes a 256 x BN tile; each CTA stages its own 128 rows of A
+  // and HALF of the weight tile, the leader issues M = 256 MMAs that read both halves, each CTA drains its own 128 TMEM lanes
+  int pair;
   // gridDim.x as mixed-radix digits (n, w, h, image tiles): tile coordinates advance by addition, not by four divisions per tile
   int dg_n, dg_w, dg_h, dg_i;
   long long* debug;          // optional [gridDim.x][8] cycle counters (FYC_TC_DEBUG diagnostics), else nullptr
@@ -97,6 +100,48 @@ __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fe
 __device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// --- CTA-pair (cta_group::2) variants.  A CTA's 32-bit shared address carries its cluster rank in bit 24; clearing it names the
+// same offset in the leader (rank 0) CTA (cute::Sm100MmaPeerBitMask).
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_MASK) : "memory");
+}
+__device__ __forceinline__ void tma2_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & PEER_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & PEER_MASK), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+// arrives on the barrier at this offset in BOTH CTAs of the pair once the leader's earlier MMAs have retired
+__device__ __forceinline__ void tcgen05_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// epilogue warp -> MMA issuer: this warp has drained its part of the accumulator (8 arrivals per CTA)
+template <int PAIR>
+__device__ __forceinline__ void epi_release(uint64_t* tempty_bar, int lane) {
+  tcgen05_fence_before();
+  __syncwarp();
+  if (lane == 0) { if (PAIR) mbar_arrive_leader(tempty_bar); else mbar_arrive(tempty_bar); }
+}
+
 // D[tmem] (+)= A[smem] * B[smem]^T   (both operands K-major, 128B swizzle)
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -150,19 +195,37 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
 }
 
 // ---------------------------------------------------------------------------------------------- tile coordinates
-struct TileCoord { int n, w, h, i; };   // n block; patch column / row / image-group of the 128-pixel m block
-__device__ __forceinline__ TileCoord tile_coord(const TcParams& p, uint32_t tile) {
+// A CTA (or CTA pair) walks tiles t0, t0 + stride, ... < num.  Plain: tile = m_blk * n_tiles + n_blk.  Pair: the cluster's tile names
+// (pair of m blocks, n block) and CTA `rank` owns m block 2 * pm + rank (a phantom block past the end is zero-filled by TMA and never
+// stored).
+struct TileSched { int64_t t0, stride, num; int rank; };
+struct TileCoord { int64_t t; int n, w, h, i; };   // linear index; n block; patch column / row / image-group of the 128-pixel m block
+template <int PAIR>
+__device__ __forceinline__ TileSched tile_sched(const TcParams& p) {
+  TileSched s;
+  if (PAIR) {
+    uint32_t r; asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    s.rank = (int)r; s.t0 = blockIdx.x >> 1; s.stride = gridDim.x >> 1; s.num = ((p.m_tiles + 1) >> 1) * p.n_tiles;
+  } else { s.rank = 0; s.t0 = blockIdx.x; s.stride = gridDim.x; s.num = p.m_tiles * p.n_tiles; }
+  return s;
+}
+__device__ __forceinline__ TileCoord tile_coord(const TcParams& p, const TileSched& ts, int64_t t) {
   TileCoord c;
+  c.t = t;
+  const uint32_t tile = (uint32_t)t;
   c.n = (int)(tile % (uint32_t)p.n_tiles);
-  const uint32_t m_blk = tile / (uint32_t)p.n_tiles;
+  uint32_t m_blk = tile / (uint32_t)p.n_tiles;
+  if (p.pair) m_blk = 2u * m_blk + (uint32_t)ts.rank;
   c.w = (int)(m_blk % (uint32_t)p.w_tiles);
   const uint32_t m2 = m_blk / (uint32_t)p.w_tiles;
   c.h = (int)(m2 % (uint32_t)p.h_tiles);
   c.i = (int)(m2 / (uint32_t)p.h_tiles);
   return c;
 }
-// tile += gridDim.x
-__device__ __forceinline__ void tile_advance(const TcParams& p, TileCoord& c) {
+// t += stride
+__device__ __forceinline__ void tile_advance(const TcParams& p, const TileSched& ts, TileCoord& c) {
+  if (p.pair) { c = tile_coord(p, ts, c.t + ts.stride); return; }
+  c.t += ts.stride;
   c.n += p.dg_n; int cy = c.n >= p.n_tiles ? 1 : 0; c.n -= cy ? p.n_tiles : 0;
   c.w += p.dg_w + cy; cy = c.w >= p.w_tiles ? 1 : 0; c.w -= cy ? p.w_tiles : 0;
   c.h += p.dg_h + cy; cy = c.h >= p.h_tiles ? 1 : 0; c.h -= cy ? p.h_tiles : 0;
@@ -235,8 +298,10 @@ __device__ __forceinline__ void epi_prefetch(const TcParams& p, const EpiRows& t
   }
 }
 
-__device__ __forceinline__ void epilogue_plain(const TcParams& p, uint8_t* stage, uint64_t* tfull, uint64_t* tempty, uint32_t tmem_base,
-                                               int warp, int lane, int64_t num_tiles) {
+template <int PAIR>
+__device__ __forceinline__ void epilogue_plain(const TcParams& p, const TileSched& ts, uint8_t* stage, uint64_t* tfull, uint64_t* tempty,
+                                               uint32_t tmem_base, int warp, int lane) {
+  const int64_t num_tiles = ts.num;
   const int quarter = warp & 3, egroup = (warp - 2) >> 2;
   const int rip = lane >> 2, q = lane & 3;
   const int NG = (p.BN + 31) >> 5;
@@ -258,17 +323,17 @@ __device__ __forceinline__ void epilogue_plain(const TcParams& p, uint8_t* stage
   int eg = egroup;                                  // the column half alternates per tile: NG is odd for N = 320 (3 + 2 groups)
   EpiRows cur, nxt;
   EpiPrefetch pf;
-  int64_t tile = blockIdx.x;
-  TileCoord tcn = tile_coord(p, (uint32_t)tile);     // coordinates of the NEXT tile to be decoded
+  int64_t tile = ts.t0;
+  TileCoord tcn = tile_coord(p, ts, tile);           // coordinates of the NEXT tile to be decoded
   if (tile < num_tiles) { epi_rows(p, tcn, whi, q, cur); epi_prefetch(p, cur, eg, q, pf); }
   nxt = cur;
-  for (; tile < num_tiles; tile += gridDim.x) {
+  for (; tile < num_tiles; tile += ts.stride) {
     mbar_wait(&tfull[acc], aphase);
     const long long te1 = p.debug ? clock64() : 0;
     tcgen05_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * MAX_BN;
-    const int64_t next_tile = tile + gridDim.x;
-    tile_advance(p, tcn);
+    const int64_t next_tile = tile + ts.stride;
+    tile_advance(p, ts, tcn);
     if (next_tile < num_tiles) {
       epi_rows(p, tcn, whi, q, nxt);
       if (p.flags & FYC_EPI_RESIDUAL) {             // pull the next tile's residual rows into L2 a whole tile ahead: lane q takes its
@@ -359,8 +424,7 @@ __device__ __forceinline__ void epilogue_plain(const TcParams& p, uint8_t* stage
       __syncwarp();
       pf = pn;
     }
-    tcgen05_fence_before();
-    mbar_arrive(&tempty[acc]);
+    epi_release<PAIR>(&tempty[acc], lane);
     if (p.debug) dbg_epi += clock64() - te1;
     if (++acc == 2) { acc = 0; aphase ^= 1; }
     cur = nxt;
@@ -375,8 +439,10 @@ __device__ __forceinline__ void epilogue_plain(const TcParams& p, uint8_t* stage
 // trip; the bf16 results go through a 32 x 64 staging tile so that global stores cover full 128-byte row segments.
 // The 256 bias values of a tile are fetched one tile ahead (one register per epilogue thread), parked in shared memory
 // and read back as broadcast LDS.128 - as global loads at their point of use they were an L2 round trip per chunk.
-__device__ __forceinline__ void epilogue_geglu(const TcParams& p, uint8_t* stage, float* sbias, uint64_t* tfull, uint64_t* tempty,
-                                               uint32_t tmem_base, int warp, int lane, int64_t num_tiles) {
+template <int PAIR>
+__device__ __forceinline__ void epilogue_geglu(const TcParams& p, const TileSched& ts, uint8_t* stage, float* sbias, uint64_t* tfull,
+                                               uint64_t* tempty, uint32_t tmem_base, int warp, int lane) {
+  const int64_t num_tiles = ts.num;
   const int quarter = warp & 3, egroup = (warp - 2) >> 2;
   const int r = quarter * 32 + lane;
   const int wl = r % p.bw, hl = (r / p.bw) % p.bh, il = r / (p.bw * p.bh);
@@ -388,11 +454,11 @@ __device__ __forceinline__ void epilogue_geglu(const TcParams& p, uint8_t* stage
   const uint32_t ldo8 = (uint32_t)(p.ldo >> 3);
   long long dbg_epi = 0;
   int acc = 0; uint32_t aphase = 0;
-  int64_t tile = blockIdx.x;
+  int64_t tile = ts.t0;
   float bnext = 0.f;
-  TileCoord tc = tile_coord(p, (uint32_t)tile);
+  TileCoord tc = tile_coord(p, ts, tile);
   if (tile < num_tiles) bnext = __ldg(p.bias + tc.n * 256 + et);
-  for (; tile < num_tiles; tile += gridDim.x) {
+  for (; tile < num_tiles; tile += ts.stride) {
     const int n_blk = tc.n;
     const int ow = tc.w * p.bw + wl, oh = tc.h * p.bh + hl, img = tc.i * p.bn + il;
     const int64_t pix = ((int64_t)img * p.Ho + oh) * p.Wo + ow;
@@ -401,8 +467,8 @@ __device__ __forceinline__ void epilogue_geglu(const TcParams& p, uint8_t* stage
     const uint32_t okmask = __ballot_sync(0xffffffffu, row_ok);
     float* const sb = sbias + acc * 256;
     sb[et] = bnext;
-    const int64_t next_tile = tile + gridDim.x;
-    tile_advance(p, tc);                                   // tc now describes next_tile; n_blk / ow / oh / img above are this tile's
+    const int64_t next_tile = tile + ts.stride;
+    tile_advance(p, ts, tc);                               // tc now describes next_tile; n_blk / ow / oh / img above are this tile's
     if (next_tile < num_tiles) bnext = __ldg(p.bias + tc.n * 256 + et);
     asm volatile("bar.sync 1, 256;" ::: "memory");       // the 8 epilogue warps: bias of this tile visible, previous reads done
     mbar_wait(&tfull[acc], aphase);
@@ -442,9 +508,7 @@ __device__ __forceinline__ void epilogue_geglu(const TcParams& p, uint8_t* stage
       if (((okmask >> rl) & 1u) && col_ok)
         obase[pl + ncol8] = *reinterpret_cast<const uint4*>(stage + rl * 128 + ((ch8 ^ (rl & 7)) << 4));
     }
-    __syncwarp();
-    tcgen05_fence_before();
-    mbar_arrive(&tempty[acc]);
+    epi_release<PAIR>(&tempty[acc], lane);
     if (p.debug) dbg_epi += clock64() - te1;
     if (++acc == 2) { acc = 0; aphase ^= 1; }
   }
@@ -452,6 +516,7 @@ __device__ __forceinline__ void epilogue_geglu(const TcParams& p, uint8_t* stage
 }
 
 // ---------------------------------------------------------------------------------------------- kernel
+template <int PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -464,14 +529,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint64_t* tempty = bars + 2 * MAX_STAGES + 2;
   uint64_t* wbar = bars + 2 * MAX_STAGES + 4;  // W-resident mode: the weight slab has landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 5);
-  // operand ring: [A 16 KB | W 32 KB] x 4 stages, or (resident) [W slab k_iters x BN x 128 B][A 16 KB x a_stages]
-  const int nstages = p.resident ? p.a_stages : STAGES;
+  // operand ring, three layouts:
+  //   plain     [A 16 KB | W BN x 128 B (<= 32 KB)] x 4 stages
+  //   resident  [W slab k_iters x BN x 128 B][A 16 KB x a_stages]
+  //   pair      [A 16 KB | W half BN/2 x 128 B (<= 16 KB)] x 6 stages of 32 KB
+  constexpr int pair = PAIR;
+  const int nstages = p.resident ? p.a_stages : (pair ? 6 : STAGES);
   const uint32_t slab_kb = (uint32_t)p.BN * (BK * 2);
   const uint32_t a_base = p.resident ? (uint32_t)(p.taps * p.cin_blocks) * slab_kb : 0u;
-  const uint32_t a_stride = p.resident ? (uint32_t)A_BYTES : (uint32_t)STAGE_BYTES;
+  const uint32_t a_stride = p.resident ? (uint32_t)A_BYTES : (pair ? 2u * A_BYTES : (uint32_t)STAGE_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t num_tiles = p.m_tiles * p.n_tiles;
+  const TileSched ts = tile_sched<PAIR>(p);
   const int k_iters = p.taps * p.cin_blocks;
 
   if (warp == 0 && lane == 0) {
@@ -480,16 +549,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 256); }
+    // tmem-empty: one arrival per epilogue warp; in pair mode the leader's barrier collects both CTAs' 8 warps
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], pair ? 16 : 8); }
     mbar_init(wbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {   // TMEM: all 512 columns (2 accumulator stages x 256); this warp also frees them
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (pair) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tcgen05_fence_before();
   __syncthreads();
+  if (pair) cluster_sync_all();           // the peer's barriers must exist before anything is signalled across the pair
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -497,42 +573,46 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ================================================================== TMA producer
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      const uint32_t tx_bytes = p.resident ? (uint32_t)A_BYTES : A_BYTES + slab_kb;
+      // pair: the LEADER's full barrier counts both CTAs' bytes (2 x A + the two W halves); each CTA frees / refills its own stage
+      const uint32_t tx_bytes = p.resident ? (uint32_t)A_BYTES : (pair ? 2u * A_BYTES + slab_kb : A_BYTES + slab_kb);
       if (p.resident) {   // grid % n_tiles == 0, so this CTA's n block never changes: load its weight slab once
         const int n_blk = (int)(blockIdx.x % p.n_tiles);
         mbar_expect_tx(wbar, (uint32_t)k_iters * slab_kb);
         for (int k = 0; k < k_iters; ++k)
           tma_load_3d(&map_w, wbar, smem + (uint32_t)k * slab_kb, (k % p.cin_blocks) * BK, k / p.cin_blocks, n_blk * p.BN);
       }
-      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int n_blk = (int)(tile % p.n_tiles);
-        const int64_t m_blk = tile / p.n_tiles;
-        const int wt = (int)(m_blk % p.w_tiles);
-        const int ht = (int)((m_blk / p.w_tiles) % p.h_tiles);
-        const int it = (int)(m_blk / ((int64_t)p.w_tiles * p.h_tiles));
-        const int ow0 = wt * p.bw, oh0 = ht * p.bh, img0 = it * p.bn;
+      for (int64_t tile = ts.t0; tile < ts.num; tile += ts.stride) {
+        const TileCoord tc = tile_coord(p, ts, tile);
+        const int ow0 = tc.w * p.bw, oh0 = tc.h * p.bh, img0 = tc.i * p.bn;
+        const int wrow0 = tc.n * p.BN + (pair ? ts.rank * (p.BN >> 1) : 0);
         for (int tap = 0; tap < p.taps; ++tap) {
           for (int cb = 0; cb < p.cin_blocks; ++cb) {
             mbar_wait(&empty[stage], phase ^ 1);
             uint8_t* sa = smem + a_base + (uint32_t)stage * a_stride;
-            mbar_expect_tx(&full[stage], tx_bytes);
-            tma_load_4d(&map_a, &full[stage], sa, cb * BK, ow0 + p.tap_dx[tap], oh0 + p.tap_dy[tap], img0 + p.tap_img[tap]);
-            if (!p.resident) tma_load_3d(&map_w, &full[stage], sa + A_BYTES, cb * BK, tap, n_blk * p.BN);
+            if (pair) {
+              if (ts.rank == 0) mbar_expect_tx(&full[stage], tx_bytes);
+              tma2_load_4d(&map_a, &full[stage], sa, cb * BK, ow0 + p.tap_dx[tap], oh0 + p.tap_dy[tap], img0 + p.tap_img[tap]);
+              tma2_load_3d(&map_w, &full[stage], sa + A_BYTES, cb * BK, tap, wrow0);
+            } else {
+              mbar_expect_tx(&full[stage], tx_bytes);
+              tma_load_4d(&map_a, &full[stage], sa, cb * BK, ow0 + p.tap_dx[tap], oh0 + p.tap_dy[tap], img0 + p.tap_img[tap]);
+              if (!p.resident) tma_load_3d(&map_w, &full[stage], sa + A_BYTES, cb * BK, tap, wrow0);
+            }
             if (++stage == nstages) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // ================================================================== MMA issuer
-    if (lane == 0) {
+    // ================================================================== MMA issuer (pair mode: the leader CTA only)
+    if (lane == 0 && ts.rank == 0) {
       // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=bf16, K-major both, N>>3, M>>4
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)((pair ? 2 * BM : BM) >> 4) << 24);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t aphase = 0;
       long long dbg_wfull = 0, dbg_wtempty = 0; const long long dbg_t0 = clock64();
       if (p.resident) mbar_wait(wbar, 0);
-      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int64_t tile = ts.t0; tile < ts.num; tile += ts.stride) {
         long long tw0 = clock64();
         mbar_wait(&tempty[acc], aphase ^ 1);
         dbg_wtempty += clock64() - tw0;
@@ -546,13 +626,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const uint32_t sa = smem_u32(smem + a_base + (uint32_t)stage * a_stride);
           const uint64_t a_desc = make_sw128_desc(sa);
           const uint64_t b_desc = make_sw128_desc(p.resident ? smem_u32(smem) + (uint32_t)k * slab_kb : sa + A_BYTES);
+          if (pair) {
 #pragma unroll
-          for (int kk = 0; kk < BK / 16; ++kk) {
-            // advance 16 elements (32 B) along K inside the 128B swizzle atom: +2 in the (addr >> 4) field
-            umma_bf16(d_tmem, a_desc + (uint64_t)(2 * kk), b_desc + (uint64_t)(2 * kk), idesc, (k > 0 || kk > 0) ? 1u : 0u);
+            for (int kk = 0; kk < BK / 16; ++kk)
+              umma_bf16_pair(d_tmem, a_desc + (uint64_t)(2 * kk), b_desc + (uint64_t)(2 * kk), idesc, (k > 0 || kk > 0) ? 1u : 0u);
+            tcgen05_commit_pair(&empty[stage]);                     // frees this stage in BOTH CTAs
+            if (k == k_iters - 1) tcgen05_commit_pair(&tfull[acc]); // accumulator complete, both CTAs' epilogues may drain
+          } else {
+#pragma unroll
+            for (int kk = 0; kk < BK / 16; ++kk) {
+              // advance 16 elements (32 B) along K inside the 128B swizzle atom: +2 in the (addr >> 4) field
+              umma_bf16(d_tmem, a_desc + (uint64_t)(2 * kk), b_desc + (uint64_t)(2 * kk), idesc, (k > 0 || kk > 0) ? 1u : 0u);
+            }
+            tcgen05_commit(&empty[stage]);                     // frees the smem stage when these MMAs retire
+            if (k == k_iters - 1) tcgen05_commit(&tfull[acc]); // accumulator complete
           }
-          tcgen05_commit(&empty[stage]);                     // frees the smem stage when these MMAs retire
-          if (k == k_iters - 1) tcgen05_commit(&tfull[acc]); // accumulator complete
           if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
         if (++acc == 2) { acc = 0; aphase ^= 1; }
@@ -569,14 +657,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     int acc = 0; uint32_t aphase = 0;
     const bool geglu = (p.flags & FYC_EPI_GEGLU) != 0;
     const bool out_f32 = (p.flags & FYC_EPI_OUT_F32) != 0;
-    if (geglu) epilogue_geglu(p, stage, reinterpret_cast<float*>(smem + OFF_BIAS), tfull, tempty, tmem_base, warp, lane, num_tiles);
-    else if (!out_f32) epilogue_plain(p, stage, tfull, tempty, tmem_base, warp, lane, num_tiles);
-    else for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int n_blk = (int)(tile % p.n_tiles);
-      const int64_t m_blk = tile / p.n_tiles;
-      const int wt = (int)(m_blk % p.w_tiles);
-      const int ht = (int)((m_blk / p.w_tiles) % p.h_tiles);
-      const int it = (int)(m_blk / ((int64_t)p.w_tiles * p.h_tiles));
+    if (geglu) epilogue_geglu<PAIR>(p, ts, stage, reinterpret_cast<float*>(smem + OFF_BIAS), tfull, tempty, tmem_base, warp, lane);
+    else if (!out_f32) epilogue_plain<PAIR>(p, ts, stage, tfull, tempty, tmem_base, warp, lane);
+    else for (int64_t tile = ts.t0; tile < ts.num; tile += ts.stride) {
+      const TileCoord tc = tile_coord(p, ts, tile);
+      const int n_blk = tc.n, wt = tc.w, ht = tc.h, it = tc.i;
       // row r of the tile = (image il, row hl, col wl) of the patch
       const int wl = r % p.bw, hl = (r / p.bw) % p.bh, il = r / (p.bw * p.bh);
       const int ow = wt * p.bw + wl, oh = ht * p.bh + hl, img = it * p.bn + il;
@@ -626,8 +711,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
         }
       }
-      tcgen05_fence_before();
-      mbar_arrive(&tempty[acc]);
+      epi_release<PAIR>(&tempty[acc], lane);
       dbg_epi += clock64() - te1;
       if (++acc == 2) { acc = 0; aphase ^= 1; }
     }
@@ -636,9 +720,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __syncwarp();
   tcgen05_fence_before();
   __syncthreads();
+  if (pair) cluster_sync_all();           // the peer may still be signalling this CTA's barriers / reading its operands
   if (warp == 2) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    if (pair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
 
@@ -733,28 +819,71 @@ void choose_tiles(TcParams& p, int* grid_out) {
         return;
       }
     }
-    const int64_t rounds0 = ceil_div64(tiles, sms);
+  }
+  // CTA pairs (cta_group::2): per 128 x BN of output each SM stages (128 + BN / 2) x K operand elements instead of (128 + BN) x K and
+  // reads half the B bytes from shared memory per MMA.  Measured on B200 (tests/diag_conv.py, FYC_TC_PAIR=0/1): +3..26 % for
+  // 4096 <= M <= 65536 with K >= 640 (the 32x32 / 16x16 convolutions, the FF2 and K >= 1280 projections); -7..11 % on the M = 131072
+  // level-0 shapes (long power-capped launches, where the M = 256 instruction runs at a lower clock for the same watts) and on
+  // epilogue-bound small-K tiles (the two CTAs' epilogues gate each other).  FYC_TC_PAIR=0 / 2 forces it off / on where legal.
+  const char* pair_e = getenv("FYC_TC_PAIR");
+  const int pair_env = pair_e ? atoi(pair_e) : 1;
+  const bool pair_ok = p.m_tiles >= 4 && k_iters >= 4 && sms >= 2;
+  const bool pair_wins = p.M >= 4096 && p.M <= 65536 && k_iters >= 10;
+  p.pair = (pair_ok && (pair_env == 2 || (pair_env == 1 && pair_wins))) ? 1 : 0;
+  const int64_t units = p.pair ? (p.m_tiles + 1) / 2 : p.m_tiles;      // m blocks (or pairs of them) to schedule
+  const int64_t slots = p.pair ? sms / 2 : sms;                        // CTAs (or clusters) to schedule them on
+  if (!geglu) {
+    const int64_t rounds0 = ceil_div64(units * p.n_tiles, slots);
     if (rounds0 < 8) {
-      int64_t best = rounds0 * (p.BN + 32);
+      // per k block a tile costs max(MMA, operand feed) clocks: 128 x bn x 64 MACs at 4096 MAC/clk, (128 + W rows) x 128 B at
+      // ~67 B/clk (W rows are halved per CTA in pair mode), plus a fixed per-tile overhead
+      auto cost_of = [&](int bn, int64_t nt) {
+        const int64_t mma = 2 * bn, feed = (int64_t)(1.91 * (128 + (p.pair ? bn / 2 : bn)));
+        return ceil_div64(units * nt, slots) * ((mma > feed ? mma : feed) + 48);
+      };
+      int64_t best = cost_of(p.BN, p.n_tiles);
       for (int bn = 256; bn >= 64; bn -= 16) {
         if (bn > p.N) continue;
         const int64_t nt = ceil_div64(p.N, bn);
-        const int64_t cost = ceil_div64(p.m_tiles * nt, sms) * (bn + 32) ;
+        const int64_t cost = cost_of(bn, nt);
         if (cost < best) { best = cost; p.BN = bn; p.n_tiles = (int)nt; }
       }
-      tiles = p.m_tiles * p.n_tiles;
     }
   }
-  *grid_out = (int)(tiles < sms ? tiles : sms);
+  tiles = units * p.n_tiles;
+  const int64_t g = tiles < slots ? tiles : slots;
+  *grid_out = (int)(p.pair ? 2 * g : g);
 }
 
 long long* g_tc_debug = nullptr;
 
 int32_t launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, TcParams p, int grid, cudaStream_t st) {
+  if (p.pair) {
+    p.debug = g_tc_debug;
+    static bool attr_set2 = false;
+    if (!attr_set2) {
+      FYC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+      attr_set2 = true;
+    }
+    const int64_t tiles = ((p.m_tiles + 1) / 2) * p.n_tiles;
+    FYC_CHECK(tiles < (1ll << 30) && p.M < (1ll << 31) && p.rows_per_group < (1ll << 31), "tcgen05 GEMM: problem exceeds the 32-bit tile index range");
+    FYC_CHECK(p.M * (p.ldo / 8) + p.ldo / 8 < (1ll << 32) && p.M * (p.ldr / 8) + p.ldr / 8 < (1ll << 32),
+              "tcgen05 GEMM: output larger than 64 GB is not addressable by the epilogue");
+    FYC_CHECK(grid % 2 == 0 && grid >= 2, "tcgen05 GEMM: pair mode needs an even grid");
+    p.dg_n = p.dg_w = p.dg_h = p.dg_i = 0;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    FYC_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<1>, ma, mw, p));
+    return FYC_OK;
+  }
   p.debug = g_tc_debug;
   static bool attr_set = false;
   if (!attr_set) {
-    FYC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    FYC_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_set = true;
   }
   int64_t tiles = p.m_tiles * p.n_tiles;
@@ -769,7 +898,7 @@ int32_t launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, TcParams p, int 
     p.dg_h = (int)(g % p.h_tiles); g /= p.h_tiles;
     p.dg_i = (int)g;
   }
-  gemm_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mw, p);
+  gemm_tc_kernel<0><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mw, p);
   FYC_LAUNCH_CHECK();
   return FYC_OK;
 }
@@ -825,7 +954,7 @@ int32_t fyc_gemm_tc(const fyc_gemm_args* g, cudaStream_t st) {
     {
       uint64_t dims[3] = {(uint64_t)g->K, 1, (uint64_t)g->N};
       uint64_t str[2] = {(uint64_t)g->ldw * 2, (uint64_t)g->ldw * 2};
-      uint32_t box[3] = {BK, 1, (uint32_t)p.BN};
+      uint32_t box[3] = {BK, 1, (uint32_t)(p.pair ? p.BN / 2 : p.BN)};   // pair mode: each CTA stages half of the tile's W rows
       int32_t rc = encode_map(&mw, W, 3, dims, str, box);
       if (rc) return rc;
     }
@@ -901,7 +1030,7 @@ int32_t fyc_conv3x3_tc(const fyc_conv3x3_args* c, const void* x_planes, cudaStre
   {
     uint64_t dims[3] = {(uint64_t)c->Cin, 9, (uint64_t)c->Cout};
     uint64_t str[2] = {(uint64_t)c->Cin * 2, (uint64_t)c->Cin * 2 * 9};
-    uint32_t box[3] = {BK, 1, (uint32_t)p.BN};
+    uint32_t box[3] = {BK, 1, (uint32_t)(p.pair ? p.BN / 2 : p.BN)};   // pair mode: each CTA stages half of the tile's W rows
     int32_t rc = encode_map(&mw, c->w, 3, dims, str, box);
     if (rc) return rc;
   }

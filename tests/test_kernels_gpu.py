@@ -81,6 +81,42 @@ def test_gemm_geglu(dtype, impl):
     assert out.shape == (M, 4 * C) and rel(out, ref) < tol(dtype), rel(out, ref)
 
 
+@pytest.mark.parametrize("M,N,K,res", [(128 * 9 - 30, 320, 512, True), (128 * 37, 1280, 1280, True), (128 * 16, 720, 640, False),
+                                       (128 * 301, 320, 1280, True), (128 * 5 + 1, 48, 256, False)])
+def test_gemm_tcgen05_cta_pairs(M, N, K, res, monkeypatch):
+    """CTA-pair (cta_group::2) mode of the tcgen05 GEMM: odd m-block counts (phantom block in the last pair), ragged last N
+    tile, multi-round persistent scheduling, residual prefetch across tiles."""
+    from followyourclick_b200 import ops
+    ops.set_impl("tc")
+    dtype = torch.bfloat16
+    A, W = rnd((M, K), 11, dtype), rnd((N, K), 12, dtype, K ** -0.5)
+    bias, R = rnd((N,), 13), (rnd((M, N), 14, dtype) if res else None)
+    ref = A.float() @ W.float().t() + bias + (R.float() if res else 0)
+    outs = {}
+    for mode in ("2", "0"):                     # 2 = pairs wherever legal, 0 = never (the dispatcher's own rule is FYC_TC_PAIR unset)
+        monkeypatch.setenv("FYC_TC_PAIR", mode)
+        outs[mode] = ops.gemm(A, W, bias=bias, residual=R)
+        assert rel(outs[mode], ref) < tol(dtype), (mode, rel(outs[mode], ref))
+        # bit-reproducible across launches (no atomics, fixed accumulation order)
+        assert torch.equal(outs[mode], ops.gemm(A, W, bias=bias, residual=R))
+    # same k order and fp32 accumulation in both modes: identical bits whenever both picked the same BN
+    assert rel(outs["2"], outs["0"].float()) < 2e-3
+
+
+def test_gemm_geglu_tcgen05_cta_pairs(monkeypatch):
+    from followyourclick_b200 import ops
+    from followyourclick_b200.modeling import geglu_interleave
+    monkeypatch.setenv("FYC_TC_PAIR", "2")
+    ops.set_impl("tc")
+    dtype = torch.bfloat16
+    M, C = 128 * 21, 640
+    x, w, b = rnd((M, C), 1, dtype), rnd((8 * C, C), 2, torch.float32, C ** -0.5), rnd((8 * C,), 3)
+    wi, bi = geglu_interleave(w, b)
+    out = ops.gemm(x, wi.to(dtype).contiguous(), bias=bi.contiguous(), geglu=True)
+    h = x.float() @ w.to(dtype).float().t() + b
+    a, g = h.chunk(2, dim=-1)
+    assert out.shape == (M, 4 * C) and rel(out, a * F.gelu(g)) < tol(dtype)
+
 @pytest.mark.parametrize("dtype,impl", MODES)
 def test_gemm_batched_scores_and_shared_A(dtype, impl):
     from followyourclick_b200 import ops
@@ -120,6 +156,26 @@ def test_conv3x3(dtype, impl, NB, H, W, Cin, Cout, stride, up):
     ref = ref.permute(0, 2, 3, 1) + res.float()
     assert out.shape == ref.shape and rel(out, ref) < tol(dtype), rel(out, ref)
 
+
+@pytest.mark.parametrize("NB,H,W,Cin,Cout,stride", [(6, 16, 16, 128, 160, 1), (3, 32, 32, 64, 320, 1), (4, 32, 32, 128, 64, 2)])
+def test_conv3x3_tcgen05_cta_pairs(NB, H, W, Cin, Cout, stride, monkeypatch):
+    """Implicit-GEMM convolution on CTA pairs: patch tiles split over the two CTAs (incl. an odd number of m blocks and the
+    stride-2 parity planes), row bias groups straddling a tile, residual."""
+    from followyourclick_b200 import ops
+    dtype = torch.bfloat16
+    ops.set_impl("tc")
+    x = rnd((NB, H, W, Cin), 1, dtype)
+    w = rnd((Cout, Cin, 3, 3), 2, torch.float32, (9 * Cin) ** -0.5)
+    bias, temb = rnd((Cout,), 3), rnd((NB, Cout), 4)
+    wp = w.permute(0, 2, 3, 1).to(dtype).contiguous()
+    Ho, Wo = H // stride, W // stride
+    res = rnd((NB, Ho, Wo, Cout), 5, dtype)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.to(dtype).float(), bias, stride=stride, padding=1) + temb[:, :, None, None]
+    ref = ref.permute(0, 2, 3, 1) + res.float()
+    for mode in ("2", "0"):
+        monkeypatch.setenv("FYC_TC_PAIR", mode)
+        out = ops.conv3x3(x, wp, bias=bias, residual=res, rowbias=temb, images_per_group=1, stride=stride)
+        assert out.shape == ref.shape and rel(out, ref) < tol(dtype), (mode, rel(out, ref))
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("NB,R,C,G,stat", [(2, 4 * 64, 160, 32, 2), (8, 64, 160, 32, 8), (2, 1024, 1920, 32, 2), (4, 16, 128, 32, 4),
