@@ -116,6 +116,28 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// packed fp32 pairs (FFMA2 / FADD2): one issue slot for two elements
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk2(f32x2 p, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(p)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+// 2^x for a pair on the FMA pipe (Cody-Waite: n = round(x), cubic minimax of 2^f on [-0.5, 0.5], max rel. error 7.5e-5 - fifty
+// times below the bf16 rounding P gets anyway; exponent patched in with an integer add).  x in [-126, 126].
+// The MUFU unit does 16 ex2 per clock per SM and is what bounds the softmax (128 x 128 exps per 4 MMAs); moving 3 of every 8
+// 8-element chunks here balances the two pipes.
+__device__ __forceinline__ f32x2 exp2_poly2(f32x2 x) {
+  const f32x2 magic = pk2(12582912.0f, 12582912.0f), nmagic = pk2(-12582912.0f, -12582912.0f), m1 = pk2(-1.0f, -1.0f);
+  const f32x2 c0 = pk2(0.9999280571937561f, 0.9999280571937561f), c1 = pk2(0.6932609677314758f, 0.6932609677314758f);
+  const f32x2 c2 = pk2(0.2426111251115799f, 0.2426111251115799f), c3 = pk2(0.05517164617776871f, 0.05517164617776871f);
+  const f32x2 t = add2(x, magic);                 // low mantissa bits of t = round-to-nearest integer of x
+  const f32x2 f = fma2(add2(t, nmagic), m1, x);   // x - n  in [-0.5, 0.5]
+  f32x2 p = fma2(f, c3, c2);
+  p = fma2(p, f, c1);
+  p = fma2(p, f, c0);
+  float t0, t1, p0, p1; upk2(t, t0, t1); upk2(p, p0, p1);
+  return pk2(__uint_as_float(__float_as_uint(p0) + (__float_as_uint(t0) << 23)), __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23)));
+}
 
 __global__ void __launch_bounds__(NTHREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
@@ -354,7 +376,9 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
-      mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 128); mbar_init(&p_full[i], 128); mbar_init(&p_empty[i], 1);
+      // softmax -> MMA barriers take ONE arrival per warp (lane 0 after __syncwarp): 128 per-thread arrivals on one shared-memory
+      // word serialise
+      mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4); mbar_init(&p_full[i], 4); mbar_init(&p_empty[i], 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -448,7 +472,8 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       for (int c = 0; c < 4; ++c) tmem_ld32(s_addr + c * 32, sr + c * 32);
       tmem_wait_ld();
       tc_fence_before();
-      mbar_arrive(&s_empty[g]);                               // S_g may be overwritten by tile j+1
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[g]);                // S_g may be overwritten by tile j+1
       float mt = __uint_as_float(sr[0]);
 #pragma unroll
       for (int i = 1; i < 128; ++i) mt = fmaxf(mt, __uint_as_float(sr[i]));
@@ -462,24 +487,36 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         need = true;
       }
       l *= factor;
-      const float nb = -m_used * sl2;
+      // x = s * scale*log2e - m  in (-inf, 8]; clamped at -126 so that the FMA-pipe exp2 can patch the exponent with an integer add
+      const float nbf = -m_used * sl2;
+      const f32x2 sl2p = pk2(sl2, sl2), nbp = pk2(nbf, nbf);
       mbar_wait(&p_empty[g], par ^ 1);                        // PV_g(j-1) retired: P_g is free and O_g is quiescent
       uint8_t* prow = smem + G2_OFF_P + g * P_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
-      float sum = 0.f;
+      f32x2 sum2 = pk2(0.f, 0.f);
 #pragma unroll
       for (int c = 0; c < 16; ++c) {
-        float e[8];
+        uint32_t pw[4];
+        const bool poly = ((c & 7) == 1) || ((c & 7) == 4) || ((c & 7) == 6);     // 3 of every 8 chunks on the FMA pipe
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { e[i] = ex2(fmaf(__uint_as_float(sr[c * 8 + i]), sl2, nb)); sum += e[i]; }
-        uint4 v;
-        __nv_bfloat162 t0 = __floats2bfloat162_rn(e[0], e[1]), t1 = __floats2bfloat162_rn(e[2], e[3]);
-        __nv_bfloat162 t2 = __floats2bfloat162_rn(e[4], e[5]), t3 = __floats2bfloat162_rn(e[6], e[7]);
-        v.x = *reinterpret_cast<uint32_t*>(&t0); v.y = *reinterpret_cast<uint32_t*>(&t1);
-        v.z = *reinterpret_cast<uint32_t*>(&t2); v.w = *reinterpret_cast<uint32_t*>(&t3);
+        for (int i = 0; i < 4; ++i) {
+          const f32x2 x = fma2(pk2(__uint_as_float(sr[c * 8 + 2 * i]), __uint_as_float(sr[c * 8 + 2 * i + 1])), sl2p, nbp);
+          f32x2 e;
+          if (poly) {
+            float x0, x1; upk2(x, x0, x1);
+            e = exp2_poly2(pk2(fmaxf(x0, -126.0f), fmaxf(x1, -126.0f)));
+          } else {
+            float x0, x1; upk2(x, x0, x1);
+            e = pk2(ex2(x0), ex2(x1));
+          }
+          sum2 = add2(sum2, e);
+          float e0, e1; upk2(e, e0, e1);
+          __nv_bfloat162 t = __floats2bfloat162_rn(e0, e1);
+          pw[i] = *reinterpret_cast<uint32_t*>(&t);
+        }
         const int half = c >> 3, cc = c & 7;
-        *reinterpret_cast<uint4*>(prow + half * PHALF_BYTES + ((cc ^ (r & 7)) << 4)) = v;
+        *reinterpret_cast<uint4*>(prow + half * PHALF_BYTES + ((cc ^ (r & 7)) << 4)) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
       }
-      l += sum;
+      { float a0, a1; upk2(sum2, a0, a1); l += a0 + a1; }
       if (__any_sync(0xffffffffu, need)) {
         tc_fence_after();
 #pragma unroll
@@ -495,7 +532,8 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       tc_fence_before();
-      mbar_arrive(&p_full[g]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[g]);
     }
     mbar_wait(&p_empty[g], (uint32_t)((T - 1) & 1));
     tc_fence_after();

@@ -3,13 +3,33 @@
 // fp64 across CTAs so that E[x^2]-E[x]^2 does not cancel.
 #include "common.cuh"
 
+namespace {
+// Blackwell packed fp32 pairs (FFMA2 / FADD2 / FMUL2): one issue slot for two lanes' worth of work.  The norm kernels were
+// instruction-bound (ncu: 18-20 issued instructions per element at ~50 % issue utilisation, 2.5-3 TB/s), not memory-bound.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk2(f32x2 p, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(p)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+// one 32-bit word holding two bf16 -> packed fp32 pair (element 0 in the low half)
+__device__ __forceinline__ f32x2 bf2_to_f2(uint32_t w) { return pk2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u)); }
+__device__ __forceinline__ uint32_t f2_to_bf2(f32x2 p) {
+  float lo, hi; upk2(p, lo, hi);
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float ex2_fast(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_fast(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+}  // namespace
+
 // ---------------------------------------------------------------------------------------------------------
 // stats: x viewed as [NB, R, C]; grid (chunks, NB); each CTA reduces rows [r0, r1) for all channels and writes ONE
 // partial (sum, sumsq) per group.  No atomics anywhere: the per-thread channel sums are combined through shared
 // memory in a fixed order and the per-CTA partials are summed in chunk order by gn_finalize_kernel, so the
 // statistics (and therefore the whole engine) are bit-reproducible run to run.
 template <typename T, int V>
-__global__ void __launch_bounds__(256) gn_stats_kernel(const T* __restrict__ x, float2* __restrict__ partials, int64_t R,
+__global__ void __launch_bounds__(256, 4) gn_stats_kernel(const T* __restrict__ x, float2* __restrict__ partials, int64_t R,
                                                        int C, int G, int64_t rows_per_cta) {
   extern __shared__ float s_ch[];   // [RY][C][2]
   const int cpg = C / G;
@@ -27,6 +47,26 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const T* __restrict__ x, 
 #pragma unroll
       for (int e = 0; e < V; ++e) { s[e] = 0.f; q[e] = 0.f; }
       int64_t r = r0 + ry;
+      if constexpr (sizeof(T) == 2 && V == 8) {
+        // bf16: 8 independent 16-byte loads in flight per thread, kept packed until they are summed (the 4-deep version was
+        // latency-bound at 2.6 TB/s: long_sb stalls with 45 % of the warps resident, profiles/round1_misc_full.md)
+        for (; r + 7 * RY < r1; r += 8 * RY) {
+          uint4 raw[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) raw[u] = __ldg(reinterpret_cast<const uint4*>(base + (r + (int64_t)u * RY) * C + cv * V));
+          f32x2 sp[4], qp[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { sp[e] = pk2(s[2 * e], s[2 * e + 1]); qp[e] = pk2(q[2 * e], q[2 * e + 1]); }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const uint32_t w[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { const f32x2 v2 = bf2_to_f2(w[e]); sp[e] = add2(sp[e], v2); qp[e] = fma2(v2, v2, qp[e]); }
+          }
+#pragma unroll
+          for (int e = 0; e < 4; ++e) { upk2(sp[e], s[2 * e], s[2 * e + 1]); upk2(qp[e], q[2 * e], q[2 * e + 1]); }
+        }
+      }
       for (; r + 3 * RY < r1; r += 4 * RY) {      // 4 independent 16-byte loads in flight per thread
         float f[4][8];
 #pragma unroll
@@ -65,36 +105,39 @@ __global__ void __launch_bounds__(256) gn_stats_kernel(const T* __restrict__ x, 
   }
 }
 
-// finalize: one CTA per nb.  mean/rstd per group from the chunk partials (fp64, fixed order), then per channel
-// scale = rstd * gamma, shift = beta - mean * scale   (same form as ATen's CPU kernel)
-__global__ void __launch_bounds__(256) gn_finalize_kernel(const float2* __restrict__ partials, int chunks,
+// finalize: one CTA per (group, nb).  mean/rstd of the group from the chunk partials (fp64, fixed reduction tree), then per channel
+// scale = rstd * gamma, shift = beta - mean * scale   (same form as ATen's CPU kernel).  (One CTA per nb walked all chunks x groups
+// with 8 warps: 26 us for the cross-frame case NB = 2 - as long as the statistics pass itself.)
+__global__ void __launch_bounds__(128) gn_finalize_kernel(const float2* __restrict__ partials, int chunks,
                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
                                                           float* __restrict__ scale, float* __restrict__ shift, int C, int G,
                                                           double count, float eps) {
-  extern __shared__ float s_stat[];   // [G][2] mean, rstd
-  const int64_t nb = blockIdx.x;
-  // one warp per group: lanes stride over the chunk partials, then a fixed-shape shuffle tree (deterministic)
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int g = wid; g < G; g += nw) {
-    double s = 0.0, q = 0.0;
-    for (int k = lane; k < chunks; k += 32) { float2 p = partials[(nb * chunks + k) * G + g]; s += (double)p.x; q += (double)p.y; }
+  __shared__ double s_red[2][4];
+  __shared__ float s_stat[2];
+  const int g = blockIdx.x;
+  const int64_t nb = blockIdx.y;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  double s = 0.0, q = 0.0;
+  for (int k = threadIdx.x; k < chunks; k += 128) { const float2 p = partials[(nb * chunks + k) * G + g]; s += (double)p.x; q += (double)p.y; }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
-    if (lane == 0) {
-      double mean = s / count;
-      double var = q / count - mean * mean;
-      if (var < 0) var = 0;
-      s_stat[2 * g] = (float)mean;
-      s_stat[2 * g + 1] = (float)(1.0 / sqrt(var + (double)eps));
-    }
+  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+  if (lane == 0) { s_red[0][wid] = s; s_red[1][wid] = q; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const double st = (s_red[0][0] + s_red[0][1]) + (s_red[0][2] + s_red[0][3]);
+    const double qt = (s_red[1][0] + s_red[1][1]) + (s_red[1][2] + s_red[1][3]);
+    const double mean = st / count;
+    double var = qt / count - mean * mean;
+    if (var < 0) var = 0;
+    s_stat[0] = (float)mean;
+    s_stat[1] = (float)(1.0 / sqrt(var + (double)eps));
   }
   __syncthreads();
   const int cpg = C / G;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    int g = c / cpg;
-    float sc = s_stat[2 * g + 1] * gamma[c];
+  for (int c = g * cpg + threadIdx.x; c < (g + 1) * cpg; c += 128) {
+    const float sc = s_stat[1] * gamma[c];
     scale[nb * C + c] = sc;
-    shift[nb * C + c] = beta[c] - s_stat[2 * g] * sc;
+    shift[nb * C + c] = beta[c] - s_stat[0] * sc;
   }
 }
 
@@ -105,7 +148,14 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ x, 
   const int cvn = C / V;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   constexpr int U = 4;     // vectors in flight per thread
-  for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < total_vec; i0 += stride * U) {
+  // (channel vector, row) of vector i0 and of one grid stride, so that the loop advances them by addition: the 64-bit
+  // div / mod per vector of the first version cost more issue slots than the loads
+  const int64_t i00 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  int cv = (int)(i00 % cvn);
+  int64_t row = i00 / cvn;            // row over all NB images
+  const int dcv = (int)(stride % cvn);
+  const int64_t drow = stride / cvn;
+  for (int64_t i0 = i00; i0 < total_vec; i0 += stride * U) {
     float f[U][8];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -119,36 +169,95 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ x, 
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int64_t i = i0 + u * stride;
-      if (i >= total_vec) break;
-      const int cv = (int)(i % cvn);
-      const int64_t nb = (i / cvn) / R;
-      const float* sc = scale + nb * C + cv * V;
-      const float* sh = shift + nb * C + cv * V;
-      float scv[V], shv[V];
-      if constexpr (V >= 4) {     // 16-byte parameter loads (scalar loads saturated the LSU queue: lg_throttle)
+      if (i < total_vec) {
+        const int64_t nb = (int64_t)((uint32_t)row / (uint32_t)R);      // NB * R < 2^31 (checked by the caller)
+        const float* sc = scale + nb * C + cv * V;
+        const float* sh = shift + nb * C + cv * V;
+        float scv[V], shv[V];
+        if constexpr (V >= 4) {     // 16-byte parameter loads (scalar loads saturated the LSU queue: lg_throttle)
 #pragma unroll
-        for (int e = 0; e < V; e += 4) {
-          float4 a = __ldg(reinterpret_cast<const float4*>(sc + e));
-          float4 b = __ldg(reinterpret_cast<const float4*>(sh + e));
-          scv[e] = a.x; scv[e + 1] = a.y; scv[e + 2] = a.z; scv[e + 3] = a.w;
-          shv[e] = b.x; shv[e + 1] = b.y; shv[e + 2] = b.z; shv[e + 3] = b.w;
+          for (int e = 0; e < V; e += 4) {
+            float4 a = __ldg(reinterpret_cast<const float4*>(sc + e));
+            float4 b = __ldg(reinterpret_cast<const float4*>(sh + e));
+            scv[e] = a.x; scv[e + 1] = a.y; scv[e + 2] = a.z; scv[e + 3] = a.w;
+            shv[e] = b.x; shv[e + 1] = b.y; shv[e + 2] = b.z; shv[e + 3] = b.w;
+          }
+        } else {
+          scv[0] = __ldg(sc); shv[0] = __ldg(sh);
         }
-      } else {
-        scv[0] = __ldg(sc); shv[0] = __ldg(sh);
-      }
 #pragma unroll
-      for (int e = 0; e < V; ++e) {
-        float y = fmaf(f[u][e], scv[e], shv[e]);
-        f[u][e] = SILU ? (sizeof(T) == 2 ? silu_fast(y) : silu_f(y)) : y;
+        for (int e = 0; e < V; ++e) {
+          float y = fmaf(f[u][e], scv[e], shv[e]);
+          f[u][e] = SILU ? (sizeof(T) == 2 ? silu_fast(y) : silu_f(y)) : y;
+        }
+        if constexpr (V == 8) Vec8<T>::store(out + i * V, f[u]);
+        else if constexpr (V == 4) Vec4<T>::store(out + i * V, f[u]);
+        else out[i] = from_f<T>(f[u][0]);
       }
-      if constexpr (V == 8) Vec8<T>::store(out + i * V, f[u]);
-      else if constexpr (V == 4) Vec4<T>::store(out + i * V, f[u]);
-      else out[i] = from_f<T>(f[u][0]);
+      cv += dcv; row += drow;
+      if (cv >= cvn) { cv -= cvn; ++row; }
     }
   }
 }
 
-static int64_t gn_max_chunks(int64_t NB) { return ((int64_t)fyc_sm_count() * 4 + NB - 1) / NB + 1; }
+// bf16 apply, second form: a thread owns ONE 8-channel vector (scale / shift live in 16 registers, loaded once) and walks rows,
+// U rows in flight; the math is packed fp32x2.  The grid-stride form above re-derived (image, channel) and re-loaded four
+// parameter vectors for every 16 bytes of data: 160 issued instructions per vector, 51 us for an 84 MB tensor.
+template <bool SILU>
+__global__ void __launch_bounds__(256) gn_apply_rows_kernel(const bf16* __restrict__ x, const float* __restrict__ scale,
+                                                            const float* __restrict__ shift, bf16* __restrict__ out, int64_t R,
+                                                            int C, int64_t rows_per_cta) {
+  constexpr int U = 4;
+  const int cvn = C / 8;
+  const int TX = cvn < 256 ? cvn : 256;
+  const int RY = 256 / TX;
+  const int tx = threadIdx.x % TX, ry = threadIdx.x / TX;
+  if (ry >= RY) return;
+  const int64_t nb = blockIdx.y;
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t r1 = (r0 + rows_per_cta < R) ? r0 + rows_per_cta : R;
+  const bf16* xb = x + nb * R * C;
+  bf16* ob = out + nb * R * C;
+  for (int cv = tx; cv < cvn; cv += TX) {
+    f32x2 sc[4], sh[4];
+    {
+      const float4 a0 = __ldg(reinterpret_cast<const float4*>(scale + nb * C + cv * 8)), a1 = __ldg(reinterpret_cast<const float4*>(scale + nb * C + cv * 8 + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(shift + nb * C + cv * 8)), b1 = __ldg(reinterpret_cast<const float4*>(shift + nb * C + cv * 8 + 4));
+      sc[0] = pk2(a0.x, a0.y); sc[1] = pk2(a0.z, a0.w); sc[2] = pk2(a1.x, a1.y); sc[3] = pk2(a1.z, a1.w);
+      sh[0] = pk2(b0.x, b0.y); sh[1] = pk2(b0.z, b0.w); sh[2] = pk2(b1.x, b1.y); sh[3] = pk2(b1.z, b1.w);
+    }
+    const f32x2 nl2e = pk2(-1.4426950408889634f, -1.4426950408889634f), one2 = pk2(1.0f, 1.0f);
+    for (int64_t r = r0 + ry; r < r1; r += (int64_t)RY * U) {
+      uint4 raw[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t rr = r + (int64_t)u * RY;
+        raw[u] = make_uint4(0, 0, 0, 0);
+        if (rr < r1) raw[u] = __ldg(reinterpret_cast<const uint4*>(xb + rr * C + cv * 8));
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t rr = r + (int64_t)u * RY;
+        if (rr >= r1) break;
+        const uint32_t w[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
+        uint32_t o[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          f32x2 y = fma2(bf2_to_f2(w[e]), sc[e], sh[e]);
+          if (SILU) {                       // y * sigmoid(y) = y / (1 + 2^(-y log2 e))
+            float t0, t1; upk2(mul2(y, nl2e), t0, t1);
+            float d0, d1; upk2(add2(pk2(ex2_fast(t0), ex2_fast(t1)), one2), d0, d1);
+            y = mul2(y, pk2(rcp_fast(d0), rcp_fast(d1)));
+          }
+          o[e] = f2_to_bf2(y);
+        }
+        *reinterpret_cast<uint4*>(ob + rr * C + cv * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+    }
+  }
+}
+
+static int64_t gn_max_chunks(int64_t NB) { return ((int64_t)fyc_sm_count() * 12 + NB - 1) / NB + 1; }   // ~3 waves of 4 CTAs per SM
 static int64_t gn_partials(int64_t NB, int64_t G) { return (NB * gn_max_chunks(NB) * G + 1) / 2 * 2; }   // even: keeps scale/shift 16-byte aligned
 
 extern "C" size_t fyc_groupnorm_workspace_bytes(int64_t NB, int64_t C, int64_t G) {
@@ -166,7 +275,7 @@ static int32_t groupnorm_impl(const T* x, const float* gamma, const float* beta,
   const int RY = 256 / TX;
   int64_t target = gn_max_chunks(NB) - 1;                                 // CTAs per nb
   int64_t rows_per_cta = ceil_div64(R, target);
-  if (rows_per_cta < 4 * RY) rows_per_cta = 4 * RY;
+  if (rows_per_cta < 8 * RY) rows_per_cta = 8 * RY;
   rows_per_cta = ceil_div64(rows_per_cta, RY) * RY;
   const int chunks = (int)ceil_div64(R, rows_per_cta);
   FYC_CHECK(chunks <= gn_max_chunks(NB), "groupnorm: internal chunk count");
@@ -177,9 +286,20 @@ static int32_t groupnorm_impl(const T* x, const float* gamma, const float* beta,
   dim3 grid((unsigned)chunks, (unsigned)NB);
   kern<<<grid, 256, smem, st>>>(x, partials, R, C, G, rows_per_cta);
   FYC_LAUNCH_CHECK();
-  gn_finalize_kernel<<<(unsigned)NB, 256, 2 * G * sizeof(float), st>>>(partials, chunks, gamma, beta, scale, shift, C, G,
-                                                                        (double)R * (C / G), eps);
+  gn_finalize_kernel<<<dim3((unsigned)G, (unsigned)NB), 128, 0, st>>>(partials, chunks, gamma, beta, scale, shift, C, G,
+                                                                       (double)R * (C / G), eps);
   FYC_LAUNCH_CHECK();
+  if constexpr (sizeof(T) == 2 && V == 8) {
+    // ~8 CTAs per SM, rows per CTA a multiple of the RY x 4 rows one CTA iteration covers
+    int64_t want = ceil_div64((int64_t)fyc_sm_count() * 8, NB);
+    int64_t rpc = ceil_div64(R, want);
+    rpc = ceil_div64(rpc, (int64_t)RY * 4) * RY * 4;
+    dim3 ga((unsigned)ceil_div64(R, rpc), (unsigned)NB);
+    if (silu) gn_apply_rows_kernel<true><<<ga, 256, 0, st>>>((const bf16*)x, scale, shift, (bf16*)out, R, C, rpc);
+    else gn_apply_rows_kernel<false><<<ga, 256, 0, st>>>((const bf16*)x, scale, shift, (bf16*)out, R, C, rpc);
+    FYC_LAUNCH_CHECK();
+    return FYC_OK;
+  }
   int64_t total_vec = NB * R * cvn;
   int64_t blocks = ceil_div64(total_vec, 256);
   int64_t cap = (int64_t)fyc_sm_count() * 16;
@@ -195,7 +315,7 @@ extern "C" int32_t fyc_groupnorm(const void* x, const float* gamma, const float*
                                  size_t workspace_bytes, void* stream) {
   FYC_CHECK(G > 0 && C % G == 0, "groupnorm: C=%lld not divisible by G=%lld", (long long)C, (long long)G);
   FYC_CHECK(workspace && workspace_bytes >= fyc_groupnorm_workspace_bytes(NB, C, G), "groupnorm: workspace too small");
-  FYC_CHECK(NB > 0 && NB < 65536 && R > 0 && C < (1 << 20), "groupnorm: bad shape");
+  FYC_CHECK(NB > 0 && NB < 65536 && R > 0 && C < (1 << 20) && NB * R < (1ll << 31), "groupnorm: bad shape");
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == FYC_BF16) {
     if (C % 8 == 0) return groupnorm_impl<bf16, 8>((const bf16*)x, gamma, beta, (bf16*)out, NB, R, (int)C, (int)G, eps, silu, workspace, st);
@@ -270,6 +390,171 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const T* __restrict__ x,
   }
 }
 
+// bf16 LayerNorm, RPW rows per warp: every row's 16-byte vectors are requested before any is used (RPW x NV loads in
+// flight per lane instead of NV), gamma / beta are read once per warp instead of once per row.  The one-row kernel ran at
+// 2.6 TB/s of the 6.6 TB/s the copy benchmark reaches: too few bytes in flight per SM and ~5 parameter loads per data load.
+template <int NV, int RPW>
+__global__ void __launch_bounds__(256) layernorm_bf16_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, bf16* __restrict__ out, int64_t M,
+                                                             int C, float eps, const float* __restrict__ pe,
+                                                             int64_t rows_per_frame, int64_t frames) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW;
+  if (row0 >= M) return;
+  const int cvn = C / 8;
+  uint4 raw[RPW][NV];
+#pragma unroll
+  for (int r = 0; r < RPW; ++r)
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int cv = lane + 32 * i;
+      raw[r][i] = make_uint4(0, 0, 0, 0);
+      if (cv < cvn && row0 + r < M) raw[r][i] = __ldg(reinterpret_cast<const uint4*>(x + (row0 + r) * C + cv * 8));
+    }
+  float gm[NV][8], bt[NV][8];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int cv = lane + 32 * i;
+    if (cv < cvn) {
+#pragma unroll
+      for (int e = 0; e < 8; e += 4) {
+        const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + cv * 8 + e));
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(beta + cv * 8 + e));
+        gm[i][e] = g4.x; gm[i][e + 1] = g4.y; gm[i][e + 2] = g4.z; gm[i][e + 3] = g4.w;
+        bt[i][e] = b4.x; bt[i][e + 1] = b4.y; bt[i][e + 2] = b4.z; bt[i][e + 3] = b4.w;
+      }
+    }
+  }
+  const float inv_c = 1.0f / (float)C;
+#pragma unroll
+  for (int r = 0; r < RPW; ++r) {
+    const int64_t row = row0 + r;
+    if (row >= M) break;                      // warp-uniform
+    float v[NV][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const uint32_t w[4] = {raw[r][i].x, raw[r][i].y, raw[r][i].z, raw[r][i].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { v[i][2 * e] = __uint_as_float(w[e] << 16); v[i][2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u); }
+      if (lane + 32 * i < cvn) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sum += v[i][e];
+      }
+    }
+    const float mean = warp_sum(sum) * inv_c;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+      if (lane + 32 * i < cvn) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { const float d = v[i][e] - mean; sq = fmaf(d, d, sq); }
+      }
+    const float rstd = rsqrtf(warp_sum(sq) * inv_c + eps);
+    const float* per = pe ? pe + ((row / rows_per_frame) % frames) * C : nullptr;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int cv = lane + 32 * i;
+      if (cv < cvn) {
+        float o[8], pb[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (per) {
+          const float4 p0 = __ldg(reinterpret_cast<const float4*>(per + cv * 8)), p1 = __ldg(reinterpret_cast<const float4*>(per + cv * 8 + 4));
+          pb[0] = p0.x; pb[1] = p0.y; pb[2] = p0.z; pb[3] = p0.w; pb[4] = p1.x; pb[5] = p1.y; pb[6] = p1.z; pb[7] = p1.w;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = (v[i][e] - mean) * rstd * gm[i][e] + (bt[i][e] + pb[e]);
+        Vec8<bf16>::store(out + row * C + cv * 8, o);
+      }
+    }
+  }
+}
+
+// bf16 LayerNorm for C = 40 * LPR (320 / 640 / 1280): LPR lanes share a row, five 16-byte vectors per lane - every lane is busy
+// (the warp-per-row kernels idle 24 of 32 lanes on the second vector of a 320-wide row), 32 / LPR rows per warp pass, PASSES passes
+// with all loads of a pass issued up front.  gamma / beta stay in registers for the warp's lifetime; the arithmetic is the same
+// two-pass (mean, then centred variance) as the reference kernel, on packed fp32 pairs: ~5 issued instructions per element
+// instead of ~18 (ncu, profiles/round1_norms.md).
+template <int LPR, int PASSES, bool HAS_PE>
+__global__ void __launch_bounds__(256, 2) layernorm_lpr_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, bf16* __restrict__ out, int64_t M,
+                                                               float eps, const float* __restrict__ pe, int64_t rows_per_frame,
+                                                               int64_t frames) {
+  constexpr int C = LPR * 40, RPP = 32 / LPR;           // channels; rows per warp pass
+  constexpr int VS = LPR * 8;                           // element stride between a lane's consecutive vectors
+  const int lane = threadIdx.x & 31, sub = lane % LPR, rr = lane / LPR;
+  const int64_t row_base = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * (RPP * PASSES);
+  if (row_base >= M) return;
+  f32x2 gm[5][4];                                       // beta is re-read from L1 per vector: 40 more registers would halve the occupancy
+  const float* gp = gamma + sub * 8;
+  const float* bp = beta + sub * 8;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gp + i * VS)), g1 = __ldg(reinterpret_cast<const float4*>(gp + i * VS + 4));
+    gm[i][0] = pk2(g0.x, g0.y); gm[i][1] = pk2(g0.z, g0.w); gm[i][2] = pk2(g1.x, g1.y); gm[i][3] = pk2(g1.z, g1.w);
+  }
+  const float inv_c = 1.0f / (float)C;
+#pragma unroll 1
+  for (int ps = 0; ps < PASSES; ++ps) {
+    const int64_t row = row_base + ps * RPP + rr;
+    const bool ok = row < M;
+    const int64_t rowc = ok ? row : M - 1;            // out-of-range lanes shadow the last row (shuffles stay full-warp), never store
+    const bf16* xr = x + rowc * C + sub * 8;
+    uint4 raw[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) raw[i] = __ldg(reinterpret_cast<const uint4*>(xr + i * VS));
+    f32x2 v[5][4];
+    f32x2 s2 = pk2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const uint32_t w[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { v[i][e] = bf2_to_f2(w[e]); s2 = add2(s2, v[i][e]); }
+    }
+    float s0, s1; upk2(s2, s0, s1);
+    float sum = s0 + s1;
+#pragma unroll
+    for (int o = 1; o < LPR; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum * inv_c;
+    const f32x2 nmean = pk2(-mean, -mean);
+    f32x2 q2 = pk2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { v[i][e] = add2(v[i][e], nmean); q2 = fma2(v[i][e], v[i][e], q2); }
+    float q0, q1; upk2(q2, q0, q1);
+    float sq = q0 + q1;
+#pragma unroll
+    for (int o = 1; o < LPR; o <<= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq * inv_c + eps);
+    const f32x2 rstd2 = pk2(rstd, rstd);
+    const float* pp = HAS_PE ? pe + ((rowc / rows_per_frame) % frames) * C + sub * 8 : nullptr;
+    bf16* orow = out + rowc * C + sub * 8;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bp + i * VS)), b1 = __ldg(reinterpret_cast<const float4*>(bp + i * VS + 4));
+      f32x2 bb[4] = {pk2(b0.x, b0.y), pk2(b0.z, b0.w), pk2(b1.x, b1.y), pk2(b1.z, b1.w)};
+      if (HAS_PE) {
+        const float4 p0 = __ldg(reinterpret_cast<const float4*>(pp + i * VS)), p1 = __ldg(reinterpret_cast<const float4*>(pp + i * VS + 4));
+        bb[0] = add2(bb[0], pk2(p0.x, p0.y)); bb[1] = add2(bb[1], pk2(p0.z, p0.w));
+        bb[2] = add2(bb[2], pk2(p1.x, p1.y)); bb[3] = add2(bb[3], pk2(p1.z, p1.w));
+      }
+      uint32_t o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[e] = f2_to_bf2(fma2(mul2(v[i][e], rstd2), gm[i][e], bb[e]));
+      if (ok) *reinterpret_cast<uint4*>(orow + i * VS) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+template <int LPR>
+static void launch_ln_lpr(const bf16* xb, const float* gamma, const float* beta, bf16* ob, int64_t M, float eps, const float* pe,
+                          int64_t rows_per_frame, int64_t frames, cudaStream_t st) {
+  constexpr int PASSES = 2;
+  const unsigned grid = (unsigned)ceil_div64(M, 8 * (32 / LPR) * PASSES);
+  if (pe) layernorm_lpr_kernel<LPR, PASSES, true><<<grid, 256, 0, st>>>(xb, gamma, beta, ob, M, eps, pe, rows_per_frame, frames);
+  else layernorm_lpr_kernel<LPR, PASSES, false><<<grid, 256, 0, st>>>(xb, gamma, beta, ob, M, eps, pe, rows_per_frame, frames);
+}
+
 extern "C" int32_t fyc_layernorm(const void* x, const float* gamma, const float* beta, void* out, int64_t M, int64_t C,
                                  float eps, const float* pe, int64_t rows_per_frame, int64_t frames, int32_t dtype,
                                  void* stream) {
@@ -279,9 +564,15 @@ extern "C" int32_t fyc_layernorm(const void* x, const float* gamma, const float*
   unsigned grid = (unsigned)ceil_div64(M, 8);
   if (dtype == FYC_BF16) {
     FYC_CHECK(C % 8 == 0 && C <= 8 * 32 * 8, "layernorm(bf16): C=%lld must be a multiple of 8 and <= 2048", (long long)C);
-    if (C <= 8 * 32 * 2) layernorm_kernel<bf16, 8, 2><<<grid, 256, 0, st>>>((const bf16*)x, gamma, beta, (bf16*)out, M, (int)C, eps, pe, rows_per_frame, frames);
-    else if (C <= 8 * 32 * 5) layernorm_kernel<bf16, 8, 5><<<grid, 256, 0, st>>>((const bf16*)x, gamma, beta, (bf16*)out, M, (int)C, eps, pe, rows_per_frame, frames);
-    else layernorm_kernel<bf16, 8, 8><<<grid, 256, 0, st>>>((const bf16*)x, gamma, beta, (bf16*)out, M, (int)C, eps, pe, rows_per_frame, frames);
+    FYC_CHECK((((uintptr_t)x | (uintptr_t)out) & 15) == 0 && (((uintptr_t)gamma | (uintptr_t)beta | (uintptr_t)pe) & 15) == 0, "layernorm(bf16): 16-byte alignment");
+    const bf16* xb = (const bf16*)x; bf16* ob = (bf16*)out;
+    if (C == 320) launch_ln_lpr<8>(xb, gamma, beta, ob, M, eps, pe, rows_per_frame, frames, st);
+    else if (C == 640) launch_ln_lpr<16>(xb, gamma, beta, ob, M, eps, pe, rows_per_frame, frames, st);
+    else if (C == 1280) launch_ln_lpr<32>(xb, gamma, beta, ob, M, eps, pe, rows_per_frame, frames, st);
+    else if (C <= 8 * 32 * 2) layernorm_bf16_kernel<2, 4><<<(unsigned)ceil_div64(M, 8 * 4), 256, 0, st>>>(xb, gamma, beta, ob, M, (int)C, eps, pe, rows_per_frame, frames);
+    else if (C <= 8 * 32 * 3) layernorm_bf16_kernel<3, 2><<<(unsigned)ceil_div64(M, 8 * 2), 256, 0, st>>>(xb, gamma, beta, ob, M, (int)C, eps, pe, rows_per_frame, frames);
+    else if (C <= 8 * 32 * 5) layernorm_kernel<bf16, 8, 5><<<grid, 256, 0, st>>>(xb, gamma, beta, ob, M, (int)C, eps, pe, rows_per_frame, frames);
+    else layernorm_kernel<bf16, 8, 8><<<grid, 256, 0, st>>>(xb, gamma, beta, ob, M, (int)C, eps, pe, rows_per_frame, frames);
   } else if (dtype == FYC_F32) {
     FYC_CHECK(C % 4 == 0 && C <= 4 * 32 * 16, "layernorm(f32): C=%lld must be a multiple of 4 and <= 2048", (long long)C);
     if (C <= 4 * 32 * 5) layernorm_kernel<float, 4, 5><<<grid, 256, 0, st>>>((const float*)x, gamma, beta, (float*)out, M, (int)C, eps, pe, rows_per_frame, frames);

@@ -169,7 +169,8 @@ def groupnorm(x, gamma, beta, groups, eps, silu=False, stat_batches=None):
     out = torch.empty_like(x)
     nbytes = lib().fyc_groupnorm_workspace_bytes(NB, Cc, groups)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
-    with _rec("groupnorm", 0, 3 * x.numel() * x.element_size()):
+    fam = f"groupnorm[{NB}x{R}x{Cc}]" if _prof_shapes else "groupnorm"
+    with _rec(fam, 0, 3 * x.numel() * x.element_size()):
         check(lib().fyc_groupnorm(ptr(x), ptr(gamma), ptr(beta), ptr(out), NB, R, Cc, groups, float(eps), int(silu),
                                   dtype_code(x.dtype), ptr(ws), nbytes, stream_ptr()))
     return out
@@ -180,7 +181,8 @@ def layernorm(x, gamma, beta, eps=1e-5, pe=None, rows_per_frame=0, frames=0):
     assert x.is_contiguous()
     Cc = x.shape[-1]
     out = torch.empty_like(x)
-    with _rec("layernorm", 0, 2 * x.numel() * x.element_size()):
+    fam = f"layernorm[{x.numel() // Cc}x{Cc}]" if _prof_shapes else "layernorm"
+    with _rec(fam, 0, 2 * x.numel() * x.element_size()):
         check(lib().fyc_layernorm(ptr(x), ptr(gamma), ptr(beta), ptr(out), x.numel() // Cc, Cc, float(eps), ptr(pe),
                                   rows_per_frame, frames, dtype_code(x.dtype), stream_ptr()))
     return out
@@ -201,7 +203,7 @@ def attention(q, k, v, heads, scale, out=None, out_alpha=1.0, accumulate=False, 
     a = L.AttnArgs(ptr(q), ptr(k), ptr(v), ptr(out), B, heads, Lq, Lk, D, q.stride(1), k.stride(1), v.stride(1),
                    out.stride(1), q.stride(0), k.stride(0), v.stride(0), out.stride(0), kv_batch_div, float(scale),
                    float(out_alpha), int(accumulate), dtype_code(q.dtype), _impl if impl is None else impl)
-    with _rec("attention", 4.0 * B * heads * Lq * Lk * D, q.element_size() * (2 * B * Lq * heads * D + 2 * (B // kv_batch_div) * Lk * heads * D)):
+    with _rec(f"attention[{B}x{heads}x{Lq}x{Lk}x{D}]" if _prof_shapes else "attention", 4.0 * B * heads * Lq * Lk * D, q.element_size() * (2 * B * Lq * heads * D + 2 * (B // kv_batch_div) * Lk * heads * D)):
         check(lib().fyc_attention(C.byref(a), stream_ptr()))
     return out
 
@@ -237,7 +239,7 @@ def temporal_attention(qkv, heads, scale):
     B, F, HW, C3 = qkv.shape
     Cc = C3 // 3
     out = torch.empty((B, F, HW, Cc), dtype=qkv.dtype, device=qkv.device)
-    with _rec("temporal_attention", 4.0 * B * HW * heads * F * F * (Cc // heads), (qkv.numel() + out.numel()) * qkv.element_size()):
+    with _rec(f"temporal_attention[{B}x{F}x{HW}x{heads}x{Cc // heads}]" if _prof_shapes else "temporal_attention", 4.0 * B * HW * heads * F * F * (Cc // heads), (qkv.numel() + out.numel()) * qkv.element_size()):
         check(lib().fyc_temporal_attention(ptr(qkv), ptr(out), B, F, HW, heads, Cc // heads, float(scale),
                                            dtype_code(qkv.dtype), stream_ptr()))
     return out

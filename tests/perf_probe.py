@@ -54,7 +54,7 @@ def main():
         with ops.profile() as prof2: run()
         ops._prof_shapes = False
         rows = sorted(prof2.summary.items(), key=lambda kv: -kv[1]["ms"])
-        for fam, d in rows[:70]:
+        for fam, d in rows[:110]:
             if d["ms"]:
                 print(f"   {fam:46s} {d['ms']:7.3f} ms x{d['launches']:3d}  {d['flops']/d['ms']/1e9:7.1f} TFLOP/s  {d['bytes']/d['ms']/1e6:7.1f} GB/s(alg)")
     # VAE decode of F frames
