@@ -302,8 +302,16 @@ def main():
         tc_ms, tc_fl, tc_n = sum(d["ms"] for d in tc), sum(d["flops"] for d in tc), sum(d["launches"] for d in tc)
         total_ms = sum(d["ms"] for d in prof.summary.values())
         ach = tc_fl / (tc_ms * 1e-3) / 1e12 if tc_ms else 0.0
+        # DRAM bytes per launch of the same kernel from the committed ncu capture of this command (profiles/round1_traffic.json,
+        # written by profiles/summarize_launches.py from dram__bytes_read.sum + dram__bytes_write.sum); null when absent
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "round1_traffic.json")
+        if os.path.exists(tpath) and not mini:
+            tk = [v for k, v in json.load(open(tpath)).items() if k.startswith("gemm_tc_kernel")]     # <0> single-CTA, <1> CTA-pair
+            if tk:
+                traffic = sum(v["dram_bytes_per_launch"] * v["launches"] for v in tk) / sum(v["launches"] for v in tk)
         roof = dict(bound="tensor", kernel="gemm_tc_kernel (tcgen05 GEMM + implicit-GEMM conv3x3)", achieved=ach, peak=pk["tflops"],
-                    unit="TFLOP/s", frac=ach / pk["tflops"], traffic=None, peak_source=pk["src"], launches_per_unet_forward=tc_n,
+                    unit="TFLOP/s", frac=ach / pk["tflops"], traffic=traffic, peak_source=pk["src"], launches_per_unet_forward=tc_n,
                     avg_launch_ms=tc_ms / max(tc_n, 1), share_of_unet_forward=tc_ms / max(total_ms, 1e-9),
                     algorithmic_tflop_per_unet_forward=tc_fl / 1e12,
                     step_frac=(fps / world) * TFLOP_PER_FRAME / pk["tflops"] if not mini else None,

@@ -342,9 +342,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 // per scheduler overlap each other's MUFU / FMA / shared-memory latencies, and every K / V^T tile is loaded once for 256 rows.
 constexpr int G2_THREADS = 320;
 constexpr int G2_OFF_K = 2 * Q_BYTES, G2_OFF_V = G2_OFF_K + 2 * K_BYTES, G2_OFF_P = G2_OFF_V + 2 * V_BYTES;
-constexpr int G2_OFF_BAR = G2_OFF_P + 2 * P_BYTES, G2_SMEM_BYTES = G2_OFF_BAR + 256 + 1024;
+constexpr int G2_OFF_BAR = G2_OFF_P + 4 * P_BYTES, G2_SMEM_BYTES = G2_OFF_BAR + 256 + 1024;   // P is double-buffered per group
 constexpr int G2_TM_S = 0 /* +128 g */, G2_TM_O = 256 /* +64 g */;
 
+template <int POLYMASK>      // bit c & 7 set: that 8-element chunk takes its exp2 on the FMA pipe (exp2_poly2), else on the MUFU
 __global__ void __launch_bounds__(G2_THREADS, 1)
 attention_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                      const __grid_constant__ CUtensorMap map_vt, const AttnTcParams p) {
@@ -360,8 +361,8 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   uint64_t* s_full = bars + 9;        // [2] per group
   uint64_t* s_empty = bars + 11;      // [2]
   uint64_t* p_full = bars + 13;       // [2]
-  uint64_t* p_empty = bars + 15;      // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+  uint64_t* p_empty = bars + 15;      // [2 groups][2 buffers]: PV of the tile that used this P buffer has retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
@@ -378,7 +379,8 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
       // softmax -> MMA barriers take ONE arrival per warp (lane 0 after __syncwarp): 128 per-thread arrivals on one shared-memory
       // word serialise
-      mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4); mbar_init(&p_full[i], 4); mbar_init(&p_empty[i], 1);
+      mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4); mbar_init(&p_full[i], 4);
+      mbar_init(&p_empty[2 * i], 1); mbar_init(&p_empty[2 * i + 1], 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -442,13 +444,13 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
           tc_fence_after();
 #pragma unroll
           for (int hh = 0; hh < 2; ++hh) {
-            const uint64_t a_desc = sw128_desc(smem_u32(smem + G2_OFF_P + g * P_BYTES + hh * PHALF_BYTES));
+            const uint64_t a_desc = sw128_desc(smem_u32(smem + G2_OFF_P + (2 * g + (j & 1)) * P_BYTES + hh * PHALF_BYTES));
             const uint64_t b_desc = sw128_desc(smem_u32(smem + G2_OFF_V + st * V_BYTES + hh * VBOX_BYTES));
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk)
               umma(tmem_base + G2_TM_O + g * 64, a_desc + 2 * kk, b_desc + 2 * kk, idesc_o, (j > 0 || hh > 0 || kk > 0) ? 1u : 0u);
           }
-          tc_commit(&p_empty[g]);
+          tc_commit(&p_empty[2 * g + (j & 1)]);
         }
         tc_commit(&v_empty[st]);
       }
@@ -490,13 +492,14 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       // x = s * scale*log2e - m  in (-inf, 8]; clamped at -126 so that the FMA-pipe exp2 can patch the exponent with an integer add
       const float nbf = -m_used * sl2;
       const f32x2 sl2p = pk2(sl2, sl2), nbp = pk2(nbf, nbf);
-      mbar_wait(&p_empty[g], par ^ 1);                        // PV_g(j-1) retired: P_g is free and O_g is quiescent
-      uint8_t* prow = smem + G2_OFF_P + g * P_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
+      // P buffer j & 1 was last read by PV_g(j-2): with two buffers the exponentials of tile j overlap PV_g(j-1) instead of waiting
+      mbar_wait(&p_empty[2 * g + (j & 1)], (uint32_t)(((j >> 1) & 1) ^ 1));
+      uint8_t* prow = smem + G2_OFF_P + (2 * g + (j & 1)) * P_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
       f32x2 sum2 = pk2(0.f, 0.f);
 #pragma unroll
       for (int c = 0; c < 16; ++c) {
         uint32_t pw[4];
-        const bool poly = ((c & 7) == 1) || ((c & 7) == 4) || ((c & 7) == 6);     // 3 of every 8 chunks on the FMA pipe
+        const bool poly = ((POLYMASK >> (c & 7)) & 1) != 0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const f32x2 x = fma2(pk2(__uint_as_float(sr[c * 8 + 2 * i]), __uint_as_float(sr[c * 8 + 2 * i + 1])), sl2p, nbp);
@@ -518,6 +521,8 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       }
       { float a0, a1; upk2(sum2, a0, a1); l += a0 + a1; }
       if (__any_sync(0xffffffffu, need)) {
+        // O_g must be quiescent: PV_g(j-1), the last MMA that accumulates into it before PV_g(j) (which waits for this warp), retired
+        mbar_wait(&p_empty[2 * g + ((j - 1) & 1)], (uint32_t)(((j - 1) >> 1) & 1));
         tc_fence_after();
 #pragma unroll
         for (int c = 0; c < DV / 16; ++c) {
@@ -535,7 +540,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[g]);
     }
-    mbar_wait(&p_empty[g], (uint32_t)((T - 1) & 1));
+    mbar_wait(&p_empty[2 * g + ((T - 1) & 1)], (uint32_t)(((T - 1) >> 1) & 1));
     tc_fence_after();
     const float inv = p.out_alpha / l;
     bf16* orow = p.out + (int64_t)n * p.bso + ((int64_t)qt * 2 * BQ + g * BQ + r) * p.ldo + h * p.D;
@@ -661,11 +666,21 @@ extern "C" int32_t fyc_self_attention_tc(const void* qk, int64_t ldqk, int64_t q
   if (L % (2 * BQ) == 0) {       // two query tiles per CTA (ping-pong softmax warpgroups)
     static bool attr2 = false;
     if (!attr2) {
-      FYC_CUDA(cudaFuncSetAttribute(attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES));
+      FYC_CUDA(cudaFuncSetAttribute(attention_tc2_kernel<0x00>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES));
+      FYC_CUDA(cudaFuncSetAttribute(attention_tc2_kernel<0x02>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES));
+      FYC_CUDA(cudaFuncSetAttribute(attention_tc2_kernel<0x12>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES));
+      FYC_CUDA(cudaFuncSetAttribute(attention_tc2_kernel<0x52>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES));
       attr2 = true;
     }
     dim3 grid2((unsigned)(L / (2 * BQ)), (unsigned)heads, (unsigned)NB);
-    attention_tc2_kernel<<<grid2, G2_THREADS, G2_SMEM_BYTES, (cudaStream_t)stream>>>(mq, mk, mv, p);
+    // share of the exponentials moved from the MUFU to the FMA pipe, in eighths (FYC_ATTN_POLY=0..3 overrides; measured optimum below)
+    const char* pe = getenv("FYC_ATTN_POLY");
+    const int eighths = pe ? atoi(pe) : 3;          // 0: 1.574 ms, 1: 1.480, 2: 1.452, 3: 1.422 ms at 32 x 8 heads x 4096 tokens
+    cudaStream_t s2 = (cudaStream_t)stream;
+    if (eighths <= 0) attention_tc2_kernel<0x00><<<grid2, G2_THREADS, G2_SMEM_BYTES, s2>>>(mq, mk, mv, p);
+    else if (eighths == 1) attention_tc2_kernel<0x02><<<grid2, G2_THREADS, G2_SMEM_BYTES, s2>>>(mq, mk, mv, p);
+    else if (eighths == 2) attention_tc2_kernel<0x12><<<grid2, G2_THREADS, G2_SMEM_BYTES, s2>>>(mq, mk, mv, p);
+    else attention_tc2_kernel<0x52><<<grid2, G2_THREADS, G2_SMEM_BYTES, s2>>>(mq, mk, mv, p);
     FYC_LAUNCH_CHECK();
     return FYC_OK;
   }
