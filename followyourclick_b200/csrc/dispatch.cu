@@ -42,6 +42,8 @@ extern "C" int32_t fyc_conv3x3(const fyc_conv3x3_args* c, void* stream) {
   FYC_CHECK(c && c->x && c->w && c->out, "conv3x3: null pointer");
   FYC_CHECK(c->stride == 1 || c->stride == 2, "conv3x3: stride %d", c->stride);
   FYC_CHECK(c->upsample == 1 || c->upsample == 2, "conv3x3: upsample %d", c->upsample);
+  FYC_CHECK(c->pad_mode == 0 || (c->pad_mode == 1 && c->stride == 2 && c->upsample == 1 && c->H % 2 == 0 && c->W % 2 == 0),
+            "conv3x3: pad_mode %d needs stride 2, no upsampling and even H, W", c->pad_mode);
   FYC_CHECK(!(c->epilogue & FYC_EPI_BIAS) || c->bias, "conv3x3: FYC_EPI_BIAS without bias");
   FYC_CHECK(!(c->epilogue & FYC_EPI_RESIDUAL) || c->residual, "conv3x3: FYC_EPI_RESIDUAL without residual");
   FYC_CHECK(!(c->epilogue & FYC_EPI_ROWBIAS) || (c->rowbias && c->images_per_group > 0), "conv3x3: FYC_EPI_ROWBIAS without rowbias");

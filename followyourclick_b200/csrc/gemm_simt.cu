@@ -39,10 +39,11 @@ template <typename T>
 struct ConvA {   // logical A[m, k]: m = (n, oh, ow), k = (kh, kw, c);  x is NHWC (pre-upsample dims H, W)
   const T* x; int64_t NB, H, W, Cin, Ho, Wo, M, K;
   int stride, up;
+  int pad = 1;   // rows / columns of zero padding BEFORE the image (0 for pad_mode 1: bottom / right padding only)
   bool vec;  // Cin % 8 == 0
   __device__ __forceinline__ float at(int64_t n, int64_t oh, int64_t ow, int64_t k) const {
     int tap = (int)(k / Cin); int64_t c = k - (int64_t)tap * Cin;
-    int64_t ih = oh * stride + tap / 3 - 1, iw = ow * stride + tap % 3 - 1;
+    int64_t ih = oh * stride + tap / 3 - pad, iw = ow * stride + tap % 3 - pad;
     if (ih < 0 || iw < 0 || ih >= H * up || iw >= W * up) return 0.f;
     return to_f(x[((n * H + ih / up) * W + iw / up) * Cin + c]);
   }
@@ -55,7 +56,7 @@ struct ConvA {   // logical A[m, k]: m = (n, oh, ow), k = (kh, kw, c);  x is NHW
     int64_t ow = m % Wo; int64_t t = m / Wo; int64_t oh = t % Ho; int64_t n = t / Ho;
     if (vec && k0 + 8 <= K) {   // 8 consecutive k stay inside one tap because Cin % 8 == 0
       int tap = (int)(k0 / Cin); int64_t c = k0 - (int64_t)tap * Cin;
-      int64_t ih = oh * stride + tap / 3 - 1, iw = ow * stride + tap % 3 - 1;
+      int64_t ih = oh * stride + tap / 3 - pad, iw = ow * stride + tap % 3 - pad;
       if (ih < 0 || iw < 0 || ih >= H * up || iw >= W * up) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) f[e] = 0.f;
@@ -194,17 +195,18 @@ int32_t fyc_gemm_simt(const fyc_gemm_args* g, cudaStream_t st) {
 
 int32_t fyc_conv3x3_simt(const fyc_conv3x3_args* c, cudaStream_t st) {
   const int up = c->upsample, s = c->stride;
-  const int64_t Ho = (c->H * up + 2 - 3) / s + 1, Wo = (c->W * up + 2 - 3) / s + 1;
+  const int pad = c->pad_mode == 1 ? 0 : 1;       // pad_mode 1: the single padding row / column is on the bottom / right
+  const int64_t Ho = (c->H * up + 2 - 3) / s + 1, Wo = (c->W * up + 2 - 3) / s + 1;   // = H / 2 for stride 2 in both modes (even H)
   const int64_t M = c->NB * Ho * Wo, K = 9 * c->Cin, N = c->Cout;
   Epilogue ep{c->bias, c->residual, c->rowbias, N, N, (c->images_per_group > 0 ? c->images_per_group : 1) * Ho * Wo, 1.0f, c->epilogue};
   const bool f32out = (c->epilogue & FYC_EPI_OUT_F32) != 0;
   if (c->dtype == FYC_F32) {
     ConvAS<float> al; al.x = (const float*)c->x; al.NB = c->NB; al.H = c->H; al.W = c->W; al.Cin = c->Cin; al.Ho = Ho; al.Wo = Wo;
-    al.M = M; al.K = K; al.stride = s; al.up = up; al.vec = (c->Cin % 8 == 0) && (((uintptr_t)c->x) % 32 == 0);
+    al.M = M; al.K = K; al.stride = s; al.up = up; al.pad = pad; al.vec = (c->Cin % 8 == 0) && (((uintptr_t)c->x) % 32 == 0);
     return launch<float, float>(al, (const float*)c->w, (float*)c->out, M, N, K, K, 1, 0, 0, 0, ep, st);
   } else if (c->dtype == FYC_BF16) {
     ConvAS<bf16> al; al.x = (const bf16*)c->x; al.NB = c->NB; al.H = c->H; al.W = c->W; al.Cin = c->Cin; al.Ho = Ho; al.Wo = Wo;
-    al.M = M; al.K = K; al.stride = s; al.up = up; al.vec = (c->Cin % 8 == 0) && (((uintptr_t)c->x) % 16 == 0);
+    al.M = M; al.K = K; al.stride = s; al.up = up; al.pad = pad; al.vec = (c->Cin % 8 == 0) && (((uintptr_t)c->x) % 16 == 0);
     if (f32out) return launch<bf16, float>(al, (const bf16*)c->w, (float*)c->out, M, N, K, K, 1, 0, 0, 0, ep, st);
     return launch<bf16, bf16>(al, (const bf16*)c->w, (bf16*)c->out, M, N, K, K, 1, 0, 0, 0, ep, st);
   }

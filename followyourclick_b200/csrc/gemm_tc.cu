@@ -1013,7 +1013,11 @@ int32_t fyc_conv3x3_tc(const fyc_conv3x3_args* c, const void* x_planes, cudaStre
   for (int t = 0; t < 9; ++t) {
     int kh = t / 3, kw = t % 3;
     if (s == 1) { p.tap_dy[t] = kh - 1; p.tap_dx[t] = kw - 1; p.tap_img[t] = 0; }
-    else {   // ih = 2*oh + kh - 1: kh=0 -> odd plane, row oh-1; kh=1 -> even plane, row oh; kh=2 -> odd plane, row oh
+    else if (c->pad_mode == 1) {   // ih = 2*oh + kh: kh=0 -> even plane, row oh; kh=1 -> odd plane, row oh; kh=2 -> even plane, row oh+1
+      int ph = (kh == 1) ? 1 : 0, pw = (kw == 1) ? 1 : 0;       // (row H/2 of a plane is out of bounds: TMA zero fill = the bottom / right pad)
+      p.tap_dy[t] = (kh == 2) ? 1 : 0; p.tap_dx[t] = (kw == 2) ? 1 : 0;
+      p.tap_img[t] = (2 * ph + pw) * (int)c->NB;
+    } else {   // ih = 2*oh + kh - 1: kh=0 -> odd plane, row oh-1; kh=1 -> even plane, row oh; kh=2 -> odd plane, row oh
       int ph = (kh == 1) ? 0 : 1, pw = (kw == 1) ? 0 : 1;
       p.tap_dy[t] = (kh == 0) ? -1 : 0; p.tap_dx[t] = (kw == 0) ? -1 : 0;
       p.tap_img[t] = (2 * ph + pw) * (int)c->NB;

@@ -125,8 +125,10 @@ def gemm(A, W, bias=None, residual=None, rowbias=None, rows_per_group=0, alpha=1
     return o
 
 
-def conv3x3(x, w, bias=None, residual=None, rowbias=None, images_per_group=0, stride=1, upsample=1, out_f32=False, impl=None):
-    """x [NB, H, W, Cin] (NHWC), w [Cout, 3, 3, Cin] -> [NB, Ho, Wo, Cout]; pad 1."""
+def conv3x3(x, w, bias=None, residual=None, rowbias=None, images_per_group=0, stride=1, upsample=1, out_f32=False, impl=None,
+            pad_mode=0):
+    """x [NB, H, W, Cin] (NHWC), w [Cout, 3, 3, Cin] -> [NB, Ho, Wo, Cout]; pad 1 (pad_mode 1: stride-2 conv with the padding on
+    the bottom / right only - diffusers Downsample2D(padding=0), used by the VAE encoder)."""
     _cuda(x, "conv.x"); _cuda(w, "conv.w"); _cuda(residual, "conv.residual")
     _f32vec(bias, "conv.bias"); _f32vec(rowbias, "conv.rowbias")
     assert x.is_contiguous() and w.is_contiguous() and x.dtype == w.dtype
@@ -145,7 +147,7 @@ def conv3x3(x, w, bias=None, residual=None, rowbias=None, images_per_group=0, st
     epi = (L.EPI_BIAS if bias is not None else 0) | (L.EPI_RESIDUAL if residual is not None else 0) | \
           (L.EPI_ROWBIAS if rowbias is not None else 0) | (L.EPI_OUT_F32 if out_f32 else 0)
     a = L.ConvArgs(ptr(x), ptr(w), ptr(out), ptr(bias), ptr(residual), ptr(rowbias), NB, H, W_, Cin, Cout, stride,
-                   upsample, images_per_group, dtype_code(x.dtype), epi, impl, None, 0)
+                   upsample, images_per_group, dtype_code(x.dtype), epi, impl, None, 0, pad_mode)
     nbytes = lib().fyc_conv3x3_workspace_bytes(C.byref(a))
     ws = None
     if nbytes:

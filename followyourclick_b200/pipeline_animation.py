@@ -72,6 +72,22 @@ class _GraphedUNetStep:
                 dst.copy_(src)
 
 
+@torch.no_grad()
+def prepare_first_frame_condition(vae, first_images, first_images_mask, generator=None, vae_scale_factor=8):
+    """The per-clip conditioning prep that precedes the loop in the reference driver (scripts/inference.py:355-365):
+
+        first_image_latents = vae.encode(first_images).latent_dist.sample() * 0.18215
+        first_images_mask   = clamp(F.interpolate(mask, size=(H / 8, W / 8))[:, None], 0, 1)     # nearest
+
+    first_images (n, 3, H, W) in [-1, 1]; first_images_mask (n, 1, H, W).  Returns the two tensors AnimationPipeline.__call__ takes
+    as ``first_image_latents`` / ``first_images_mask`` (with this the whole I2V clip stays on the GPU)."""
+    lat = vae.encode(first_images).latent_dist.sample(generator=generator) * 0.18215
+    h, w = first_images.shape[-2] // vae_scale_factor, first_images.shape[-1] // vae_scale_factor
+    mask = first_images_mask.to(device=lat.device, dtype=torch.float32)
+    mask = torch.nn.functional.interpolate(mask, size=(h, w))[:, None]           # a (n, 1, h, w) nearest resize: index plumbing, once per clip
+    return lat, torch.clamp(mask, 0, 1)
+
+
 class AnimationPipeline:
     _optional_components = []
     use_cuda_graph = True          # replay one captured UNet forward per DDIM step (set False to launch kernel by kernel)

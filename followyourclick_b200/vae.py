@@ -1,12 +1,13 @@
 """AutoencoderKL: reference call surface (diffusers/models/vae.py:500-638), CUDA engine underneath.
 
-Round-1 scope is the decoder half: ``decode(z).sample`` and the batched ``decode_frames`` used by
+The decoder half is SURVEY 8a row a12: ``decode(z).sample`` and the batched ``decode_frames`` used by
 ``AnimationPipeline.decode_latents``.  All frames of a clip are decoded in ONE batch (the reference loops batch-1
 calls, pipeline_animation.py:405-408); GroupNorm statistics are per image so the result is identical.
 The mid-block attention (one 512-wide head over H*W tokens, softmax in fp32 - diffusers/models/attention.py:331-379)
 is three tensor-core GEMMs (QK^T with fp32 scores, PV on V^T) around an fp32 row-softmax kernel.
-The encoder (``encode``) is a "next" row: its parameters are part of the state dict so checkpoints load,
-but calling it raises.
+The encoder half (``encode`` -> ``latent_dist``; SURVEY 8f row 1, the first-frame conditioning prep of
+scripts/inference.py:340-365) reuses the same kernels; its downsamplers are the bottom/right-padded stride-2
+convolution of diffusers Downsample2D(padding=0) (``pad_mode=1`` of fyc_conv3x3).
 """
 from collections import OrderedDict
 from dataclasses import dataclass
@@ -20,6 +21,41 @@ from .modeling import FrozenDict, ParamTreeModel
 @dataclass
 class DecoderOutput:
     sample: torch.Tensor
+
+
+class DiagonalGaussianDistribution:
+    """diffusers/models/vae.py:341-397: moments (n, 2c, h, w) -> mean / clamped logvar / std / var, ``sample`` and ``mode``.
+    A per-clip one-off on a 2 x 4 x 64 x 64 tensor: plain tensor arithmetic on the device the moments live on."""
+
+    def __init__(self, parameters, deterministic=False):
+        self.parameters = parameters
+        self.mean, self.logvar = torch.chunk(parameters, 2, dim=1)
+        self.logvar = torch.clamp(self.logvar, -30.0, 20.0)
+        self.deterministic = deterministic
+        self.std = torch.exp(0.5 * self.logvar)
+        self.var = torch.exp(self.logvar)
+        if deterministic:
+            self.var = self.std = torch.zeros_like(self.mean)
+
+    def sample(self, generator=None):
+        noise = torch.randn(self.mean.shape, generator=generator, device=self.parameters.device)
+        return self.mean + self.std * noise.to(self.parameters.dtype)
+
+    def mode(self):
+        return self.mean
+
+    def kl(self, other=None):
+        if self.deterministic:
+            return torch.Tensor([0.0])
+        if other is None:
+            return 0.5 * torch.sum(torch.pow(self.mean, 2) + self.var - 1.0 - self.logvar, dim=[1, 2, 3])
+        return 0.5 * torch.sum(torch.pow(self.mean - other.mean, 2) / other.var + self.var / other.var - 1.0 - self.logvar
+                               + other.logvar, dim=[1, 2, 3])
+
+
+@dataclass
+class AutoencoderKLOutput:
+    latent_dist: DiagonalGaussianDistribution
 
 
 def vae_param_spec(cfg):
@@ -113,8 +149,44 @@ class AutoencoderKL(ParamTreeModel):
     def disable_slicing(self):
         self.use_slicing = False
 
+    def encode_nhwc(self, x):
+        """x [N, H, W, 3] channels-last in the compute dtype -> moments [N, H/8, W/8, 2 * latent] (compute dtype).
+        diffusers/models/vae.py:127-144 (Encoder.forward) + :567 (quant_conv)."""
+        if not x.is_cuda:
+            raise RuntimeError("AutoencoderKL.encode runs only on CUDA (B200); the CPU path is the reference/oracle")
+        boc = self._cfg["block_out_channels"]
+        x = ops.conv3x3(x, self._conv_w("encoder.conv_in.weight"), bias=self._f("encoder.conv_in.bias"))
+        for i in range(len(boc)):
+            for j in range(self._cfg["layers_per_block"]):
+                x = self._resnet(f"encoder.down_blocks.{i}.resnets.{j}", x)
+            if i < len(boc) - 1:      # Downsample2D(padding=0): F.pad (0, 1, 0, 1) + valid stride-2 conv (resnet.py:183-188)
+                p = f"encoder.down_blocks.{i}.downsamplers.0.conv"
+                x = ops.conv3x3(x, self._conv_w(p + ".weight"), bias=self._f(p + ".bias"), stride=2, pad_mode=1)
+        x = self._resnet("encoder.mid_block.resnets.0", x)
+        x = self._attn("encoder.mid_block.attentions.0", x)
+        x = self._resnet("encoder.mid_block.resnets.1", x)
+        x = self._gn("encoder.conv_norm_out", x, True)
+        x = ops.conv3x3(x, self._conv_w("encoder.conv_out.weight"), bias=self._f("encoder.conv_out.bias"))
+        NB, H, W, c2 = x.shape
+        return ops.gemm(x.view(-1, c2), self._w1x1("quant_conv.weight"), bias=self._f("quant_conv.bias")).view(NB, H, W, c2)
+
+    @torch.no_grad()
     def encode(self, x, return_dict=True):
-        raise NotImplementedError("AutoencoderKL.encode (first-frame conditioning prep) is SURVEY 8f row 1 - not built yet")
+        """diffusers/models/vae.py:565-573: x (n, 3, H, W) -> .latent_dist (DiagonalGaussianDistribution over (n, 4, H/8, W/8)),
+        moments in fp32."""
+        x = x.to(device=self.device, dtype=torch.float32).contiguous()
+        if not x.is_cuda:
+            raise RuntimeError("AutoencoderKL.encode runs only on CUDA (B200); the CPU path is the reference/oracle")
+        n, c, h, w = x.shape
+        if h % 8 or w % 8:
+            raise ValueError(f"AutoencoderKL.encode: image size {h}x{w} must be a multiple of 8")
+        xx = ops.ncfhw_to_nfhwc(x.view(n, c, 1, h, w), self._compute_dtype).view(n, h, w, c)
+        m = self.encode_nhwc(xx)
+        moments = ops.nfhwc_to_ncfhw(m.view(n, 1, m.shape[1], m.shape[2], m.shape[3])).view(n, m.shape[3], m.shape[1], m.shape[2])
+        posterior = DiagonalGaussianDistribution(moments)
+        if not return_dict:
+            return (posterior,)
+        return AutoencoderKLOutput(latent_dist=posterior)
 
     # ------------------------------------------------------------------------------------------ decoder engine
     def _gn(self, p, x, silu):
@@ -180,5 +252,11 @@ class AutoencoderKL(ParamTreeModel):
             return (out,)
         return DecoderOutput(sample=out)
 
-    def forward(self, *a, **kw):
-        raise NotImplementedError("AutoencoderKL.forward (encode+decode) needs the encoder: SURVEY 8f row 1")
+    def forward(self, sample, sample_posterior=False, return_dict=True, generator=None):
+        """diffusers/models/vae.py:612-638."""
+        posterior = self.encode(sample).latent_dist
+        z = posterior.sample(generator=generator) if sample_posterior else posterior.mode()
+        dec = self.decode(z).sample
+        if not return_dict:
+            return (dec,)
+        return DecoderOutput(sample=dec)

@@ -82,6 +82,10 @@ typedef struct {
   int32_t dtype, epilogue, impl;
   void* workspace;              /* fyc_conv3x3_workspace_bytes() bytes (stride-2 / upsample on the tcgen05 path) */
   size_t workspace_bytes;
+  int32_t pad_mode;             /* 0: zero pad 1 on every side.  1 (stride 2, even H and W, upsample 1 only): pad 1 on the bottom /
+                                   right only - diffusers Downsample2D with padding=0, F.pad(x, (0,1,0,1)) + valid conv
+                                   (diffusers/models/resnet.py:183-188), the VAE Encoder's downsamplers (vae.py:95);
+                                   Ho = H/2 either way, input row = 2*oh + kh instead of 2*oh + kh - 1 */
 } fyc_conv3x3_args;
 size_t fyc_conv3x3_workspace_bytes(const fyc_conv3x3_args* a);
 int32_t fyc_conv3x3(const fyc_conv3x3_args* a, void* stream);

@@ -1,9 +1,13 @@
-"""Oracle: functional fp32 restatement of ``AutoencoderKL.decode`` (decoder half only).
+"""Oracle: functional fp32 restatement of ``AutoencoderKL.decode`` and ``AutoencoderKL.encode``.
 
 TEST INFRASTRUCTURE (see oracle/__init__.py).  Reference: diffusers/models/vae.py:147-224
 (Decoder), :575-610 (post_quant_conv + decode), unet_2d_blocks.py:320-396 (UNetMidBlock2D),
 :1646-1697 (UpDecoderBlock2D), resnet.py:367-495 (ResnetBlock2D, temb=None), :77-143
 (Upsample2D), attention.py:247-379 (AttentionBlock, single head, fp32 softmax).
+Encoder half (the first-frame conditioning prep of scripts/inference.py:340-365):
+vae.py:67-144 (Encoder), :565-573 (encode + quant_conv), :341-361 (DiagonalGaussianDistribution),
+unet_2d_blocks.py DownEncoderBlock2D, resnet.py:146-188 (Downsample2D with padding=0:
+F.pad(x, (0, 1, 0, 1)) then a valid stride-2 conv).
 """
 import torch
 import torch.nn.functional as F
@@ -64,6 +68,33 @@ def vae_decode(sd, cfg, z):
             x = _conv(sd, f"decoder.up_blocks.{i}.upsamplers.0.conv", x)
     x = F.silu(F.group_norm(x, g, sd["decoder.conv_norm_out.weight"], sd["decoder.conv_norm_out.bias"], 1e-6))
     return _conv(sd, "decoder.conv_out", x)
+
+
+def vae_encode_moments(sd, cfg, x):
+    """AutoencoderKL.encode(x).latent_dist.parameters (vae.py:565-568): x (n, 3, H, W) -> moments (n, 8, H/8, W/8)."""
+    sd = {k: v.float() for k, v in sd.items()}
+    g = cfg["norm_num_groups"]
+    boc = cfg["block_out_channels"]
+    h = _conv(sd, "encoder.conv_in", x.float())
+    for i in range(len(boc)):
+        for j in range(cfg["layers_per_block"]):
+            h = resnet_block_2d(sd, f"encoder.down_blocks.{i}.resnets.{j}", h, g)
+        if i < len(boc) - 1:                                   # resnet.py:183-188: pad bottom/right by one, valid conv, stride 2
+            p = f"encoder.down_blocks.{i}.downsamplers.0.conv"
+            h = F.conv2d(F.pad(h, (0, 1, 0, 1)), sd[p + ".weight"], sd[p + ".bias"], stride=2)
+    h = resnet_block_2d(sd, "encoder.mid_block.resnets.0", h, g)
+    h = attention_block(sd, "encoder.mid_block.attentions.0", h, g)
+    h = resnet_block_2d(sd, "encoder.mid_block.resnets.1", h, g)
+    h = F.silu(F.group_norm(h, g, sd["encoder.conv_norm_out.weight"], sd["encoder.conv_norm_out.bias"], 1e-6))
+    h = _conv(sd, "encoder.conv_out", h)
+    return F.conv2d(h, sd["quant_conv.weight"], sd["quant_conv.bias"])                    # vae.py:567
+
+
+def gaussian_sample(moments, noise):
+    """DiagonalGaussianDistribution(moments).sample() with the normal draw supplied (vae.py:341-361):
+    mean + exp(0.5 * clamp(logvar, -30, 20)) * noise."""
+    mean, logvar = torch.chunk(moments.float(), 2, dim=1)
+    return mean + torch.exp(0.5 * torch.clamp(logvar, -30.0, 20.0)) * noise
 
 
 def decode_latents(sd, cfg, latents):

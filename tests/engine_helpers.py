@@ -96,6 +96,17 @@ def run_vae_case(dtype):
     return stats(out, torch.from_numpy(g["out"]))
 
 
+def run_vae_encode_case(dtype):
+    """AutoencoderKL.encode against the reference's moments / reparameterised sample (golden vae_encode.npz)."""
+    vae, sd = make_vae(dtype)
+    g = golden("vae_encode.npz")
+    dist = vae.encode(torch.from_numpy(g["x"]).cuda()).latent_dist
+    noise = torch.from_numpy(g["noise"]).cuda()
+    sample = dist.mean + dist.std * noise
+    torch.cuda.synchronize()
+    return stats(dist.parameters, torch.from_numpy(g["moments"])), stats(sample, torch.from_numpy(g["sample"])), dist
+
+
 class FakeTokenizer:
     model_max_length = 77
 

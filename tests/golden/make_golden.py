@@ -70,10 +70,38 @@ def maxabs(a, b):
     return float((a - b).abs().max())
 
 
+def vae_encode_fixture(VAE):
+    """encoder moments of the unmodified reference on a seeded image, oracle checked against them."""
+    from tests.cfgs import MINI_VAE
+    vae = VAE(in_channels=3, out_channels=3, down_block_types=("DownEncoderBlock2D",) * 4,
+              up_block_types=("UpDecoderBlock2D",) * 4, block_out_channels=MINI_VAE["block_out_channels"],
+              layers_per_block=MINI_VAE["layers_per_block"], latent_channels=4, norm_num_groups=32).eval()
+    vsd = load_synth(vae)
+    x = torch.rand(2, 3, 64, 64, generator=torch.Generator().manual_seed(11)) * 2 - 1
+    noise = torch.randn(2, 4, 8, 8, generator=torch.Generator().manual_seed(12))
+    with torch.no_grad():
+        dist = vae.encode(x).latent_dist
+        ref_m = dist.parameters
+        ref_s = dist.mean + dist.std * noise
+        orc_m = ref_vae.vae_encode_moments(vsd, MINI_VAE, x)
+        orc_s = ref_vae.gaussian_sample(orc_m, noise)
+    err = max(maxabs(ref_m, orc_m), maxabs(ref_s, orc_s))
+    print(f"vae encode moments {tuple(ref_m.shape)} |ref|max={float(ref_m.abs().max()):.3f} oracle-vs-ref maxabs={err:.3e}")
+    assert err < 2e-4 * max(1.0, float(ref_m.abs().max()))
+    np.savez_compressed(os.path.join(HERE, "vae_encode.npz"), x=x.numpy(), noise=noise.numpy(), moments=ref_m.numpy(), sample=ref_s.numpy())
+    return err
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(8)
     UNet, Pipe, VAE, DDIM, ImageProjModel = import_reference()
+    if "--only-vae-encode" in sys.argv:          # add the encoder fixture without regenerating the others
+        pj = os.path.join(HERE, "pins.json")
+        d = json.load(open(pj))
+        d["oracle_vs_reference_maxabs"]["vae_encode"] = vae_encode_fixture(VAE)
+        json.dump(d, open(pj, "w"), indent=1)
+        return
     pins = {}
 
     # ------------------------------------------------------------------ DDIM known answers (SURVEY App. D)
@@ -209,6 +237,7 @@ def main():
     print(f"pipeline video {tuple(ref_video.shape)} oracle-vs-ref maxabs={err:.3e}")
     assert err < 2e-3
     pins["pipeline"] = err
+    pins["vae_encode"] = vae_encode_fixture(VAE)
     np.savez_compressed(os.path.join(HERE, "pipeline.npz"), video=ref_video.numpy().astype(np.float32),
                         final_latents=lat.numpy())
     with open(os.path.join(HERE, "pins.json"), "w") as f:

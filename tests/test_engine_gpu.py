@@ -45,6 +45,33 @@ def test_vae_decode_matches_reference_golden(dtype, tol):
     assert s["finite"] and s["rel_l2"] < tol, s
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 3e-2)])
+def test_vae_encode_matches_reference_golden(dtype, tol):
+    from tests.engine_helpers import run_vae_encode_case
+    m, s, dist = run_vae_encode_case(dtype)
+    assert m["finite"] and m["rel_l2"] < tol, m
+    assert s["finite"] and s["rel_l2"] < tol, s
+    assert dist.mean.shape == (2, 4, 8, 8) and dist.parameters.dtype == torch.float32
+    assert torch.equal(dist.mode(), dist.mean) and dist.sample(generator=torch.Generator(device="cuda").manual_seed(0)).shape == (2, 4, 8, 8)
+
+
+def test_first_frame_condition_prep():
+    """scripts/inference.py:355-365: encode -> sample * 0.18215, mask nearest-resized to the latent grid and clamped."""
+    import torch.nn.functional as F
+    from followyourclick_b200.pipeline_animation import prepare_first_frame_condition
+    from tests.engine_helpers import golden, make_vae
+    vae, _ = make_vae(torch.float32)
+    g = golden("vae_encode.npz")
+    x = torch.from_numpy(g["x"]).cuda()
+    mask = (torch.rand(2, 1, 64, 64, generator=torch.Generator().manual_seed(3)) * 3 - 1).cuda()
+    lat, m = prepare_first_frame_condition(vae, x, mask, generator=torch.Generator(device="cuda").manual_seed(5))
+    noise = torch.randn((2, 4, 8, 8), generator=torch.Generator(device="cuda").manual_seed(5), device="cuda")
+    mom = torch.from_numpy(g["moments"]).cuda()
+    ref = (mom[:, :4] + torch.exp(0.5 * mom[:, 4:].clamp(-30, 20)) * noise) * 0.18215
+    assert float((lat - ref).abs().max()) < 1e-3
+    assert m.shape == (2, 1, 1, 8, 8) and torch.equal(m, F.interpolate(mask, size=(8, 8))[:, None].clamp(0, 1))
+
+
 def test_pipeline_fp32_matches_reference_golden():
     from tests.engine_helpers import run_pipeline_case
     r = run_pipeline_case(torch.float32, steps=3, against="golden")

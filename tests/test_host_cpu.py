@@ -126,7 +126,7 @@ def test_pipeline_input_validation_and_no_cpu_fallback():
         unet.forward_nfhwc(torch.zeros(2, 4, 16, 16, 9), 1, torch.zeros(2, 77, 768))
     with pytest.raises(RuntimeError):
         vae.decode_nhwc(torch.zeros(1, 8, 8, 4))
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError):
         vae.encode(torch.zeros(1, 3, 64, 64))
 
 

@@ -157,6 +157,21 @@ def test_conv3x3(dtype, impl, NB, H, W, Cin, Cout, stride, up):
     assert out.shape == ref.shape and rel(out, ref) < tol(dtype), rel(out, ref)
 
 
+@pytest.mark.parametrize("dtype,impl", MODES)
+@pytest.mark.parametrize("NB,H,W,Cin,Cout", [(2, 16, 16, 64, 64), (3, 32, 32, 128, 160), (1, 8, 12, 24, 8)])
+def test_conv3x3_stride2_bottom_right_pad(dtype, impl, NB, H, W, Cin, Cout):
+    """pad_mode 1 = diffusers Downsample2D(padding=0): F.pad(x, (0, 1, 0, 1)) + valid stride-2 conv (VAE encoder)."""
+    from followyourclick_b200 import ops
+    if impl == "tc" and (Cin % 8 or Cout % 16):
+        pytest.skip("shape not eligible for the tcgen05 path")
+    ops.set_impl("auto" if impl == "tc" else impl)
+    x = rnd((NB, H, W, Cin), 1, dtype)
+    w = rnd((Cout, Cin, 3, 3), 2, torch.float32, (9 * Cin) ** -0.5)
+    bias = rnd((Cout,), 3)
+    out = ops.conv3x3(x, w.permute(0, 2, 3, 1).to(dtype).contiguous(), bias=bias, stride=2, pad_mode=1)
+    ref = F.conv2d(F.pad(x.float().permute(0, 3, 1, 2), (0, 1, 0, 1)), w.to(dtype).float(), bias, stride=2).permute(0, 2, 3, 1)
+    assert out.shape == ref.shape == (NB, H // 2, W // 2, Cout) and rel(out, ref) < tol(dtype), rel(out, ref)
+
 @pytest.mark.parametrize("NB,H,W,Cin,Cout,stride", [(6, 16, 16, 128, 160, 1), (3, 32, 32, 64, 320, 1), (4, 32, 32, 128, 64, 2)])
 def test_conv3x3_tcgen05_cta_pairs(NB, H, W, Cin, Cout, stride, monkeypatch):
     """Implicit-GEMM convolution on CTA pairs: patch tiles split over the two CTAs (incl. an odd number of m blocks and the

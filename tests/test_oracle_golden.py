@@ -69,6 +69,16 @@ def test_unet_oracle_vs_reference_fixture(variant):
     assert float((out - ref).abs().max()) < 5e-4 * max(1.0, float(ref.abs().max()))
 
 
+def test_vae_encode_oracle_vs_reference_fixture():
+    """the encoder restatement against the unmodified reference's moments and reparameterised sample."""
+    vsd = _synth(json.load(open(os.path.join(GOLD, "vae_keys.json"))))
+    g = np.load(os.path.join(GOLD, "vae_encode.npz"))
+    m = ref_vae.vae_encode_moments(vsd, MINI_VAE, torch.from_numpy(g["x"]))
+    assert m.shape == (2, 8, 8, 8) and float((m - torch.from_numpy(g["moments"])).abs().max()) < 1e-4
+    s = ref_vae.gaussian_sample(m, torch.from_numpy(g["noise"]))
+    assert float((s - torch.from_numpy(g["sample"])).abs().max()) < 1e-4
+
+
 def test_vae_and_pipeline_oracle_vs_reference_fixture():
     from followyourclick_b200.synth import synth_clip_inputs
     vkeys = json.load(open(os.path.join(GOLD, "vae_keys.json")))
