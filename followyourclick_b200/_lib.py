@@ -30,7 +30,7 @@ class ConvArgs(C.Structure):
     _fields_ = [("x", _vp), ("w", _vp), ("out", _vp), ("bias", _vp), ("residual", _vp), ("rowbias", _vp),
                 ("NB", _i64), ("H", _i64), ("W", _i64), ("Cin", _i64), ("Cout", _i64), ("stride", _i32),
                 ("upsample", _i32), ("images_per_group", _i64), ("dtype", _i32), ("epilogue", _i32), ("impl", _i32),
-                ("workspace", _vp), ("workspace_bytes", _sz), ("pad_mode", _i32)]
+                ("workspace", _vp), ("workspace_bytes", _sz), ("pad_mode", _i32), ("w_phases", _vp)]
 
 
 class AttnArgs(C.Structure):
@@ -53,6 +53,7 @@ SIGNATURES = {
     "fyc_gemm": (_i32, [C.POINTER(GemmArgs), _vp]),
     "fyc_conv3x3_workspace_bytes": (_sz, [C.POINTER(ConvArgs)]),
     "fyc_conv3x3": (_i32, [C.POINTER(ConvArgs), _vp]),
+    "fyc_conv3x3_up2_eligible": (_i32, [C.POINTER(ConvArgs)]),
     "fyc_groupnorm_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "fyc_groupnorm": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _f32, _i32, _i32, _vp, _sz, _vp]),
     "fyc_layernorm": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _f32, _vp, _i64, _i64, _i32, _vp]),

@@ -8,6 +8,8 @@ bool fyc_gemm_tc_eligible(const fyc_gemm_args* g);
 int32_t fyc_conv3x3_simt(const fyc_conv3x3_args* c, cudaStream_t st);
 int32_t fyc_conv3x3_tc(const fyc_conv3x3_args* c, const void* x_planes, cudaStream_t st);
 bool fyc_conv3x3_tc_eligible(const fyc_conv3x3_args* c);
+int32_t fyc_conv3x3_up2_tc(const fyc_conv3x3_args* c, cudaStream_t st);
+bool fyc_conv3x3_up2_tc_eligible(const fyc_conv3x3_args* c);
 int32_t fyc_space_to_planes(const void* x, void* out, int64_t NB, int64_t H, int64_t W, int64_t C, cudaStream_t st);
 int32_t fyc_attention_simt(const fyc_attention_args* a, cudaStream_t st);
 int32_t fyc_attention_mma(const fyc_attention_args* a, cudaStream_t st);
@@ -37,6 +39,10 @@ extern "C" size_t fyc_conv3x3_workspace_bytes(const fyc_conv3x3_args* c) {
   return 0;
 }
 
+extern "C" int32_t fyc_conv3x3_up2_eligible(const fyc_conv3x3_args* c) {
+  return (c && c->impl != FYC_IMPL_SIMT && fyc_tcgen05_available() == 1 && fyc_conv3x3_up2_tc_eligible(c)) ? 1 : 0;
+}
+
 extern "C" int32_t fyc_conv3x3(const fyc_conv3x3_args* c, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   FYC_CHECK(c && c->x && c->w && c->out, "conv3x3: null pointer");
@@ -47,6 +53,7 @@ extern "C" int32_t fyc_conv3x3(const fyc_conv3x3_args* c, void* stream) {
   FYC_CHECK(!(c->epilogue & FYC_EPI_BIAS) || c->bias, "conv3x3: FYC_EPI_BIAS without bias");
   FYC_CHECK(!(c->epilogue & FYC_EPI_RESIDUAL) || c->residual, "conv3x3: FYC_EPI_RESIDUAL without residual");
   FYC_CHECK(!(c->epilogue & FYC_EPI_ROWBIAS) || (c->rowbias && c->images_per_group > 0), "conv3x3: FYC_EPI_ROWBIAS without rowbias");
+  if (c->impl != FYC_IMPL_SIMT && c->upsample == 2 && c->w_phases && fyc_conv3x3_up2_tc_eligible(c)) return fyc_conv3x3_up2_tc(c, st);
   bool tc = (c->impl != FYC_IMPL_SIMT) && fyc_conv3x3_tc_eligible(c);
   if (tc && c->stride == 2 && (!c->workspace || c->workspace_bytes < fyc_conv3x3_workspace_bytes(c))) {
     FYC_CHECK(c->impl != FYC_IMPL_TCGEN05, "conv3x3(tcgen05): stride-2 needs %zu workspace bytes", fyc_conv3x3_workspace_bytes(c));

@@ -1045,6 +1045,64 @@ int32_t fyc_conv3x3_tc(const fyc_conv3x3_args* c, const void* x_planes, cudaStre
   return launch_tc(ma, mw, p, grid, st);
 }
 
+// nearest-x2 upsample + padded 3x3 conv as four 2x2-tap implicit GEMMs on the low-resolution image (fyc.h: w_phases).
+// Phase (py, px) produces output pixels (2*oh + py, 2*ow + px).  No kernel change is needed: the A boxes are the usual shifted
+// patches of x (TMA zero fill = the conv's zero padding, because an upsampled halo pixel is out of bounds exactly when its source
+// pixel is), and the interleaved destination is expressed through the epilogue's own address arithmetic - it computes
+// pix = (img * Ho + oh) * Wo + ow and stores at out + pix * ldo: with Wo := 2 W, ldo := 2 Cout and out advanced by
+// (py * 2W + px) * Cout that is ((img * 2H + 2 oh + py) * 2W + 2 ow + px) * Cout, the NHWC offset of the upsampled pixel.
+bool fyc_conv3x3_up2_tc_eligible(const fyc_conv3x3_args* c) {
+  if (c->dtype != FYC_BF16 || c->upsample != 2 || c->stride != 1 || c->pad_mode != 0 || !c->w_phases) return false;
+  if (c->Cin % 8 || c->Cout % 16) return false;
+  if (((uintptr_t)c->x | (uintptr_t)c->w_phases | (uintptr_t)c->out) & 15) return false;
+  if (c->epilogue & ~FYC_EPI_BIAS) return false;          // the upsamplers carry a bias only (resnet.py:168, diffusers resnet.py:139)
+  int bw, bh, bn;
+  if (!pick_patch(c->NB, c->H, c->W, &bw, &bh, &bn)) return false;
+  return get_encode_fn() != nullptr;
+}
+
+int32_t fyc_conv3x3_up2_tc(const fyc_conv3x3_args* c, cudaStream_t st) {
+  FYC_CHECK(fyc_conv3x3_up2_tc_eligible(c), "conv3x3 up2(tcgen05): shape/alignment not eligible");
+  const int64_t H = c->H, W = c->W;
+  TcParams p{};
+  pick_patch(c->NB, H, W, &p.bw, &p.bh, &p.bn);
+  p.M = c->NB * H * W; p.N = (int)c->Cout; p.N_out = p.N;
+  p.taps = 4; p.cin_blocks = (int)ceil_div64(c->Cin, BK);
+  p.Wo = (int)W; p.Ho = (int)H; p.w_tiles = (int)(W / p.bw); p.h_tiles = (int)(H / p.bh);
+  p.m_tiles = (int64_t)p.w_tiles * p.h_tiles * (c->NB / p.bn);
+  p.flags = c->epilogue;
+  int grid = 0;
+  choose_tiles(p, &grid);                       // tile shape / staging mode from the true (low-resolution) problem size
+  p.Wo = (int)(2 * W); p.M = c->NB * H * 2 * W;  // epilogue addressing only (see above); every ow < W < Wo, every pix < M
+  p.ldo = 2 * c->Cout; p.ldr = p.ldo; p.alpha = 1.0f;
+  p.bias = c->bias; p.rowbias = nullptr; p.residual = nullptr; p.rows_per_group = 1;
+  CUtensorMap ma;
+  {
+    uint64_t dims[4] = {(uint64_t)c->Cin, (uint64_t)W, (uint64_t)H, (uint64_t)c->NB};
+    uint64_t str[3] = {(uint64_t)c->Cin * 2, (uint64_t)c->Cin * 2 * W, (uint64_t)c->Cin * 2 * W * H};
+    uint32_t box[4] = {BK, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
+    int32_t rc = encode_map(&ma, c->x, 4, dims, str, box);
+    if (rc) return rc;
+  }
+  for (int ph = 0; ph < 4; ++ph) {
+    const int py = ph >> 1, px = ph & 1;
+    for (int t = 0; t < 4; ++t) {               // tap (a, b): input row oh + a - 1 + py, column ow + b - 1 + px
+      p.tap_dy[t] = (t >> 1) - 1 + py; p.tap_dx[t] = (t & 1) - 1 + px; p.tap_img[t] = 0;
+    }
+    CUtensorMap mw;
+    const bf16* wp = (const bf16*)c->w_phases + (int64_t)ph * c->Cout * 4 * c->Cin;
+    uint64_t dims[3] = {(uint64_t)c->Cin, 4, (uint64_t)c->Cout};
+    uint64_t str[2] = {(uint64_t)c->Cin * 2, (uint64_t)c->Cin * 2 * 4};
+    uint32_t box[3] = {BK, 1, (uint32_t)(p.pair ? p.BN / 2 : p.BN)};
+    int32_t rc = encode_map(&mw, wp, 3, dims, str, box);
+    if (rc) return rc;
+    p.out = (bf16*)c->out + ((int64_t)py * 2 * W + px) * c->Cout;
+    rc = launch_tc(ma, mw, p, grid, st);
+    if (rc) return rc;
+  }
+  return FYC_OK;
+}
+
 int32_t fyc_space_to_planes(const void* x, void* out, int64_t NB, int64_t H, int64_t W, int64_t C, cudaStream_t st) {
   FYC_CHECK(H % 2 == 0 && W % 2 == 0 && C % 8 == 0, "space_to_planes: H, W must be even and C a multiple of 8");
   int64_t total = NB * H * W * C / 8;

@@ -173,6 +173,12 @@ class ParamTreeModel(nn.Module):
         """[Cout, Cin, 3, 3] -> [Cout, 3, 3, Cin] in compute dtype"""
         return self._cached(("c", key), lambda: self._p(key).detach().permute(0, 2, 3, 1).to(self._compute_dtype).contiguous())
 
+    def _conv_w_up2(self, key):
+        """phase-summed filter of an upsampler conv, [4, Cout, 2, 2, Cin] (bf16 tensor-core mode only, else None)"""
+        if self._compute_dtype != torch.bfloat16:
+            return None
+        return self._cached(("up2", key), lambda: upsample_phase_weights(self._p(key).detach().float()).to(self._compute_dtype).contiguous())
+
     def _w1x1(self, key):
         """1x1 conv weight [Cout, Cin, 1, 1] -> [Cout, Cin]"""
         return self._cached(("1", key), lambda: self._p(key).detach().flatten(1).to(self._compute_dtype).contiguous())
@@ -187,3 +193,25 @@ def geglu_interleave(w, b):
     wi = torch.cat([a, g], dim=1).reshape(2 * hd, -1)
     ba, bg = b[:hd].reshape(hd // 128, 128), b[hd:].reshape(hd // 128, 128)
     return wi.contiguous(), torch.cat([ba, bg], dim=1).reshape(2 * hd).contiguous()
+
+
+def upsample_phase_weights(w):
+    """[Cout, Cin, 3, 3] fp32 -> [4, Cout, 2, 2, Cin]: nearest-x2 upsampling followed by a zero-padded 3x3 convolution
+    (animatediff/models/resnet.py:155-168, diffusers/models/resnet.py:128-139) restated per output parity.  Output pixel
+    (2*oh + py, 2*ow + px) reads upsampled rows 2*oh + py + kh - 1, i.e. source rows {oh-1, oh, oh} for py = 0 and {oh, oh, oh+1}
+    for py = 1, so the three filter rows collapse to two taps: py = 0 -> (oh-1: w[0]; oh: w[1]+w[2]), py = 1 -> (oh: w[0]+w[1];
+    oh+1: w[2]); columns alike.  Phase index 2*py + px, tap (a, b) reads source pixel (oh + a - 1 + py, ow + b - 1 + px).
+    The sums are taken in fp32 before the single rounding to the compute dtype."""
+    rows = (((0,), (1, 2)), ((0, 1), (2,)))
+    Cout, Cin = w.shape[:2]
+    out = torch.zeros(4, Cout, 2, 2, Cin, dtype=torch.float32, device=w.device)
+    for py in range(2):
+        for px in range(2):
+            for a in range(2):
+                for b in range(2):
+                    acc = 0
+                    for kh in rows[py][a]:
+                        for kw in rows[px][b]:
+                            acc = acc + w[:, :, kh, kw]
+                    out[2 * py + px, :, a, b, :] = acc
+    return out

@@ -5,6 +5,7 @@ a kernel of libfyc_sm100a.so.  All tensors must be CUDA, contiguous in the last 
 all fp32 (strict parity mode) or all bf16 (tensor-core mode).
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -125,16 +126,32 @@ def gemm(A, W, bias=None, residual=None, rowbias=None, rows_per_group=0, alpha=1
     return o
 
 
+use_up2_phases = os.environ.get("FYC_UP2_PHASES", "1") != "0"    # A/B switch for the four-phase upsample convolution
+
+
 def conv3x3(x, w, bias=None, residual=None, rowbias=None, images_per_group=0, stride=1, upsample=1, out_f32=False, impl=None,
-            pad_mode=0):
+            pad_mode=0, w_phases=None):
     """x [NB, H, W, Cin] (NHWC), w [Cout, 3, 3, Cin] -> [NB, Ho, Wo, Cout]; pad 1 (pad_mode 1: stride-2 conv with the padding on
-    the bottom / right only - diffusers Downsample2D(padding=0), used by the VAE encoder)."""
-    _cuda(x, "conv.x"); _cuda(w, "conv.w"); _cuda(residual, "conv.residual")
+    the bottom / right only - diffusers Downsample2D(padding=0), used by the VAE encoder).  upsample=2 with ``w_phases``
+    ([4, Cout, 2, 2, Cin], modeling.upsample_phase_weights): nearest-x2 + conv as four 2x2-tap convs on the low-res image."""
+    _cuda(x, "conv.x"); _cuda(w, "conv.w"); _cuda(residual, "conv.residual"); _cuda(w_phases, "conv.w_phases")
     _f32vec(bias, "conv.bias"); _f32vec(rowbias, "conv.rowbias")
     assert x.is_contiguous() and w.is_contiguous() and x.dtype == w.dtype
     impl = _impl if impl is None else impl
     NB, H, W_, Cin = x.shape
     Cout = w.shape[0]
+    if upsample == 2 and w_phases is not None and use_up2_phases and impl != L.IMPL_SIMT and tc_ok(x.dtype, NB * H * W_) \
+            and residual is None and rowbias is None and not out_f32:
+        assert w_phases.is_contiguous() and w_phases.dtype == x.dtype and tuple(w_phases.shape) == (4, Cout, 2, 2, Cin)
+        out = torch.empty((NB, 2 * H, 2 * W_, Cout), dtype=x.dtype, device=x.device)
+        a = L.ConvArgs(ptr(x), ptr(w), ptr(out), ptr(bias), None, None, NB, H, W_, Cin, Cout, 1, 2, 0, dtype_code(x.dtype),
+                       L.EPI_BIAS if bias is not None else 0, impl, None, 0, 0, ptr(w_phases))
+        if lib().fyc_conv3x3_up2_eligible(C.byref(a)) == 1:
+            fam = "conv_tc_up2" + (f"[{NB}x{H}x{W_} {Cin}->{Cout}]" if _prof_shapes else "")
+            # executed work: 4 phases x 4 taps on the low-res grid (the reference's upsample + 3x3 conv is 36 MACs per input pixel)
+            with _rec(fam, 2.0 * NB * H * W_ * Cout * 16 * Cin, x.element_size() * (x.numel() + w_phases.numel() + out.numel())):
+                check(lib().fyc_conv3x3(C.byref(a), stream_ptr()))
+            return out
     if upsample == 2 and impl != L.IMPL_SIMT and tc_ok(x.dtype, NB * H * W_):
         x = upsample_nearest2x(x)            # the tensor-core path reads unit-stride boxes: materialise the upsample
         NB, H, W_, Cin = x.shape
@@ -147,7 +164,7 @@ def conv3x3(x, w, bias=None, residual=None, rowbias=None, images_per_group=0, st
     epi = (L.EPI_BIAS if bias is not None else 0) | (L.EPI_RESIDUAL if residual is not None else 0) | \
           (L.EPI_ROWBIAS if rowbias is not None else 0) | (L.EPI_OUT_F32 if out_f32 else 0)
     a = L.ConvArgs(ptr(x), ptr(w), ptr(out), ptr(bias), ptr(residual), ptr(rowbias), NB, H, W_, Cin, Cout, stride,
-                   upsample, images_per_group, dtype_code(x.dtype), epi, impl, None, 0, pad_mode)
+                   upsample, images_per_group, dtype_code(x.dtype), epi, impl, None, 0, pad_mode, None)
     nbytes = lib().fyc_conv3x3_workspace_bytes(C.byref(a))
     ws = None
     if nbytes:

@@ -517,7 +517,8 @@ class UNet3DConditionModel(ParamTreeModel):
                 if motion_on(lvl, True):
                     x = self._motion(f"{p}.motion_modules.{j}", x, B, F)
             if i < n - 1:
-                x = ops.conv3x3(x, self._conv_w(f"{p}.upsamplers.0.conv.weight"), bias=self._f(f"{p}.upsamplers.0.conv.bias"), upsample=2)
+                x = ops.conv3x3(x, self._conv_w(f"{p}.upsamplers.0.conv.weight"), bias=self._f(f"{p}.upsamplers.0.conv.bias"), upsample=2,
+                                w_phases=self._conv_w_up2(f"{p}.upsamplers.0.conv.weight"))
             self._tap(f"up{i}", x)
         x = self._gn("conv_norm_out", x, B, True, False)
         y = ops.conv3x3(x, self._conv_w("conv_out.weight"), bias=self._f("conv_out.bias"), out_f32=True)

@@ -235,7 +235,7 @@ class AutoencoderKL(ParamTreeModel):
                 x = self._resnet(f"decoder.up_blocks.{i}.resnets.{j}", x)
             if i < len(boc) - 1:
                 p = f"decoder.up_blocks.{i}.upsamplers.0.conv"
-                x = ops.conv3x3(x, self._conv_w(p + ".weight"), bias=self._f(p + ".bias"), upsample=2)
+                x = ops.conv3x3(x, self._conv_w(p + ".weight"), bias=self._f(p + ".bias"), upsample=2, w_phases=self._conv_w_up2(p + ".weight"))
         x = self._gn("decoder.conv_norm_out", x, True)
         return ops.conv3x3(x, self._conv_w("decoder.conv_out.weight"), bias=self._f("decoder.conv_out.bias"))
 

@@ -86,9 +86,19 @@ typedef struct {
                                    right only - diffusers Downsample2D with padding=0, F.pad(x, (0,1,0,1)) + valid conv
                                    (diffusers/models/resnet.py:183-188), the VAE Encoder's downsamplers (vae.py:95);
                                    Ho = H/2 either way, input row = 2*oh + kh instead of 2*oh + kh - 1 */
+  const void* w_phases;         /* optional (upsample == 2, bf16): the filter pre-summed per output parity, [4 phases = 2*py+px]
+                                   [Cout][2][2][Cin].  nearest-x2 followed by a padded 3x3 conv is, for each output parity (py, px),
+                                   a 2x2 conv on the LOW-resolution image: rows {oh-1 | w[0], oh | w[1]+w[2]} for py = 0 and
+                                   {oh | w[0]+w[1], oh+1 | w[2]} for py = 1 (columns alike) - 16 instead of 36 MACs per input
+                                   pixel and channel pair, and the upsampled tensor is never written.  The tcgen05 path runs the
+                                   four phases as four 4-tap implicit GEMMs whose rows are written interleaved; without it (or on
+                                   the CUDA-core path) `w` is used with the upsample folded into the input index. */
 } fyc_conv3x3_args;
 size_t fyc_conv3x3_workspace_bytes(const fyc_conv3x3_args* a);
 int32_t fyc_conv3x3(const fyc_conv3x3_args* a, void* stream);
+/* 1 when a (upsample == 2, w_phases != NULL) call will take the four-phase tcgen05 path, else 0 (the caller then either
+ * materialises the upsample and runs the plain 3x3 path, or lets fyc_conv3x3 fold it into the CUDA-core kernel's index). */
+int32_t fyc_conv3x3_up2_eligible(const fyc_conv3x3_args* a);
 
 /* ---- normalisation ------------------------------------------------------------------------------------
  * GroupNorm (+ optional SiLU) over x viewed as [NB, R, C]: statistics per (nb, group) over R rows x C/G

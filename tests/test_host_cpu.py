@@ -138,3 +138,27 @@ def test_synth_weights_are_deterministic_and_nonzero():
     assert set(s1) == set(shapes) - {"m.pos_encoder.pe"}
     assert all(torch.equal(s1[k], s2[k]) for k in s1) and float(s1["b.proj_out.weight"].abs().sum()) > 0
     assert abs(float(s1["n.norm.weight"].mean()) - 1.0) < 0.3
+
+
+def test_upsample_phase_weights_restates_upsample_plus_conv():
+    """modeling.upsample_phase_weights: nearest-x2 + padded 3x3 conv == four 2x2-tap convs on the low-res image (fp64 check of the
+    restatement the tcgen05 upsampler path runs; the kernel-level parity is tests/test_kernels_gpu.py)."""
+    import torch.nn.functional as F
+    from followyourclick_b200.modeling import upsample_phase_weights
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 5, 6, 7, generator=g, dtype=torch.float64)
+    w = torch.randn(4, 5, 3, 3, generator=g, dtype=torch.float64)
+    ref = F.conv2d(F.interpolate(x, scale_factor=2, mode="nearest"), w, padding=1)
+    wp = upsample_phase_weights(w.float()).double()
+    assert wp.shape == (4, 4, 2, 2, 5)
+    xp = F.pad(x, (1, 1, 1, 1))
+    out = torch.zeros_like(ref)
+    for py in range(2):
+        for px in range(2):
+            acc = 0
+            for a in range(2):
+                for b in range(2):
+                    dy, dx = a - 1 + py, b - 1 + px
+                    acc = acc + torch.einsum("nchw,oc->nohw", xp[:, :, 1 + dy:7 + dy, 1 + dx:8 + dx], wp[2 * py + px, :, a, b, :])
+            out[:, :, py::2, px::2] = acc
+    assert float((out - ref).abs().max()) < 1e-5

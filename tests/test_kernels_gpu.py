@@ -192,6 +192,36 @@ def test_conv3x3_tcgen05_cta_pairs(NB, H, W, Cin, Cout, stride, monkeypatch):
         out = ops.conv3x3(x, wp, bias=bias, residual=res, rowbias=temb, images_per_group=1, stride=stride)
         assert out.shape == ref.shape and rel(out, ref) < tol(dtype), (mode, rel(out, ref))
 
+@pytest.mark.parametrize("NB,H,W,Cin,Cout", [(2, 8, 8, 64, 48), (4, 16, 16, 128, 160), (32, 8, 8, 320, 320), (2, 32, 32, 64, 64),
+                                             (3, 16, 8, 72, 32), (2, 64, 64, 128, 128)])
+@pytest.mark.parametrize("pair", ["1", "2", "0"])
+def test_conv3x3_upsample_phases_tcgen05(NB, H, W, Cin, Cout, pair, monkeypatch):
+    """nearest-x2 + conv3x3 as four 2x2-tap implicit GEMMs written interleaved (fyc.h w_phases): against the fp32 PyTorch
+    upsample + conv, and against the engine's own materialised-upsample path (same kernel, 9 taps)."""
+    from followyourclick_b200 import _lib, ops
+    from followyourclick_b200.modeling import upsample_phase_weights
+    import ctypes as C
+    dtype = torch.bfloat16
+    ops.set_impl("auto")
+    monkeypatch.setenv("FYC_TC_PAIR", pair)
+    x = rnd((NB, H, W, Cin), 1, dtype)
+    w = rnd((Cout, Cin, 3, 3), 2, torch.float32, (9 * Cin) ** -0.5)
+    bias = rnd((Cout,), 3)
+    wp = w.permute(0, 2, 3, 1).to(dtype).contiguous()
+    wph = upsample_phase_weights(w).to(dtype).contiguous()
+    a = _lib.ConvArgs(x.data_ptr(), wp.data_ptr(), x.data_ptr(), None, None, None, NB, H, W, Cin, Cout, 1, 2, 0, _lib.BF16, 0,
+                      _lib.IMPL_AUTO, None, 0, 0, wph.data_ptr())
+    assert _lib.lib().fyc_conv3x3_up2_eligible(C.byref(a)) == 1
+    out = ops.conv3x3(x, wp, bias=bias, upsample=2, w_phases=wph)
+    ref = F.conv2d(F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest"), w.to(dtype).float(), bias,
+                   padding=1).permute(0, 2, 3, 1)
+    assert out.shape == ref.shape == (NB, 2 * H, 2 * W, Cout) and rel(out, ref) < tol(dtype), rel(out, ref)
+    old = ops.conv3x3(x, wp, bias=bias, upsample=2)                   # materialised upsample + 9-tap path
+    assert rel(out, old) < 6e-3, rel(out, old)                        # two bf16 roundings of the same fp32 sums
+    monkeypatch.setattr(ops, "use_up2_phases", False)
+    assert torch.equal(ops.conv3x3(x, wp, bias=bias, upsample=2, w_phases=wph), old)
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("NB,R,C,G,stat", [(2, 4 * 64, 160, 32, 2), (8, 64, 160, 32, 8), (2, 1024, 1920, 32, 2), (4, 16, 128, 32, 4),
                                             (3, 100, 36, 4, 3)])
