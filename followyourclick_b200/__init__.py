@@ -7,6 +7,6 @@ from .unet import UNet3DConditionModel, UNet3DConditionOutput, ImageProjModel  #
 from .vae import AutoencoderKL  # noqa: F401
 from .scheduling_ddim import DDIMScheduler  # noqa: F401
 from .pipeline_animation import AnimationPipeline, AnimationPipelineOutput  # noqa: F401
-from .ip_adapter import IPAttnProcessor, IPAttnProcessor2_0, MyIPAdapter  # noqa: F401
+from .ip_adapter import IPAttnProcessor, IPAttnProcessor2_0, MyIPAdapter, MyIPAdapterPlus, Resampler  # noqa: F401
 
 __version__ = "0.1.0"

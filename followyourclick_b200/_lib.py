@@ -64,14 +64,15 @@ SIGNATURES = {
     "fyc_softmax_rows": (_i32, [_vp, _vp, _i64, _i64, _i32, _vp]),
     "fyc_timestep_embed": (_i32, [_vp, _vp, _vp, _i64, _i64, _i32, _vp]),
     "fyc_silu": (_i32, [_vp, _vp, _i64, _i32, _vp]),
+    "fyc_gelu": (_i32, [_vp, _vp, _i64, _i32, _vp]),
     "fyc_geglu": (_i32, [_vp, _vp, _i64, _i64, _i32, _vp]),
     "fyc_upsample_nearest2x": (_i32, [_vp, _vp, _i64, _i64, _i64, _i64, _i32, _vp]),
     "fyc_concat_channels": (_i32, [_vp, _vp, _vp, _i64, _i64, _i64, _i32, _vp]),
     "fyc_ncfhw_to_nfhwc": (_i32, [_vp, _vp, _i64, _i64, _i64, _i64, _f32, _i32, _vp]),
-    "fyc_nfhwc_to_ncfhw": (_i32, [_vp, _vp, _i64, _i64, _i64, _i64, _i32, _vp]),
+    "fyc_nfhwc_to_ncfhw": (_i32, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _i32, _vp]),
     "fyc_build_unet_input": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i32, _i32, _i32, _vp]),
     "fyc_cfg_ddim_step": (_i32, [_vp, _vp, _vp, _vp, _i64, C.POINTER(DdimCoefs), _vp]),
-    "fyc_frames_finalize": (_i32, [_vp, _vp, _i64, _i64, _i64, _i32, _vp]),
+    "fyc_frames_finalize": (_i32, [_vp, _vp, _i64, _i64, _i64, _i64, _i32, _vp]),
 }
 
 _lib = None

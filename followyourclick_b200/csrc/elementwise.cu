@@ -43,6 +43,18 @@ extern "C" int32_t fyc_silu(const void* x, void* out, int64_t n, int32_t dtype, 
   return FYC_OK;
 }
 
+// exact-erf GELU (nn.GELU() of the Perceiver Resampler's feed-forward, ip_adapter/resampler.py:14-21)
+template <typename T>
+__global__ void gelu_kernel(const T* __restrict__ x, T* __restrict__ out, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = from_f<T>(gelu_erf_f(to_f(x[i])));
+}
+extern "C" int32_t fyc_gelu(const void* x, void* out, int64_t n, int32_t dtype, void* stream) {
+  FYC_DISPATCH(dtype, gelu_kernel<T><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, (T*)out, n));
+  FYC_LAUNCH_CHECK();
+  return FYC_OK;
+}
+
 // GEGLU for the SIMT path.  in [M, 2*Hd]: column block t of 256 holds a[128t:128t+128] | gate[128t:128t+128].
 template <typename T>
 __global__ void geglu_kernel(const T* __restrict__ in, T* __restrict__ out, int64_t M, int64_t Hd) {
@@ -136,13 +148,13 @@ __global__ void ncfhw_to_nfhwc_kernel(const float* __restrict__ in, T* __restric
   }
 }
 template <typename T>
-__global__ void nfhwc_to_ncfhw_kernel(const T* __restrict__ in, float* __restrict__ out, int64_t B, int64_t C, int64_t F, int64_t HW) {
+__global__ void nfhwc_to_ncfhw_kernel(const T* __restrict__ in, float* __restrict__ out, int64_t B, int64_t C, int64_t F, int64_t HW, int64_t ldc) {
   int64_t total = B * F * HW * C;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t p = i % HW; int64_t r = i / HW;
     int64_t f = r % F; r /= F;
     int64_t c = r % C; int64_t b = r / C;
-    out[i] = to_f(in[((b * F + f) * HW + p) * C + c]);
+    out[i] = to_f(in[((b * F + f) * HW + p) * ldc + c]);
   }
 }
 extern "C" int32_t fyc_ncfhw_to_nfhwc(const float* in, void* out, int64_t B, int64_t C, int64_t F, int64_t HW, float scale, int32_t dtype, void* stream) {
@@ -150,8 +162,10 @@ extern "C" int32_t fyc_ncfhw_to_nfhwc(const float* in, void* out, int64_t B, int
   FYC_LAUNCH_CHECK();
   return FYC_OK;
 }
-extern "C" int32_t fyc_nfhwc_to_ncfhw(const void* in, float* out, int64_t B, int64_t C, int64_t F, int64_t HW, int32_t dtype, void* stream) {
-  FYC_DISPATCH(dtype, nfhwc_to_ncfhw_kernel<T><<<grid_for(B * C * F * HW, 256), 256, 0, (cudaStream_t)stream>>>((const T*)in, out, B, C, F, HW));
+extern "C" int32_t fyc_nfhwc_to_ncfhw(const void* in, float* out, int64_t B, int64_t C, int64_t F, int64_t HW, int64_t ldc, int32_t dtype, void* stream) {
+  if (ldc <= 0) ldc = C;
+  FYC_CHECK(ldc >= C, "nfhwc_to_ncfhw: channel stride %lld < C %lld", (long long)ldc, (long long)C);
+  FYC_DISPATCH(dtype, nfhwc_to_ncfhw_kernel<T><<<grid_for(B * C * F * HW, 256), 256, 0, (cudaStream_t)stream>>>((const T*)in, out, B, C, F, HW, ldc));
   FYC_LAUNCH_CHECK();
   return FYC_OK;
 }
@@ -242,19 +256,21 @@ extern "C" int32_t fyc_cfg_ddim_step(const float* pred, const float* sample, con
 // ---------------------------------------------------------------------------------------------------------
 // decode_latents epilogue (pipeline_animation.py:409-410): [b*F, HW, 3] -> (b, 3, F, HW) fp32, (x/2+0.5).clamp(0,1)
 template <typename T>
-__global__ void frames_finalize_kernel(const T* __restrict__ x, float* __restrict__ video, int64_t b, int64_t F, int64_t HW) {
+__global__ void frames_finalize_kernel(const T* __restrict__ x, float* __restrict__ video, int64_t b, int64_t F, int64_t HW, int64_t ldc) {
   int64_t total = b * 3 * F * HW;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t p = i % HW; int64_t r = i / HW;
     int64_t f = r % F; r /= F;
     int64_t c = r % 3; int64_t bi = r / 3;
-    float v = to_f(x[((bi * F + f) * HW + p) * 3 + c]);
+    float v = to_f(x[((bi * F + f) * HW + p) * ldc + c]);
     v = __fadd_rn(__fdiv_rn(v, 2.0f), 0.5f);
     video[i] = fminf(fmaxf(v, 0.f), 1.f);
   }
 }
-extern "C" int32_t fyc_frames_finalize(const void* x, float* video, int64_t b, int64_t F, int64_t HW, int32_t dtype, void* stream) {
-  FYC_DISPATCH(dtype, frames_finalize_kernel<T><<<grid_for(b * 3 * F * HW, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, video, b, F, HW));
+extern "C" int32_t fyc_frames_finalize(const void* x, float* video, int64_t b, int64_t F, int64_t HW, int64_t ldc, int32_t dtype, void* stream) {
+  if (ldc <= 0) ldc = 3;
+  FYC_CHECK(ldc >= 3, "frames_finalize: channel stride %lld < 3", (long long)ldc);
+  FYC_DISPATCH(dtype, frames_finalize_kernel<T><<<grid_for(b * 3 * F * HW, 256), 256, 0, (cudaStream_t)stream>>>((const T*)x, video, b, F, HW, ldc));
   FYC_LAUNCH_CHECK();
   return FYC_OK;
 }

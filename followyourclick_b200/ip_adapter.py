@@ -6,11 +6,71 @@ mirroring IPCrossAttention.forward, animatediff/models/attention.py:49-127).  ``
 processor-style entry for callers that drive an attention layer themselves: identical arithmetic
 ``softmax(q k_text^T s) v_text + scale * softmax(q k_ip^T s) v_ip`` followed by ``to_out``, on the same kernels.
 """
+from collections import OrderedDict
+
 import torch
 from torch import nn
 
 from . import ops
+from .modeling import ParamTreeModel
 from .unet import ImageProjModel
+
+
+class Resampler(ParamTreeModel):
+    """Perceiver resampler of IP-Adapter-Plus (ip_adapter/resampler.py:87-158), engine underneath; same constructor kwargs and
+    state-dict keys (``latents``, ``proj_in``, ``layers.{i}.0.{norm1,norm2,to_q,to_kv,to_out}``, ``layers.{i}.1.{0,1,3}``,
+    ``proj_out``, ``norm_out``).  It is a per-clip one-off (its input, the CLIP penultimate hidden states, does not change over the
+    DDIM loop - SURVEY 8f row 2), so it always runs in fp32 on the CUDA-core kernels: LayerNorm, GEMM (+bias / +residual),
+    flash attention over the [image tokens ; latents] keys, exact-erf GELU - every FLOP a libfyc kernel, none in torch."""
+
+    def __init__(self, dim=1024, depth=8, dim_head=64, heads=16, num_queries=8, embedding_dim=768, output_dim=1024, ff_mult=4,
+                 max_seq_len=257, apply_pos_emb=False, num_latents_mean_pooled=0):
+        super().__init__()
+        if apply_pos_emb or num_latents_mean_pooled:
+            raise NotImplementedError("Resampler: apply_pos_emb / num_latents_mean_pooled are off in MyIPAdapterPlus.init_proj")
+        self.dim, self.depth, self.dim_head, self.heads, self.num_queries = dim, depth, dim_head, heads, num_queries
+        self.embedding_dim, self.output_dim, self.ff_mult = embedding_dim, output_dim, ff_mult
+        inner = dim_head * heads
+        spec = OrderedDict([("latents", (1, num_queries, dim)), ("proj_in.weight", (dim, embedding_dim)), ("proj_in.bias", (dim,)),
+                            ("proj_out.weight", (output_dim, dim)), ("proj_out.bias", (output_dim,)),
+                            ("norm_out.weight", (output_dim,)), ("norm_out.bias", (output_dim,))])
+        for i in range(depth):
+            p = f"layers.{i}"
+            for n in ("norm1", "norm2"):
+                spec[f"{p}.0.{n}.weight"] = (dim,); spec[f"{p}.0.{n}.bias"] = (dim,)
+            spec[f"{p}.0.to_q.weight"] = (inner, dim); spec[f"{p}.0.to_kv.weight"] = (2 * inner, dim)
+            spec[f"{p}.0.to_out.weight"] = (dim, inner)
+            spec[f"{p}.1.0.weight"] = (dim,); spec[f"{p}.1.0.bias"] = (dim,)
+            spec[f"{p}.1.1.weight"] = (dim * ff_mult, dim); spec[f"{p}.1.3.weight"] = (dim, dim * ff_mult)
+        self._build_tree(spec)
+
+    @torch.no_grad()
+    def forward(self, x):
+        """x (b, n1, embedding_dim) -> (b, num_queries, output_dim) fp32."""
+        ops.require_cuda(x, "Resampler")
+        f = self._f
+        B, n1, E = x.shape
+        d, Q, H, inner = self.dim, self.num_queries, self.heads, self.heads * self.dim_head
+        xin = ops.gemm(x.float().contiguous().view(B * n1, E), f("proj_in.weight"), bias=f("proj_in.bias"))        # [B n1, d]
+        lat = f("latents").expand(B, Q, d).contiguous().view(B * Q, d)
+        for i in range(self.depth):
+            a, ff = f"layers.{i}.0", f"layers.{i}.1"
+            xn = ops.layernorm(xin, f(a + ".norm1.weight"), f(a + ".norm1.bias"))
+            ln = ops.layernorm(lat, f(a + ".norm2.weight"), f(a + ".norm2.bias"))
+            q = ops.gemm(ln, f(a + ".to_q.weight")).view(B, Q, inner)
+            # k, v of [x ; latents] (resampler.py:66-67): the two row blocks are projected straight into one [B, n1 + Q, 2 inner] buffer
+            wkv = f(a + ".to_kv.weight").unsqueeze(0).expand(B, 2 * inner, d)
+            kv = torch.empty((B, n1 + Q, 2 * inner), dtype=torch.float32, device=x.device)
+            ops.gemm(xn.view(B, n1, d), wkv, out=kv[:, :n1])
+            ops.gemm(ln.view(B, Q, d), wkv, out=kv[:, n1:])
+            # (q s)(k s)^T with s = d_h^-1/4 (:74-75) == q k^T d_h^-1/2; softmax in fp32 (:76)
+            o = ops.attention(q, kv[:, :, :inner], kv[:, :, inner:], H, self.dim_head ** -0.5)
+            lat = ops.gemm(o.view(B * Q, inner), f(a + ".to_out.weight"), residual=lat)
+            h = ops.layernorm(lat, f(ff + ".0.weight"), f(ff + ".0.bias"))
+            h = ops.gelu(ops.gemm(h, f(ff + ".1.weight")))
+            lat = ops.gemm(h, f(ff + ".3.weight"), residual=lat)
+        out = ops.gemm(lat, f("proj_out.weight"), bias=f("proj_out.bias"))
+        return ops.layernorm(out, f("norm_out.weight"), f("norm_out.bias")).view(B, Q, self.output_dim)
 
 
 class IPAttnProcessor(nn.Module):
@@ -26,8 +86,7 @@ class IPAttnProcessor(nn.Module):
         .scale = d^-1/2).  hidden_states (B, L, C) or (B, C, H, W); encoder_hidden_states (B, 77+T, Dc)."""
         if attention_mask is not None:
             raise NotImplementedError("attention_mask is None on the whole inference path (SURVEY App. A.4)")
-        if not hidden_states.is_cuda:
-            raise RuntimeError("IPAttnProcessor runs only on CUDA (B200)")
+        ops.require_cuda(hidden_states, "IPAttnProcessor")
         nd = hidden_states.dim()
         x = hidden_states
         if nd == 4:
@@ -96,3 +155,30 @@ class MyIPAdapter:
             input_image = self.clip_image_processor(images=imgs, return_tensors="pt").pixel_values
         emb = self.image_encoder(input_image.to(self.device)).image_embeds
         return emb, torch.zeros_like(emb)
+
+
+class MyIPAdapterPlus(MyIPAdapter):
+    """ip_adapter/my_ip_adapter.py:215-290: fine-grained image features - the projector is the Perceiver ``Resampler`` (depth 4,
+    12 heads x 64, ``num_tokens`` queries) over the CLIP vision tower's penultimate hidden states."""
+
+    def __init__(self, unet, image_encoder_path=None, ip_ckpt=None, device="cuda", num_tokens=16, image_encoder=None,
+                 clip_embeddings_dim=None):
+        super().__init__(unet, image_encoder_path, ip_ckpt, device, num_tokens, image_encoder, clip_embeddings_dim)
+
+    def init_proj(self):
+        hidden = getattr(getattr(self.image_encoder, "config", None), "hidden_size", None) or self._clip_dim
+        return Resampler(dim=self.unet.config.cross_attention_dim, depth=4, dim_head=64, heads=12, num_queries=self.num_tokens,
+                         embedding_dim=hidden, output_dim=self.unet.config.cross_attention_dim, ff_mult=4).to(self.device)
+
+    @torch.no_grad()
+    def get_image_clip_feat(self, input_image=None):
+        if not torch.is_tensor(input_image):
+            if self.clip_image_processor is None:
+                from transformers import CLIPImageProcessor
+                self.clip_image_processor = CLIPImageProcessor()
+            imgs = input_image if isinstance(input_image, list) else [input_image]
+            input_image = self.clip_image_processor(images=imgs, return_tensors="pt").pixel_values
+        input_image = input_image.to(self.device)
+        cond = self.image_encoder(input_image, output_hidden_states=True).hidden_states[-2]
+        uncond = self.image_encoder(torch.zeros_like(input_image), output_hidden_states=True).hidden_states[-2]
+        return cond, uncond

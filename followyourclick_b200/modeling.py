@@ -179,6 +179,25 @@ class ParamTreeModel(nn.Module):
             return None
         return self._cached(("up2", key), lambda: upsample_phase_weights(self._p(key).detach().float()).to(self._compute_dtype).contiguous())
 
+    def _conv_head(self, name, pixels):
+        """(filter [N, 3, 3, Cin], bias [N], true Cout) of a 3- / 4-channel output convolution.  In tensor-core mode the output
+        channels are zero-padded to N = 16 so the head is a tcgen05 implicit GEMM (its N must be a multiple of 16) instead of a
+        CUDA-core kernel; consumers read the first Cout of the 16 channels (fyc_nfhwc_to_ncfhw / fyc_frames_finalize `ldc`)."""
+        from . import ops
+        cout = self._p(name + ".weight").shape[0]
+        if not (ops.use_tc_head and cout < 16 and ops.tc_ok(self._compute_dtype, pixels)):
+            return self._conv_w(name + ".weight"), self._f(name + ".bias"), cout
+
+        def make():
+            w = self._conv_w(name + ".weight")
+            wp = torch.zeros((16,) + tuple(w.shape[1:]), dtype=w.dtype, device=w.device)
+            wp[:cout] = w
+            bp = torch.zeros(16, dtype=torch.float32, device=w.device)
+            bp[:cout] = self._f(name + ".bias")
+            return wp, bp
+        wp, bp = self._cached(("head16", name), make)
+        return wp, bp, cout
+
     def _w1x1(self, key):
         """1x1 conv weight [Cout, Cin, 1, 1] -> [Cout, Cin]"""
         return self._cached(("1", key), lambda: self._p(key).detach().flatten(1).to(self._compute_dtype).contiguous())

@@ -75,6 +75,12 @@ def _cuda(t, name):
         raise L.FycError(f"{name}: last dimension must be contiguous")
 
 
+def require_cuda(t, what):
+    """The engine has no CPU path: every model entry point calls this on its input."""
+    if not t.is_cuda:
+        raise RuntimeError(f"{what} runs only on CUDA (B200); the CPU path is the reference/oracle")
+
+
 def _f32vec(t, name):
     if t is not None and (t.dtype != torch.float32 or not t.is_contiguous()):
         raise L.FycError(f"{name}: expected a contiguous fp32 tensor")
@@ -127,6 +133,7 @@ def gemm(A, W, bias=None, residual=None, rowbias=None, rows_per_group=0, alpha=1
 
 
 use_up2_phases = os.environ.get("FYC_UP2_PHASES", "1") != "0"    # A/B switch for the four-phase upsample convolution
+use_tc_head = os.environ.get("FYC_TC_HEAD", "1") != "0"          # A/B switch: 3- / 4-channel output convs zero-padded to N = 16 on tcgen05
 
 
 def conv3x3(x, w, bias=None, residual=None, rowbias=None, images_per_group=0, stride=1, upsample=1, out_f32=False, impl=None,
@@ -287,6 +294,14 @@ def silu(x):
     return out
 
 
+def gelu(x):
+    _cuda(x, "gelu.x")
+    assert x.is_contiguous()
+    out = torch.empty_like(x)
+    check(lib().fyc_gelu(ptr(x), ptr(out), x.numel(), dtype_code(x.dtype), stream_ptr()))
+    return out
+
+
 def upsample_nearest2x(x):
     assert x.is_contiguous()
     NB, H, W_, Cc = x.shape
@@ -312,12 +327,26 @@ def ncfhw_to_nfhwc(x, dtype, scale=1.0):
     return out
 
 
+def _channel_sliced(x):
+    """x [..., C] that is either contiguous or a leading-channel slice x_full[..., :C] of a contiguous tensor -> channel stride."""
+    assert x.stride(-1) == 1
+    ld = x.stride(-2)
+    # strides of the enclosing contiguous [.., ld] tensor
+    want, acc = [1], ld
+    for n in reversed(x.shape[:-1]):
+        want.insert(0, acc)
+        acc *= n
+    ok = all(n == 1 or st == wt for n, st, wt in zip(x.shape, x.stride(), want))
+    assert ld >= x.shape[-1] and ok, "expected a contiguous tensor or a [..., :C] slice of one"
+    return ld
+
+
 def nfhwc_to_ncfhw(x):
-    """dtype [b, f, h, w, c] -> fp32 (b, c, f, h, w)."""
-    assert x.is_contiguous() and x.is_cuda
+    """dtype [b, f, h, w, c] (or its [..., :c] slice of a wider channels-last tensor) -> fp32 (b, c, f, h, w)."""
+    ld = _channel_sliced(x)
     b, f, h, w, c = x.shape
     out = torch.empty((b, c, f, h, w), dtype=torch.float32, device=x.device)
-    check(lib().fyc_nfhwc_to_ncfhw(ptr(x), ptr(out), b, c, f, h * w, dtype_code(x.dtype), stream_ptr()))
+    check(lib().fyc_nfhwc_to_ncfhw(ptr(x), ptr(out), b, c, f, h * w, ld, dtype_code(x.dtype), stream_ptr()))
     return out
 
 
@@ -344,10 +373,11 @@ def cfg_ddim_step(pred, sample, coefs, noise=None, out=None):
 
 
 def frames_finalize(x, b, f):
-    """x [b*f, H, W, 3] -> video (b, 3, f, H, W) fp32 = (x / 2 + 0.5).clamp(0, 1)."""
-    assert x.is_contiguous()
+    """x [b*f, H, W, 3] (or the [..., :3] slice of a wider channels-last tensor) -> video (b, 3, f, H, W) fp32 =
+    (x / 2 + 0.5).clamp(0, 1)."""
+    ld = _channel_sliced(x)
     _, H, W_, c = x.shape
     assert c == 3
     out = torch.empty((b, 3, f, H, W_), dtype=torch.float32, device=x.device)
-    check(lib().fyc_frames_finalize(ptr(x), ptr(out), b, f, H * W_, dtype_code(x.dtype), stream_ptr()))
+    check(lib().fyc_frames_finalize(ptr(x), ptr(out), b, f, H * W_, ld, dtype_code(x.dtype), stream_ptr()))
     return out

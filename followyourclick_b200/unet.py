@@ -32,6 +32,28 @@ class UNet3DConditionOutput:
     sample: torch.Tensor
 
 
+class ClipContext:
+    """Everything in a UNet forward that depends only on a clip's text / image conditioning and therefore not on the DDIM step
+    (SURVEY 8f row 2): the context tokens in the compute dtype (text, with the image-prompt tokens of the IP-Adapter projector
+    appended), and per transformer block the cross-attention K/V projections of those tokens (and K_ip/V_ip).  The reference
+    recomputes all of it in every forward (unet.py:592-594, attention.py:60-75,98-106); the engine builds it once per clip
+    (``UNet3DConditionModel.prepare_context``) and the per-step forward only reads it."""
+
+    def __init__(self, ctx, kv, kvi, ip_tokens):
+        self.ctx, self.kv, self.kvi, self.ip_tokens = ctx, kv, kvi, ip_tokens
+
+    def tensors(self):
+        return [self.ctx] + [self.kv[k] for k in sorted(self.kv)] + [self.kvi[k] for k in sorted(self.kvi)]
+
+    def copy_(self, other):
+        """refresh in place (the static buffers a captured CUDA graph reads)"""
+        a, b = self.tensors(), other.tensors()
+        assert len(a) == len(b) and all(x.shape == y.shape and x.dtype == y.dtype for x, y in zip(a, b))
+        for x, y in zip(a, b):
+            x.copy_(y)
+        return self
+
+
 def _as_tuple(v, n):
     return tuple(v) if isinstance(v, (tuple, list)) else (v,) * n
 
@@ -356,17 +378,17 @@ class UNet3DConditionModel(ParamTreeModel):
             qkv = qkv.view(NB, HW, 3 * C)
             o = ops.attention(qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:], heads, d ** -0.5)
         tok = ops.gemm(o.view(M, C), self._w(q + ".attn1.to_out.0.weight"), bias=self._f(q + ".attn1.to_out.0.bias"), residual=tok)
-        # cross attention (attention.py:516-521; IPCrossAttention.forward :49-127)
+        # cross attention (attention.py:516-521; IPCrossAttention.forward :49-127); K/V of the context come from the per-clip cache
         n2 = ops.layernorm(tok, self._f(q + ".norm2.weight"), self._f(q + ".norm2.bias"))
         qx = ops.gemm(n2, self._w(q + ".attn2.to_q.weight")).view(NB, HW, C)
-        Bc, L, xd = ctx.shape
-        kv = ops.gemm(ctx.view(Bc * L, xd), self._cat_w(q + ".attn2", [q + ".attn2.to_k.weight", q + ".attn2.to_v.weight"])).view(Bc, L, 2 * C)
+        kv = ctx.kv[p]
+        L = kv.shape[1]
         if self._cfg["use_ip_cross_attention"]:
             T = self._cfg["num_tokens"]
             # reference quirk (animatediff/models/attention.py:43): without xformers the IP scale replaces d^-1/2
             sc = d ** -0.5 if self._xformers_semantics else float(self._cfg["scale"])
             o = ops.attention(qx, kv[:, :L - T, :C], kv[:, :L - T, C:], heads, sc, kv_batch_div=F)
-            kvi = ops.gemm(ctx.view(Bc * L, xd), self._cat_w(q + ".attn2ip", [q + ".attn2.to_k_ip.weight", q + ".attn2.to_v_ip.weight"])).view(Bc, L, 2 * C)
+            kvi = ctx.kvi[p]
             ops.attention(qx, kvi[:, L - T:, :C], kvi[:, L - T:, C:], heads, sc, out=o, out_alpha=float(self._cfg["scale"]),
                           accumulate=True, kv_batch_div=F)
         else:
@@ -418,6 +440,39 @@ class UNet3DConditionModel(ParamTreeModel):
         h = ops.silu(ops.gemm(s, self._fw(name + ".linear_1.weight"), bias=self._f(name + ".linear_1.bias")))
         return ops.gemm(h, self._fw(name + ".linear_2.weight"), bias=self._f(name + ".linear_2.bias"), residual=residual)
 
+    def _transformer_prefixes(self):
+        cfg = self._cfg
+        n = len(cfg["block_out_channels"])
+        out = [f"down_blocks.{i}.attentions.{j}" for i in range(n - 1) for j in range(cfg["layers_per_block"])]
+        out.append("mid_block.attentions.0")
+        out += [f"up_blocks.{i}.attentions.{j}" for i in range(1, n) for j in range(cfg["layers_per_block"] + 1)]
+        return out
+
+    @torch.no_grad()
+    def prepare_context(self, encoder_hidden_states, reference_images_clip_feat=None, use_ip_cross_attention=False, ip_tokens=None):
+        """Per-clip, step-invariant part of the forward -> ClipContext: text tokens (b, 77, D) [+ image-prompt tokens from
+        ``image_proj_model(reference_images_clip_feat)`` (unet.py:592-594), or ``ip_tokens`` if the caller already has them] in the
+        compute dtype, and every transformer block's fused [K | V] (and [K_ip | V_ip]) projection of them."""
+        ctx = self._to_compute(encoder_hidden_states)
+        B = ctx.shape[0]
+        tokens = None
+        if use_ip_cross_attention:
+            if ip_tokens is None:
+                ipm = self.image_proj_model
+                if ipm is None:
+                    raise RuntimeError("use_ip_cross_attention=True but unet.image_proj_model is not set (scripts/inference.py:166)")
+                ip_tokens = ipm(reference_images_clip_feat.to(self.device))
+            tokens = self._to_compute(ip_tokens.float())
+            ctx = ops.concat_channels(ctx.view(B, -1), tokens.view(B, -1)).view(B, -1, ctx.shape[-1])   # unet.py:592-594
+        Bc, L, xd = ctx.shape
+        kv, kvi = {}, {}
+        for p in self._transformer_prefixes():
+            q = p + ".transformer_blocks.0"
+            kv[p] = ops.gemm(ctx.view(Bc * L, xd), self._cat_w(q + ".attn2", [q + ".attn2.to_k.weight", q + ".attn2.to_v.weight"])).view(Bc, L, -1)
+            if self._cfg["use_ip_cross_attention"]:
+                kvi[p] = ops.gemm(ctx.view(Bc * L, xd), self._cat_w(q + ".attn2ip", [q + ".attn2.to_k_ip.weight", q + ".attn2.to_v_ip.weight"])).view(Bc, L, -1)
+        return ClipContext(ctx, kv, kvi, tokens)
+
     def input_channel_pad(self):
         """Channel count the engine wants for its channels-last input: 16 (zero padded) in tensor-core mode so the stem
         conv runs on tcgen05, else the model's true input channels."""
@@ -442,10 +497,12 @@ class UNet3DConditionModel(ParamTreeModel):
 
     def forward_nfhwc(self, x, timestep, encoder_hidden_states, fps_tensor=None, flow_control=None,
                       reference_images_clip_feat=None, camera_movement_type_tensor=None, use_ip_cross_attention=False,
-                      use_camera_motion_condition=False, use_fps_condition=False, use_first_frame_condition_concat=False):
-        """Engine entry: x [B, F, H, W, Cin] channels-last in the compute dtype -> fp32 [B, F, H, W, out_channels]."""
-        if not x.is_cuda:
-            raise RuntimeError("UNet3DConditionModel runs only on CUDA (B200); the CPU path is the reference/oracle")
+                      use_camera_motion_condition=False, use_fps_condition=False, use_first_frame_condition_concat=False,
+                      context=None):
+        """Engine entry: x [B, F, H, W, Cin] channels-last in the compute dtype -> fp32 [B, F, H, W, out_channels] (possibly a
+        [..., :out_channels] view of a wider buffer; ops.nfhwc_to_ncfhw takes it as is).  ``context``: a ClipContext from
+        ``prepare_context`` - then encoder_hidden_states / reference_images_clip_feat are not read (hoisted out of the loop)."""
+        ops.require_cuda(x, "UNet3DConditionModel")
         cfg = self._cfg
         B, F, H, W, Cin = x.shape
         x = x.reshape(B * F, H, W, Cin)
@@ -458,14 +515,9 @@ class UNet3DConditionModel(ParamTreeModel):
             emb = self._embed("fps_embedding", fps_tensor, B, residual=emb)
             emb = self._embed("motion_embedding", flow_control, B, residual=emb)
         semb = ops.silu(emb)                                     # every resnet applies SiLU to emb first (resnet.py:307)
-        ctx = self._to_compute(encoder_hidden_states)
-        if use_ip_cross_attention:
-            ipm = self.image_proj_model
-            if ipm is None:
-                raise RuntimeError("use_ip_cross_attention=True but unet.image_proj_model is not set (scripts/inference.py:166)")
-            tokens = ipm(reference_images_clip_feat.to(self.device))
-            tokens = self._to_compute(tokens.float())
-            ctx = ops.concat_channels(ctx.view(B, -1), tokens.view(B, -1)).view(B, -1, ctx.shape[-1])   # unet.py:592-594
+        # step-invariant conditioning: built here when the caller has not hoisted it out of the DDIM loop (``context``)
+        ctx = context if context is not None else self.prepare_context(
+            encoder_hidden_states, reference_images_clip_feat, use_ip_cross_attention)
         if use_first_frame_condition_concat:
             w_in = self._cached(("cin_half",), lambda: (self._conv_w("conv_in.weight") * 0.5).contiguous())
             b_in = self._cached(("bin_half",), lambda: self._f("conv_in.bias") * 0.5)
@@ -521,8 +573,9 @@ class UNet3DConditionModel(ParamTreeModel):
                                 w_phases=self._conv_w_up2(f"{p}.upsamplers.0.conv.weight"))
             self._tap(f"up{i}", x)
         x = self._gn("conv_norm_out", x, B, True, False)
-        y = ops.conv3x3(x, self._conv_w("conv_out.weight"), bias=self._f("conv_out.bias"), out_f32=True)
-        return y.view(B, F, H, W, -1)
+        w_out, b_out, cout = self._conv_head("conv_out", x.shape[0] * H * W)
+        y = ops.conv3x3(x, w_out, bias=b_out, out_f32=True)
+        return y.view(B, F, H, W, -1)[..., :cout]          # a channel slice of the (possibly 16-wide) head output
 
     @torch.no_grad()
     def forward(self, sample, timestep, encoder_hidden_states, class_labels=None, attention_mask=None, return_dict=True,

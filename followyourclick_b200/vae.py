@@ -152,8 +152,7 @@ class AutoencoderKL(ParamTreeModel):
     def encode_nhwc(self, x):
         """x [N, H, W, 3] channels-last in the compute dtype -> moments [N, H/8, W/8, 2 * latent] (compute dtype).
         diffusers/models/vae.py:127-144 (Encoder.forward) + :567 (quant_conv)."""
-        if not x.is_cuda:
-            raise RuntimeError("AutoencoderKL.encode runs only on CUDA (B200); the CPU path is the reference/oracle")
+        ops.require_cuda(x, "AutoencoderKL.encode")
         boc = self._cfg["block_out_channels"]
         x = ops.conv3x3(x, self._conv_w("encoder.conv_in.weight"), bias=self._f("encoder.conv_in.bias"))
         for i in range(len(boc)):
@@ -175,8 +174,7 @@ class AutoencoderKL(ParamTreeModel):
         """diffusers/models/vae.py:565-573: x (n, 3, H, W) -> .latent_dist (DiagonalGaussianDistribution over (n, 4, H/8, W/8)),
         moments in fp32."""
         x = x.to(device=self.device, dtype=torch.float32).contiguous()
-        if not x.is_cuda:
-            raise RuntimeError("AutoencoderKL.encode runs only on CUDA (B200); the CPU path is the reference/oracle")
+        ops.require_cuda(x, "AutoencoderKL.encode")
         n, c, h, w = x.shape
         if h % 8 or w % 8:
             raise ValueError(f"AutoencoderKL.encode: image size {h}x{w} must be a multiple of 8")
@@ -220,9 +218,9 @@ class AutoencoderKL(ParamTreeModel):
         return out.view(NB, H, W, C)
 
     def decode_nhwc(self, z):
-        """z [N, h, w, latent] channels-last in the compute dtype -> [N, 8h, 8w, 3] (compute dtype)."""
-        if not z.is_cuda:
-            raise RuntimeError("AutoencoderKL.decode runs only on CUDA (B200); the CPU path is the reference/oracle")
+        """z [N, h, w, latent] channels-last in the compute dtype -> [N, 8h, 8w, 3] (compute dtype; possibly a [..., :3] view
+        of a 16-channel buffer, which ops.frames_finalize / ops.nfhwc_to_ncfhw read through their channel stride)."""
+        ops.require_cuda(z, "AutoencoderKL.decode")
         NB, H, W, lc = z.shape
         boc = self._cfg["block_out_channels"]
         x = ops.gemm(z.reshape(-1, lc), self._w1x1("post_quant_conv.weight"), bias=self._f("post_quant_conv.bias")).view(NB, H, W, lc)
@@ -237,7 +235,8 @@ class AutoencoderKL(ParamTreeModel):
                 p = f"decoder.up_blocks.{i}.upsamplers.0.conv"
                 x = ops.conv3x3(x, self._conv_w(p + ".weight"), bias=self._f(p + ".bias"), upsample=2, w_phases=self._conv_w_up2(p + ".weight"))
         x = self._gn("decoder.conv_norm_out", x, True)
-        return ops.conv3x3(x, self._conv_w("decoder.conv_out.weight"), bias=self._f("decoder.conv_out.bias"))
+        w_out, b_out, cout = self._conv_head("decoder.conv_out", x.shape[0] * x.shape[1] * x.shape[2])
+        return ops.conv3x3(x, w_out, bias=b_out)[..., :cout]
 
     @torch.no_grad()
     def decode(self, z, return_dict=True):

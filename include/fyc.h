@@ -157,6 +157,8 @@ int32_t fyc_softmax_rows(const float* scores, void* probs, int64_t rows, int64_t
 int32_t fyc_timestep_embed(const int64_t* t, const float* freqs, float* out, int64_t n, int64_t dim,
                            int32_t flip_sin_to_cos, void* stream);
 int32_t fyc_silu(const void* x, void* out, int64_t n, int32_t dtype, void* stream);
+/* exact-erf GELU, elementwise (nn.GELU of the IP-Adapter Perceiver Resampler, ip_adapter/resampler.py:14-21) */
+int32_t fyc_gelu(const void* x, void* out, int64_t n, int32_t dtype, void* stream);
 /* GEGLU for the SIMT path: in [M, 2*Hd] (128-col granule interleave) -> out [M, Hd]. */
 int32_t fyc_geglu(const void* in, void* out, int64_t M, int64_t Hd, int32_t dtype, void* stream);
 int32_t fyc_upsample_nearest2x(const void* x, void* out, int64_t NB, int64_t H, int64_t W, int64_t C,
@@ -168,7 +170,9 @@ int32_t fyc_concat_channels(const void* a, const void* b, void* out, int64_t M, 
  * (1/0.18215 latent scaling of decode_latents, pipeline_animation.py:402). */
 int32_t fyc_ncfhw_to_nfhwc(const float* in, void* out, int64_t B, int64_t C, int64_t F, int64_t HW, float scale,
                            int32_t dtype, void* stream);
-int32_t fyc_nfhwc_to_ncfhw(const void* in, float* out, int64_t B, int64_t C, int64_t F, int64_t HW,
+/* `ldc` = channel stride of `in` in elements (0 or C: packed); ldc > C reads the first C of ldc channels - the 4-channel
+ * conv_out head runs on tcgen05 with its output channels zero-padded to 16 (unet.py:351). */
+int32_t fyc_nfhwc_to_ncfhw(const void* in, float* out, int64_t B, int64_t C, int64_t F, int64_t HW, int64_t ldc,
                            int32_t dtype, void* stream);
 /* AnimationPipeline.__call__ step prologue (pipeline_animation.py:625-635,693-711): builds the channels-last
  * UNet input [dup*b, F, H, W, Cin] from latents (b,4,F,H,W) fp32, mask (b,1,1,H,W) fp32 (NULL -> 1 on frame 0)
@@ -185,9 +189,9 @@ typedef struct {
 } fyc_ddim_coefs;
 int32_t fyc_cfg_ddim_step(const float* pred, const float* sample, const float* noise, float* prev, int64_t n,
                           const fyc_ddim_coefs* c, void* stream);
-/* decode_latents epilogue (pipeline_animation.py:409-410): x [b*F, HW, 3] -> video (b, 3, F, H, W) fp32,
- * (x / 2 + 0.5).clamp(0, 1). */
-int32_t fyc_frames_finalize(const void* x, float* video, int64_t b, int64_t F, int64_t HW, int32_t dtype,
+/* decode_latents epilogue (pipeline_animation.py:409-410): x [b*F, HW, ldc >= 3] -> video (b, 3, F, H, W) fp32,
+ * (x / 2 + 0.5).clamp(0, 1)  (ldc 0 or 3: packed RGB; 16 when the VAE's 3-channel head ran zero-padded on tcgen05). */
+int32_t fyc_frames_finalize(const void* x, float* video, int64_t b, int64_t F, int64_t HW, int64_t ldc, int32_t dtype,
                             void* stream);
 
 #ifdef __cplusplus

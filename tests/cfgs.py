@@ -8,11 +8,15 @@ import torch
 from oracle.ref_ddim import default_scheduler_config
 from oracle.ref_unet import default_unet_config
 from oracle.ref_vae import default_vae_config
+from oracle.ref_resampler import default_resampler_config
 
 CLIP_DIM = 1024
 MINI_UNET_VARIANTS = ("base", "ip", "cam")
 MINI_VAE = default_vae_config(block_out_channels=(32, 64, 128, 128), layers_per_block=1)
 SCHED_V = default_scheduler_config()
+# Perceiver resampler at reduced size: keeps dim_head 64 (the real head size) and an odd image-token count like CLIP's 257
+MINI_RESAMPLER = default_resampler_config(dim=128, depth=2, dim_head=64, heads=3, num_queries=8, embedding_dim=96, output_dim=768)
+RESAMPLER_TOKENS = 33
 SCHED_EPS = default_scheduler_config(prediction_type="epsilon", rescale_betas_zero_snr=False)
 
 _MM = dict(num_attention_heads=4, num_transformer_block=1, attention_block_types=("Temporal_Self", "Temporal_Self"),

@@ -74,11 +74,16 @@ def stats(a, b):
                 finite=bool(torch.isfinite(a).all()))
 
 
-def run_unet_case(variant, dtype, against="golden"):
-    unet, sd = make_unet(variant, dtype)
+def _sync(device):
+    if str(device).startswith("cuda"):
+        torch.cuda.synchronize()
+
+
+def run_unet_case(variant, dtype, against="golden", device="cuda"):
+    unet, sd = make_unet(variant, dtype, device)
     inp = unet_inputs(variant)
-    out = unet(inp["sample"].cuda(), inp["timestep"], **unet_forward_kwargs(variant, inp, "cuda")).sample
-    torch.cuda.synchronize()
+    out = unet(inp["sample"].to(device), inp["timestep"], **unet_forward_kwargs(variant, inp, device)).sample
+    _sync(device)
     if against == "golden":
         ref = torch.from_numpy(golden(f"unet_{variant}.npz")["out"])
     else:
@@ -88,22 +93,22 @@ def run_unet_case(variant, dtype, against="golden"):
     return stats(out, ref)
 
 
-def run_vae_case(dtype):
-    vae, sd = make_vae(dtype)
+def run_vae_case(dtype, device="cuda"):
+    vae, sd = make_vae(dtype, device)
     g = golden("vae.npz")
-    out = vae.decode(torch.from_numpy(g["z"]).cuda()).sample
-    torch.cuda.synchronize()
+    out = vae.decode(torch.from_numpy(g["z"]).to(device)).sample
+    _sync(device)
     return stats(out, torch.from_numpy(g["out"]))
 
 
-def run_vae_encode_case(dtype):
+def run_vae_encode_case(dtype, device="cuda"):
     """AutoencoderKL.encode against the reference's moments / reparameterised sample (golden vae_encode.npz)."""
-    vae, sd = make_vae(dtype)
+    vae, sd = make_vae(dtype, device)
     g = golden("vae_encode.npz")
-    dist = vae.encode(torch.from_numpy(g["x"]).cuda()).latent_dist
-    noise = torch.from_numpy(g["noise"]).cuda()
+    dist = vae.encode(torch.from_numpy(g["x"]).to(device)).latent_dist
+    noise = torch.from_numpy(g["noise"]).to(device)
     sample = dist.mean + dist.std * noise
-    torch.cuda.synchronize()
+    _sync(device)
     return stats(dist.parameters, torch.from_numpy(g["moments"])), stats(sample, torch.from_numpy(g["sample"])), dist
 
 
@@ -149,10 +154,12 @@ def pipeline_call(pipe, ci, F, h, w, steps, gs):
                 flow_control=torch.tensor([4]), first_images_mask=ci["first_images_mask"]).videos
 
 
-def run_pipeline_case(dtype, steps=3, against="oracle"):
+def run_pipeline_case(dtype, steps=3, against="oracle", device="cuda"):
     """cfg1-style plumbing at mini size: F=4, 8x8 latents, CFG 8.0, mask/first-frame concat, fps/flow condition."""
     F, h, w, gs = 4, 8, 8, 8.0
-    pipe, ci, usd, vsd = make_pipeline(dtype)
+    pipe, ci, usd, vsd = make_pipeline(dtype, device=device)
+    if not str(device).startswith("cuda"):
+        pipe.use_cuda_graph = False
     video = pipeline_call(pipe, ci, F, h, w, steps, gs)
     if against == "golden":
         assert steps == 3

@@ -92,10 +92,35 @@ def vae_encode_fixture(VAE):
     return err
 
 
+def resampler_fixture():
+    """the unmodified reference Resampler (ip_adapter/resampler.py) on seeded CLIP-like features."""
+    from ip_adapter.resampler import Resampler
+    from oracle import ref_resampler
+    from tests.cfgs import MINI_RESAMPLER, RESAMPLER_TOKENS
+    m = Resampler(**MINI_RESAMPLER).eval()
+    sd = load_synth(m)
+    assert {k: tuple(v.shape) for k, v in sd.items()} == ref_resampler.resampler_param_shapes(MINI_RESAMPLER)
+    x = torch.randn(2, RESAMPLER_TOKENS, MINI_RESAMPLER["embedding_dim"], generator=torch.Generator().manual_seed(21))
+    with torch.no_grad():
+        ref = m(x)
+        orc = ref_resampler.resampler_forward(sd, MINI_RESAMPLER, x)
+    err = maxabs(ref, orc)
+    print(f"resampler out {tuple(ref.shape)} |ref|max={float(ref.abs().max()):.3f} oracle-vs-ref maxabs={err:.3e}")
+    assert err < 2e-5
+    np.savez_compressed(os.path.join(HERE, "resampler.npz"), x=x.numpy(), out=ref.numpy())
+    return err
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(8)
     UNet, Pipe, VAE, DDIM, ImageProjModel = import_reference()
+    if "--only-resampler" in sys.argv:           # add the resampler fixture without regenerating the others
+        pj = os.path.join(HERE, "pins.json")
+        d = json.load(open(pj))
+        d["oracle_vs_reference_maxabs"]["resampler"] = resampler_fixture()
+        json.dump(d, open(pj, "w"), indent=1)
+        return
     if "--only-vae-encode" in sys.argv:          # add the encoder fixture without regenerating the others
         pj = os.path.join(HERE, "pins.json")
         d = json.load(open(pj))
@@ -238,6 +263,7 @@ def main():
     assert err < 2e-3
     pins["pipeline"] = err
     pins["vae_encode"] = vae_encode_fixture(VAE)
+    pins["resampler"] = resampler_fixture()
     np.savez_compressed(os.path.join(HERE, "pipeline.npz"), video=ref_video.numpy().astype(np.float32),
                         final_latents=lat.numpy())
     with open(os.path.join(HERE, "pins.json"), "w") as f:

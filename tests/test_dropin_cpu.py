@@ -23,6 +23,8 @@ def test_dropin_resolution(tmp_path):
             "from animatediff.utils.util import save_videos_grid\n"
             "from diffusers import AutoencoderKL, DDIMScheduler, StableDiffusionPipeline\n"
             "from ip_adapter import MyIPAdapter, MyIPAdapterPlus\n"
+            "from ip_adapter.resampler import Resampler\n"
+            "assert MyIPAdapterPlus is not MyIPAdapter and Resampler.__module__ == 'followyourclick_b200.ip_adapter'\n"
             "assert U.__module__ == 'followyourclick_b200.unet' and P.__module__ == 'followyourclick_b200.pipeline_animation'\n"
             "assert save_videos_grid() == 'reference' and StableDiffusionPipeline.origin == 'reference'\n"
             "assert AutoencoderKL.__module__ == 'followyourclick_b200.vae' and DDIMScheduler.__module__ == 'followyourclick_b200.scheduling_ddim'\n"

@@ -115,3 +115,72 @@ def test_batch_independence_and_determinism():
     ctx2[1] += 1.0
     c = unet(inp["sample"].cuda(), inp["timestep"], **dict(kw, encoder_hidden_states=ctx2)).sample
     assert torch.equal(a[0], c[0]) and not torch.equal(a[1], c[1])
+
+
+def test_resampler_matches_reference_golden():
+    """engine Resampler (IP-Adapter-Plus image-prompt projector) vs the unmodified reference's output; fp32
+    CUDA-core kernels, tolerance rel-L2 <= 1e-4 (max-abs 1e-3 on O(4) outputs)."""
+    from followyourclick_b200 import Resampler
+    from tests.cfgs import MINI_RESAMPLER
+    from tests.engine_helpers import golden, load_synth, stats
+    m = Resampler(**MINI_RESAMPLER)
+    load_synth(m)
+    m.to("cuda")
+    g = golden("resampler.npz")
+    out = m(torch.from_numpy(g["x"]).cuda())
+    s = stats(out, torch.from_numpy(g["out"]))
+    assert out.dtype == torch.float32 and s["finite"] and s["rel_l2"] < 1e-4 and s["maxabs"] < 1e-3, s
+    assert set(m.state_dict().keys()) == set(__import__("oracle.ref_resampler", fromlist=["x"]).resampler_param_shapes(MINI_RESAMPLER))
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_context_hoisting_is_bit_identical_and_ip_plus_matches_oracle(dtype):
+    """The step-invariant conditioning (IP tokens via the Resampler, cross-attention K/V) built once by prepare_context gives
+    bit-identical forwards to rebuilding it per call; and a UNet whose image_proj_model is the Resampler (MyIPAdapterPlus)
+    matches oracle(UNet with the oracle Resampler's tokens appended to the context)."""
+    from followyourclick_b200 import Resampler, ops
+    from oracle import ref_resampler, ref_unet
+    from tests.cfgs import MINI_RESAMPLER, RESAMPLER_TOKENS, mini_unet_oracle_cfg, mini_unet_ref_kwargs, unet_inputs
+    from tests.engine_helpers import load_synth, stats
+    from followyourclick_b200 import UNet3DConditionModel
+    kw = dict(mini_unet_ref_kwargs("ip"), num_tokens=MINI_RESAMPLER["num_queries"])
+    unet = UNet3DConditionModel(**kw)
+    sd = load_synth(unet)
+    unet.to("cuda").to(dtype)
+    rs = Resampler(**MINI_RESAMPLER)
+    rsd = load_synth(rs)
+    unet.image_proj_model = rs.to("cuda")
+    inp = unet_inputs("ip")
+    clip = torch.randn(2, RESAMPLER_TOKENS, MINI_RESAMPLER["embedding_dim"], generator=torch.Generator().manual_seed(5))
+    x = ops.ncfhw_to_nfhwc(inp["sample"].cuda().contiguous(), dtype)
+    args = dict(fps_tensor=inp["fps"].cuda(), flow_control=inp["flow"].cuda(), use_fps_condition=True, use_ip_cross_attention=True)
+    a = unet.forward_nfhwc(x, inp["timestep"], inp["ctx"].cuda(), reference_images_clip_feat=clip.cuda(), **args)
+    ctx = unet.prepare_context(inp["ctx"].cuda(), clip.cuda(), True)
+    b = unet.forward_nfhwc(x, inp["timestep"], None, context=ctx, **args)
+    assert torch.equal(a, b)
+    assert ctx.ip_tokens.shape == (2, MINI_RESAMPLER["num_queries"], 768) and len(ctx.kv) == len(ctx.kvi) == len(unet._transformer_prefixes())
+    # oracle: tokens from the oracle Resampler appended to the text context; the oracle UNet is told not to project again
+    tokens = ref_resampler.resampler_forward(rsd, MINI_RESAMPLER, clip)
+    ocfg = dict(mini_unet_oracle_cfg("ip"), num_tokens=MINI_RESAMPLER["num_queries"])
+    ref = ref_unet.unet3d_forward(sd, ocfg, inp["sample"], inp["timestep"], torch.cat([inp["ctx"], tokens], dim=1),
+                                  fps_tensor=inp["fps"], flow_control=inp["flow"], reference_images_clip_feat=None)
+    s = stats(ops.nfhwc_to_ncfhw(a), ref)
+    assert s["finite"] and s["rel_l2"] < (1e-4 if dtype == torch.float32 else 3e-2), s
+
+
+def test_pipeline_hoisted_context_equals_per_step_context():
+    """AnimationPipeline with the per-clip ClipContext (default) and with the reference's per-step recomputation: same video, bit for
+    bit, through both the CUDA-graph and the kernel-by-kernel loop."""
+    from followyourclick_b200 import AnimationPipeline
+    from tests.engine_helpers import make_pipeline, pipeline_call
+    vids = []
+    for graph in (True, False):
+        for hoist in (True, False):
+            pipe, ci, _, _ = make_pipeline(torch.bfloat16)
+            pipe.use_cuda_graph = graph
+            AnimationPipeline.hoist_context = hoist
+            try:
+                vids.append(pipeline_call(pipe, ci, 4, 8, 8, 2, 8.0))
+            finally:
+                AnimationPipeline.hoist_context = True
+    assert all(torch.equal(vids[0], v) for v in vids[1:])

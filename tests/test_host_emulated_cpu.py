@@ -1,0 +1,126 @@
+"""CPU: the HOST logic of the drop-in classes, with every kernel launch replaced by tests/ops_emulator.py (torch restatements of
+the documented kernel contracts).  The product has no CPU path; these tests exist so that weight packing, layout plumbing, the
+ClipContext hoisting, the Resampler and the pipeline loop are checked against the reference fixtures in the GPU-less build
+container too.  The real kernels are checked by the ``-m gpu`` suites through the C ABI.
+
+Tolerances are the engine's own (tests/test_engine_gpu.py): fp32 rel-L2 <= 1e-4, bf16 rel-L2 <= 3e-2, video PSNR >= 30 dB.
+"""
+import pytest
+import torch
+
+from tests import ops_emulator
+from tests.cfgs import MINI_UNET_VARIANTS
+
+DTYPES = [(torch.float32, 1e-4), (torch.bfloat16, 3e-2)]
+
+
+@pytest.fixture(autouse=True)
+def _emulated(monkeypatch):
+    ops_emulator.install(monkeypatch)
+    torch.set_num_threads(8)
+    yield
+
+
+@pytest.mark.parametrize("variant", MINI_UNET_VARIANTS)
+@pytest.mark.parametrize("dtype,tol", DTYPES)
+def test_unet_host_logic_vs_reference_golden(variant, dtype, tol):
+    from tests.engine_helpers import run_unet_case
+    s = run_unet_case(variant, dtype, device="cpu")
+    assert s["finite"] and s["rel_l2"] < tol, s
+
+
+@pytest.mark.parametrize("dtype,tol", DTYPES)
+def test_vae_host_logic_vs_reference_golden(dtype, tol):
+    from tests.engine_helpers import run_vae_case, run_vae_encode_case
+    s = run_vae_case(dtype, device="cpu")
+    assert s["finite"] and s["rel_l2"] < tol, s
+    m, smp, dist = run_vae_encode_case(dtype, device="cpu")
+    assert m["rel_l2"] < tol and smp["rel_l2"] < tol, (m, smp)
+
+
+def test_pipeline_host_logic_vs_reference_golden():
+    from tests.engine_helpers import run_pipeline_case
+    r = run_pipeline_case(torch.float32, steps=3, against="golden", device="cpu")
+    assert r["finite"] and r["shape"] == (1, 3, 4, 64, 64) and r["video_maxabs"] < 2e-3, r
+    r = run_pipeline_case(torch.bfloat16, steps=3, against="golden", device="cpu")
+    assert r["finite"] and r["psnr"] > 30.0, r
+
+
+def test_upsampler_phase_path_and_padded_heads_are_the_ones_exercised(monkeypatch):
+    """bf16 mode must route the upsamplers through w_phases and the 3- / 4-channel heads through 16 padded channels; switching
+    either off (FYC_UP2_PHASES=0 / FYC_TC_HEAD=0 equivalents) changes the result only by bf16 rounding."""
+    from followyourclick_b200 import ops
+    from tests.engine_helpers import run_unet_case, run_vae_case
+    calls = {"phases": 0, "head16": 0}
+    conv = ops.conv3x3
+
+    def spy(x, w, *a, **kw):
+        calls["phases"] += kw.get("w_phases") is not None
+        calls["head16"] += (w.shape[0] == 16 and kw.get("w_phases") is None)
+        return conv(x, w, *a, **kw)
+    monkeypatch.setattr(ops, "conv3x3", spy)
+    a = run_unet_case("base", torch.bfloat16, device="cpu")
+    v = run_vae_case(torch.bfloat16, device="cpu")
+    assert calls["phases"] == 3 + 3 and calls["head16"] == 2, calls      # 3 upsamplers each; conv_out of each model
+    monkeypatch.setattr(ops, "use_up2_phases", False)
+    monkeypatch.setattr(ops, "use_tc_head", False)
+    b = run_unet_case("base", torch.bfloat16, device="cpu")
+    v2 = run_vae_case(torch.bfloat16, device="cpu")
+    assert abs(a["rel_l2"] - b["rel_l2"]) < 1e-2 and abs(v["rel_l2"] - v2["rel_l2"]) < 1e-2, (a, b, v, v2)
+
+
+def test_resampler_host_logic_vs_reference_golden():
+    from followyourclick_b200 import Resampler
+    from tests.cfgs import MINI_RESAMPLER
+    from tests.engine_helpers import golden, load_synth, stats
+    m = Resampler(**MINI_RESAMPLER)
+    load_synth(m)
+    g = golden("resampler.npz")
+    s = stats(m(torch.from_numpy(g["x"])), torch.from_numpy(g["out"]))
+    assert s["finite"] and s["rel_l2"] < 1e-5, s
+
+
+@pytest.mark.parametrize("dtype,tol", DTYPES)
+def test_context_hoisting_and_ip_plus_host_logic(dtype, tol):
+    """prepare_context once == rebuilding per forward (bit for bit); UNet + Resampler projector (MyIPAdapterPlus) vs the oracle."""
+    from followyourclick_b200 import Resampler, UNet3DConditionModel, ops
+    from oracle import ref_resampler, ref_unet
+    from tests.cfgs import MINI_RESAMPLER, RESAMPLER_TOKENS, mini_unet_oracle_cfg, mini_unet_ref_kwargs, unet_inputs
+    from tests.engine_helpers import load_synth, stats
+    kw = dict(mini_unet_ref_kwargs("ip"), num_tokens=MINI_RESAMPLER["num_queries"])
+    unet = UNet3DConditionModel(**kw)
+    sd = load_synth(unet)
+    unet.to(dtype)
+    rs = Resampler(**MINI_RESAMPLER)
+    rsd = load_synth(rs)
+    unet.image_proj_model = rs
+    inp = unet_inputs("ip")
+    clip = torch.randn(2, RESAMPLER_TOKENS, MINI_RESAMPLER["embedding_dim"], generator=torch.Generator().manual_seed(5))
+    x = ops.ncfhw_to_nfhwc(inp["sample"].contiguous(), dtype)
+    args = dict(fps_tensor=inp["fps"], flow_control=inp["flow"], use_fps_condition=True, use_ip_cross_attention=True)
+    a = unet.forward_nfhwc(x, inp["timestep"], inp["ctx"], reference_images_clip_feat=clip, **args)
+    ctx = unet.prepare_context(inp["ctx"], clip, True)
+    b = unet.forward_nfhwc(x, inp["timestep"], None, context=ctx, **args)
+    assert torch.equal(a, b)
+    assert len(ctx.kv) == len(ctx.kvi) == len(unet._transformer_prefixes()) == 10
+    tokens = ref_resampler.resampler_forward(rsd, MINI_RESAMPLER, clip)
+    ocfg = dict(mini_unet_oracle_cfg("ip"), num_tokens=MINI_RESAMPLER["num_queries"])
+    ref = ref_unet.unet3d_forward(sd, ocfg, inp["sample"], inp["timestep"], torch.cat([inp["ctx"], tokens], dim=1),
+                                  fps_tensor=inp["fps"], flow_control=inp["flow"], reference_images_clip_feat=None)
+    s = stats(ops.nfhwc_to_ncfhw(a), ref)
+    assert s["finite"] and s["rel_l2"] < tol, s
+
+
+def test_pipeline_hoisted_equals_per_step_host_logic():
+    from followyourclick_b200 import AnimationPipeline
+    from tests.engine_helpers import make_pipeline, pipeline_call
+    vids = []
+    for hoist in (True, False):
+        pipe, ci, _, _ = make_pipeline(torch.bfloat16, device="cpu")
+        pipe.use_cuda_graph = False
+        AnimationPipeline.hoist_context = hoist
+        try:
+            vids.append(pipeline_call(pipe, ci, 4, 8, 8, 2, 8.0))
+        finally:
+            AnimationPipeline.hoist_context = True
+    assert torch.equal(vids[0], vids[1])

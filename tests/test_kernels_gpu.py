@@ -376,6 +376,34 @@ def test_build_unet_input_and_finalize(cuda):
     vid = ops.frames_finalize(x, b, f)
     refv = (x.view(b, f, 8, 8, 3).permute(0, 4, 1, 2, 3) / 2 + 0.5).clamp(0, 1)
     assert torch.equal(vid, refv.contiguous())
+    # channel-strided readers: the first 3 / 4 of 16 channels (zero-padded tcgen05 heads)
+    wide = rnd((b * f, 8, 8, 16), 5) * 2
+    assert torch.equal(ops.frames_finalize(wide[..., :3], b, f), (wide[..., :3].reshape(b, f, 8, 8, 3).permute(0, 4, 1, 2, 3) / 2 + 0.5).clamp(0, 1))
+    wb = wide.to(torch.bfloat16).view(b, f, 8, 8, 16)
+    assert torch.equal(ops.nfhwc_to_ncfhw(wb[..., :4]), wb[..., :4].float().permute(0, 4, 1, 2, 3).contiguous())
+    assert torch.equal(ops.nfhwc_to_ncfhw(wb), wb.float().permute(0, 4, 1, 2, 3).contiguous())
+
+
+@pytest.mark.parametrize("NB,H,W,Cin,cout,f32", [(32, 16, 16, 320, 4, True), (2, 64, 64, 128, 3, False), (4, 32, 32, 64, 4, True)])
+def test_conv_head_zero_padded_to_16_on_tcgen05(cuda, NB, H, W, Cin, cout, f32):
+    """conv_out heads (UNet 320 -> 4 fp32, VAE 128 -> 3): N = 16 tiles on the tcgen05 path, first `cout` channels == the conv."""
+    from followyourclick_b200 import ops
+    dtype = torch.bfloat16
+    ops.set_impl("tc")
+    x = rnd((NB, H, W, Cin), 1, dtype)
+    w = rnd((cout, Cin, 3, 3), 2, torch.float32, (9 * Cin) ** -0.5)
+    bias = rnd((cout,), 3)
+    wp = torch.zeros(16, 3, 3, Cin, dtype=dtype, device="cuda")
+    wp[:cout] = w.permute(0, 2, 3, 1).to(dtype)
+    bp = torch.zeros(16, device="cuda")
+    bp[:cout] = bias
+    out = ops.conv3x3(x, wp, bias=bp, out_f32=f32)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.to(dtype).float(), bias, padding=1).permute(0, 2, 3, 1)
+    assert out.dtype == (torch.float32 if f32 else dtype) and out.shape == (NB, H, W, 16)
+    assert rel(out[..., :cout], ref) < (2e-3 if f32 else tol(dtype)), rel(out[..., :cout], ref)
+    assert float(out[..., cout:].float().abs().max()) == 0.0
+    A, Wm = rnd((300, 72), 4, dtype), rnd((16, 72), 5, dtype, 72 ** -0.5)
+    assert rel(ops.gemm(A, Wm), A.float() @ Wm.float().t()) < tol(dtype)
 
 
 def test_cfg_ddim_step_bit_exact_vs_golden(cuda):

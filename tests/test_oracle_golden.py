@@ -95,3 +95,19 @@ def test_vae_and_pipeline_oracle_vs_reference_fixture():
     assert float((lat - torch.from_numpy(p["final_latents"])).abs().max()) < 1e-3
     video = ref_vae.decode_latents(vsd, MINI_VAE, lat)
     assert float((video - torch.from_numpy(p["video"])).abs().max()) < 2e-3
+
+
+def test_resampler_oracle_vs_reference_fixture():
+    """oracle restatement of the Perceiver Resampler against the unmodified reference's output."""
+    from oracle import ref_resampler
+    from followyourclick_b200.synth import synth_state_dict
+    from tests.cfgs import MINI_RESAMPLER, RESAMPLER_TOKENS
+    g = np.load(os.path.join(GOLD, "resampler.npz"))
+    sd = synth_state_dict(ref_resampler.resampler_param_shapes(MINI_RESAMPLER))
+    x = torch.from_numpy(g["x"])
+    assert x.shape == (2, RESAMPLER_TOKENS, MINI_RESAMPLER["embedding_dim"])
+    out = ref_resampler.resampler_forward(sd, MINI_RESAMPLER, x)
+    assert out.shape == (2, MINI_RESAMPLER["num_queries"], MINI_RESAMPLER["output_dim"])
+    assert float((out - torch.from_numpy(g["out"])).abs().max()) < 2e-5
+    pins = json.load(open(os.path.join(GOLD, "pins.json")))["oracle_vs_reference_maxabs"]
+    assert pins["resampler"] < 2e-5
