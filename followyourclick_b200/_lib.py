@@ -30,7 +30,7 @@ class ConvArgs(C.Structure):
     _fields_ = [("x", _vp), ("w", _vp), ("out", _vp), ("bias", _vp), ("residual", _vp), ("rowbias", _vp),
                 ("NB", _i64), ("H", _i64), ("W", _i64), ("Cin", _i64), ("Cout", _i64), ("stride", _i32),
                 ("upsample", _i32), ("images_per_group", _i64), ("dtype", _i32), ("epilogue", _i32), ("impl", _i32),
-                ("workspace", _vp), ("workspace_bytes", _sz), ("pad_mode", _i32), ("w_phases", _vp)]
+                ("workspace", _vp), ("workspace_bytes", _sz), ("pad_mode", _i32), ("w_phases", _vp), ("ld_rowbias", _i64)]
 
 
 class AttnArgs(C.Structure):

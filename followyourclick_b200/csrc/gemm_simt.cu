@@ -21,6 +21,7 @@ struct Epilogue {
   int64_t ldo, ldr, rows_per_group;
   float alpha;
   int flags;
+  int64_t ldrb;            // row stride of rowbias (elements)
 };
 
 // ---- A loaders: fetch 8 consecutive k of logical row m (zero outside the matrix) -------------------------
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(ALoader al, const T* __re
       if (n >= N) continue;
       float v = acc[i][j] * ep.alpha;
       if (ep.flags & FYC_EPI_BIAS) v += ep.bias[n];
-      if (ep.flags & FYC_EPI_ROWBIAS) v += ep.rowbias[(m / ep.rows_per_group) * N + n];
+      if (ep.flags & FYC_EPI_ROWBIAS) v += ep.rowbias[(m / ep.rows_per_group) * ep.ldrb + n];
       if (ep.flags & FYC_EPI_RESIDUAL) v += to_f(reinterpret_cast<const TO*>(ep.residual)[bz * strideO + m * ep.ldr + n]);
       ob[m * ep.ldo + n] = from_f<TO>(v);
     }
@@ -177,7 +178,7 @@ int32_t launch(const AL& al, const T* W, TO* out, int64_t M, int64_t N, int64_t 
 }  // namespace
 
 int32_t fyc_gemm_simt(const fyc_gemm_args* g, cudaStream_t st) {
-  Epilogue ep{g->bias, g->residual, g->rowbias, g->ldo, g->ldr, g->rows_per_group > 0 ? g->rows_per_group : 1, g->alpha, g->epilogue};
+  Epilogue ep{g->bias, g->residual, g->rowbias, g->ldo, g->ldr, g->rows_per_group > 0 ? g->rows_per_group : 1, g->alpha, g->epilogue, g->N};
   FYC_CHECK(!(g->epilogue & FYC_EPI_GEGLU), "gemm_simt: GEGLU epilogue is a separate kernel on this path (fyc_geglu)");
   const bool f32out = (g->epilogue & FYC_EPI_OUT_F32) != 0;
   if (g->dtype == FYC_F32) {
@@ -198,7 +199,8 @@ int32_t fyc_conv3x3_simt(const fyc_conv3x3_args* c, cudaStream_t st) {
   const int pad = c->pad_mode == 1 ? 0 : 1;       // pad_mode 1: the single padding row / column is on the bottom / right
   const int64_t Ho = (c->H * up + 2 - 3) / s + 1, Wo = (c->W * up + 2 - 3) / s + 1;   // = H / 2 for stride 2 in both modes (even H)
   const int64_t M = c->NB * Ho * Wo, K = 9 * c->Cin, N = c->Cout;
-  Epilogue ep{c->bias, c->residual, c->rowbias, N, N, (c->images_per_group > 0 ? c->images_per_group : 1) * Ho * Wo, 1.0f, c->epilogue};
+  Epilogue ep{c->bias, c->residual, c->rowbias, N, N, (c->images_per_group > 0 ? c->images_per_group : 1) * Ho * Wo, 1.0f, c->epilogue,
+              c->ld_rowbias > 0 ? c->ld_rowbias : N};
   const bool f32out = (c->epilogue & FYC_EPI_OUT_F32) != 0;
   if (c->dtype == FYC_F32) {
     ConvAS<float> al; al.x = (const float*)c->x; al.NB = c->NB; al.H = c->H; al.W = c->W; al.Cin = c->Cin; al.Ho = Ho; al.Wo = Wo;

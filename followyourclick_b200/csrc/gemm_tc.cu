@@ -48,6 +48,7 @@ struct TcParams {
   // epilogue
   const float* bias; const void* residual; const float* rowbias; void* out;
   int64_t ldo, ldr, rows_per_group;
+  int64_t ldrb;              // row stride of rowbias (elements; N unless the caller passes a slice of a wider table)
   float alpha;
   int flags;
   // W-resident mode (small K): the CTA keeps its whole BN x K weight slab in shared memory and only streams A
@@ -374,7 +375,7 @@ __device__ __forceinline__ void epilogue_plain(const TcParams& p, const TileSche
       if (p.flags & FYC_EPI_ROWBIAS) {
         if (cur.rgu >= 0) {                                // the 32 rows share one row-bias vector (the usual case)
           if (col_ok) {
-            const float* rbp = p.rowbias + (int64_t)cur.rgu * p.N + cur.n0 + c0;
+            const float* rbp = p.rowbias + (int64_t)cur.rgu * p.ldrb + cur.n0 + c0;
             const float4 r0 = __ldg(reinterpret_cast<const float4*>(rbp)), r1 = __ldg(reinterpret_cast<const float4*>(rbp + 4));
             pf.b0.x += r0.x; pf.b0.y += r0.y; pf.b0.z += r0.z; pf.b0.w += r0.w;
             pf.b1.x += r1.x; pf.b1.y += r1.y; pf.b1.z += r1.z; pf.b1.w += r1.w;
@@ -384,7 +385,7 @@ __device__ __forceinline__ void epilogue_plain(const TcParams& p, const TileSche
           for (int ps = 0; ps < 4; ++ps) {
             if (!(((cur.ok >> ps) & 1u) && col_ok)) continue;
             const uint32_t pix = (uint32_t)((((uint64_t)cur.oo[ps] << 3) - (uint32_t)(cur.n0 + q * 8)) / (uint64_t)p.ldo);
-            const float* rbp = p.rowbias + (int64_t)(pix / (uint32_t)p.rows_per_group) * p.N + cur.n0 + c0;
+            const float* rbp = p.rowbias + (int64_t)(pix / (uint32_t)p.rows_per_group) * p.ldrb + cur.n0 + c0;
             const float4 r0 = __ldg(reinterpret_cast<const float4*>(rbp)), r1 = __ldg(reinterpret_cast<const float4*>(rbp + 4));
             float4* s0 = reinterpret_cast<float4*>(const_cast<uint8_t*>(prow) + ps * 1024 + px0);
             float4* s1 = reinterpret_cast<float4*>(const_cast<uint8_t*>(prow) + ps * 1024 + px1);
@@ -672,7 +673,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const long long te1 = clock64();
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)acc * MAX_BN;
-      const float* rb = (p.flags & FYC_EPI_ROWBIAS) ? p.rowbias + (row_ok ? pix / p.rows_per_group : 0) * p.N : nullptr;
+      const float* rb = (p.flags & FYC_EPI_ROWBIAS) ? p.rowbias + (row_ok ? pix / p.rows_per_group : 0) * p.ldrb : nullptr;
       if (out_f32) {
         // fp32 output (attention scores of the VAE mid block): direct per-thread stores, 16-column chunks split between
         // the two warps of a lane quarter
@@ -959,7 +960,7 @@ int32_t fyc_gemm_tc(const fyc_gemm_args* g, cudaStream_t st) {
       if (rc) return rc;
     }
     FYC_CHECK(g->M < (1ll << 31), "gemm(tcgen05): M too large");
-    p.bias = g->bias; p.rowbias = g->rowbias; p.rows_per_group = g->rows_per_group > 0 ? g->rows_per_group : 1;
+    p.bias = g->bias; p.rowbias = g->rowbias; p.rows_per_group = g->rows_per_group > 0 ? g->rows_per_group : 1; p.ldrb = g->N;
     p.residual = g->residual ? (f32 ? (const void*)((const float*)g->residual + b * g->strideO) : (const void*)((const bf16*)g->residual + b * g->strideO)) : nullptr;
     p.out = f32 ? (void*)((float*)g->out + b * g->strideO) : (void*)((bf16*)g->out + b * g->strideO);
     p.ldo = g->ldo; p.ldr = g->ldr; p.alpha = g->alpha; p.flags = g->epilogue;
@@ -986,6 +987,7 @@ bool fyc_conv3x3_tc_eligible(const fyc_conv3x3_args* c) {
   if (c->stride == 2 && (c->H % 2 || c->W % 2)) return false;
   if (((uintptr_t)c->x | (uintptr_t)c->w | (uintptr_t)c->out) & 15) return false;
   if ((c->epilogue & FYC_EPI_RESIDUAL) && ((uintptr_t)c->residual & 15)) return false;
+  if ((c->epilogue & FYC_EPI_ROWBIAS) && (((uintptr_t)c->rowbias & 15) || (c->ld_rowbias > 0 && c->ld_rowbias % 4))) return false;
   if (c->epilogue & FYC_EPI_GEGLU) return false;
   int bw, bh, bn;
   if (!pick_patch(c->NB, c->H / c->stride, c->W / c->stride, &bw, &bh, &bn)) return false;
@@ -1039,6 +1041,7 @@ int32_t fyc_conv3x3_tc(const fyc_conv3x3_args* c, const void* x_planes, cudaStre
     if (rc) return rc;
   }
   p.bias = c->bias; p.rowbias = c->rowbias; p.residual = c->residual; p.out = c->out;
+  p.ldrb = c->ld_rowbias > 0 ? c->ld_rowbias : c->Cout;
   p.rows_per_group = (c->images_per_group > 0 ? c->images_per_group : 1) * Ho * Wo;
   p.ldo = c->Cout; p.ldr = c->Cout; p.alpha = 1.0f; p.flags = c->epilogue;
   (void)f32;
@@ -1075,7 +1078,7 @@ int32_t fyc_conv3x3_up2_tc(const fyc_conv3x3_args* c, cudaStream_t st) {
   choose_tiles(p, &grid);                       // tile shape / staging mode from the true (low-resolution) problem size
   p.Wo = (int)(2 * W); p.M = c->NB * H * 2 * W;  // epilogue addressing only (see above); every ow < W < Wo, every pix < M
   p.ldo = 2 * c->Cout; p.ldr = p.ldo; p.alpha = 1.0f;
-  p.bias = c->bias; p.rowbias = nullptr; p.residual = nullptr; p.rows_per_group = 1;
+  p.bias = c->bias; p.rowbias = nullptr; p.residual = nullptr; p.rows_per_group = 1; p.ldrb = p.N;
   CUtensorMap ma;
   {
     uint64_t dims[4] = {(uint64_t)c->Cin, (uint64_t)W, (uint64_t)H, (uint64_t)c->NB};

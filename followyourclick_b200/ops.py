@@ -142,7 +142,13 @@ def conv3x3(x, w, bias=None, residual=None, rowbias=None, images_per_group=0, st
     the bottom / right only - diffusers Downsample2D(padding=0), used by the VAE encoder).  upsample=2 with ``w_phases``
     ([4, Cout, 2, 2, Cin], modeling.upsample_phase_weights): nearest-x2 + conv as four 2x2-tap convs on the low-res image."""
     _cuda(x, "conv.x"); _cuda(w, "conv.w"); _cuda(residual, "conv.residual"); _cuda(w_phases, "conv.w_phases")
-    _f32vec(bias, "conv.bias"); _f32vec(rowbias, "conv.rowbias")
+    _f32vec(bias, "conv.bias")
+    ld_rb = 0
+    if rowbias is not None:        # [groups, Cout] fp32, rows possibly strided (a column block of a wider table: fyc.h ld_rowbias)
+        if rowbias.dtype != torch.float32 or rowbias.dim() != 2 or rowbias.stride(1) != 1 or rowbias.shape[1] != w.shape[0]:
+            raise L.FycError("conv.rowbias: expected fp32 [groups, Cout] with unit column stride")
+        _cuda(rowbias, "conv.rowbias")
+        ld_rb = rowbias.stride(0) if rowbias.shape[0] > 1 else rowbias.shape[1]
     assert x.is_contiguous() and w.is_contiguous() and x.dtype == w.dtype
     impl = _impl if impl is None else impl
     NB, H, W_, Cin = x.shape
@@ -152,7 +158,7 @@ def conv3x3(x, w, bias=None, residual=None, rowbias=None, images_per_group=0, st
         assert w_phases.is_contiguous() and w_phases.dtype == x.dtype and tuple(w_phases.shape) == (4, Cout, 2, 2, Cin)
         out = torch.empty((NB, 2 * H, 2 * W_, Cout), dtype=x.dtype, device=x.device)
         a = L.ConvArgs(ptr(x), ptr(w), ptr(out), ptr(bias), None, None, NB, H, W_, Cin, Cout, 1, 2, 0, dtype_code(x.dtype),
-                       L.EPI_BIAS if bias is not None else 0, impl, None, 0, 0, ptr(w_phases))
+                       L.EPI_BIAS if bias is not None else 0, impl, None, 0, 0, ptr(w_phases), 0)
         if lib().fyc_conv3x3_up2_eligible(C.byref(a)) == 1:
             fam = "conv_tc_up2" + (f"[{NB}x{H}x{W_} {Cin}->{Cout}]" if _prof_shapes else "")
             # executed work: 4 phases x 4 taps on the low-res grid (the reference's upsample + 3x3 conv is 36 MACs per input pixel)
@@ -171,7 +177,7 @@ def conv3x3(x, w, bias=None, residual=None, rowbias=None, images_per_group=0, st
     epi = (L.EPI_BIAS if bias is not None else 0) | (L.EPI_RESIDUAL if residual is not None else 0) | \
           (L.EPI_ROWBIAS if rowbias is not None else 0) | (L.EPI_OUT_F32 if out_f32 else 0)
     a = L.ConvArgs(ptr(x), ptr(w), ptr(out), ptr(bias), ptr(residual), ptr(rowbias), NB, H, W_, Cin, Cout, stride,
-                   upsample, images_per_group, dtype_code(x.dtype), epi, impl, None, 0, pad_mode, None)
+                   upsample, images_per_group, dtype_code(x.dtype), epi, impl, None, 0, pad_mode, None, ld_rb)
     nbytes = lib().fyc_conv3x3_workspace_bytes(C.byref(a))
     ws = None
     if nbytes:

@@ -341,9 +341,26 @@ class UNet3DConditionModel(ParamTreeModel):
         nb = x.shape[0] if (per_frame or self._cfg["use_inflated_groupnorm"]) else B
         return ops.groupnorm(x, self._f(p + ".weight"), self._f(p + ".bias"), g, eps, silu=silu, stat_batches=nb)
 
-    def _resnet(self, p, x, semb, B, F):
+    def _temb_pack(self):
+        """Every ResnetBlock3D's time_emb_proj (resnet.py:307-313) stacked into one [sum Cout, temb] fp32 matrix: the forward runs
+        ONE GEMV on SiLU(emb) and each conv1 reads its column block of the [B, sum Cout] result as its row bias (fyc.h ld_rowbias)
+        instead of 22 latency-bound M = 2 launches."""
+        def make():
+            keys = [k[:-len(".time_emb_proj.weight")] for k in self._flat_params() if k.endswith(".time_emb_proj.weight")]
+            offs, o = {}, 0
+            for p in keys:
+                n = self._p(p + ".time_emb_proj.weight").shape[0]
+                offs[p] = (o, n)
+                o += n
+            w = torch.cat([self._p(p + ".time_emb_proj.weight").detach().float() for p in keys], dim=0).contiguous()
+            b = torch.cat([self._p(p + ".time_emb_proj.bias").detach().float() for p in keys], dim=0).contiguous()
+            return w, b, offs
+        return self._cached(("temb_pack",), make)
+
+    def _resnet(self, p, x, temb_all, B, F):
         NB, H, W, Cin = x.shape
-        temb = ops.gemm(semb, self._fw(p + ".time_emb_proj.weight"), bias=self._f(p + ".time_emb_proj.bias"))   # [B, Cout] fp32
+        o, n = self._temb_pack()[2][p]
+        temb = temb_all[:, o:o + n]                      # [B, Cout] fp32 view, row stride = sum Cout
         h = self._gn(p + ".norm1", x, B, True, False)
         h = ops.conv3x3(h, self._conv_w(p + ".conv1.weight"), bias=self._f(p + ".conv1.bias"), rowbias=temb, images_per_group=F)
         h = self._gn(p + ".norm2", h, B, True, False)
@@ -515,6 +532,8 @@ class UNet3DConditionModel(ParamTreeModel):
             emb = self._embed("fps_embedding", fps_tensor, B, residual=emb)
             emb = self._embed("motion_embedding", flow_control, B, residual=emb)
         semb = ops.silu(emb)                                     # every resnet applies SiLU to emb first (resnet.py:307)
+        tw, tb, _ = self._temb_pack()
+        semb = ops.gemm(semb, tw, bias=tb)                       # [B, sum Cout]: all 22 time_emb_proj at once (see _temb_pack)
         # step-invariant conditioning: built here when the caller has not hoisted it out of the DDIM loop (``context``)
         ctx = context if context is not None else self.prepare_context(
             encoder_hidden_states, reference_images_clip_feat, use_ip_cross_attention)

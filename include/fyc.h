@@ -93,6 +93,9 @@ typedef struct {
                                    pixel and channel pair, and the upsampled tensor is never written.  The tcgen05 path runs the
                                    four phases as four 4-tap implicit GEMMs whose rows are written interleaved; without it (or on
                                    the CUDA-core path) `w` is used with the upsample folded into the input index. */
+  int64_t ld_rowbias;           /* row stride of `rowbias` in elements; 0 = Cout.  > Cout when rowbias points into a wider table -
+                                   all ResnetBlock3D time-embedding projections of a forward (resnet.py:307-313) come out of ONE
+                                   fused GEMV as [B, sum Cout], each conv reading its own column block */
 } fyc_conv3x3_args;
 size_t fyc_conv3x3_workspace_bytes(const fyc_conv3x3_args* a);
 int32_t fyc_conv3x3(const fyc_conv3x3_args* a, void* stream);

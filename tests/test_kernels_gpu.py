@@ -158,6 +158,25 @@ def test_conv3x3(dtype, impl, NB, H, W, Cin, Cout, stride, up):
 
 
 @pytest.mark.parametrize("dtype,impl", MODES)
+def test_conv3x3_rowbias_column_block_of_wider_table(dtype, impl):
+    """fyc.h ld_rowbias: the row bias of a conv is a column block of the fused [B, sum Cout] time-embedding projection."""
+    from followyourclick_b200 import ops
+    ops.set_impl("auto" if impl == "tc" else impl)
+    NB, H, W, Cin, Cout, ipg = 4, 16, 16, 64, 32, 2
+    x = rnd((NB, H, W, Cin), 1, dtype)
+    w = rnd((Cout, Cin, 3, 3), 2, torch.float32, (9 * Cin) ** -0.5)
+    wp = w.permute(0, 2, 3, 1).to(dtype).contiguous()
+    table = rnd((NB // ipg, 5 * Cout), 3)
+    rb = table[:, 2 * Cout:3 * Cout]
+    assert not rb.is_contiguous()
+    out = ops.conv3x3(x, wp, rowbias=rb, images_per_group=ipg)
+    same = ops.conv3x3(x, wp, rowbias=rb.contiguous(), images_per_group=ipg)
+    assert torch.equal(out, same)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.to(dtype).float(), padding=1) + rb.repeat_interleave(ipg, 0)[:, :, None, None]
+    assert rel(out, ref.permute(0, 2, 3, 1)) < tol(dtype)
+
+
+@pytest.mark.parametrize("dtype,impl", MODES)
 @pytest.mark.parametrize("NB,H,W,Cin,Cout", [(2, 16, 16, 64, 64), (3, 32, 32, 128, 160), (1, 8, 12, 24, 8)])
 def test_conv3x3_stride2_bottom_right_pad(dtype, impl, NB, H, W, Cin, Cout):
     """pad_mode 1 = diffusers Downsample2D(padding=0): F.pad(x, (0, 1, 0, 1)) + valid stride-2 conv (VAE encoder)."""
