@@ -216,11 +216,16 @@ extern "C" int32_t fyc_build_unet_input(const float* latents, const float* mask,
 //   scheduling_ddim.py:330           clip x0
 //   scheduling_ddim.py:346-349       prev = sap*x0 + dir*eps
 //   scheduling_ddim.py:366-368       prev += noise_coef * noise        (eta > 0)
-__global__ void cfg_ddim_kernel(const float* __restrict__ pred, const float* __restrict__ sample,
+//   pipeline_animation.py:757-761    n   = s + vs * (u - s) + g * (c - u)      (video_scale > 0: s = per-frame prediction)
+__global__ void cfg_ddim_kernel(const float* __restrict__ pred, const float* __restrict__ single, float video_scale,
+                                const float* __restrict__ sample,
                                 const float* __restrict__ noise, float* __restrict__ prev, int64_t n, fyc_ddim_coefs c) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float m;
-    if (c.guidance > 1.0f) {
+    if (single) {
+      float u = pred[i], t = pred[n + i], s = single[i];
+      m = __fadd_rn(__fadd_rn(s, __fmul_rn(video_scale, __fsub_rn(u, s))), __fmul_rn(c.guidance, __fsub_rn(t, u)));
+    } else if (c.guidance > 1.0f) {
       float u = pred[i], t = pred[n + i];
       m = __fadd_rn(u, __fmul_rn(c.guidance, __fsub_rn(t, u)));
     } else {
@@ -248,7 +253,16 @@ extern "C" int32_t fyc_cfg_ddim_step(const float* pred, const float* sample, con
                                      const fyc_ddim_coefs* c, void* stream) {
   FYC_CHECK(c != nullptr && n > 0, "cfg_ddim_step: bad arguments");
   FYC_CHECK(c->prediction_type >= 0 && c->prediction_type <= 2, "cfg_ddim_step: unknown prediction_type %d", c->prediction_type);
-  cfg_ddim_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(pred, sample, noise, prev, n, *c);
+  cfg_ddim_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(pred, nullptr, 0.f, sample, noise, prev, n, *c);
+  FYC_LAUNCH_CHECK();
+  return FYC_OK;
+}
+extern "C" int32_t fyc_cfg_video_ddim_step(const float* pred, const float* single, float video_scale, const float* sample,
+                                           const float* noise, float* prev, int64_t n, const fyc_ddim_coefs* c, void* stream) {
+  FYC_CHECK(c != nullptr && n > 0 && pred && single, "cfg_video_ddim_step: bad arguments");
+  FYC_CHECK(c->prediction_type >= 0 && c->prediction_type <= 2, "cfg_video_ddim_step: unknown prediction_type %d", c->prediction_type);
+  FYC_CHECK(c->guidance > 1.0f, "cfg_video_ddim_step: the per-frame guidance branch exists only under classifier-free guidance");
+  cfg_ddim_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(pred, single, video_scale, sample, noise, prev, n, *c);
   FYC_LAUNCH_CHECK();
   return FYC_OK;
 }

@@ -37,10 +37,14 @@ class _GraphedUNetStep:
     configuration, so the ~700 kernel launches of a forward are replayed with one call; inputs live in static buffers
     (x: channels-last UNet input, t: timestep, text / fps / flow / camera / clip features)."""
 
-    def __init__(self, unet, x_shape, text, fps, flow, cam, clip, flags):
+    def __init__(self, unet, x_shape, text, fps, flow, cam, clip, flags, x=None, out_frames=None):
+        """``x``: use this (view of another step's) static input instead of allocating one; ``out_frames`` = (b, f): the input is
+        b * f single frames (F = 1) whose prediction is returned regrouped as (b, 4, f, h, w) (video_scale branch)."""
         dev = unet.device
         self.version = unet._pack_version
-        self.x = torch.zeros(x_shape, dtype=unet.dtype, device=dev)
+        self.out_frames = out_frames
+        self.x = torch.zeros(x_shape, dtype=unet.dtype, device=dev) if x is None else x
+        assert tuple(self.x.shape) == tuple(x_shape)
         self.t = torch.zeros((), dtype=torch.int64, device=dev)
         self.text = text.to(dev).float().contiguous().clone()
         cl = lambda v: None if v is None else v.to(dev).contiguous().clone()
@@ -71,7 +75,7 @@ class _GraphedUNetStep:
         y = unet.forward_nfhwc(self.x, self.t, self.text, fps_tensor=self.fps, flow_control=self.flow,
                                reference_images_clip_feat=self.clip, camera_movement_type_tensor=self.cam, context=self.context,
                                **self.flags)
-        return ops.nfhwc_to_ncfhw(y)
+        return ops.nfhwc_to_ncfhw(_regroup_frames(y, self.out_frames))
 
     def load(self, unet, text, fps, flow, cam, clip):
         self.text.copy_(text)
@@ -80,6 +84,15 @@ class _GraphedUNetStep:
                 dst.copy_(src)
         if self.hoist:
             self.context.copy_(self._context(unet))
+
+
+def _regroup_frames(y, out_frames):
+    """[(b f), 1, h, w, c] -> [b, f, h, w, c] (a view: `(b f) c 1 h w -> b c f h w` of pipeline_animation.py:755 is free in
+    the channels-last layout)."""
+    if out_frames is None:
+        return y
+    b, f = out_frames
+    return y.view(b, f, y.shape[2], y.shape[3], y.shape[4])
 
 
 @torch.no_grad()
@@ -232,10 +245,15 @@ class AnimationPipeline:
                 first_images_mask=None, use_first_frame_mask_condition_concat=False, fps_tensor=None, flow_control=None,
                 use_fps_condition=False, use_ip_cross_attention=False, image_clip_feat_pair=None,
                 use_camera_motion_condition=False, camera_movement_type=None, eta=0.0, generator=None, callback=None,
-                callback_steps=1, progress=False):
-        """pipeline_animation.py:686-773 on the engine.  latents fp32 (b,4,F,h,w) on device; returns final latents."""
+                callback_steps=1, progress=False, video_scale=0):
+        """pipeline_animation.py:686-773 on the engine.  latents fp32 (b,4,F,h,w) on device; returns final latents.
+        video_scale > 0 (:738-761): a second forward per step on the clip's frames taken one at a time, combined as
+        ``s + video_scale (u - s) + guidance (c - u)``."""
         dev = self.unet.device
         do_cfg = guidance_scale > 1.0
+        if video_scale > 0 and not do_cfg:
+            raise NotImplementedError("video_scale > 0 without classifier-free guidance (the reference only uses the per-frame "
+                                      "prediction inside its CFG combine, pipeline_animation.py:757-761)")
         dup = 2 if do_cfg else 1
         sched, unet = self.scheduler, self.unet
         sched.set_timesteps(num_inference_steps, device=dev)
@@ -261,9 +279,15 @@ class AnimationPipeline:
         flags = dict(use_ip_cross_attention=use_ip_cross_attention, use_camera_motion_condition=use_camera_motion_condition,
                      use_fps_condition=use_fps_condition)
         clip_d = None if image_clip_feat_pair is None else image_clip_feat_pair.to(dev)
-        graphed = context = None
+        graphed = context = graphed_sf = context_sf = None
+        b, _, f, h, w = latents.shape
+        text_sf = None
+        if video_scale > 0:
+            # :743-747 - the text rows for the b*f single frames are the first half of [text] * f, i.e. they ALTERNATE uncond / cond
+            # (reference behaviour, kept); the single-frame forward gets no fps / camera / image conditioning (:748-752)
+            text_sf = torch.cat([text_embeddings] * f, dim=0).chunk(2, dim=0)[0].contiguous()
+            flags_sf = dict(use_ip_cross_attention=False, use_camera_motion_condition=False, use_fps_condition=False)
         if self.use_cuda_graph and hasattr(unet, "forward_nfhwc"):
-            b, _, f, h, w = latents.shape
             cin = c_pad if c_pad is not None else (9 if first is not None else 4)
             key = (dup * b, f, h, w, cin, unet.dtype, tuple(sorted(flags.items())), tuple(text_embeddings.shape),
                    None if clip_d is None else tuple(clip_d.shape))
@@ -272,6 +296,13 @@ class AnimationPipeline:
             if graphed is None or graphed.version != unet._pack_version:
                 graphed = cache[key] = _GraphedUNetStep(unet, (dup * b, f, h, w, cin), text_embeddings, fps_d, flow_d, cam_d, clip_d, flags)
             graphed.load(unet, text_embeddings, fps_d, flow_d, cam_d, clip_d)
+            if video_scale > 0:
+                graphed_sf = cache.get(key + ("sf",))
+                if graphed_sf is None or graphed_sf.version != unet._pack_version or graphed_sf.x.data_ptr() != graphed.x.data_ptr():
+                    graphed_sf = cache[key + ("sf",)] = _GraphedUNetStep(
+                        unet, (b * f, 1, h, w, cin), text_sf, None, None, None, None, flags_sf,
+                        x=graphed.x[:b].view(b * f, 1, h, w, cin), out_frames=(b, f))     # the uncond copy's frames: a view, no copy
+                graphed_sf.load(unet, text_sf, None, None, None, None)
         with bar as pb:
             for i, t in enumerate(t_host):
                 if graphed is not None:
@@ -280,6 +311,11 @@ class AnimationPipeline:
                     graphed.graph.replay()
                     _lib.launch_count += graphed.n_calls
                     pred = graphed.pred
+                    if graphed_sf is not None:
+                        graphed_sf.t.copy_(t_dev[i])
+                        graphed_sf.graph.replay()
+                        _lib.launch_count += graphed_sf.n_calls
+                        single = graphed_sf.pred
                 else:
                     if i == 0 and self.hoist_context and hasattr(unet, "prepare_context"):
                         context = unet.prepare_context(text_embeddings, clip_d, use_ip_cross_attention)
@@ -288,7 +324,13 @@ class AnimationPipeline:
                                            reference_images_clip_feat=clip_d, camera_movement_type_tensor=cam_d, context=context,
                                            **flags)
                     pred = ops.nfhwc_to_ncfhw(y)
-                latents = sched.step_cfg(pred, t, latents, guidance_scale if do_cfg else 1.0, eta=eta, generator=generator)
+                    if video_scale > 0:
+                        if i == 0 and self.hoist_context and hasattr(unet, "prepare_context"):
+                            context_sf = unet.prepare_context(text_sf, None, False)
+                        ys = unet.forward_nfhwc(x[:b].view(b * f, 1, h, w, x.shape[-1]), t_dev[i], text_sf, context=context_sf, **flags_sf)
+                        single = ops.nfhwc_to_ncfhw(_regroup_frames(ys, (b, f)))
+                latents = sched.step_cfg(pred, t, latents, guidance_scale if do_cfg else 1.0, eta=eta, generator=generator,
+                                         single_frame_output=single if video_scale > 0 else None, video_scale=video_scale)
                 pb.update()
                 if callback is not None and i % callback_steps == 0:
                     callback(i, t, latents)
@@ -307,8 +349,6 @@ class AnimationPipeline:
         if use_first_frame_condition or use_first_frame_condition_concat or use_text_encoder_2 or use_first_image_as_init_latents \
                 or use_first_frame_mask_condition_concat_image_partial_mask is not None:
             raise NotImplementedError("option outside the scripts/inference.py path (SURVEY 8f)")
-        if video_scale > 0:
-            raise NotImplementedError("video_scale > 0 (per-frame guidance branch, pipeline_animation.py:738-761) is SURVEY 8f row 3")
         height = height or self.unet.config.sample_size * self.vae_scale_factor
         width = width or self.unet.config.sample_size * self.vae_scale_factor
         self.check_inputs(prompt, height, width, callback_steps)
@@ -338,7 +378,7 @@ class AnimationPipeline:
                                use_ip_cross_attention=use_ip_cross_attention, image_clip_feat_pair=clip_pair,
                                use_camera_motion_condition=use_camera_motion_condition, camera_movement_type=camera_movement_type,
                                eta=eta, generator=generator if not isinstance(generator, list) else None,
-                               callback=callback, callback_steps=callback_steps, progress=self._progress)
+                               callback=callback, callback_steps=callback_steps, progress=self._progress, video_scale=video_scale)
         video = self.decode_latents(latents)
         if output_type == "tensor":
             video = torch.from_numpy(video)

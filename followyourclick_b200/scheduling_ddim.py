@@ -116,11 +116,14 @@ class DDIMScheduler:
         return DDIMSchedulerOutput(prev_sample=prev)
 
     @torch.no_grad()
-    def step_cfg(self, model_output_pair, timestep, sample, guidance_scale, eta=0.0, generator=None, variance_noise=None):
-        """CFG combine (pipeline_animation.py:763-764) fused with the step: model_output_pair = [uncond; cond]."""
+    def step_cfg(self, model_output_pair, timestep, sample, guidance_scale, eta=0.0, generator=None, variance_noise=None,
+                 single_frame_output=None, video_scale=0.0):
+        """CFG combine (pipeline_animation.py:763-764) fused with the step: model_output_pair = [uncond; cond].  With
+        ``single_frame_output`` (the per-frame prediction, :738-755) the combine is the video_scale form of :757-761."""
         c = self.coefs(timestep, eta, guidance_scale)
         return ops.cfg_ddim_step(model_output_pair, sample, c,
-                                 noise=self._noise(sample.shape, eta, generator, variance_noise, sample.device))
+                                 noise=self._noise(sample.shape, eta, generator, variance_noise, sample.device),
+                                 single=single_frame_output, video_scale=video_scale)
 
     def add_noise(self, original_samples, noise, timesteps):
         """scheduling_ddim.py:378-398 (training/inversion helper, not on the sampling path; plain torch)."""

@@ -192,6 +192,10 @@ typedef struct {
 } fyc_ddim_coefs;
 int32_t fyc_cfg_ddim_step(const float* pred, const float* sample, const float* noise, float* prev, int64_t n,
                           const fyc_ddim_coefs* c, void* stream);
+/* The video_scale > 0 variant (pipeline_animation.py:738-761): `single` [n] is the UNet's prediction on the clip's frames
+ * taken one at a time (F = 1, no temporal context); n = s + video_scale * (u - s) + guidance * (c - u), then the same step. */
+int32_t fyc_cfg_video_ddim_step(const float* pred, const float* single, float video_scale, const float* sample,
+                                const float* noise, float* prev, int64_t n, const fyc_ddim_coefs* c, void* stream);
 /* decode_latents epilogue (pipeline_animation.py:409-410): x [b*F, HW, ldc >= 3] -> video (b, 3, F, H, W) fp32,
  * (x / 2 + 0.5).clamp(0, 1)  (ldc 0 or 3: packed RGB; 16 when the VAE's 3-channel head ran zero-padded on tcgen05). */
 int32_t fyc_frames_finalize(const void* x, float* video, int64_t b, int64_t F, int64_t HW, int64_t ldc, int32_t dtype,

@@ -30,8 +30,9 @@ def build_unet_input(latents, first_image_latents, first_images_mask, use_mask_c
 
 def denoise(unet_sd, unet_cfg, sched_cfg, latents, text_embeddings, num_inference_steps, guidance_scale,
             first_image_latents=None, first_images_mask=None, fps_tensor=None, flow_control=None,
-            image_clip_feat=None, uncond_image_clip_feat=None, camera_movement_type=None, trace=None):
-    """The hot loop: returns final latents (b, 4, f, h, w).  guidance_scale must be > 1 (CFG on)."""
+            image_clip_feat=None, uncond_image_clip_feat=None, camera_movement_type=None, trace=None, video_scale=0):
+    """The hot loop: returns final latents (b, 4, f, h, w).  guidance_scale must be > 1 (CFG on).
+    video_scale > 0: the per-frame guidance branch of pipeline_animation.py:738-761."""
     sched = DDIMOracle(sched_cfg)
     latents = latents.float().clone()
     use_concat = unet_cfg["use_first_frame_mask_condition_concat"]
@@ -45,7 +46,17 @@ def denoise(unet_sd, unet_cfg, sched_cfg, latents, text_embeddings, num_inferenc
                               fps_tensor=dup(fps_tensor), flow_control=dup(flow_control),
                               reference_images_clip_feat=clip,
                               camera_movement_type_tensor=dup(camera_movement_type))
-        latents = sched.step(cfg_combine(pred, guidance_scale), t, latents)
+        if video_scale > 0:
+            b, f = latents.shape[0], latents.shape[2]
+            xs = x.permute(0, 2, 1, 3, 4).reshape(-1, x.shape[1], x.shape[3], x.shape[4]).unsqueeze(2).chunk(2, dim=0)[0]     # :742,745
+            ts = torch.cat([text_embeddings] * f, dim=0).chunk(2, dim=0)[0]                                                   # :743,746
+            single = unet3d_forward(unet_sd, unet_cfg, xs, t, ts)                                                               # :747-751
+            single = single.squeeze(2).reshape(b, f, *single.shape[1:2], *single.shape[3:]).permute(0, 2, 1, 3, 4)            # :755
+            u, c = pred.chunk(2)
+            noise = single + video_scale * (u - single) + guidance_scale * (c - u)                                            # :757-761
+            latents = sched.step(noise, t, latents)
+        else:
+            latents = sched.step(cfg_combine(pred, guidance_scale), t, latents)
         if trace is not None:
             trace.append(latents.clone())
     return latents

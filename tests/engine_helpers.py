@@ -146,12 +146,24 @@ def make_pipeline(dtype, variant="base", vae_cfg=MINI_VAE, device="cuda", clip_i
     return pipe, ci, usd, vsd
 
 
-def pipeline_call(pipe, ci, F, h, w, steps, gs):
+def pipeline_call(pipe, ci, F, h, w, steps, gs, **extra):
     pipe.text_encoder.calls = 0
     return pipe("p", negative_prompt="n", video_length=F, height=h * 8, width=w * 8, num_inference_steps=steps,
                 guidance_scale=gs, latents=ci["latents"].clone(), use_first_frame_mask_condition_concat=True,
                 first_image_latents=ci["first_image_latents"], use_fps_condition=True, fps_tensor=torch.tensor([2]),
-                flow_control=torch.tensor([4]), first_images_mask=ci["first_images_mask"]).videos
+                flow_control=torch.tensor([4]), first_images_mask=ci["first_images_mask"], **extra).videos
+
+
+def run_video_scale_case(dtype, device="cuda", graph=True):
+    """per-frame guidance branch (video_scale > 0) against the reference fixture pipeline_video_scale.npz."""
+    g = golden("pipeline_video_scale.npz")
+    pipe, ci, usd, vsd = make_pipeline(dtype, device=device)
+    pipe.use_cuda_graph = graph and str(device).startswith("cuda")
+    video = pipeline_call(pipe, ci, 4, 8, 8, int(g["steps"]), 8.0, video_scale=float(g["video_scale"]))
+    ref = torch.from_numpy(g["video"])
+    s = stats(video, ref)
+    mse = float(((video.float() - ref) ** 2).mean())
+    return dict(video_maxabs=s["maxabs"], psnr=float(10 * np.log10(1.0 / max(mse, 1e-20))), finite=s["finite"], shape=tuple(video.shape))
 
 
 def run_pipeline_case(dtype, steps=3, against="oracle", device="cuda"):

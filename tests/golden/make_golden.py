@@ -111,10 +111,73 @@ def resampler_fixture():
     return err
 
 
+class FakeTok:
+    model_max_length = 77
+
+    def __call__(self, prompt, **kw):
+        n = len(prompt) if isinstance(prompt, list) else 1
+        ids = torch.zeros(n, 77, dtype=torch.long)
+        return types.SimpleNamespace(input_ids=ids, attention_mask=torch.ones_like(ids))
+
+    def batch_decode(self, x):
+        return [""]
+
+
+class FakeText(torch.nn.Module):
+    """Returns the seeded 'cond' embedding for the prompt call and 'uncond' for the negative-prompt call."""
+    def __init__(self, emb):
+        super().__init__()
+        self.emb, self.calls = emb, 0
+        self.config = types.SimpleNamespace()
+        self.dummy = torch.nn.Parameter(torch.zeros(1))
+
+    def forward(self, ids, attention_mask=None):
+        i = self.calls
+        self.calls += 1
+        return (self.emb[1:2] if i % 2 == 0 else self.emb[0:1],)     # prompt first, then negative prompt
+
+
+def video_scale_fixture(UNet, Pipe, VAE, DDIM):
+    """the reference pipeline with video_scale > 0 (per-frame guidance branch, pipeline_animation.py:738-761)."""
+    vae = VAE(in_channels=3, out_channels=3, down_block_types=("DownEncoderBlock2D",) * 4,
+              up_block_types=("UpDecoderBlock2D",) * 4, block_out_channels=MINI_VAE["block_out_channels"],
+              layers_per_block=MINI_VAE["layers_per_block"], latent_channels=4, norm_num_groups=32).eval()
+    vsd = load_synth(vae)
+    unet = UNet(**mini_unet_ref_kwargs("base")).eval()
+    usd = load_synth(unet)
+    F_, h, w, steps, gs, vs = 4, 8, 8, 2, 8.0, 0.7
+    ci = synth_clip_inputs(1, F_, h, w)
+    sched = DDIM(**{k: v for k, v in SCHED_V.items() if k != "set_alpha_to_one"})
+    pipe = Pipe(vae=vae, text_encoder=FakeText(ci["text_embeddings"]), tokenizer=FakeTok(), unet=unet, scheduler=sched)
+    with torch.no_grad():
+        ref_video = pipe("p", negative_prompt="n", video_length=F_, height=h * 8, width=w * 8,
+                         num_inference_steps=steps, guidance_scale=gs, latents=ci["latents"].clone(),
+                         use_first_frame_mask_condition_concat=True, first_image_latents=ci["first_image_latents"],
+                         use_fps_condition=True, fps_tensor=torch.tensor([2]), flow_control=torch.tensor([4]),
+                         first_images_mask=ci["first_images_mask"], video_scale=vs).videos
+        lat = ref_pipeline.denoise(usd, mini_unet_oracle_cfg("base"), SCHED_V, ci["latents"], ci["text_embeddings"],
+                                   steps, gs, first_image_latents=ci["first_image_latents"],
+                                   first_images_mask=ci["first_images_mask"], fps_tensor=torch.tensor([2]),
+                                   flow_control=torch.tensor([4]), video_scale=vs)
+        orc_video = ref_vae.decode_latents(vsd, MINI_VAE, lat)
+    err = maxabs(ref_video, orc_video)
+    print(f"pipeline video_scale={vs} video {tuple(ref_video.shape)} oracle-vs-ref maxabs={err:.3e}")
+    assert err < 2e-3
+    np.savez_compressed(os.path.join(HERE, "pipeline_video_scale.npz"), video=ref_video.numpy().astype(np.float32),
+                        final_latents=lat.numpy(), video_scale=np.float32(vs), steps=np.int64(steps))
+    return err
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(8)
     UNet, Pipe, VAE, DDIM, ImageProjModel = import_reference()
+    if "--only-video-scale" in sys.argv:
+        pj = os.path.join(HERE, "pins.json")
+        d = json.load(open(pj))
+        d["oracle_vs_reference_maxabs"]["pipeline_video_scale"] = video_scale_fixture(UNet, Pipe, VAE, DDIM)
+        json.dump(d, open(pj, "w"), indent=1)
+        return
     if "--only-resampler" in sys.argv:           # add the resampler fixture without regenerating the others
         pj = os.path.join(HERE, "pins.json")
         d = json.load(open(pj))
@@ -264,6 +327,7 @@ def main():
     pins["pipeline"] = err
     pins["vae_encode"] = vae_encode_fixture(VAE)
     pins["resampler"] = resampler_fixture()
+    pins["pipeline_video_scale"] = video_scale_fixture(UNet, Pipe, VAE, DDIM)
     np.savez_compressed(os.path.join(HERE, "pipeline.npz"), video=ref_video.numpy().astype(np.float32),
                         final_latents=lat.numpy())
     with open(os.path.join(HERE, "pins.json"), "w") as f:

@@ -215,11 +215,15 @@ def build_unet_input(latents, mask, first, dup, dtype, c_pad=None, out=None):
     return x
 
 
-def cfg_ddim_step(pred, sample, coefs, noise=None, out=None):
+def cfg_ddim_step(pred, sample, coefs, noise=None, out=None, single=None, video_scale=0.0):
     c = coefs
     n = sample.numel()
     p = pred.reshape(-1)
-    m = p[:n] + c.guidance * (p[n:2 * n] - p[:n]) if c.guidance > 1.0 else p[:n]
+    if single is not None:
+        sg = single.reshape(-1)
+        m = sg + video_scale * (p[:n] - sg) + c.guidance * (p[n:2 * n] - p[:n])
+    else:
+        m = p[:n] + c.guidance * (p[n:2 * n] - p[:n]) if c.guidance > 1.0 else p[:n]
     x = sample.reshape(-1)
     if c.prediction_type == _lib.PRED["epsilon"]:
         x0, eps = (x - c.sqrt_beta_t * m) / c.sqrt_alpha_t, m

@@ -124,3 +124,12 @@ def test_pipeline_hoisted_equals_per_step_host_logic():
         finally:
             AnimationPipeline.hoist_context = True
     assert torch.equal(vids[0], vids[1])
+
+
+def test_video_scale_branch_host_logic_vs_reference_golden():
+    """per-frame guidance (video_scale > 0) through the product pipeline (eager loop) vs the reference's frames."""
+    from tests.engine_helpers import run_video_scale_case
+    r = run_video_scale_case(torch.float32, device="cpu")
+    assert r["finite"] and r["shape"] == (1, 3, 4, 64, 64) and r["video_maxabs"] < 2e-3, r
+    r = run_video_scale_case(torch.bfloat16, device="cpu")
+    assert r["finite"] and r["psnr"] > 30.0, r

@@ -111,3 +111,20 @@ def test_resampler_oracle_vs_reference_fixture():
     assert float((out - torch.from_numpy(g["out"])).abs().max()) < 2e-5
     pins = json.load(open(os.path.join(GOLD, "pins.json")))["oracle_vs_reference_maxabs"]
     assert pins["resampler"] < 2e-5
+
+
+def test_pipeline_video_scale_oracle_vs_reference_fixture():
+    """oracle's per-frame guidance branch (pipeline_animation.py:738-761) against the reference's frames."""
+    from followyourclick_b200.synth import synth_clip_inputs
+    from tests.cfgs import MINI_VAE as VCFG
+    g = np.load(os.path.join(GOLD, "pipeline_video_scale.npz"))
+    keys = json.load(open(os.path.join(GOLD, "unet_keys.json")))["base"]
+    vkeys = json.load(open(os.path.join(GOLD, "vae_keys.json")))
+    usd, vsd = _synth(keys), _synth(vkeys)
+    ci = synth_clip_inputs(1, 4, 8, 8)
+    lat = ref_pipeline.denoise(usd, mini_unet_oracle_cfg("base"), SCHED_V, ci["latents"], ci["text_embeddings"], int(g["steps"]), 8.0,
+                               first_image_latents=ci["first_image_latents"], first_images_mask=ci["first_images_mask"],
+                               fps_tensor=torch.tensor([2]), flow_control=torch.tensor([4]), video_scale=float(g["video_scale"]))
+    assert float((lat - torch.from_numpy(g["final_latents"])).abs().max()) < 1e-4
+    video = ref_vae.decode_latents(vsd, VCFG, lat)
+    assert float((video - torch.from_numpy(g["video"])).abs().max()) < 2e-4
