@@ -3,7 +3,7 @@
 Public surface = the reference's own class names; see INTEGRATION.md for how
 ``scripts/inference.py`` mounts them.  Everything below the Python classes is libfyc_sm100a.so (include/fyc.h).
 """
-from .unet import UNet3DConditionModel, UNet3DConditionOutput, ImageProjModel  # noqa: F401
+from .unet import UNet2DConditionModel, UNet3DConditionModel, UNet3DConditionOutput, ImageProjModel  # noqa: F401
 from .vae import AutoencoderKL  # noqa: F401
 from .scheduling_ddim import DDIMScheduler  # noqa: F401
 from .pipeline_animation import AnimationPipeline, AnimationPipelineOutput  # noqa: F401

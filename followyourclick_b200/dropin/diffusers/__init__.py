@@ -8,6 +8,7 @@ import sys
 
 from followyourclick_b200.scheduling_ddim import DDIMScheduler  # noqa: F401
 from followyourclick_b200.vae import AutoencoderKL  # noqa: F401
+from followyourclick_b200.unet import UNet2DConditionModel  # noqa: F401  (T2I first-frame generator, scripts/inference.py:195-204)
 
 __version__ = "0.11.1"
 _ref = None

@@ -622,3 +622,65 @@ class UNet3DConditionModel(ParamTreeModel):
         if not return_dict:
             return (out,)
         return UNet3DConditionOutput(sample=out)
+
+
+@dataclass
+class UNet2DConditionOutput:
+    sample: torch.Tensor
+
+
+class UNet2DConditionModel(UNet3DConditionModel):
+    """Stock SD-1.5 ``UNet2DConditionModel`` (diffusers/models/unet_2d_condition.py:44-439) on the engine - the T2I first-frame
+    generator of scripts/inference.py:195-204,300-306 (`pipeline_base`).  It is the 3-D model without motion
+    modules run on one frame: an inflated conv on F = 1 is the 2-D conv, cross-frame GroupNorm over one frame is the per-image
+    GroupNorm, and the state-dict keys are the 2-D checkpoint's own (``from_pretrained_2d`` relies on exactly that).  Same
+    constructor kwargs and ``forward(sample (b, 4, h, w), timestep, encoder_hidden_states).sample`` as the reference class."""
+
+    _BLOCKS_2D_TO_3D = {"CrossAttnDownBlock2D": "CrossAttnDownBlock3D", "DownBlock2D": "DownBlock3D", "UpBlock2D": "UpBlock3D",
+                        "CrossAttnUpBlock2D": "CrossAttnUpBlock3D", "UNetMidBlock2DCrossAttn": "UNetMidBlock3DCrossAttn"}
+
+    def __init__(self, sample_size=None, in_channels=4, out_channels=4, center_input_sample=False, flip_sin_to_cos=True, freq_shift=0,
+                 down_block_types=("CrossAttnDownBlock2D", "CrossAttnDownBlock2D", "CrossAttnDownBlock2D", "DownBlock2D"),
+                 mid_block_type="UNetMidBlock2DCrossAttn",
+                 up_block_types=("UpBlock2D", "CrossAttnUpBlock2D", "CrossAttnUpBlock2D", "CrossAttnUpBlock2D"),
+                 only_cross_attention=False, block_out_channels=(320, 640, 1280, 1280), layers_per_block=2, downsample_padding=1,
+                 mid_block_scale_factor=1, act_fn="silu", norm_num_groups=32, norm_eps=1e-5, cross_attention_dim=1280,
+                 attention_head_dim=8, dual_cross_attention=False, use_linear_projection=False, class_embed_type=None,
+                 num_class_embeds=None, upcast_attention=False, resnet_time_scale_shift="default"):
+        m = self._BLOCKS_2D_TO_3D
+        for name in tuple(down_block_types) + tuple(up_block_types) + (mid_block_type,):
+            if name not in m:
+                raise NotImplementedError(f"UNet2DConditionModel: block type {name}")
+        super().__init__(sample_size=sample_size, in_channels=in_channels, out_channels=out_channels,
+                         center_input_sample=center_input_sample, flip_sin_to_cos=flip_sin_to_cos, freq_shift=freq_shift,
+                         down_block_types=tuple(m[b] for b in down_block_types), mid_block_type=m[mid_block_type],
+                         up_block_types=tuple(m[b] for b in up_block_types), only_cross_attention=only_cross_attention,
+                         block_out_channels=block_out_channels, layers_per_block=layers_per_block,
+                         downsample_padding=downsample_padding, mid_block_scale_factor=mid_block_scale_factor, act_fn=act_fn,
+                         norm_num_groups=norm_num_groups, norm_eps=norm_eps, cross_attention_dim=cross_attention_dim,
+                         attention_head_dim=attention_head_dim, dual_cross_attention=dual_cross_attention,
+                         use_linear_projection=use_linear_projection, class_embed_type=class_embed_type,
+                         num_class_embeds=num_class_embeds, upcast_attention=upcast_attention,
+                         resnet_time_scale_shift=resnet_time_scale_shift, use_motion_module=False)
+        cfg2d = {k: v for k, v in locals().items() if k not in ("self", "m", "name", "__class__")}
+        self.config = FrozenDict(dict(cfg2d, _class_name="UNet2DConditionModel", _diffusers_version="0.11.1"))
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_path, subfolder=None, **kwargs):
+        """config.json + diffusion_pytorch_model.bin of an SD-1.5 ``unet/`` folder (diffusers/modeling_utils.py:from_pretrained)."""
+        if subfolder is not None:
+            pretrained_model_path = os.path.join(pretrained_model_path, subfolder)
+        with open(os.path.join(pretrained_model_path, "config.json")) as f:
+            config = {k: v for k, v in json.load(f).items() if not k.startswith("_")}
+        model = cls(**config)
+        model.load_state_dict(torch.load(os.path.join(pretrained_model_path, "diffusion_pytorch_model.bin"), map_location="cpu"))
+        return model
+
+    @torch.no_grad()
+    def forward(self, sample, timestep, encoder_hidden_states, class_labels=None, attention_mask=None, return_dict=True):
+        if class_labels is not None or attention_mask is not None:
+            raise NotImplementedError("forward option outside the SD-1.5 text-to-image path")
+        out = UNet3DConditionModel.forward(self, sample.unsqueeze(2), timestep, encoder_hidden_states).sample.squeeze(2)
+        if not return_dict:
+            return (out,)
+        return UNet2DConditionOutput(sample=out)

@@ -70,3 +70,13 @@ def unet_inputs(variant, b=2, f=4, h=16, w=16, seed=11):
     if variant == "cam":
         d["camera"] = torch.tensor([3, 3])
     return d
+
+
+# stock 2-D UNet (diffusers UNet2DConditionModel) at the mini width: the T2I first-frame generator
+MINI_UNET2D = dict(sample_size=16, in_channels=4, out_channels=4, block_out_channels=(160, 320, 640, 640), layers_per_block=1,
+                   attention_head_dim=4, cross_attention_dim=768, norm_num_groups=32)
+
+
+def mini_unet2d_oracle_cfg():
+    return default_unet_config(block_out_channels=MINI_UNET2D["block_out_channels"], layers_per_block=1, attention_head_dim=4,
+                               use_motion_module=False, use_first_frame_mask_condition_concat=False, use_fps_condition=False)

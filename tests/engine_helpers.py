@@ -185,3 +185,22 @@ def run_pipeline_case(dtype, steps=3, against="oracle", device="cuda"):
     mse = float(((video.float() - ref) ** 2).mean())
     return dict(video_maxabs=s["maxabs"], video_rel_l2=s["rel_l2"], psnr=float(10 * np.log10(1.0 / max(mse, 1e-20))),
                 shape=tuple(video.shape), finite=s["finite"])
+
+
+def run_unet2d_case(dtype, device="cuda"):
+    """SURVEY 8f row 3: UNet2DConditionModel (T2I first-frame generator) against the reference's 2-D UNet output (unet2d.npz);
+    also checks the state-dict key set is the 2-D checkpoint's."""
+    import json
+    from followyourclick_b200 import UNet2DConditionModel
+    from tests.cfgs import MINI_UNET2D
+    m = UNet2DConditionModel(**MINI_UNET2D)
+    keys = json.load(open(os.path.join(GOLD, "unet2d_keys.json")))
+    assert {k: list(v.shape) for k, v in m.state_dict().items()} == keys
+    load_synth(m)
+    m.to(device)
+    m.to(dtype)
+    g = golden("unet2d.npz")
+    out = m(torch.from_numpy(g["x"]).to(device), torch.tensor(501), encoder_hidden_states=torch.from_numpy(g["ctx"]).to(device)).sample
+    _sync(device)
+    assert out.shape == (2, 4, 16, 16)
+    return stats(out, torch.from_numpy(g["out"]))

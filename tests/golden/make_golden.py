@@ -168,10 +168,38 @@ def video_scale_fixture(UNet, Pipe, VAE, DDIM):
     return err
 
 
+def unet2d_fixture():
+    """SURVEY 8f row 3: the stock 2-D UNet (T2I first-frame generator) of the vendored diffusers, mini size, synthetic weights;
+    the oracle is the 3-D restatement without motion modules on one frame."""
+    from diffusers.models.unet_2d_condition import UNet2DConditionModel as UNet2D
+    from tests.cfgs import MINI_UNET2D
+    m = UNet2D(**MINI_UNET2D).eval()
+    sd = load_synth(m)
+    g = torch.Generator().manual_seed(31)
+    x, ctx, t = torch.randn(2, 4, 16, 16, generator=g), torch.randn(2, 77, 768, generator=g), torch.tensor(501)
+    from tests.cfgs import mini_unet2d_oracle_cfg
+    with torch.no_grad():
+        ref = m(x, t, encoder_hidden_states=ctx).sample
+        orc = ref_unet.unet3d_forward(sd, mini_unet2d_oracle_cfg(), x.unsqueeze(2), t, ctx).squeeze(2)
+    err = maxabs(ref, orc)
+    print(f"unet2d out {tuple(ref.shape)} |ref|max={float(ref.abs().max()):.3f} oracle-vs-ref maxabs={err:.3e}")
+    assert err < 2e-4 * max(1.0, float(ref.abs().max()))
+    np.savez_compressed(os.path.join(HERE, "unet2d.npz"), x=x.numpy(), ctx=ctx.numpy(), out=ref.numpy())
+    with open(os.path.join(HERE, "unet2d_keys.json"), "w") as f:
+        json.dump({k: list(v.shape) for k, v in sd.items()}, f)
+    return err
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(8)
     UNet, Pipe, VAE, DDIM, ImageProjModel = import_reference()
+    if "--only-unet2d" in sys.argv:
+        pj = os.path.join(HERE, "pins.json")
+        d = json.load(open(pj))
+        d["oracle_vs_reference_maxabs"]["unet2d"] = unet2d_fixture()
+        json.dump(d, open(pj, "w"), indent=1)
+        return
     if "--only-video-scale" in sys.argv:
         pj = os.path.join(HERE, "pins.json")
         d = json.load(open(pj))
@@ -327,6 +355,7 @@ def main():
     pins["pipeline"] = err
     pins["vae_encode"] = vae_encode_fixture(VAE)
     pins["resampler"] = resampler_fixture()
+    pins["unet2d"] = unet2d_fixture()
     pins["pipeline_video_scale"] = video_scale_fixture(UNet, Pipe, VAE, DDIM)
     np.savez_compressed(os.path.join(HERE, "pipeline.npz"), video=ref_video.numpy().astype(np.float32),
                         final_latents=lat.numpy())

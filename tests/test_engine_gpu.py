@@ -208,3 +208,12 @@ def test_cfg_video_ddim_step_bit_exact():
     fused = sch.step_cfg(torch.cat([u, c]), 481, x, 8.0, single_frame_output=s, video_scale=0.7)
     two = sch.step(s + 0.7 * (u - s) + 8.0 * (c - u), 481, x).prev_sample
     assert torch.equal(fused, two)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 3e-2)])
+def test_unet2d_matches_reference_golden(dtype, tol):
+    """the stock 2-D UNet (T2I first-frame generator, scripts/inference.py:195-204) = the engine's 3-D model
+    without motion modules on one frame, vs the vendored diffusers UNet2DConditionModel output."""
+    from tests.engine_helpers import run_unet2d_case
+    s = run_unet2d_case(dtype)
+    assert s["finite"] and s["rel_l2"] < tol, s

@@ -133,3 +133,10 @@ def test_video_scale_branch_host_logic_vs_reference_golden():
     assert r["finite"] and r["shape"] == (1, 3, 4, 64, 64) and r["video_maxabs"] < 2e-3, r
     r = run_video_scale_case(torch.bfloat16, device="cpu")
     assert r["finite"] and r["psnr"] > 30.0, r
+
+
+@pytest.mark.parametrize("dtype,tol", DTYPES)
+def test_unet2d_host_logic_vs_reference_golden(dtype, tol):
+    from tests.engine_helpers import run_unet2d_case
+    s = run_unet2d_case(dtype, device="cpu")
+    assert s["finite"] and s["rel_l2"] < tol, s

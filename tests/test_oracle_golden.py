@@ -128,3 +128,13 @@ def test_pipeline_video_scale_oracle_vs_reference_fixture():
     assert float((lat - torch.from_numpy(g["final_latents"])).abs().max()) < 1e-4
     video = ref_vae.decode_latents(vsd, VCFG, lat)
     assert float((video - torch.from_numpy(g["video"])).abs().max()) < 2e-4
+
+
+def test_unet2d_oracle_vs_reference_fixture():
+    """oracle (3-D restatement, no motion modules, one frame) vs the reference's 2-D UNet output."""
+    from tests.cfgs import mini_unet2d_oracle_cfg
+    g = np.load(os.path.join(GOLD, "unet2d.npz"))
+    sd = _synth(json.load(open(os.path.join(GOLD, "unet2d_keys.json"))))
+    out = ref_unet.unet3d_forward(sd, mini_unet2d_oracle_cfg(), torch.from_numpy(g["x"]).unsqueeze(2), torch.tensor(501),
+                                  torch.from_numpy(g["ctx"])).squeeze(2)
+    assert float((out - torch.from_numpy(g["out"])).abs().max()) < 1e-4
