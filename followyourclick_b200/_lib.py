@@ -74,6 +74,7 @@ SIGNATURES = {
     "fyc_cfg_ddim_step": (_i32, [_vp, _vp, _vp, _vp, _i64, C.POINTER(DdimCoefs), _vp]),
     "fyc_cfg_video_ddim_step": (_i32, [_vp, _vp, _f32, _vp, _vp, _vp, _i64, C.POINTER(DdimCoefs), _vp]),
     "fyc_frames_finalize": (_i32, [_vp, _vp, _i64, _i64, _i64, _i64, _i32, _vp]),
+    "fyc_video_grid_u8": (_i32, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i32, _vp]),
 }
 
 _lib = None

@@ -290,6 +290,42 @@ extern "C" int32_t fyc_frames_finalize(const void* x, float* video, int64_t b, i
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// save_videos_grid's per-frame tiling + 8-bit conversion (animatediff/utils/util.py:18-27) on the device: for every frame t the b
+// clips are tiled like torchvision.utils.make_grid(nrow, padding, pad_value 0) - a single clip is passed through unpadded - then
+// (x [+1)/2 if rescale]) * 255 truncated to uint8.  video (b, 3, F, H, W) fp32 -> out [F, Hg, Wg, 3] uint8: a quarter of the bytes of
+// the fp32 video cross PCIe, already in the layout the GIF writer wants.
+__global__ void video_grid_u8_kernel(const float* __restrict__ video, uint8_t* __restrict__ out, int64_t b, int64_t F, int64_t H, int64_t W,
+                                     int64_t xmaps, int64_t pad, int64_t Hg, int64_t Wg, int rescale) {
+  const int64_t total = F * Hg * Wg * 3;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t c = i % 3; int64_t r = i / 3;
+    const int64_t x = r % Wg; r /= Wg;
+    const int64_t y = r % Hg; const int64_t t = r / Hg;
+    float v = 0.f;                                      // pad_value
+    const int64_t ch = H + pad, cw = W + pad;           // cell pitch
+    const int64_t yy = y - pad, xx = x - pad;
+    if (yy >= 0 && xx >= 0) {
+      const int64_t gy = yy / ch, gx = xx / cw, iy = yy % ch, ix = xx % cw;
+      const int64_t k = gy * xmaps + gx;
+      if (gx < xmaps && k < b && iy < H && ix < W) v = video[(((k * 3 + c) * F + t) * H + iy) * W + ix];
+    }
+    if (rescale) v = __fdiv_rn(__fadd_rn(v, 1.0f), 2.0f);
+    v = __fmul_rn(v, 255.0f);
+    out[i] = (uint8_t)(int)fminf(fmaxf(v, 0.f), 255.f);     // numpy astype(uint8) of an in-range float truncates toward zero
+  }
+}
+extern "C" int32_t fyc_video_grid_u8(const float* video, uint8_t* out, int64_t b, int64_t F, int64_t H, int64_t W, int64_t nrow,
+                                     int64_t padding, int32_t rescale, void* stream) {
+  FYC_CHECK(video && out && b > 0 && F > 0 && H > 0 && W > 0 && nrow > 0 && padding >= 0, "video_grid_u8: bad arguments");
+  const int64_t pad = (b == 1) ? 0 : padding;            // make_grid returns a single image as is
+  const int64_t xmaps = b < nrow ? b : nrow, ymaps = (b + xmaps - 1) / xmaps;
+  const int64_t Hg = (H + pad) * ymaps + pad, Wg = (W + pad) * xmaps + pad;
+  video_grid_u8_kernel<<<grid_for(F * Hg * Wg * 3, 256), 256, 0, (cudaStream_t)stream>>>(video, out, b, F, H, W, xmaps, pad, Hg, Wg, rescale);
+  FYC_LAUNCH_CHECK();
+  return FYC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // fp32 row softmax (VAE AttentionBlock, diffusers/models/attention.py:366).  One block per row.
 template <typename T>
 __global__ void softmax_rows_kernel(const float* __restrict__ s, T* __restrict__ p, int64_t L) {

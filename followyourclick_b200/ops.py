@@ -393,3 +393,20 @@ def frames_finalize(x, b, f):
     out = torch.empty((b, 3, f, H, W_), dtype=torch.float32, device=x.device)
     check(lib().fyc_frames_finalize(ptr(x), ptr(out), b, f, H * W_, ld, dtype_code(x.dtype), stream_ptr()))
     return out
+
+
+def video_grid_shape(b, F, H, W, nrow, padding=2):
+    pad = 0 if b == 1 else padding
+    xmaps = min(nrow, b)
+    ymaps = (b + xmaps - 1) // xmaps
+    return F, (H + pad) * ymaps + pad, (W + pad) * xmaps + pad, 3
+
+
+def video_grid_u8(video, nrow=6, padding=2, rescale=False):
+    """video (b, 3, F, H, W) fp32 on device -> uint8 [F, Hg, Wg, 3]: per-frame make_grid tiling + trunc(x * 255) (util.py:18-27)."""
+    assert video.dtype == torch.float32 and video.is_contiguous() and video.dim() == 5 and video.shape[1] == 3
+    require_cuda(video, "video_grid_u8")
+    b, _, F, H, W_ = video.shape
+    out = torch.empty(video_grid_shape(b, F, H, W_, nrow, padding), dtype=torch.uint8, device=video.device)
+    check(lib().fyc_video_grid_u8(ptr(video), ptr(out), b, F, H, W_, nrow, padding, int(bool(rescale)), stream_ptr()))
+    return out

@@ -201,6 +201,13 @@ int32_t fyc_cfg_video_ddim_step(const float* pred, const float* single, float vi
 int32_t fyc_frames_finalize(const void* x, float* video, int64_t b, int64_t F, int64_t HW, int64_t ldc, int32_t dtype,
                             void* stream);
 
+/* Output side, save_videos_grid's tiling + 8-bit conversion (animatediff/utils/util.py:18-27): video (b, 3, F, H, W)
+ * fp32 -> out [F, Hg, Wg, 3] uint8 where frame t tiles the b clips like torchvision.utils.make_grid(nrow, padding, pad_value 0)
+ * (b == 1: the image unpadded; else xmaps = min(nrow, b), Hg = (H + padding) * ceil(b / xmaps) + padding, Wg alike) and each value is
+ * trunc(((x + 1) / 2 if rescale else x) * 255). */
+int32_t fyc_video_grid_u8(const float* video, uint8_t* out, int64_t b, int64_t F, int64_t H, int64_t W, int64_t nrow,
+                          int64_t padding, int32_t rescale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

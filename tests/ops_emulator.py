@@ -250,9 +250,15 @@ def frames_finalize(x, b, f):
     return (x.float().reshape(b, f, H, W_, 3).permute(0, 4, 1, 2, 3) / 2 + 0.5).clamp(0, 1).contiguous()
 
 
+def video_grid_u8(video, nrow=6, padding=2, rescale=False):
+    import numpy as np
+    from oracle import ref_util
+    return torch.from_numpy(np.stack(ref_util.video_frames_uint8(video, rescale=rescale, n_rows=nrow)))
+
+
 _NAMES = ["tc_ok", "require_cuda", "gemm", "conv3x3", "groupnorm", "layernorm", "attention", "transpose_tokens", "self_attention_tc_ok",
           "self_attention_tc", "temporal_attention", "softmax_rows", "timestep_embed", "silu", "gelu", "upsample_nearest2x",
-          "concat_channels", "ncfhw_to_nfhwc", "nfhwc_to_ncfhw", "build_unet_input", "cfg_ddim_step", "frames_finalize"]
+          "concat_channels", "ncfhw_to_nfhwc", "nfhwc_to_ncfhw", "build_unet_input", "cfg_ddim_step", "frames_finalize", "video_grid_u8"]
 
 
 def install(monkeypatch):

@@ -452,3 +452,29 @@ def test_cfg_ddim_step_bit_exact_vs_golden(cuda):
     fused = sch.step_cfg(torch.cat([u, c]), 481, x, 8.0)
     two = sch.step(u + 8.0 * (c - u), 481, x).prev_sample
     assert torch.equal(fused, two)
+
+
+@pytest.mark.parametrize("b,nrow,rescale", [(1, 6, False), (3, 6, False), (7, 4, False), (4, 2, True)])
+def test_video_grid_u8_bit_exact(cuda, b, nrow, rescale):
+    """fyc_video_grid_u8 == save_videos_grid's make_grid + (x * 255).astype(uint8) (oracle/ref_util.py), byte for byte."""
+    import numpy as np
+    from followyourclick_b200 import ops
+    from oracle import ref_util
+    g = torch.Generator().manual_seed(9)
+    v = torch.rand(b, 3, 3, 10, 12, generator=g)
+    if rescale:
+        v = v * 2 - 1
+    v[0, 0, 0, 0, 0], v[0, 1, 0, 0, 0] = 1.0, (-1.0 if rescale else 0.0)
+    out = ops.video_grid_u8(v.cuda(), nrow=nrow, rescale=rescale).cpu().numpy()
+    ref = np.stack(ref_util.video_frames_uint8(v, rescale=rescale, n_rows=nrow))
+    assert out.shape == ref.shape == ops.video_grid_shape(b, 3, 10, 12, nrow) and np.array_equal(out, ref)
+
+
+def test_save_videos_grid_writes_a_gif(cuda, tmp_path):
+    from PIL import Image
+    from followyourclick_b200.util import save_videos_grid
+    v = torch.rand(2, 3, 4, 16, 16, generator=torch.Generator().manual_seed(1))
+    p = save_videos_grid(v.cuda(), str(tmp_path / "a" / "s.gif"), n_rows=2)
+    im = Image.open(p)
+    assert im.n_frames == 4 and im.size == (2 * 18 + 2, 18 + 2)
+    save_videos_grid(v, str(tmp_path / "b.gif"))           # a host tensor (the reference API's return type) also works

@@ -138,3 +138,16 @@ def test_unet2d_oracle_vs_reference_fixture():
     out = ref_unet.unet3d_forward(sd, mini_unet2d_oracle_cfg(), torch.from_numpy(g["x"]).unsqueeze(2), torch.tensor(501),
                                   torch.from_numpy(g["ctx"])).squeeze(2)
     assert float((out - torch.from_numpy(g["out"])).abs().max()) < 1e-4
+
+
+def test_video_grid_oracle_pinned_against_torchvision():
+    """the oracle's make_grid == torchvision.utils.make_grid (what save_videos_grid calls) for 1, 3 and 7 clips."""
+    torchvision = pytest.importorskip("torchvision")
+    from oracle import ref_util
+    g = torch.Generator().manual_seed(4)
+    for b, nrow in ((1, 6), (3, 6), (7, 4), (4, 4)):
+        x = torch.rand(b, 3, 5, 6, generator=g)
+        assert torch.equal(ref_util.make_grid(x, nrow), torchvision.utils.make_grid(x, nrow=nrow))
+    v = torch.rand(3, 3, 2, 5, 6, generator=g)
+    fr = ref_util.video_frames_uint8(v, n_rows=2)
+    assert len(fr) == 2 and fr[0].shape == (2 * 7 + 2, 2 * 8 + 2, 3) and fr[0].dtype == np.uint8
