@@ -1,7 +1,17 @@
 // GroupNorm (cross-frame or per-frame statistics) and LayerNorm.  Both are HBM-bound: one read for the
 // statistics, one read + one write for the apply; statistics are accumulated in fp32 per thread, combined in
 // fp64 across CTAs so that E[x^2]-E[x]^2 does not cancel.
+#include <stdlib.h>
+
 #include "common.cuh"
+
+// FYC_ZIGZAG (default 1): the norm kernels walk their input back to front.  Activations at the 64x64 level are 84 MB, the L2 is 126
+// MB: a consumer that starts where its producer stopped finds the most recently written half still cached, one that starts at the
+// front finds nothing.  GEMM / conv / attention write front to back, so the norms between them run back to front.
+static int fyc_zigzag() {
+  const char* e = getenv("FYC_ZIGZAG");
+  return (e && e[0] == '0') ? 0 : 1;
+}
 
 namespace {
 // Blackwell packed fp32 pairs (FFMA2 / FADD2 / FMUL2): one issue slot for two lanes' worth of work.  The norm kernels were
@@ -30,15 +40,17 @@ __device__ __forceinline__ float rcp_fast(float x) { float y; asm("rcp.approx.ft
 // statistics (and therefore the whole engine) are bit-reproducible run to run.
 template <typename T, int V>
 __global__ void __launch_bounds__(256, 4) gn_stats_kernel(const T* __restrict__ x, float2* __restrict__ partials, int64_t R,
-                                                       int C, int G, int64_t rows_per_cta) {
+                                                       int C, int G, int64_t rows_per_cta, int rev) {
   extern __shared__ float s_ch[];   // [RY][C][2]
   const int cpg = C / G;
   const int cvn = C / V;
   const int TX = cvn < 256 ? cvn : 256;
   const int RY = 256 / TX;
   const int tx = threadIdx.x % TX, ry = threadIdx.x / TX;
-  const int64_t nb = blockIdx.y;
-  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
+  // rev: walk the tensor back to front (zig-zag against the producer, which wrote it front to back: its tail is what L2 still holds)
+  const int64_t nb = rev ? gridDim.y - 1 - blockIdx.y : blockIdx.y;
+  const int64_t bx = rev ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
+  const int64_t r0 = bx * rows_per_cta;
   const int64_t r1 = (r0 + rows_per_cta < R) ? r0 + rows_per_cta : R;
   const T* base = x + nb * R * C;
   if (ry < RY) {
@@ -101,7 +113,7 @@ __global__ void __launch_bounds__(256, 4) gn_stats_kernel(const T* __restrict__ 
     float as = 0.f, aq = 0.f;
     for (int y = 0; y < RY; ++y)
       for (int c = g * cpg; c < (g + 1) * cpg; ++c) { as += s_ch[((size_t)y * C + c) * 2]; aq += s_ch[((size_t)y * C + c) * 2 + 1]; }
-    partials[((int64_t)nb * gridDim.x + blockIdx.x) * G + g] = make_float2(as, aq);
+    partials[((int64_t)nb * gridDim.x + bx) * G + g] = make_float2(as, aq);      // slot = logical chunk: the finalize order is unchanged
   }
 }
 
@@ -284,7 +296,7 @@ static int32_t groupnorm_impl(const T* x, const float* gamma, const float* beta,
   auto kern = gn_stats_kernel<T, V>;
   if (smem > 48 * 1024) FYC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)chunks, (unsigned)NB);
-  kern<<<grid, 256, smem, st>>>(x, partials, R, C, G, rows_per_cta);
+  kern<<<grid, 256, smem, st>>>(x, partials, R, C, G, rows_per_cta, fyc_zigzag());
   FYC_LAUNCH_CHECK();
   gn_finalize_kernel<<<dim3((unsigned)G, (unsigned)NB), 128, 0, st>>>(partials, chunks, gamma, beta, scale, shift, C, G,
                                                                        (double)R * (C / G), eps);
@@ -478,11 +490,14 @@ template <int LPR, int PASSES, bool HAS_PE>
 __global__ void __launch_bounds__(256, 2) layernorm_lpr_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma,
                                                                const float* __restrict__ beta, bf16* __restrict__ out, int64_t M,
                                                                float eps, const float* __restrict__ pe, int64_t rows_per_frame,
-                                                               int64_t frames) {
+                                                               int64_t frames, int rev) {
   constexpr int C = LPR * 40, RPP = 32 / LPR;           // channels; rows per warp pass
   constexpr int VS = LPR * 8;                           // element stride between a lane's consecutive vectors
   const int lane = threadIdx.x & 31, sub = lane % LPR, rr = lane / LPR;
-  const int64_t row_base = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * (RPP * PASSES);
+  // rev: CTAs take the row blocks back to front - the GEMM that produced x wrote it front to back (its tail is still in L2) and the
+  // GEMM that consumes `out` reads front to back (the front is what this kernel then wrote last)
+  const int64_t bxl = rev ? (int64_t)gridDim.x - 1 - blockIdx.x : (int64_t)blockIdx.x;
+  const int64_t row_base = (bxl * (blockDim.x >> 5) + (threadIdx.x >> 5)) * (RPP * PASSES);
   if (row_base >= M) return;
   f32x2 gm[5][4];                                       // beta is re-read from L1 per vector: 40 more registers would halve the occupancy
   const float* gp = gamma + sub * 8;
@@ -551,8 +566,8 @@ static void launch_ln_lpr(const bf16* xb, const float* gamma, const float* beta,
                           int64_t rows_per_frame, int64_t frames, cudaStream_t st) {
   constexpr int PASSES = 2;
   const unsigned grid = (unsigned)ceil_div64(M, 8 * (32 / LPR) * PASSES);
-  if (pe) layernorm_lpr_kernel<LPR, PASSES, true><<<grid, 256, 0, st>>>(xb, gamma, beta, ob, M, eps, pe, rows_per_frame, frames);
-  else layernorm_lpr_kernel<LPR, PASSES, false><<<grid, 256, 0, st>>>(xb, gamma, beta, ob, M, eps, pe, rows_per_frame, frames);
+  if (pe) layernorm_lpr_kernel<LPR, PASSES, true><<<grid, 256, 0, st>>>(xb, gamma, beta, ob, M, eps, pe, rows_per_frame, frames, fyc_zigzag());
+  else layernorm_lpr_kernel<LPR, PASSES, false><<<grid, 256, 0, st>>>(xb, gamma, beta, ob, M, eps, pe, rows_per_frame, frames, fyc_zigzag());
 }
 
 extern "C" int32_t fyc_layernorm(const void* x, const float* gamma, const float* beta, void* out, int64_t M, int64_t C,

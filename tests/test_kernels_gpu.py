@@ -245,8 +245,10 @@ def test_conv3x3_upsample_phases_tcgen05(NB, H, W, Cin, Cout, pair, monkeypatch)
 @pytest.mark.parametrize("NB,R,C,G,stat", [(2, 4 * 64, 160, 32, 2), (8, 64, 160, 32, 8), (2, 1024, 1920, 32, 2), (4, 16, 128, 32, 4),
                                             (3, 100, 36, 4, 3)])
 @pytest.mark.parametrize("silu", [False, True])
-def test_groupnorm(cuda, dtype, NB, R, C, G, stat, silu):
+@pytest.mark.parametrize("zigzag", ["1", "0"])
+def test_groupnorm(cuda, dtype, NB, R, C, G, stat, silu, zigzag, monkeypatch):
     from followyourclick_b200 import ops
+    monkeypatch.setenv("FYC_ZIGZAG", zigzag)       # back-to-front / front-to-back traversal of the statistics pass: same numbers
     x = (rnd((NB, R, C), 1) * 2 + 3).to(dtype)
     gamma, beta = rnd((C,), 2) + 1, rnd((C,), 3)
     out = ops.groupnorm(x, gamma, beta, G, 1e-5, silu=silu, stat_batches=stat)
@@ -257,8 +259,15 @@ def test_groupnorm(cuda, dtype, NB, R, C, G, stat, silu):
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("C", [160, 320, 640, 1280, 768])
-def test_layernorm_with_pe(cuda, dtype, C):
+def test_layernorm_with_pe(cuda, dtype, C, monkeypatch):
     from followyourclick_b200 import ops
+    x0 = (rnd((2 * 4 * 16 + 3, C), 1) * 1.5 + 0.5).to(dtype)          # ragged row count: the last row block is partial
+    g0, b0 = rnd((C,), 2) + 1, rnd((C,), 3)
+    monkeypatch.setenv("FYC_ZIGZAG", "0")
+    fwd = ops.layernorm(x0, g0, b0)
+    monkeypatch.setenv("FYC_ZIGZAG", "1")
+    assert torch.equal(ops.layernorm(x0, g0, b0), fwd)                  # traversal order does not change a single bit
+    assert rel(fwd, F.layer_norm(x0.float(), (C,), g0, b0, 1e-5)) < (1e-5 if dtype == torch.float32 else 6e-3)
     Fr, HW = 4, 16
     x = (rnd((2 * Fr * HW, C), 1) * 1.5 + 0.5).to(dtype)
     gamma, beta, pe = rnd((C,), 2) + 1, rnd((C,), 3), rnd((24, C), 4)
