@@ -6,6 +6,8 @@
 //
 // NOTE (round 1): this kernel uses the legacy warp-level MMA path (HMMA); porting QK^T/PV to tcgen05 with S/P in
 // TMEM is the next optimisation step for this kernel ("what comes next").
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -210,8 +212,183 @@ __global__ void __launch_bounds__(NTHR) attention_mma_kernel(fyc_attention_args 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Short-context variant (Lk <= 128: the 77 text tokens of every cross-attention, the 4 / 16 IP tokens).  The generic kernel above
+// launches one CTA per 64 query rows, and each of those 16 K CTAs at the 64x64 level re-stages the same K / V tiles and pays the
+// full launch -> cp.async -> barrier latency for ~100 MMAs of work (960 GB/s of a 6.5 TB/s stream, profiles/round1).  Here a CTA
+// owns one (image, head), stages K and V ONCE, and walks a strided set of query tiles with the next Q tile prefetched (cp.async
+// double buffer) while the current one is in the tensor cores; the arithmetic (and therefore the result) is the generic kernel's.
+template <int D, int DP>
+__global__ void __launch_bounds__(NTHR) attention_mma_shortk_kernel(fyc_attention_args a, int nqt) {
+  constexpr int LDS = DP + 8;
+  constexpr int KS = DP / 16;
+  constexpr int NO = DP / 8;
+  constexpr bool ONES = DP > D;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  bf16* sQ = reinterpret_cast<bf16*>(smem_raw);   // [2][64][LDS]
+  bf16* sK = sQ + 2 * 64 * LDS;                   // [2][64][LDS]  key tiles 0, 1
+  bf16* sV = sK + 2 * 64 * LDS;                   // [2][64][LDS]
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int64_t n = blockIdx.z, h = blockIdx.y;
+  const int64_t nk = n / a.kv_batch_div;
+  const bf16* qg = (const bf16*)a.q + n * a.bsq + h * D;
+  const bf16* kg = (const bf16*)a.k + nk * a.bsk + h * D;
+  const bf16* vg = (const bf16*)a.v + nk * a.bsv + h * D;
+  bf16* og = (bf16*)a.out + n * a.bso + h * D;
+  const int nkt = (int)((a.Lk + BKV - 1) / BKV);  // 1 or 2
+  const float sl2 = a.scale * 1.4426950408889634f;
+
+  for (int kt = 0; kt < nkt; ++kt) {
+    load_tile<D, DP, LDS>(sK + kt * 64 * LDS, kg, a.ldk, (int64_t)kt * BKV, a.Lk, tid);
+    load_tile<D, DP, LDS, (DP > D)>(sV + kt * 64 * LDS, vg, a.ldv, (int64_t)kt * BKV, a.Lk, tid);
+  }
+  int qt = blockIdx.x;
+  if (qt < nqt) load_tile<D, DP, LDS>(sQ, qg, a.ldq, (int64_t)qt * BQ, a.Lq, tid);
+  cp_async_commit();
+
+  for (int it = 0; qt < nqt; qt += gridDim.x, ++it) {
+    const int qb = it & 1;
+    const int nq = qt + (int)gridDim.x;
+    if (nq < nqt) {
+      load_tile<D, DP, LDS>(sQ + (qb ^ 1) * 64 * LDS, qg, a.ldq, (int64_t)nq * BQ, a.Lq, tid);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    uint32_t qf[KS][4];
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks)
+      ldmatrix_x4(qf[ks], sQ + qb * 64 * LDS + (w * 16 + (lane & 15)) * LDS + ks * 16 + (lane >> 4) * 8);
+    float o[NO][4];
+#pragma unroll
+    for (int i = 0; i < NO; ++i) { o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f; }
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+
+    for (int kt = 0; kt < nkt; ++kt) {
+      const bf16* kb = sK + kt * 64 * LDS;
+      const bf16* vb = sV + kt * 64 * LDS;
+      float s[8][4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f; }
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+#pragma unroll
+        for (int jp = 0; jp < 4; ++jp) {
+          uint32_t b[4];
+          const int mi = lane >> 3;
+          ldmatrix_x4(b, kb + (jp * 16 + (lane & 7) + (mi >> 1) * 8) * LDS + ks * 16 + (mi & 1) * 8);
+          mma_bf16(s[2 * jp], qf[ks], b[0], b[1]);
+          mma_bf16(s[2 * jp + 1], qf[ks], b[2], b[3]);
+        }
+      }
+      if (kt == nkt - 1 && (a.Lk & (BKV - 1))) {
+        const int64_t kbase = (int64_t)kt * BKV;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+#pragma unroll
+          for (int e = 0; e < 2; ++e)
+            if (kbase + 8 * j + 2 * t + e >= a.Lk) { s[j][e] = -INFINITY; s[j][2 + e] = -INFINITY; }
+      }
+      float mx0 = s[0][0], mx1 = s[0][2];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        mx0 = fmaxf(mx0, fmaxf(s[j][0], s[j][1]));
+        mx1 = fmaxf(mx1, fmaxf(s[j][2], s[j][3]));
+      }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);
+      const float c0 = (m0 == -INFINITY) ? 0.f : ex2_approx((m0 - mn0) * sl2), c1 = (m1 == -INFINITY) ? 0.f : ex2_approx((m1 - mn1) * sl2);
+      m0 = mn0; m1 = mn1;
+      const float nb0 = -mn0 * sl2, nb1 = -mn1 * sl2;
+      float rs0 = 0.f, rs1 = 0.f;
+      uint32_t pf[4][4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float p0 = ex2_approx(fmaf(s[j][0], sl2, nb0)), p1 = ex2_approx(fmaf(s[j][1], sl2, nb0));
+        float p2 = ex2_approx(fmaf(s[j][2], sl2, nb1)), p3 = ex2_approx(fmaf(s[j][3], sl2, nb1));
+        if constexpr (!ONES) { rs0 += p0 + p1; rs1 += p2 + p3; }
+        pf[j >> 1][(j & 1) * 2 + 0] = pack_bf16(p0, p1);
+        pf[j >> 1][(j & 1) * 2 + 1] = pack_bf16(p2, p3);
+      }
+      if constexpr (!ONES) {
+        rs0 += __shfl_xor_sync(0xffffffffu, rs0, 1); rs0 += __shfl_xor_sync(0xffffffffu, rs0, 2);
+        rs1 += __shfl_xor_sync(0xffffffffu, rs1, 1); rs1 += __shfl_xor_sync(0xffffffffu, rs1, 2);
+        l0 = l0 * c0 + rs0; l1 = l1 * c1 + rs1;
+      }
+#pragma unroll
+      for (int i = 0; i < NO; ++i) { o[i][0] *= c0; o[i][1] *= c0; o[i][2] *= c1; o[i][3] *= c1; }
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+        for (int np = 0; np < NO / 2; ++np) {
+          uint32_t b[4];
+          const int mi = lane >> 3;
+          ldmatrix_x4_trans(b, vb + (kk * 16 + (lane & 7) + (mi & 1) * 8) * LDS + np * 16 + (mi >> 1) * 8);
+          mma_bf16(o[2 * np], pf[kk], b[0], b[1]);
+          mma_bf16(o[2 * np + 1], pf[kk], b[2], b[3]);
+        }
+      }
+    }
+    if constexpr (ONES) {
+      constexpr int NTL = D / 8, SRC = (D % 8) / 2;
+      l0 = __shfl_sync(0xffffffffu, o[NTL][0], (lane & ~3) | SRC);
+      l1 = __shfl_sync(0xffffffffu, o[NTL][2], (lane & ~3) | SRC);
+    }
+    const float i0 = a.out_alpha / l0, i1 = a.out_alpha / l1;
+    const int64_t r0 = (int64_t)qt * BQ + w * 16 + g, r1 = r0 + 8;
+#pragma unroll
+    for (int i = 0; i < NO; ++i) {
+      const int col = i * 8 + 2 * t;
+      if (col < D) {
+        if (r0 < a.Lq) {
+          __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(og + r0 * a.ldo + col);
+          float x = o[i][0] * i0, y = o[i][1] * i0;
+          if (a.accumulate) { float2 e = __bfloat1622float2(*dst); x += e.x; y += e.y; }
+          *dst = __floats2bfloat162_rn(x, y);
+        }
+        if (r1 < a.Lq) {
+          __nv_bfloat162* dst = reinterpret_cast<__nv_bfloat162*>(og + r1 * a.ldo + col);
+          float x = o[i][2] * i1, y = o[i][3] * i1;
+          if (a.accumulate) { float2 e = __bfloat1622float2(*dst); x += e.x; y += e.y; }
+          *dst = __floats2bfloat162_rn(x, y);
+        }
+      }
+    }
+    __syncthreads();      // every warp is done with sQ[qb] before the next iteration's prefetch refills it
+  }
+}
+
+static bool shortk_enabled() {
+  const char* e = getenv("FYC_ATTN_SHORTK");
+  return !(e && e[0] == '0');
+}
+
+template <int D, int DP>
+int32_t launch_mma_shortk(const fyc_attention_args* a, cudaStream_t st) {
+  constexpr int LDS = DP + 8;
+  const size_t smem = (size_t)6 * 64 * LDS * sizeof(bf16);
+  auto kern = attention_mma_shortk_kernel<D, DP>;
+  FYC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int nqt = (int)ceil_div64(a->Lq, BQ);
+  // CTAs per (image, head): enough to fill the machine (~227 KB of shared memory per SM), at most one per query tile
+  const int64_t per_sm = (int64_t)(227 * 1024) / (int64_t)(smem + 1024);
+  const int64_t pairs = a->heads * a->batch;
+  int64_t gx = ceil_div64((int64_t)fyc_sm_count() * (per_sm > 8 ? 8 : per_sm), pairs);
+  if (gx < 1) gx = 1;
+  if (gx > nqt) gx = nqt;
+  dim3 grid((unsigned)gx, (unsigned)a->heads, (unsigned)a->batch);
+  kern<<<grid, NTHR, smem, st>>>(*a, nqt);
+  FYC_LAUNCH_CHECK();
+  return FYC_OK;
+}
+
 template <int D, int DP>
 int32_t launch_mma(const fyc_attention_args* a, cudaStream_t st) {
+  if (a->Lk <= 2 * BKV && a->Lq >= 4 * BQ && DP <= 80 && shortk_enabled()) return launch_mma_shortk<D, DP>(a, st);
   constexpr int LDS = DP + 8;
   const size_t smem = (size_t)5 * 64 * LDS * sizeof(bf16);
   auto kern = attention_mma_kernel<D, DP>;

@@ -315,6 +315,31 @@ def test_attention_self_and_cross(dtype, impl, heads, D, Lq, Lk):
     assert rel(out, ref2) < tol(dtype) * 1.5, rel(out, ref2)
 
 
+@pytest.mark.parametrize("heads,D,Lq,Lk,div", [(8, 40, 4096, 77, 2), (8, 80, 1000, 77, 4), (4, 64, 512, 128, 1), (8, 40, 1024, 16, 2),
+                                               (2, 80, 256, 65, 1), (8, 40, 300, 4, 1)])
+def test_attention_short_context_persistent_kernel(cuda, heads, D, Lq, Lk, div, monkeypatch):
+    """Lk <= 128 (text / IP cross-attention): one CTA per (image, head) keeps K / V in shared memory and walks query tiles.  Same
+    arithmetic as the generic kernel -> bit-identical to it, and within tolerance of the fp32 reference; ragged Lq / Lk, shared
+    contexts (kv_batch_div) and the accumulated IP pass included."""
+    from followyourclick_b200 import ops
+    dtype = torch.bfloat16
+    ops.set_impl("auto")
+    B, C = 4, heads * D
+    q = rnd((B, Lq, C), 1, dtype)
+    kv = rnd((B // div, Lk, 2 * C), 2, dtype)
+    scale = D ** -0.5
+    outs = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("FYC_ATTN_SHORTK", mode)
+        o = ops.attention(q, kv[:, :, :C], kv[:, :, C:], heads, scale, kv_batch_div=div)
+        ops.attention(q, kv[:, :3, :C], kv[:, :3, C:], heads, scale, out=o, out_alpha=0.5, accumulate=True, kv_batch_div=div)
+        outs[mode] = o
+    assert torch.equal(outs["1"], outs["0"])
+    kk, vv = kv[:, :, :C].repeat_interleave(div, 0), kv[:, :, C:].repeat_interleave(div, 0)
+    ref = _mha_ref(q, kk, vv, heads, scale) + 0.5 * _mha_ref(q, kk[:, :3], vv[:, :3], heads, scale)
+    assert rel(outs["1"], ref) < tol(dtype) * 1.5, rel(outs["1"], ref)
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("B,Fr,HW,heads,D", [(2, 4, 64, 4, 40), (2, 16, 16, 8, 40), (1, 8, 16, 4, 80), (2, 16, 4, 8, 160), (1, 24, 9, 2, 40),
                                              (1, 32, 4, 4, 160)])
