@@ -31,7 +31,9 @@ def main():
     unet = UNet3DConditionModel(**kw).to("cuda").to(torch.bfloat16)
     gpu_synth_(unet)
     print("unet build+synth s:", time.time() - t0, "params(M):", sum(p.numel() for p in unet.parameters()) / 1e6)
-    x = torch.randn(2, F, h, w, 9, device="cuda").bfloat16()
+    cp = unet.input_channel_pad()                       # 16 in tensor-core mode: the 9-channel stem runs on tcgen05 (as in the pipeline)
+    x = torch.zeros(2, F, h, w, cp, device="cuda").bfloat16()
+    x[..., :9] = torch.randn(2, F, h, w, 9, device="cuda").bfloat16()
     ctx = torch.randn(2, 77, 768, device="cuda")
     t = torch.tensor(501, device="cuda")
     fps, flow = torch.tensor([2, 2], device="cuda"), torch.tensor([4, 4], device="cuda")
@@ -68,6 +70,13 @@ def main():
     with ops.profile() as prof: vae.decode_nhwc(z)
     for fam, d in sorted(prof.summary.items(), key=lambda kv: -kv[1]["ms"]):
         print(f"   {fam:20s} {d['ms']:8.2f} ms launches {d['launches']:4d}  {d['flops']/d['ms']/1e9 if d['ms'] else 0:8.1f} TFLOP/s")
+    if os.environ.get("SHAPES"):
+        ops._prof_shapes = True
+        with ops.profile() as prof2: vae.decode_nhwc(z)
+        ops._prof_shapes = False
+        for fam, d in sorted(prof2.summary.items(), key=lambda kv: -kv[1]["ms"])[:25]:
+            if d["ms"]:
+                print(f"   {fam:46s} {d['ms']:7.3f} ms x{d['launches']:3d}  {d['flops']/d['ms']/1e9:7.1f} TFLOP/s  {d['bytes']/d['ms']/1e6:7.1f} GB/s(alg)")
     print("max mem GB", torch.cuda.max_memory_allocated() / 2**30)
 
 if __name__ == "__main__":
