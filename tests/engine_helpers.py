@@ -204,3 +204,18 @@ def run_unet2d_case(dtype, device="cuda"):
     _sync(device)
     assert out.shape == (2, 4, 16, 16)
     return stats(out, torch.from_numpy(g["out"]))
+
+
+def run_unet_ragged_case(dtype, device="cuda", b=1, f=3, h=24, w=40):
+    """Non-square, non-power-of-two latent grid, odd frame count, batch 1 (no CFG pair): the shapes where tile pickers fall back
+    (tcgen05 self-attention needs L % 128 == 0, conv patches need power-of-two factors).  Checked against the oracle run in place."""
+    from tests.cfgs import unet_inputs
+    unet, sd = make_unet("base", dtype, device)
+    inp = unet_inputs("base", b=b, f=f, h=h, w=w, seed=23)
+    inp["fps"], inp["flow"] = torch.tensor([2] * b), torch.tensor([4] * b)
+    out = unet(inp["sample"].to(device), inp["timestep"], **unet_forward_kwargs("base", inp, device)).sample
+    _sync(device)
+    ref = ref_unet.unet3d_forward(sd, mini_unet_oracle_cfg("base"), inp["sample"], inp["timestep"], inp["ctx"],
+                                  fps_tensor=inp["fps"], flow_control=inp["flow"])
+    assert out.shape == ref.shape == (b, 4, f, h, w)
+    return stats(out, ref)

@@ -217,3 +217,12 @@ def test_unet2d_matches_reference_golden(dtype, tol):
     from tests.engine_helpers import run_unet2d_case
     s = run_unet2d_case(dtype)
     assert s["finite"] and s["rel_l2"] < tol, s
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 3e-2)])
+@pytest.mark.parametrize("b,f,h,w", [(1, 3, 24, 40), (2, 1, 8, 8), (1, 5, 40, 72)])
+def test_unet_ragged_shapes_vs_oracle(dtype, tol, b, f, h, w):
+    """Edge shapes: non-square / non-power-of-two latent grids (320x576 and 192x320 images), odd frame counts, a single frame, batch 1."""
+    from tests.engine_helpers import run_unet_ragged_case
+    s = run_unet_ragged_case(dtype, b=b, f=f, h=h, w=w)
+    assert s["finite"] and s["rel_l2"] < tol, s

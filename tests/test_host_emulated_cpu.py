@@ -140,3 +140,9 @@ def test_unet2d_host_logic_vs_reference_golden(dtype, tol):
     from tests.engine_helpers import run_unet2d_case
     s = run_unet2d_case(dtype, device="cpu")
     assert s["finite"] and s["rel_l2"] < tol, s
+
+
+def test_unet_ragged_shape_host_logic():
+    from tests.engine_helpers import run_unet_ragged_case
+    s = run_unet_ragged_case(torch.bfloat16, device="cpu")
+    assert s["finite"] and s["rel_l2"] < 3e-2, s
