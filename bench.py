@@ -304,10 +304,12 @@ def main():
         tc_ms, tc_fl, tc_n = sum(d["ms"] for d in tc), sum(d["flops"] for d in tc), sum(d["launches"] for d in tc) + 3 * tc[2]["launches"]   # an up2 call = 4 kernel launches
         total_ms = sum(d["ms"] for d in prof.summary.values())
         ach = tc_fl / (tc_ms * 1e-3) / 1e12 if tc_ms else 0.0
-        # DRAM bytes per launch of the same kernel from the committed ncu capture of this command (profiles/round1_traffic.json,
+        # DRAM bytes per launch of the same kernel from the committed ncu capture of this command (profiles/round1d_traffic.json,
         # written by profiles/summarize_launches.py from dram__bytes_read.sum + dram__bytes_write.sum); null when absent
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "round1_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "round1d_traffic.json")        # end-of-round capture (profiles/round1d_launches.md)
+        if not os.path.exists(tpath):
+            tpath = os.path.join(ROOT, "profiles", "round1_traffic.json")
         if os.path.exists(tpath) and not mini:
             tk = [v for k, v in json.load(open(tpath)).items() if k.startswith("gemm_tc_kernel")]     # <0> single-CTA, <1> CTA-pair
             if tk:
