@@ -26,7 +26,7 @@ def main():
               unet_use_temporal_attention=False, motion_module_type="Vanilla", use_fps_condition=True,
               use_first_frame_mask_condition_concat=True,
               motion_module_kwargs=dict(num_attention_heads=8, num_transformer_block=1, attention_block_types=("Temporal_Self", "Temporal_Self"),
-                                        temporal_position_encoding=True, temporal_position_encoding_max_len=24, temporal_attention_dim_div=1))
+                                        temporal_position_encoding=True, temporal_position_encoding_max_len=max(24, F), temporal_attention_dim_div=1))
     t0 = time.time()
     unet = UNet3DConditionModel(**kw).to("cuda").to(torch.bfloat16)
     gpu_synth_(unet)
