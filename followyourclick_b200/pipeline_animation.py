@@ -7,6 +7,7 @@ The prompt / image encoders are outside the hot path (their outputs are computed
 :676-680) and are used as given (any callable with the transformers interface).
 """
 import inspect
+import os
 from dataclasses import dataclass
 from typing import Union
 
@@ -37,12 +38,12 @@ class _GraphedUNetStep:
     configuration, so the ~700 kernel launches of a forward are replayed with one call; inputs live in static buffers
     (x: channels-last UNet input, t: timestep, text / fps / flow / camera / clip features)."""
 
-    def __init__(self, unet, x_shape, text, fps, flow, cam, clip, flags, x=None, out_frames=None):
+    def __init__(self, unet, x_shape, text, fps, flow, cam, clip, flags, x=None, out_frames=None, cfg_dup=1):
         """``x``: use this (view of another step's) static input instead of allocating one; ``out_frames`` = (b, f): the input is
         b * f single frames (F = 1) whose prediction is returned regrouped as (b, 4, f, h, w) (video_scale branch)."""
         dev = unet.device
         self.version = unet._pack_version
-        self.out_frames = out_frames
+        self.out_frames, self.cfg_dup = out_frames, cfg_dup
         self.x = torch.zeros(x_shape, dtype=unet.dtype, device=dev) if x is None else x
         assert tuple(self.x.shape) == tuple(x_shape)
         self.t = torch.zeros((), dtype=torch.int64, device=dev)
@@ -74,7 +75,7 @@ class _GraphedUNetStep:
     def _run(self, unet):
         y = unet.forward_nfhwc(self.x, self.t, self.text, fps_tensor=self.fps, flow_control=self.flow,
                                reference_images_clip_feat=self.clip, camera_movement_type_tensor=self.cam, context=self.context,
-                               **self.flags)
+                               cfg_dup=self.cfg_dup, **self.flags)
         return ops.nfhwc_to_ncfhw(_regroup_frames(y, self.out_frames))
 
     def load(self, unet, text, fps, flow, cam, clip):
@@ -115,6 +116,11 @@ class AnimationPipeline:
     _optional_components = []
     use_cuda_graph = True          # replay one captured UNet forward per DDIM step (set False to launch kernel by kernel)
     hoist_context = True           # build the step-invariant conditioning (ClipContext) once per clip instead of once per step
+    # Shared CFG prefix (UNet3DConditionModel.forward_nfhwc cfg_dup): the uncond / cond halves of the reference's batch are identical
+    # until the first cross-attention, so that prefix (incl. the first 64x64 self-attention) is computed once.  Exact, and verified
+    # against the reference fixtures through the CPU emulation of the kernels (tests/test_host_emulated_cpu.py); it has not had its
+    # GPU run yet (the round's GPU budget was spent), so it is opt-in: FYC_SHARED_PREFIX=1.
+    share_cfg_prefix = os.environ.get("FYC_SHARED_PREFIX", "0") == "1"
 
     def __init__(self, vae, text_encoder, tokenizer, unet, scheduler, image_encoder=None, text_encoder_2=None,
                  tokenizer_2=None, ip_adapter=None):
@@ -287,14 +293,18 @@ class AnimationPipeline:
             # (reference behaviour, kept); the single-frame forward gets no fps / camera / image conditioning (:748-752)
             text_sf = torch.cat([text_embeddings] * f, dim=0).chunk(2, dim=0)[0].contiguous()
             flags_sf = dict(use_ip_cross_attention=False, use_camera_motion_condition=False, use_fps_condition=False)
+        # shared CFG prefix: the UNet gets ONE copy of the input and fans out at its first cross-attention (cfg_dup)
+        share = 2 if (self.share_cfg_prefix and do_cfg and hasattr(unet, "prepare_context")) else 1
+        xdup = dup // share
         if self.use_cuda_graph and hasattr(unet, "forward_nfhwc"):
             cin = c_pad if c_pad is not None else (9 if first is not None else 4)
-            key = (dup * b, f, h, w, cin, unet.dtype, tuple(sorted(flags.items())), tuple(text_embeddings.shape),
+            key = (xdup * b, share, f, h, w, cin, unet.dtype, tuple(sorted(flags.items())), tuple(text_embeddings.shape),
                    None if clip_d is None else tuple(clip_d.shape))
             cache = self.__dict__.setdefault("_graph_cache", {})
             graphed = cache.get(key)
             if graphed is None or graphed.version != unet._pack_version:
-                graphed = cache[key] = _GraphedUNetStep(unet, (dup * b, f, h, w, cin), text_embeddings, fps_d, flow_d, cam_d, clip_d, flags)
+                graphed = cache[key] = _GraphedUNetStep(unet, (xdup * b, f, h, w, cin), text_embeddings, fps_d, flow_d, cam_d, clip_d, flags,
+                                                        cfg_dup=share)
             graphed.load(unet, text_embeddings, fps_d, flow_d, cam_d, clip_d)
             if video_scale > 0:
                 graphed_sf = cache.get(key + ("sf",))
@@ -306,7 +316,7 @@ class AnimationPipeline:
         with bar as pb:
             for i, t in enumerate(t_host):
                 if graphed is not None:
-                    ops.build_unet_input(latents, mask, first, dup, unet.dtype, c_pad=c_pad, out=graphed.x)
+                    ops.build_unet_input(latents, mask, first, xdup, unet.dtype, c_pad=c_pad, out=graphed.x)
                     graphed.t.copy_(t_dev[i])
                     graphed.graph.replay()
                     _lib.launch_count += graphed.n_calls
@@ -319,10 +329,10 @@ class AnimationPipeline:
                 else:
                     if i == 0 and self.hoist_context and hasattr(unet, "prepare_context"):
                         context = unet.prepare_context(text_embeddings, clip_d, use_ip_cross_attention)
-                    x = ops.build_unet_input(latents, mask, first, dup, unet.dtype, c_pad=c_pad)
+                    x = ops.build_unet_input(latents, mask, first, xdup, unet.dtype, c_pad=c_pad)
                     y = unet.forward_nfhwc(x, t_dev[i], text_embeddings, fps_tensor=fps_d, flow_control=flow_d,
                                            reference_images_clip_feat=clip_d, camera_movement_type_tensor=cam_d, context=context,
-                                           **flags)
+                                           **(dict(flags, cfg_dup=share) if share > 1 else flags))
                     pred = ops.nfhwc_to_ncfhw(y)
                     if video_scale > 0:
                         if i == 0 and self.hoist_context and hasattr(unet, "prepare_context"):

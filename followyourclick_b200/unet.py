@@ -376,7 +376,10 @@ class UNet3DConditionModel(ParamTreeModel):
         h = ops.gemm(n, w1, bias=b1, geglu=True)
         return ops.gemm(h, self._w(p + ".net.2.weight"), bias=self._f(p + ".net.2.bias"), residual=tok)
 
-    def _transformer(self, p, x, ctx, heads, F):
+    def _transformer(self, p, x, ctx, heads, F, dup=1):
+        """dup > 1 (shared CFG prefix, see forward_nfhwc): x holds ONE copy of the clip(s) while the context holds `dup` (uncond,
+        cond); everything up to the cross-attention query is computed once, the cross-attention runs once per context replica on
+        the same queries, and from its output projection on the tokens exist `dup` times.  Returns [dup * NB, H, W, C]."""
         NB, H, W, C = x.shape
         M, HW, d = NB * H * W, H * W, C // heads
         res = x.view(M, C)
@@ -400,22 +403,39 @@ class UNet3DConditionModel(ParamTreeModel):
         qx = ops.gemm(n2, self._w(q + ".attn2.to_q.weight")).view(NB, HW, C)
         kv = ctx.kv[p]
         L = kv.shape[1]
-        if self._cfg["use_ip_cross_attention"]:
-            T = self._cfg["num_tokens"]
-            # reference quirk (animatediff/models/attention.py:43): without xformers the IP scale replaces d^-1/2
-            sc = d ** -0.5 if self._xformers_semantics else float(self._cfg["scale"])
-            o = ops.attention(qx, kv[:, :L - T, :C], kv[:, :L - T, C:], heads, sc, kv_batch_div=F)
-            kvi = ctx.kvi[p]
-            ops.attention(qx, kvi[:, L - T:, :C], kvi[:, L - T:, C:], heads, sc, out=o, out_alpha=float(self._cfg["scale"]),
-                          accumulate=True, kv_batch_div=F)
-        else:
-            o = ops.attention(qx, kv[:, :, :C], kv[:, :, C:], heads, d ** -0.5, kv_batch_div=F)
-        tok = ops.gemm(o.view(M, C), self._w(q + ".attn2.to_out.0.weight"), bias=self._f(q + ".attn2.to_out.0.bias"), residual=tok)
+        Bq = kv.shape[0] // dup                 # clips per context replica
+        o = torch.empty((dup * NB, HW, C), dtype=qx.dtype, device=qx.device)
+        for r in range(dup):                    # one pass per context replica over the SAME queries (dup = 1: the plain case)
+            o_r, kv_r = o[r * NB:(r + 1) * NB], kv[r * Bq:(r + 1) * Bq]
+            if self._cfg["use_ip_cross_attention"]:
+                T = self._cfg["num_tokens"]
+                # reference quirk (animatediff/models/attention.py:43): without xformers the IP scale replaces d^-1/2
+                sc = d ** -0.5 if self._xformers_semantics else float(self._cfg["scale"])
+                ops.attention(qx, kv_r[:, :L - T, :C], kv_r[:, :L - T, C:], heads, sc, out=o_r, kv_batch_div=F)
+                kvi = ctx.kvi[p][r * Bq:(r + 1) * Bq]
+                ops.attention(qx, kvi[:, L - T:, :C], kvi[:, L - T:, C:], heads, sc, out=o_r, out_alpha=float(self._cfg["scale"]),
+                              accumulate=True, kv_batch_div=F)
+            else:
+                ops.attention(qx, kv_r[:, :, :C], kv_r[:, :, C:], heads, d ** -0.5, out=o_r, kv_batch_div=F)
+        w_o, b_o = self._w(q + ".attn2.to_out.0.weight"), self._f(q + ".attn2.to_out.0.bias")
+        if dup == 1:
+            tok = ops.gemm(o.view(M, C), w_o, bias=b_o, residual=tok)
+        else:                                   # the shared residual stream fans out here: same `tok` added to every replica's projection
+            tok_d = torch.empty((dup * M, C), dtype=tok.dtype, device=tok.device)
+            for r in range(dup):
+                ops.gemm(o[r * NB:(r + 1) * NB].view(M, C), w_o, bias=b_o, residual=tok, out=tok_d[r * M:(r + 1) * M])
+            tok = tok_d
         # feed forward (attention.py:563)
         n3 = ops.layernorm(tok, self._f(q + ".norm3.weight"), self._f(q + ".norm3.bias"))
         tok = self._ff(q + ".ff", tok, n3)
-        out = ops.gemm(tok, self._w1x1(p + ".proj_out.weight"), bias=self._f(p + ".proj_out.bias"), residual=res)
-        return out.view(NB, H, W, C)
+        w_p, b_p = self._w1x1(p + ".proj_out.weight"), self._f(p + ".proj_out.bias")
+        if dup == 1:
+            out = ops.gemm(tok, w_p, bias=b_p, residual=res)
+        else:
+            out = torch.empty((dup * M, C), dtype=tok.dtype, device=tok.device)
+            for r in range(dup):
+                ops.gemm(tok[r * M:(r + 1) * M], w_p, bias=b_p, residual=res, out=out[r * M:(r + 1) * M])
+        return out.view(dup * NB, H, W, C)
 
     def _motion(self, p, x, B, F):
         p = p + ".temporal_transformer"
@@ -515,16 +535,25 @@ class UNet3DConditionModel(ParamTreeModel):
     def forward_nfhwc(self, x, timestep, encoder_hidden_states, fps_tensor=None, flow_control=None,
                       reference_images_clip_feat=None, camera_movement_type_tensor=None, use_ip_cross_attention=False,
                       use_camera_motion_condition=False, use_fps_condition=False, use_first_frame_condition_concat=False,
-                      context=None):
+                      context=None, cfg_dup=1):
         """Engine entry: x [B, F, H, W, Cin] channels-last in the compute dtype -> fp32 [B, F, H, W, out_channels] (possibly a
         [..., :out_channels] view of a wider buffer; ops.nfhwc_to_ncfhw takes it as is).  ``context``: a ClipContext from
-        ``prepare_context`` - then encoder_hidden_states / reference_images_clip_feat are not read (hoisted out of the loop)."""
+        ``prepare_context`` - then encoder_hidden_states / reference_images_clip_feat are not read (hoisted out of the loop).
+        ``cfg_dup`` = 2 (shared CFG prefix): ``x`` holds ONE copy of the b clips although the context / fps / flow / camera tensors
+        hold the CFG pair (2b rows, [uncond..., cond...]).  The reference feeds ``torch.cat([latents] * 2)`` (pipeline_animation.py:
+        709), so until the first cross-attention reads the text context both halves of its batch carry identical values: conv_in, the
+        first ResnetBlock3D and the first transformer's GroupNorm, proj_in, self-attention (the most expensive attention of the
+        network) and query projection are computed once here and fan out at that cross-attention.  Output: [2b, F, H, W, out]."""
         ops.require_cuda(x, "UNet3DConditionModel")
         cfg = self._cfg
         B, F, H, W, Cin = x.shape
         x = x.reshape(B * F, H, W, Cin)
         boc = tuple(cfg["block_out_channels"])
         n = len(boc)
+        dup = int(cfg_dup)
+        if dup > 1 and not (n > 1 and cfg["layers_per_block"] >= 1):
+            raise ValueError("cfg_dup needs a cross-attention block at the first level")
+        B = B * dup                       # batch of everything from the first cross-attention on (and of the embeddings)
         emb = self._embed("time_embedding", timestep, B)
         if use_camera_motion_condition:
             emb = self._embed("camera_motion_embedding", camera_movement_type_tensor, B, residual=emb)
@@ -558,12 +587,14 @@ class UNet3DConditionModel(ParamTreeModel):
             return on and (decoder or not cfg["motion_module_decoder_only"])
 
         skips = [x]
+        shared = dup > 1                  # x still holds one copy per clip (rows of `semb` are identical across the CFG pair)
         for i in range(n):
             p = f"down_blocks.{i}"
             for j in range(cfg["layers_per_block"]):
-                x = self._resnet(f"{p}.resnets.{j}", x, semb, B, F)
+                x = self._resnet(f"{p}.resnets.{j}", x, semb, B // dup if shared else B, F)
                 if i < n - 1:
-                    x = self._transformer(f"{p}.attentions.{j}", x, ctx, self._heads[i], F)
+                    x = self._transformer(f"{p}.attentions.{j}", x, ctx, self._heads[i], F, dup=dup if shared else 1)
+                    shared = False
                 if motion_on(i, False):
                     x = self._motion(f"{p}.motion_modules.{j}", x, B, F)
                 skips.append(x)
@@ -581,7 +612,10 @@ class UNet3DConditionModel(ParamTreeModel):
             p = f"up_blocks.{i}"
             lvl = n - 1 - i
             for j in range(cfg["layers_per_block"] + 1):
-                x = ops.concat_channels(x, skips.pop())
+                skip = skips.pop()
+                if skip.shape[0] != x.shape[0]:          # the conv_in output of the shared prefix: one copy per clip -> the CFG pair
+                    skip = skip.repeat(dup, 1, 1, 1)     # (a 2 x 42 MB device copy per forward at cfg2)
+                x = ops.concat_channels(x, skip)
                 x = self._resnet(f"{p}.resnets.{j}", x, semb, B, F)
                 if i > 0:
                     x = self._transformer(f"{p}.attentions.{j}", x, ctx, self._heads[lvl], F)

@@ -146,3 +146,38 @@ def test_unet_ragged_shape_host_logic():
     from tests.engine_helpers import run_unet_ragged_case
     s = run_unet_ragged_case(torch.bfloat16, device="cpu")
     assert s["finite"] and s["rel_l2"] < 3e-2, s
+
+
+@pytest.mark.parametrize("variant", MINI_UNET_VARIANTS)
+@pytest.mark.parametrize("dtype,tol", DTYPES)
+def test_shared_cfg_prefix_equals_duplicated_batch(variant, dtype, tol):
+    """forward_nfhwc(cfg_dup=2) on ONE copy of the input == the reference's duplicated batch (both halves carry identical values up to
+    the first cross-attention, pipeline_animation.py:709), and therefore matches the reference fixture computed on [x, x]."""
+    from followyourclick_b200 import ops
+    from tests.engine_helpers import golden, make_unet, stats, unet_forward_kwargs
+    from tests.cfgs import unet_inputs
+    unet, _ = make_unet(variant, dtype, "cpu")
+    inp = unet_inputs(variant)
+    one = inp["sample"][:1]                                   # the fixture's batch is two DIFFERENT samples: use a CFG-style pair of sample 0
+    kw = unet_forward_kwargs(variant, inp, "cpu")
+    nf = dict(fps_tensor=kw["fps_tensor"], flow_control=kw["flow_control"], reference_images_clip_feat=kw["reference_images_clip_feat"],
+              camera_movement_type_tensor=kw["camera_movement_type_tensor"], use_ip_cross_attention=kw["use_ip_cross_attention"],
+              use_camera_motion_condition=kw["use_camera_motion_condition"], use_fps_condition=kw["use_fps_condition"])
+    x1 = ops.ncfhw_to_nfhwc(one.contiguous(), dtype)
+    full = unet.forward_nfhwc(torch.cat([x1, x1]), inp["timestep"], kw["encoder_hidden_states"], **nf)
+    shared = unet.forward_nfhwc(x1, inp["timestep"], kw["encoder_hidden_states"], cfg_dup=2, **nf)
+    assert shared.shape == full.shape
+    s = stats(shared, full)
+    assert s["finite"] and s["rel_l2"] < (1e-6 if dtype == torch.float32 else 2e-3), s
+    assert not torch.equal(full[0], full[1])                  # the two halves do differ after the cross-attention (different text rows)
+
+
+def test_pipeline_with_shared_cfg_prefix_vs_reference_golden():
+    from followyourclick_b200 import AnimationPipeline
+    from tests.engine_helpers import run_pipeline_case
+    AnimationPipeline.share_cfg_prefix = True
+    try:
+        r = run_pipeline_case(torch.float32, steps=3, against="golden", device="cpu")
+    finally:
+        AnimationPipeline.share_cfg_prefix = False
+    assert r["finite"] and r["video_maxabs"] < 2e-3, r
