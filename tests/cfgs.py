@@ -80,3 +80,22 @@ MINI_UNET2D = dict(sample_size=16, in_channels=4, out_channels=4, block_out_chan
 def mini_unet2d_oracle_cfg():
     return default_unet_config(block_out_channels=MINI_UNET2D["block_out_channels"], layers_per_block=1, attention_head_dim=4,
                                use_motion_module=False, use_first_frame_mask_condition_concat=False, use_fps_condition=False)
+
+
+def pipeline_variant_inputs(variant):
+    """Pipeline-level plumbing cases beyond the shipped YAML: returns (clip inputs, reference-pipeline kwargs, oracle-denoise kwargs,
+    scheduler config, steps, guidance)."""
+    from followyourclick_b200.synth import synth_clip_inputs
+    ci = synth_clip_inputs(1, 4, 8, 8, clip_dim=CLIP_DIM)
+    ci["uncond_image_clip_feat"] = torch.randn(1, CLIP_DIM, generator=torch.Generator().manual_seed(77)) * 0.1   # a non-zero uncond feature: ordering bugs show
+    if variant == "ip":        # cfg3: shipped YAML + IP-Adapter image condition
+        kw = dict(use_first_frame_mask_condition_concat=True, first_image_latents=ci["first_image_latents"], use_fps_condition=True,
+                  fps_tensor=torch.tensor([2]), flow_control=torch.tensor([4]), first_images_mask=ci["first_images_mask"])
+        okw = dict(first_image_latents=ci["first_image_latents"], first_images_mask=ci["first_images_mask"], fps_tensor=torch.tensor([2]),
+                   flow_control=torch.tensor([4]))
+        return ci, kw, okw, SCHED_V, 2, 8.0
+    if variant == "cam":       # cfg5: camera-LoRA model, 4-channel input, epsilon prediction
+        kw = dict(use_camera_motion_condition=True, camera_movement_type=torch.tensor([3]))
+        okw = dict(camera_movement_type=torch.tensor([3]))
+        return ci, kw, okw, SCHED_EPS, 2, 7.5
+    raise KeyError(variant)

@@ -219,3 +219,33 @@ def run_unet_ragged_case(dtype, device="cuda", b=1, f=3, h=24, w=40):
                                   fps_tensor=inp["fps"], flow_control=inp["flow"])
     assert out.shape == ref.shape == (b, 4, f, h, w)
     return stats(out, ref)
+
+
+class FakeIPAdapter:
+    """MyIPAdapter stand-in at pipeline level: seeded (cond, uncond) CLIP features (the vision tower is outside the hot path)."""
+
+    def __init__(self, cond, uncond):
+        self.cond, self.uncond = cond, uncond
+
+    def get_image_clip_feat(self, input_image=None):
+        return self.cond, self.uncond
+
+
+def run_pipeline_variant_case(variant, dtype, device="cuda", graph=True):
+    """BASELINE configs[2] ('ip': shipped YAML + IP-Adapter image condition) and configs[4] ('cam': camera-LoRA model, epsilon prediction,
+    4-channel input) plumbing at mini size against the UNMODIFIED reference pipeline's frames (tests/golden/pipeline_{variant}.npz)."""
+    from tests.cfgs import pipeline_variant_inputs
+    ci, kw, _, sched_cfg, steps, gs = pipeline_variant_inputs(variant)
+    unet, _ = make_unet(variant, dtype, device)
+    vae, _ = make_vae(dtype, device)
+    pipe = AnimationPipeline(vae=vae, text_encoder=FakeTextEncoder(ci["text_embeddings"]), tokenizer=FakeTokenizer(), unet=unet,
+                             scheduler=DDIMScheduler(**sched_cfg),
+                             ip_adapter=FakeIPAdapter(ci["image_clip_feat"].to(device), ci["uncond_image_clip_feat"].to(device)))
+    pipe.set_progress_bar_config(disable=True)
+    pipe.use_cuda_graph = graph and str(device).startswith("cuda")
+    video = pipe("p", negative_prompt="n", video_length=4, height=64, width=64, num_inference_steps=steps, guidance_scale=gs,
+                 latents=ci["latents"].clone(), use_ip_cross_attention=True, condition_images=torch.zeros(1, 3, 8, 8), **kw).videos
+    ref = torch.from_numpy(golden(f"pipeline_{variant}.npz")["video"])
+    s = stats(video, ref)
+    mse = float(((video.float() - ref) ** 2).mean())
+    return dict(video_maxabs=s["maxabs"], psnr=float(10 * np.log10(1.0 / max(mse, 1e-20))), finite=s["finite"], shape=tuple(video.shape))

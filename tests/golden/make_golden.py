@@ -190,10 +190,56 @@ def unet2d_fixture():
     return err
 
 
+class FakeIP:
+    """Stands in for MyIPAdapter at pipeline level (pipeline_animation.py:676-680): returns seeded (cond, uncond) CLIP features."""
+    def __init__(self, cond, uncond):
+        self.cond, self.uncond = cond, uncond
+
+    def get_image_clip_feat(self, input_image=None):
+        return self.cond, self.uncond
+
+
+def pipeline_variant_fixture(UNet, Pipe, VAE, DDIM, ImageProjModel, variant):
+    """BASELINE configs[2] / [4] plumbing at mini size through the UNMODIFIED reference pipeline: 'ip' = shipped YAML + IP-Adapter
+    image condition ([uncond, cond] CLIP features, 9-channel input, v-prediction); 'cam' = the camera-LoRA model of
+    inference_w_camera_lora.py (4-channel input, epsilon prediction, camera-motion embedding, temporal LoRA, IP tokens)."""
+    from tests.cfgs import pipeline_variant_inputs
+    vae = VAE(in_channels=3, out_channels=3, down_block_types=("DownEncoderBlock2D",) * 4,
+              up_block_types=("UpDecoderBlock2D",) * 4, block_out_channels=MINI_VAE["block_out_channels"],
+              layers_per_block=MINI_VAE["layers_per_block"], latent_channels=4, norm_num_groups=32).eval()
+    vsd = load_synth(vae)
+    unet = UNet(**mini_unet_ref_kwargs(variant)).eval()
+    ocfg = mini_unet_oracle_cfg(variant)
+    unet.image_proj_model = ImageProjModel(cross_attention_dim=768, clip_embeddings_dim=CLIP_DIM, clip_extra_context_tokens=ocfg["num_tokens"])
+    usd = load_synth(unet)
+    ci, kw, okw, sched_cfg, steps, gs = pipeline_variant_inputs(variant)
+    sched = DDIM(**{k: v for k, v in sched_cfg.items() if k != "set_alpha_to_one"})
+    pipe = Pipe(vae=vae, text_encoder=FakeText(ci["text_embeddings"]), tokenizer=FakeTok(), unet=unet, scheduler=sched,
+                ip_adapter=FakeIP(ci["image_clip_feat"], ci["uncond_image_clip_feat"]))
+    with torch.no_grad():
+        ref_video = pipe("p", negative_prompt="n", video_length=4, height=64, width=64, num_inference_steps=steps, guidance_scale=gs,
+                         latents=ci["latents"].clone(), use_ip_cross_attention=True, condition_images=torch.zeros(1, 3, 8, 8), **kw).videos
+        lat = ref_pipeline.denoise(usd, ocfg, sched_cfg, ci["latents"], ci["text_embeddings"], steps, gs,
+                                   image_clip_feat=ci["image_clip_feat"], uncond_image_clip_feat=ci["uncond_image_clip_feat"], **okw)
+        orc_video = ref_vae.decode_latents(vsd, MINI_VAE, lat)
+    err = maxabs(ref_video, orc_video)
+    print(f"pipeline[{variant}] video {tuple(ref_video.shape)} oracle-vs-ref maxabs={err:.3e}")
+    assert err < 2e-3
+    np.savez_compressed(os.path.join(HERE, f"pipeline_{variant}.npz"), video=ref_video.numpy().astype(np.float32), final_latents=lat.numpy())
+    return err
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(8)
     UNet, Pipe, VAE, DDIM, ImageProjModel = import_reference()
+    if "--only-pipeline-variants" in sys.argv:
+        pj = os.path.join(HERE, "pins.json")
+        d = json.load(open(pj))
+        for v in ("ip", "cam"):
+            d["oracle_vs_reference_maxabs"][f"pipeline_{v}"] = pipeline_variant_fixture(UNet, Pipe, VAE, DDIM, ImageProjModel, v)
+        json.dump(d, open(pj, "w"), indent=1)
+        return
     if "--only-unet2d" in sys.argv:
         pj = os.path.join(HERE, "pins.json")
         d = json.load(open(pj))
@@ -356,6 +402,8 @@ def main():
     pins["vae_encode"] = vae_encode_fixture(VAE)
     pins["resampler"] = resampler_fixture()
     pins["unet2d"] = unet2d_fixture()
+    for v in ("ip", "cam"):
+        pins[f"pipeline_{v}"] = pipeline_variant_fixture(UNet, Pipe, VAE, DDIM, ImageProjModel, v)
     pins["pipeline_video_scale"] = video_scale_fixture(UNet, Pipe, VAE, DDIM)
     np.savez_compressed(os.path.join(HERE, "pipeline.npz"), video=ref_video.numpy().astype(np.float32),
                         final_latents=lat.numpy())

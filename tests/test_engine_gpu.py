@@ -253,3 +253,14 @@ def test_shared_cfg_prefix_on_gpu(dtype):
     finally:
         AnimationPipeline.share_cfg_prefix = False
     assert r["finite"] and (r["video_maxabs"] < 2e-3 if dtype == torch.float32 else r["psnr"] > 30.0), r
+
+
+@pytest.mark.parametrize("variant", ["ip", "cam"])
+@pytest.mark.parametrize("graph", [True, False])
+def test_pipeline_ip_and_camera_variants_match_reference_golden(variant, graph):
+    """BASELINE configs[2] / [4] plumbing at mini size vs the reference pipeline's frames: fp32 max-abs <= 2e-3, bf16 PSNR >= 30 dB."""
+    from tests.engine_helpers import run_pipeline_variant_case
+    r = run_pipeline_variant_case(variant, torch.float32, graph=graph)
+    assert r["finite"] and r["shape"] == (1, 3, 4, 64, 64) and r["video_maxabs"] < 2e-3, r
+    r = run_pipeline_variant_case(variant, torch.bfloat16, graph=graph)
+    assert r["finite"] and r["psnr"] > 30.0, r

@@ -181,3 +181,11 @@ def test_pipeline_with_shared_cfg_prefix_vs_reference_golden():
     finally:
         AnimationPipeline.share_cfg_prefix = False
     assert r["finite"] and r["video_maxabs"] < 2e-3, r
+
+
+@pytest.mark.parametrize("variant", ["ip", "cam"])
+def test_pipeline_ip_and_camera_variants_host_logic_vs_reference_golden(variant):
+    """configs[2] / [4] plumbing: [uncond, cond] image features, camera-motion embedding, epsilon prediction, 4-channel input."""
+    from tests.engine_helpers import run_pipeline_variant_case
+    r = run_pipeline_variant_case(variant, torch.float32, device="cpu")
+    assert r["finite"] and r["shape"] == (1, 3, 4, 64, 64) and r["video_maxabs"] < 2e-3, r

@@ -151,3 +151,16 @@ def test_video_grid_oracle_pinned_against_torchvision():
     v = torch.rand(3, 3, 2, 5, 6, generator=g)
     fr = ref_util.video_frames_uint8(v, n_rows=2)
     assert len(fr) == 2 and fr[0].shape == (2 * 7 + 2, 2 * 8 + 2, 3) and fr[0].dtype == np.uint8
+
+
+@pytest.mark.parametrize("variant", ["ip", "cam"])
+def test_pipeline_variant_oracle_vs_reference_fixture(variant):
+    """configs[2] / [4] plumbing (IP-Adapter image condition; camera-LoRA model with epsilon prediction) - oracle vs reference frames."""
+    from tests.cfgs import CLIP_DIM, pipeline_variant_inputs
+    g = np.load(os.path.join(GOLD, f"pipeline_{variant}.npz"))
+    keys = dict(json.load(open(os.path.join(GOLD, "unet_keys.json")))[variant])
+    usd = _synth(keys)
+    ci, _, okw, sched_cfg, steps, gs = pipeline_variant_inputs(variant)
+    lat = ref_pipeline.denoise(usd, mini_unet_oracle_cfg(variant), sched_cfg, ci["latents"], ci["text_embeddings"], steps, gs,
+                               image_clip_feat=ci["image_clip_feat"], uncond_image_clip_feat=ci["uncond_image_clip_feat"], **okw)
+    assert float((lat - torch.from_numpy(g["final_latents"])).abs().max()) < 1e-4
