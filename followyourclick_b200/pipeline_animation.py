@@ -38,7 +38,7 @@ class _GraphedUNetStep:
     configuration, so the ~700 kernel launches of a forward are replayed with one call; inputs live in static buffers
     (x: channels-last UNet input, t: timestep, text / fps / flow / camera / clip features)."""
 
-    def __init__(self, unet, x_shape, text, fps, flow, cam, clip, flags, x=None, out_frames=None, cfg_dup=1):
+    def __init__(self, unet, x_shape, text, fps, flow, cam, clip, flags, x=None, out_frames=None, cfg_dup=1, hoist=True):
         """``x``: use this (view of another step's) static input instead of allocating one; ``out_frames`` = (b, f): the input is
         b * f single frames (F = 1) whose prediction is returned regrouped as (b, 4, f, h, w) (video_scale branch)."""
         dev = unet.device
@@ -53,21 +53,36 @@ class _GraphedUNetStep:
         self.flags = flags
         # step-invariant conditioning (context tokens, image-prompt tokens, every block's cross-attention K/V): built once per clip
         # into static buffers the captured forward reads; the reference redoes it every step
-        self.hoist = hasattr(unet, "prepare_context") and AnimationPipeline.hoist_context
+        self.hoist = hasattr(unet, "prepare_context") and hoist
         self.context = self._context(unet) if self.hoist else None
-        cur = torch.cuda.current_stream()
-        side = torch.cuda.Stream()
-        side.wait_stream(cur)
-        with torch.cuda.stream(side):           # warm-up outside capture: packs weights, sets kernel attributes
-            for _ in range(2):
-                self._run(unet)
-        cur.wait_stream(side)
-        torch.cuda.synchronize()
-        self.graph = torch.cuda.CUDAGraph()
-        n0 = _lib.launch_count
-        with torch.cuda.graph(self.graph):
+        self._unet = unet
+        if self.capture:
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):           # warm-up outside capture: packs weights, sets kernel attributes
+                for _ in range(2):
+                    self._run(unet)
+            cur.wait_stream(side)
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            n0 = _lib.launch_count
+            with torch.cuda.graph(self.graph):
+                self.pred = self._run(unet)
+            self.n_calls = _lib.launch_count - n0      # kernel-launching C-ABI calls replayed by one graph launch
+        else:                                          # bookkeeping-only mode of the CPU host-logic tests: replay() re-executes
+            self.graph, self.n_calls = None, 0
             self.pred = self._run(unet)
-        self.n_calls = _lib.launch_count - n0      # kernel-launching C-ABI calls replayed by one graph launch
+
+    capture = True         # False: no CUDA graph, replay() re-runs the forward (tests/test_host_emulated_cpu.py walks this class's
+                           # buffer / cache / context bookkeeping on CPU with the kernel launches emulated)
+
+    def replay(self):
+        if self.graph is not None:
+            self.graph.replay()
+            _lib.launch_count += self.n_calls
+        else:
+            self.pred = self._run(self._unet)
 
     def _context(self, unet):
         return unet.prepare_context(self.text, self.clip, self.flags.get("use_ip_cross_attention", False))
@@ -298,33 +313,31 @@ class AnimationPipeline:
         xdup = dup // share
         if self.use_cuda_graph and hasattr(unet, "forward_nfhwc"):
             cin = c_pad if c_pad is not None else (9 if first is not None else 4)
-            key = (xdup * b, share, f, h, w, cin, unet.dtype, tuple(sorted(flags.items())), tuple(text_embeddings.shape),
+            key = (xdup * b, share, self.hoist_context, f, h, w, cin, unet.dtype, tuple(sorted(flags.items())), tuple(text_embeddings.shape),
                    None if clip_d is None else tuple(clip_d.shape))
             cache = self.__dict__.setdefault("_graph_cache", {})
             graphed = cache.get(key)
             if graphed is None or graphed.version != unet._pack_version:
                 graphed = cache[key] = _GraphedUNetStep(unet, (xdup * b, f, h, w, cin), text_embeddings, fps_d, flow_d, cam_d, clip_d, flags,
-                                                        cfg_dup=share)
+                                                        cfg_dup=share, hoist=self.hoist_context)
             graphed.load(unet, text_embeddings, fps_d, flow_d, cam_d, clip_d)
             if video_scale > 0:
                 graphed_sf = cache.get(key + ("sf",))
                 if graphed_sf is None or graphed_sf.version != unet._pack_version or graphed_sf.x.data_ptr() != graphed.x.data_ptr():
                     graphed_sf = cache[key + ("sf",)] = _GraphedUNetStep(
                         unet, (b * f, 1, h, w, cin), text_sf, None, None, None, None, flags_sf,
-                        x=graphed.x[:b].view(b * f, 1, h, w, cin), out_frames=(b, f))     # the uncond copy's frames: a view, no copy
+                        x=graphed.x[:b].view(b * f, 1, h, w, cin), out_frames=(b, f), hoist=self.hoist_context)   # the uncond copy's frames: a view
                 graphed_sf.load(unet, text_sf, None, None, None, None)
         with bar as pb:
             for i, t in enumerate(t_host):
                 if graphed is not None:
                     ops.build_unet_input(latents, mask, first, xdup, unet.dtype, c_pad=c_pad, out=graphed.x)
                     graphed.t.copy_(t_dev[i])
-                    graphed.graph.replay()
-                    _lib.launch_count += graphed.n_calls
+                    graphed.replay()
                     pred = graphed.pred
                     if graphed_sf is not None:
                         graphed_sf.t.copy_(t_dev[i])
-                        graphed_sf.graph.replay()
-                        _lib.launch_count += graphed_sf.n_calls
+                        graphed_sf.replay()
                         single = graphed_sf.pred
                 else:
                     if i == 0 and self.hoist_context and hasattr(unet, "prepare_context"):

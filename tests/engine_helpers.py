@@ -74,6 +74,13 @@ def stats(a, b):
                 finite=bool(torch.isfinite(a).all()))
 
 
+def graph_bookkeeping_on_cpu():
+    """True when a CPU test has switched _GraphedUNetStep to its capture-free mode (replay() re-executes the forward): the pipeline's
+    graph branch - static input buffers and their views, the graph cache, ClipContext refresh - then runs on CPU too."""
+    from followyourclick_b200.pipeline_animation import _GraphedUNetStep
+    return not _GraphedUNetStep.capture
+
+
 def _sync(device):
     if str(device).startswith("cuda"):
         torch.cuda.synchronize()
@@ -158,7 +165,7 @@ def run_video_scale_case(dtype, device="cuda", graph=True):
     """per-frame guidance branch (video_scale > 0) against the reference fixture pipeline_video_scale.npz."""
     g = golden("pipeline_video_scale.npz")
     pipe, ci, usd, vsd = make_pipeline(dtype, device=device)
-    pipe.use_cuda_graph = graph and str(device).startswith("cuda")
+    pipe.use_cuda_graph = graph and (str(device).startswith("cuda") or graph_bookkeeping_on_cpu())
     video = pipeline_call(pipe, ci, 4, 8, 8, int(g["steps"]), 8.0, video_scale=float(g["video_scale"]))
     ref = torch.from_numpy(g["video"])
     s = stats(video, ref)
@@ -171,7 +178,7 @@ def run_pipeline_case(dtype, steps=3, against="oracle", device="cuda"):
     F, h, w, gs = 4, 8, 8, 8.0
     pipe, ci, usd, vsd = make_pipeline(dtype, device=device)
     if not str(device).startswith("cuda"):
-        pipe.use_cuda_graph = False
+        pipe.use_cuda_graph = graph_bookkeeping_on_cpu()
     video = pipeline_call(pipe, ci, F, h, w, steps, gs)
     if against == "golden":
         assert steps == 3
@@ -242,7 +249,7 @@ def run_pipeline_variant_case(variant, dtype, device="cuda", graph=True):
                              scheduler=DDIMScheduler(**sched_cfg),
                              ip_adapter=FakeIPAdapter(ci["image_clip_feat"].to(device), ci["uncond_image_clip_feat"].to(device)))
     pipe.set_progress_bar_config(disable=True)
-    pipe.use_cuda_graph = graph and str(device).startswith("cuda")
+    pipe.use_cuda_graph = graph and (str(device).startswith("cuda") or graph_bookkeeping_on_cpu())
     video = pipe("p", negative_prompt="n", video_length=4, height=64, width=64, num_inference_steps=steps, guidance_scale=gs,
                  latents=ci["latents"].clone(), use_ip_cross_attention=True, condition_images=torch.zeros(1, 3, 8, 8), **kw).videos
     ref = torch.from_numpy(golden(f"pipeline_{variant}.npz")["video"])

@@ -189,3 +189,44 @@ def test_pipeline_ip_and_camera_variants_host_logic_vs_reference_golden(variant)
     from tests.engine_helpers import run_pipeline_variant_case
     r = run_pipeline_variant_case(variant, torch.float32, device="cpu")
     assert r["finite"] and r["shape"] == (1, 3, 4, 64, 64) and r["video_maxabs"] < 2e-3, r
+
+
+@pytest.fixture
+def graph_branch(monkeypatch):
+    """Walk AnimationPipeline's CUDA-graph branch on CPU: _GraphedUNetStep in capture-free mode (replay() re-executes the forward)."""
+    from followyourclick_b200.pipeline_animation import _GraphedUNetStep
+    monkeypatch.setattr(_GraphedUNetStep, "capture", False)
+
+
+def test_graph_branch_bookkeeping_vs_reference_golden(graph_branch):
+    """Static input buffers, the graph cache, ClipContext refresh on a second clip, the video_scale step's VIEW of the CFG input, the
+    IP / camera variants and the shared CFG prefix - the host code of the graph branch, against the reference fixtures."""
+    from followyourclick_b200 import AnimationPipeline
+    from tests.engine_helpers import (make_pipeline, pipeline_call, run_pipeline_case, run_pipeline_variant_case, run_video_scale_case,
+                                      golden)
+    r = run_pipeline_case(torch.float32, steps=3, against="golden", device="cpu")
+    assert r["video_maxabs"] < 2e-3, r
+    r = run_video_scale_case(torch.float32, device="cpu", graph=True)
+    assert r["video_maxabs"] < 2e-3, r
+    for v in ("ip", "cam"):
+        r = run_pipeline_variant_case(v, torch.float32, device="cpu", graph=True)
+        assert r["video_maxabs"] < 2e-3, (v, r)
+    AnimationPipeline.share_cfg_prefix = True
+    try:
+        r = run_pipeline_case(torch.float32, steps=3, against="golden", device="cpu")
+        assert r["video_maxabs"] < 2e-3, r
+        r = run_video_scale_case(torch.float32, device="cpu", graph=True)
+        assert r["video_maxabs"] < 2e-3, r
+    finally:
+        AnimationPipeline.share_cfg_prefix = False
+    # a second clip through the SAME pipeline object reuses the cached step and must refresh its static buffers / context
+    pipe, ci, _, _ = make_pipeline(torch.float32, device="cpu")
+    pipe.use_cuda_graph = True
+    a = pipeline_call(pipe, ci, 4, 8, 8, 3, 8.0)
+    ci2 = dict(ci, text_embeddings=ci["text_embeddings"] * 0.5)
+    pipe.text_encoder.emb = ci2["text_embeddings"]
+    b = pipeline_call(pipe, ci2, 4, 8, 8, 3, 8.0)
+    pipe.text_encoder.emb = ci["text_embeddings"]
+    c = pipeline_call(pipe, ci, 4, 8, 8, 3, 8.0)
+    assert len(pipe._graph_cache) == 1 and torch.equal(a, c) and not torch.equal(a, b)
+    assert float((a - torch.from_numpy(golden("pipeline.npz")["video"])).abs().max()) < 2e-3
