@@ -230,3 +230,13 @@ def test_graph_branch_bookkeeping_vs_reference_golden(graph_branch):
     c = pipeline_call(pipe, ci, 4, 8, 8, 3, 8.0)
     assert len(pipe._graph_cache) == 1 and torch.equal(a, c) and not torch.equal(a, b)
     assert float((a - torch.from_numpy(golden("pipeline.npz")["video"])).abs().max()) < 2e-3
+
+
+def test_dry_run_of_the_full_size_property_tests(monkeypatch):
+    """tests/test_zz_late_gpu.py's full-size identities, executed here at reduced sizes on the emulated kernels: checks that the
+    identities themselves (and the test code) are right; on a GPU box the same functions run at cfg2 size on the real kernels."""
+    import tests.test_zz_late_gpu as late
+    monkeypatch.setattr(late, "DEV", "cpu")
+    monkeypatch.setattr(late, "SMALL", True)
+    late.test_full_size_kernel_identities()
+    late.test_full_size_unet_and_pipeline_properties()
