@@ -240,3 +240,19 @@ def test_dry_run_of_the_full_size_property_tests(monkeypatch):
     monkeypatch.setattr(late, "SMALL", True)
     late.test_full_size_kernel_identities()
     late.test_full_size_unet_and_pipeline_properties()
+
+
+def test_shared_cfg_prefix_with_two_clips():
+    """b = 2 clips: context rows are [uncond clip 0, uncond clip 1, cond clip 0, cond clip 1]; the prefix runs on the 2 clips once."""
+    from followyourclick_b200 import ops
+    from tests.cfgs import unet_inputs
+    from tests.engine_helpers import make_unet, stats
+    unet, _ = make_unet("base", torch.float32, "cpu")
+    inp = unet_inputs("base", b=2)
+    x2 = ops.ncfhw_to_nfhwc(inp["sample"].contiguous(), torch.float32)
+    ctx4 = torch.randn(4, 77, 768, generator=torch.Generator().manual_seed(8))
+    kw = dict(fps_tensor=torch.tensor([2] * 4), flow_control=torch.tensor([4] * 4), use_fps_condition=True)
+    full = unet.forward_nfhwc(torch.cat([x2, x2]), inp["timestep"], ctx4, **kw)
+    shared = unet.forward_nfhwc(x2, inp["timestep"], ctx4, cfg_dup=2, **kw)
+    s = stats(shared, full)
+    assert shared.shape == full.shape == (4, 4, 16, 16, 4) and s["rel_l2"] < 1e-6, s
