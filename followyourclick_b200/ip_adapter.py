@@ -145,16 +145,62 @@ class MyIPAdapter:
         return ImageProjModel(cross_attention_dim=self.unet.config.cross_attention_dim, clip_embeddings_dim=self._clip_dim,
                               clip_extra_context_tokens=self.num_tokens).to(self.device)
 
-    @torch.no_grad()
-    def get_image_clip_feat(self, input_image=None):
+    def get_ip_adapter_state_dict(self):
+        """ip_adapter/my_ip_adapter.py:72-83: {"image_proj": {...}, "ip_adapter": {...}} from a .bin / .safetensors IP-Adapter file."""
+        import os
+        if os.path.splitext(self.ip_ckpt)[-1] == ".safetensors":
+            from safetensors import safe_open
+            sd = {"image_proj": {}, "ip_adapter": {}}
+            with safe_open(self.ip_ckpt, framework="pt", device="cpu") as f:
+                for key in f.keys():
+                    for part in ("image_proj", "ip_adapter"):
+                        if key.startswith(part + "."):
+                            sd[part][key[len(part) + 1:]] = f.get_tensor(key)
+            return sd
+        return torch.load(self.ip_ckpt, map_location="cpu")
+
+    def load_ip_adapter(self, unet=None, use_unet_image_proj_model=False, state_dict=None):
+        """ip_adapter/my_ip_adapter.py:85-125 / :234-268 (load-time weight surgery, outside the hot path): the projector's weights go into
+        ``unet.image_proj_model`` (or this adapter's own projector), and the adapter file's ``to_k_ip`` / ``to_v_ip`` tensors replace the
+        UNet's ``*_ip*`` tensors PAIRED BY ORDER, exactly like the reference (zip of the two key lists, shapes asserted)."""
+        sd = state_dict if state_dict is not None else self.get_ip_adapter_state_dict()
+        target = unet if unet is not None else self.unet
+        if use_unet_image_proj_model:
+            if getattr(target, "image_proj_model", None) is None:
+                target.image_proj_model = self.init_proj()
+            target.image_proj_model.load_state_dict(sd["image_proj"])
+        else:
+            self.image_proj_model.load_state_dict(sd["image_proj"])
+        usd = target.state_dict()
+        ip_keys = list(sd["ip_adapter"].keys())
+        model_keys = [k for k in usd if "_ip" in k]
+        for k1, k2 in zip(model_keys, ip_keys):
+            assert tuple(usd[k1].shape) == tuple(sd["ip_adapter"][k2].shape), (k1, k2)
+            usd[k1] = sd["ip_adapter"][k2]
+        return target.load_state_dict(usd, strict=False)
+
+    def _pixel_values(self, input_image):
         if not torch.is_tensor(input_image):
             if self.clip_image_processor is None:
                 from transformers import CLIPImageProcessor
                 self.clip_image_processor = CLIPImageProcessor()
             imgs = input_image if isinstance(input_image, list) else [input_image]
             input_image = self.clip_image_processor(images=imgs, return_tensors="pt").pixel_values
-        emb = self.image_encoder(input_image.to(self.device)).image_embeds
+        return input_image.to(self.device)
+
+    @torch.no_grad()
+    def get_image_clip_feat(self, input_image=None):
+        emb = self.image_encoder(self._pixel_values(input_image)).image_embeds
         return emb, torch.zeros_like(emb)
+
+    @torch.no_grad()
+    def get_image_embeds(self, input_image=None, clip_image_embeds=None, image_proj_model=None):
+        """ip_adapter/my_ip_adapter.py:136-153: (image-prompt tokens, tokens of the zero feature)."""
+        if input_image is not None:
+            clip_image_embeds = self.image_encoder(self._pixel_values(input_image)).image_embeds
+        clip_image_embeds = clip_image_embeds.to(self.device)
+        proj = image_proj_model if image_proj_model is not None else self.image_proj_model
+        return proj(clip_image_embeds), proj(torch.zeros_like(clip_image_embeds))
 
 
 class MyIPAdapterPlus(MyIPAdapter):
@@ -172,13 +218,14 @@ class MyIPAdapterPlus(MyIPAdapter):
 
     @torch.no_grad()
     def get_image_clip_feat(self, input_image=None):
-        if not torch.is_tensor(input_image):
-            if self.clip_image_processor is None:
-                from transformers import CLIPImageProcessor
-                self.clip_image_processor = CLIPImageProcessor()
-            imgs = input_image if isinstance(input_image, list) else [input_image]
-            input_image = self.clip_image_processor(images=imgs, return_tensors="pt").pixel_values
-        input_image = input_image.to(self.device)
+        input_image = self._pixel_values(input_image)
         cond = self.image_encoder(input_image, output_hidden_states=True).hidden_states[-2]
         uncond = self.image_encoder(torch.zeros_like(input_image), output_hidden_states=True).hidden_states[-2]
         return cond, uncond
+
+    @torch.no_grad()
+    def get_image_embeds(self, input_image=None, clip_image_embeds=None, image_proj_model=None):
+        """ip_adapter/my_ip_adapter.py:286-305: tokens of the image's penultimate CLIP hidden states and of the zero image's."""
+        cond, uncond = self.get_image_clip_feat(input_image)
+        proj = image_proj_model if image_proj_model is not None else self.image_proj_model
+        return proj(cond), proj(uncond)

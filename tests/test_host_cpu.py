@@ -162,3 +162,21 @@ def test_upsample_phase_weights_restates_upsample_plus_conv():
                     acc = acc + torch.einsum("nchw,oc->nohw", xp[:, :, 1 + dy:7 + dy, 1 + dx:8 + dx], wp[2 * py + px, :, a, b, :])
             out[:, :, py::2, px::2] = acc
     assert float((out - ref).abs().max()) < 1e-5
+
+
+def test_ip_adapter_weight_surgery_pairs_keys_by_order():
+    """MyIPAdapter.load_ip_adapter (ip_adapter/my_ip_adapter.py:85-125): projector weights into unet.image_proj_model, the adapter
+    file's to_k_ip / to_v_ip tensors into the UNet's *_ip* tensors in key order."""
+    from followyourclick_b200 import MyIPAdapter, UNet3DConditionModel
+    unet = UNet3DConditionModel(**mini_unet_ref_kwargs("ip"))
+    ad = MyIPAdapter(unet, image_encoder=object(), device="cpu", num_tokens=4, clip_embeddings_dim=1024)
+    ip_keys = [k for k in unet.state_dict() if "_ip" in k]
+    assert len(ip_keys) == 2 * 10                                  # to_k_ip + to_v_ip of the 10 transformer blocks of the mini model
+    g = torch.Generator().manual_seed(0)
+    sd = {"image_proj": {k: torch.randn(v.shape, generator=g) for k, v in ad.image_proj_model.state_dict().items()},
+          "ip_adapter": {f"{i}.w": torch.randn(unet.state_dict()[k].shape, generator=g) for i, k in enumerate(ip_keys)}}
+    missing, unexpected = ad.load_ip_adapter(unet, use_unet_image_proj_model=True, state_dict=sd)
+    assert not unexpected
+    for i, k in enumerate(ip_keys):
+        assert torch.equal(unet.state_dict()[k], sd["ip_adapter"][f"{i}.w"])
+    assert torch.equal(unet.image_proj_model.state_dict()["proj.weight"], sd["image_proj"]["proj.weight"])
