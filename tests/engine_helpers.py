@@ -222,8 +222,11 @@ def run_unet_ragged_case(dtype, device="cuda", b=1, f=3, h=24, w=40):
     inp["fps"], inp["flow"] = torch.tensor([2] * b), torch.tensor([4] * b)
     out = unet(inp["sample"].to(device), inp["timestep"], **unet_forward_kwargs("base", inp, device)).sample
     _sync(device)
-    ref = ref_unet.unet3d_forward(sd, mini_unet_oracle_cfg("base"), inp["sample"], inp["timestep"], inp["ctx"],
-                                  fps_tensor=inp["fps"], flow_control=inp["flow"])
+    if (b, f, h, w) == (1, 3, 24, 40):          # this shape has a fixture from the unmodified reference (tests/golden/unet_base_ragged.npz)
+        ref = torch.from_numpy(golden("unet_base_ragged.npz")["out"])
+    else:
+        ref = ref_unet.unet3d_forward(sd, mini_unet_oracle_cfg("base"), inp["sample"], inp["timestep"], inp["ctx"],
+                                      fps_tensor=inp["fps"], flow_control=inp["flow"])
     assert out.shape == ref.shape == (b, 4, f, h, w)
     return stats(out, ref)
 

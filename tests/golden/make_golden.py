@@ -229,10 +229,33 @@ def pipeline_variant_fixture(UNet, Pipe, VAE, DDIM, ImageProjModel, variant):
     return err
 
 
+def unet_ragged_fixture(UNet):
+    """The unmodified reference UNet on a non-square, non-power-of-two latent grid with an odd frame count and batch 1 (320 x 192
+    image, 3 frames): pins the oracle (and through it the engine's tile-picker fallbacks) away from the 16 x 16 x 4 fixture shape."""
+    unet = UNet(**mini_unet_ref_kwargs("base")).eval()
+    sd = load_synth(unet)
+    inp = unet_inputs("base", b=1, f=3, h=24, w=40, seed=23)
+    fps, flow = torch.tensor([2]), torch.tensor([4])
+    with torch.no_grad():
+        ref = unet(inp["sample"], inp["timestep"], encoder_hidden_states=inp["ctx"], use_fps_condition=True, fps_tensor=fps, flow_control=flow).sample
+        orc = ref_unet.unet3d_forward(sd, mini_unet_oracle_cfg("base"), inp["sample"], inp["timestep"], inp["ctx"], fps_tensor=fps, flow_control=flow)
+    err = maxabs(ref, orc)
+    print(f"unet[base, ragged 1x3x24x40] |ref|max={float(ref.abs().max()):.3f} oracle-vs-ref maxabs={err:.3e}")
+    assert err < 2e-4 * max(1.0, float(ref.abs().max()))
+    np.savez_compressed(os.path.join(HERE, "unet_base_ragged.npz"), out=ref.numpy())
+    return err
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(8)
     UNet, Pipe, VAE, DDIM, ImageProjModel = import_reference()
+    if "--only-unet-ragged" in sys.argv:
+        pj = os.path.join(HERE, "pins.json")
+        d = json.load(open(pj))
+        d["oracle_vs_reference_maxabs"]["unet_base_ragged"] = unet_ragged_fixture(UNet)
+        json.dump(d, open(pj, "w"), indent=1)
+        return
     if "--only-pipeline-variants" in sys.argv:
         pj = os.path.join(HERE, "pins.json")
         d = json.load(open(pj))
@@ -402,6 +425,7 @@ def main():
     pins["vae_encode"] = vae_encode_fixture(VAE)
     pins["resampler"] = resampler_fixture()
     pins["unet2d"] = unet2d_fixture()
+    pins["unet_base_ragged"] = unet_ragged_fixture(UNet)
     for v in ("ip", "cam"):
         pins[f"pipeline_{v}"] = pipeline_variant_fixture(UNet, Pipe, VAE, DDIM, ImageProjModel, v)
     pins["pipeline_video_scale"] = video_scale_fixture(UNet, Pipe, VAE, DDIM)

@@ -164,3 +164,13 @@ def test_pipeline_variant_oracle_vs_reference_fixture(variant):
     lat = ref_pipeline.denoise(usd, mini_unet_oracle_cfg(variant), sched_cfg, ci["latents"], ci["text_embeddings"], steps, gs,
                                image_clip_feat=ci["image_clip_feat"], uncond_image_clip_feat=ci["uncond_image_clip_feat"], **okw)
     assert float((lat - torch.from_numpy(g["final_latents"])).abs().max()) < 1e-4
+
+
+def test_unet_oracle_vs_reference_fixture_ragged_shape():
+    """Oracle pinned on a non-square, non-power-of-two grid with an odd frame count and batch 1 (reference run on 1 x 3 x 24 x 40)."""
+    g = np.load(os.path.join(GOLD, "unet_base_ragged.npz"))
+    sd = _synth(json.load(open(os.path.join(GOLD, "unet_keys.json")))["base"])
+    inp = unet_inputs("base", b=1, f=3, h=24, w=40, seed=23)
+    out = ref_unet.unet3d_forward(sd, mini_unet_oracle_cfg("base"), inp["sample"], inp["timestep"], inp["ctx"],
+                                  fps_tensor=torch.tensor([2]), flow_control=torch.tensor([4]))
+    assert float((out - torch.from_numpy(g["out"])).abs().max()) < 1e-4
