@@ -42,7 +42,7 @@ class AttnArgs(C.Structure):
 
 class DdimCoefs(C.Structure):
     _fields_ = [("guidance", _f32), ("sqrt_alpha_t", _f32), ("sqrt_beta_t", _f32), ("sqrt_alpha_prev", _f32),
-                ("dir_coef", _f32), ("noise_coef", _f32), ("prediction_type", _i32), ("clip_sample", _i32)]
+                ("dir_coef", _f32), ("noise_coef", _f32), ("prediction_type", _i32), ("clip_sample", _i32), ("cfg_pair", _i32)]
 
 
 # every exported symbol of include/fyc.h: name -> (restype, argtypes)

@@ -225,7 +225,7 @@ __global__ void cfg_ddim_kernel(const float* __restrict__ pred, const float* __r
     if (single) {
       float u = pred[i], t = pred[n + i], s = single[i];
       m = __fadd_rn(__fadd_rn(s, __fmul_rn(video_scale, __fsub_rn(u, s))), __fmul_rn(c.guidance, __fsub_rn(t, u)));
-    } else if (c.guidance > 1.0f) {
+    } else if (c.cfg_pair) {
       float u = pred[i], t = pred[n + i];
       m = __fadd_rn(u, __fmul_rn(c.guidance, __fsub_rn(t, u)));
     } else {
@@ -261,7 +261,7 @@ extern "C" int32_t fyc_cfg_video_ddim_step(const float* pred, const float* singl
                                            const float* noise, float* prev, int64_t n, const fyc_ddim_coefs* c, void* stream) {
   FYC_CHECK(c != nullptr && n > 0 && pred && single, "cfg_video_ddim_step: bad arguments");
   FYC_CHECK(c->prediction_type >= 0 && c->prediction_type <= 2, "cfg_video_ddim_step: unknown prediction_type %d", c->prediction_type);
-  FYC_CHECK(c->guidance > 1.0f, "cfg_video_ddim_step: the per-frame guidance branch exists only under classifier-free guidance");
+  FYC_CHECK(c->cfg_pair != 0, "cfg_video_ddim_step: the per-frame guidance branch exists only under classifier-free guidance");
   cfg_ddim_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(pred, single, video_scale, sample, noise, prev, n, *c);
   FYC_LAUNCH_CHECK();
   return FYC_OK;

@@ -371,7 +371,7 @@ def build_unet_input(latents, mask, first, dup, dtype, c_pad=None, out=None):
 
 
 def cfg_ddim_step(pred, sample, coefs, noise=None, out=None, single=None, video_scale=0.0):
-    """pred fp32 [2, ...] (uncond, cond) if coefs.guidance > 1 else [1, ...]; sample fp32; returns prev sample.
+    """pred fp32 [2, ...] (uncond, cond) if coefs.cfg_pair else [1, ...]; sample fp32; returns prev sample.
     ``single`` (same shape as sample): the per-frame prediction of the video_scale > 0 branch (pipeline_animation.py:738-761)."""
     assert pred.dtype == torch.float32 and sample.dtype == torch.float32 and pred.is_contiguous() and sample.is_contiguous()
     out = torch.empty_like(sample) if out is None else out

@@ -8,6 +8,7 @@ The prompt / image encoders are outside the hot path (their outputs are computed
 """
 import inspect
 import os
+from collections import OrderedDict
 from dataclasses import dataclass
 from typing import Union
 
@@ -95,7 +96,10 @@ class _GraphedUNetStep:
 
     def load(self, unet, text, fps, flow, cam, clip):
         self.text.copy_(text)
-        for dst, src in ((self.fps, fps), (self.flow, flow), (self.cam, cam), (self.clip, clip)):
+        for name, dst, src in (("fps", self.fps, fps), ("flow", self.flow, flow), ("camera", self.cam, cam), ("clip", self.clip, clip)):
+            if (dst is None) != (src is None):
+                raise ValueError(f"captured UNet step was built {'with' if dst is not None else 'without'} a `{name}` tensor; "
+                                 "this call differs (the graph cache key should have separated them)")
             if dst is not None:
                 dst.copy_(src)
         if self.hoist:
@@ -131,6 +135,7 @@ class AnimationPipeline:
     _optional_components = []
     use_cuda_graph = True          # replay one captured UNet forward per DDIM step (set False to launch kernel by kernel)
     hoist_context = True           # build the step-invariant conditioning (ClipContext) once per clip instead of once per step
+    graph_cache_entries = 4        # captured UNet-step graphs kept per pipeline (least recently used shapes are dropped)
     # Shared CFG prefix (UNet3DConditionModel.forward_nfhwc cfg_dup): the uncond / cond halves of the reference's batch are identical
     # until the first cross-attention, so that prefix (incl. the first 64x64 self-attention) is computed once.  Exact, and verified
     # against the reference fixtures through the CPU emulation of the kernels (tests/test_host_emulated_cpu.py); it has not had its
@@ -313,14 +318,21 @@ class AnimationPipeline:
         xdup = dup // share
         if self.use_cuda_graph and hasattr(unet, "forward_nfhwc"):
             cin = c_pad if c_pad is not None else (9 if first is not None else 4)
+            # everything the captured forward's control flow depends on: shapes, dtype, flags, WHICH optional inputs exist, and the
+            # IP-attention logit-scale semantics (enable_xformers_memory_efficient_attention toggles it without re-packing weights)
             key = (xdup * b, share, self.hoist_context, f, h, w, cin, unet.dtype, tuple(sorted(flags.items())), tuple(text_embeddings.shape),
-                   None if clip_d is None else tuple(clip_d.shape))
-            cache = self.__dict__.setdefault("_graph_cache", {})
+                   None if clip_d is None else tuple(clip_d.shape), fps_d is None, flow_d is None, cam_d is None,
+                   bool(getattr(unet, "_xformers_semantics", False)))
+            cache = self.__dict__.setdefault("_graph_cache", OrderedDict())
             graphed = cache.get(key)
+            if graphed is not None:
+                cache.move_to_end(key)
             if graphed is None or graphed.version != unet._pack_version:
                 graphed = cache[key] = _GraphedUNetStep(unet, (xdup * b, f, h, w, cin), text_embeddings, fps_d, flow_d, cam_d, clip_d, flags,
                                                         cfg_dup=share, hoist=self.hoist_context)
             graphed.load(unet, text_embeddings, fps_d, flow_d, cam_d, clip_d)
+            while len(cache) > self.graph_cache_entries * 2:       # LRU bound: a graph + its private memory pool per distinct clip shape
+                cache.popitem(last=False)                           # (x2: the video_scale branch keeps a second graph per shape)
             if video_scale > 0:
                 graphed_sf = cache.get(key + ("sf",))
                 if graphed_sf is None or graphed_sf.version != unet._pack_version or graphed_sf.x.data_ptr() != graphed.x.data_ptr():

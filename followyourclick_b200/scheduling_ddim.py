@@ -64,6 +64,28 @@ class DDIMScheduler:
         self.timesteps = torch.from_numpy(np.arange(0, num_train_timesteps)[::-1].copy().astype(np.int64))
         self._timesteps_host = self.timesteps.tolist()
 
+    # ---- ConfigMixin surface used by the reference scripts (diffusers/configuration_utils.py; scripts/inference.py:199 calls
+    # DDIMScheduler.from_pretrained(path, subfolder="scheduler") on the T2I first-frame path)
+    @classmethod
+    def from_config(cls, config, **kwargs):
+        cfg = {k: v for k, v in dict(config).items() if not k.startswith("_")}
+        cfg.update(kwargs)
+        accepted = ("num_train_timesteps", "beta_start", "beta_end", "beta_schedule", "trained_betas", "clip_sample", "set_alpha_to_one",
+                    "steps_offset", "prediction_type", "rescale_betas_zero_snr")
+        return cls(**{k: v for k, v in cfg.items() if k in accepted})       # other schedulers' keys (skip_prk_steps, ...) are ignored like ConfigMixin does
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, subfolder=None, **kwargs):
+        """reads ``scheduler_config.json`` of a local diffusers model folder (no hub access: the engine runs offline)"""
+        import json
+        import os
+        path = pretrained_model_name_or_path if subfolder is None else os.path.join(pretrained_model_name_or_path, subfolder)
+        f = path if os.path.isfile(path) else os.path.join(path, "scheduler_config.json")
+        if not os.path.isfile(f):
+            raise EnvironmentError(f"{f} does not exist (DDIMScheduler.from_pretrained reads a local scheduler_config.json)")
+        with open(f) as fh:
+            return cls.from_config(json.load(fh), **kwargs)
+
     def scale_model_input(self, sample, timestep=None):
         return sample
 
@@ -75,8 +97,11 @@ class DDIMScheduler:
         self._timesteps_host = [int(t) for t in timesteps]
         self.timesteps = torch.from_numpy(timesteps).to(device)
 
-    def coefs(self, timestep, eta=0.0, guidance=1.0):
-        """Scalar coefficients of one step, computed with the reference's fp32 torch expressions (:308-349)."""
+    def coefs(self, timestep, eta=0.0, guidance=1.0, cfg_pair=None):
+        """Scalar coefficients of one step, computed with the reference's fp32 torch expressions (:308-349).  ``cfg_pair``: whether
+        the model output holds the [uncond; cond] pair - the caller's own ``guidance_scale > 1.0`` decision on the Python double
+        (pipeline_animation.py:599), never re-derived from the fp32-rounded scale inside the kernel."""
+        cfg_pair = (guidance > 1.0) if cfg_pair is None else cfg_pair
         if self.num_inference_steps is None:
             raise ValueError("Number of inference steps is 'None', you need to run 'set_timesteps' after creating the scheduler")
         t = int(timestep)
@@ -88,7 +113,8 @@ class DDIMScheduler:
         std = eta * variance ** 0.5
         direction = (1 - a_prev - std ** 2) ** 0.5
         return L.DdimCoefs(float(guidance), float(a_t ** 0.5), float(b_t ** 0.5), float(a_prev ** 0.5), float(direction),
-                           float(variance ** 0.5 * eta), L.PRED[self.config.prediction_type], int(bool(self.config.clip_sample)))
+                           float(variance ** 0.5 * eta), L.PRED[self.config.prediction_type], int(bool(self.config.clip_sample)),
+                           int(bool(cfg_pair)))
 
     def _noise(self, shape, eta, generator, variance_noise, device):
         if eta <= 0:
@@ -113,14 +139,18 @@ class DDIMScheduler:
         prev = ops.cfg_ddim_step(m, x, c, noise=self._noise(x.shape, eta, generator, variance_noise, x.device))
         if not return_dict:
             return (prev,)
-        return DDIMSchedulerOutput(prev_sample=prev)
+        # pred_original_sample (:318-330), as the reference returns it: the same kernel with sqrt(alpha_prev) := 1 and the direction
+        # coefficient := 0 leaves exactly x0 (1 * x0 + 0 * eps).  Only this public step() pays for it; the pipeline's fused step_cfg does not.
+        c0 = L.DdimCoefs(c.guidance, c.sqrt_alpha_t, c.sqrt_beta_t, 1.0, 0.0, 0.0, c.prediction_type, c.clip_sample, c.cfg_pair)
+        return DDIMSchedulerOutput(prev_sample=prev, pred_original_sample=ops.cfg_ddim_step(m, x, c0))
 
     @torch.no_grad()
     def step_cfg(self, model_output_pair, timestep, sample, guidance_scale, eta=0.0, generator=None, variance_noise=None,
                  single_frame_output=None, video_scale=0.0):
         """CFG combine (pipeline_animation.py:763-764) fused with the step: model_output_pair = [uncond; cond].  With
         ``single_frame_output`` (the per-frame prediction, :738-755) the combine is the video_scale form of :757-761."""
-        c = self.coefs(timestep, eta, guidance_scale)
+        pair = model_output_pair.numel() == 2 * sample.numel()       # the caller's do_cfg decision, visible in the shapes it passes
+        c = self.coefs(timestep, eta, guidance_scale, cfg_pair=pair)
         return ops.cfg_ddim_step(model_output_pair, sample, c,
                                  noise=self._noise(sample.shape, eta, generator, variance_noise, sample.device),
                                  single=single_frame_output, video_scale=video_scale)

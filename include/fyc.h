@@ -184,11 +184,14 @@ int32_t fyc_nfhwc_to_ncfhw(const void* in, float* out, int64_t B, int64_t C, int
 int32_t fyc_build_unet_input(const float* latents, const float* mask, const float* first, void* out, int64_t b,
                              int64_t F, int64_t HW, int32_t dup, int32_t c_pad, int32_t dtype, void* stream);
 /* CFG combine + DDIMScheduler.step (pipeline_animation.py:763-764 + scheduling_ddim.py:308-349), fp32, exact
- * reference operation order (no FMA contraction).  pred: [2, n] (uncond, cond) when guidance > 1 else [1, n]. */
+ * reference operation order (no FMA contraction).  pred: [2, n] (uncond, cond) when c->cfg_pair else [1, n]. */
 typedef struct {
-  float guidance;                 /* <= 1: no CFG */
+  float guidance;                 /* CFG scale (read only when cfg_pair != 0) */
   float sqrt_alpha_t, sqrt_beta_t, sqrt_alpha_prev, dir_coef, noise_coef;
   int32_t prediction_type, clip_sample;
+  int32_t cfg_pair;               /* 1: pred holds [uncond; cond] (2n values) and n = u + guidance (c - u); 0: pred holds n values.  Set by the
+                                     host from ITS decision `guidance_scale > 1.0` (a Python double: pipeline_animation.py:599) - the kernel must
+                                     not re-derive it from the fp32-rounded `guidance`, which is 1.0f for every scale in (1, 1 + 2^-24] */
 } fyc_ddim_coefs;
 int32_t fyc_cfg_ddim_step(const float* pred, const float* sample, const float* noise, float* prev, int64_t n,
                           const fyc_ddim_coefs* c, void* stream);

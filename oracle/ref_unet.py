@@ -50,7 +50,7 @@ def timestep_sinusoid(t, dim, flip_sin_to_cos, freq_shift):
     """diffusers/models/embeddings.py:21-61 (scale=1, max_period=10000)."""
     half = dim // 2
     exponent = -math.log(10000) * torch.arange(half, dtype=torch.float32) / (half - freq_shift)
-    ang = t[:, None].float() * torch.exp(exponent)[None, :]
+    ang = t[:, None].float() * torch.exp(exponent)[None, :].to(t.device)      # table evaluated on the host like the reference
     emb = torch.cat([torch.sin(ang), torch.cos(ang)], dim=-1)
     if flip_sin_to_cos:
         emb = torch.cat([emb[:, half:], emb[:, :half]], dim=-1)
@@ -238,7 +238,7 @@ def unet3d_forward(sd, cfg, sample, timestep, encoder_hidden_states, fps_tensor=
     mmk = cfg["motion_module_kwargs"]
 
     def as_vec(v):
-        v = torch.as_tensor(v)
+        v = torch.as_tensor(v).to(sample.device)      # device-agnostic: the -m gpu full-size parity tests run this oracle on cuda (fp32, TF32 off)
         return (v[None] if v.dim() == 0 else v).expand(B)
 
     def sinus(v):

@@ -223,7 +223,7 @@ def cfg_ddim_step(pred, sample, coefs, noise=None, out=None, single=None, video_
         sg = single.reshape(-1)
         m = sg + video_scale * (p[:n] - sg) + c.guidance * (p[n:2 * n] - p[:n])
     else:
-        m = p[:n] + c.guidance * (p[n:2 * n] - p[:n]) if c.guidance > 1.0 else p[:n]
+        m = p[:n] + c.guidance * (p[n:2 * n] - p[:n]) if c.cfg_pair else p[:n]
     x = sample.reshape(-1)
     if c.prediction_type == _lib.PRED["epsilon"]:
         x0, eps = (x - c.sqrt_beta_t * m) / c.sqrt_alpha_t, m
