@@ -37,7 +37,8 @@ class AttnArgs(C.Structure):
     _fields_ = [("q", _vp), ("k", _vp), ("v", _vp), ("out", _vp), ("batch", _i64), ("heads", _i64), ("Lq", _i64),
                 ("Lk", _i64), ("D", _i64), ("ldq", _i64), ("ldk", _i64), ("ldv", _i64), ("ldo", _i64), ("bsq", _i64),
                 ("bsk", _i64), ("bsv", _i64), ("bso", _i64), ("kv_batch_div", _i64), ("scale", _f32),
-                ("out_alpha", _f32), ("accumulate", _i32), ("dtype", _i32), ("impl", _i32)]
+                ("out_alpha", _f32), ("accumulate", _i32), ("dtype", _i32), ("impl", _i32),
+                ("k2", _vp), ("v2", _vp), ("Lk2", _i64), ("ldk2", _i64), ("ldv2", _i64), ("bsk2", _i64), ("bsv2", _i64), ("alpha2", _f32)]
 
 
 class DdimCoefs(C.Structure):

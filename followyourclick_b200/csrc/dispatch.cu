@@ -74,10 +74,19 @@ extern "C" int32_t fyc_attention(const fyc_attention_args* a, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   FYC_CHECK(a && a->q && a->k && a->v && a->out, "attention: null pointer");
   FYC_CHECK(a->batch > 0 && a->heads > 0 && a->Lq > 0 && a->Lk > 0 && a->D > 0 && a->kv_batch_div >= 1, "attention: bad shape");
+  FYC_CHECK((a->k2 == nullptr) == (a->v2 == nullptr) && (!a->k2 || a->Lk2 > 0), "attention: second context needs k2, v2 and Lk2 > 0");
   if (a->impl == FYC_IMPL_TCGEN05) {
     FYC_CHECK(fyc_attention_mma_eligible(a), "attention: tensor-core path requested but shape not eligible");
     return fyc_attention_mma(a, st);
   }
   if (a->impl == FYC_IMPL_AUTO && fyc_attention_mma_eligible(a)) return fyc_attention_mma(a, st);
+  if (a->k2) {     // CUDA-core path (strict-fp32 mode): the two softmaxes as two passes of the same kernel, the second accumulating in fp32
+    fyc_attention_args p1 = *a, p2 = *a;
+    p1.k2 = p1.v2 = nullptr;
+    p2.k = a->k2; p2.v = a->v2; p2.Lk = a->Lk2; p2.ldk = a->ldk2; p2.ldv = a->ldv2; p2.bsk = a->bsk2; p2.bsv = a->bsv2;
+    p2.k2 = p2.v2 = nullptr; p2.out_alpha = a->alpha2; p2.accumulate = 1;
+    const int32_t rc = fyc_attention_simt(&p1, st);
+    return rc ? rc : fyc_attention_simt(&p2, st);
+  }
   return fyc_attention_simt(a, st);
 }

@@ -86,12 +86,14 @@ class IPAttnProcessor(nn.Module):
         .scale = d^-1/2).  hidden_states (B, L, C) or (B, C, H, W); encoder_hidden_states (B, 77+T, Dc)."""
         if attention_mask is not None:
             raise NotImplementedError("attention_mask is None on the whole inference path (SURVEY App. A.4)")
+        if getattr(attn, "spatial_norm", None) is not None or getattr(attn, "group_norm", None) is not None or getattr(attn, "norm_cross", False):
+            raise NotImplementedError("spatial_norm / group_norm / norm_cross are None / False for every SD-1.5 attention layer")
         ops.require_cuda(hidden_states, "IPAttnProcessor")
         nd = hidden_states.dim()
         x = hidden_states
         if nd == 4:
-            b, c, h, w = x.shape
-            x = x.view(b, c, h * w).transpose(1, 2)
+            b, c, h, wd = x.shape
+            x = x.view(b, c, h * wd).transpose(1, 2)
         dt = x.dtype if x.dtype in (torch.float32, torch.bfloat16) else torch.bfloat16
         x = x.to(dt).contiguous()
         B, Lq, C = x.shape
@@ -110,16 +112,23 @@ class IPAttnProcessor(nn.Module):
         Bc, L, Dc = ctx.shape
         k = ops.gemm(ctx.view(Bc * L, Dc), w(attn.to_k)).view(Bc, L, C)
         v = ops.gemm(ctx.view(Bc * L, Dc), w(attn.to_v)).view(Bc, L, C)
-        o = ops.attention(q, k, v, heads, sc)
-        if ip is not None:
+        if ip is not None:           # the fused two-context kernel: text softmax + scale * image softmax, one launch, one write
             T = ip.shape[1]
             ki = ops.gemm(ip.view(Bc * T, Dc), w(self.to_k_ip)).view(Bc, T, C)
             vi = ops.gemm(ip.view(Bc * T, Dc), w(self.to_v_ip)).view(Bc, T, C)
-            ops.attention(q, ki, vi, heads, sc, out=o, out_alpha=float(self.scale), accumulate=True)
+            o = ops.attention(q, k, v, heads, sc, k2=ki, v2=vi, alpha2=float(self.scale))
+        else:
+            o = ops.attention(q, k, v, heads, sc)
         out_lin = attn.to_out[0]
-        y = ops.gemm(o.view(B * Lq, C), w(out_lin), bias=f(out_lin.bias) if out_lin.bias is not None else None).view(B, Lq, C)
+        # residual_connection / rescale_output_factor of the modern diffusers Attention (attention_processor.py:177-180); SD-1.5 cross
+        # attention has residual_connection False and factor 1
+        resid = x.view(B * Lq, C) if getattr(attn, "residual_connection", False) else None
+        rescale = float(getattr(attn, "rescale_output_factor", 1.0))
+        if rescale != 1.0:
+            raise NotImplementedError("rescale_output_factor != 1 is outside the SD-1.5 / IP-Adapter inference path")
+        y = ops.gemm(o.view(B * Lq, C), w(out_lin), bias=f(out_lin.bias) if out_lin.bias is not None else None, residual=resid).view(B, Lq, C)
         if nd == 4:
-            y = y.transpose(1, 2).reshape(b, c, h, w)
+            y = y.transpose(1, 2).reshape(b, c, h, wd)
         return y.to(hidden_states.dtype)
 
 

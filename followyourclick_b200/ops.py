@@ -220,10 +220,11 @@ def layernorm(x, gamma, beta, eps=1e-5, pe=None, rows_per_frame=0, frames=0):
     return out
 
 
-def attention(q, k, v, heads, scale, out=None, out_alpha=1.0, accumulate=False, kv_batch_div=1, impl=None):
+def attention(q, k, v, heads, scale, out=None, out_alpha=1.0, accumulate=False, kv_batch_div=1, impl=None, k2=None, v2=None, alpha2=1.0):
     """q [B, Lq, >=heads*D] / k, v [B', Lk, ...] are (possibly strided) views; head h occupies columns [h*D, (h+1)*D).
-    Returns out [B, Lq, heads*D].  B' = B / kv_batch_div."""
-    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+    Returns out [B, Lq, heads*D].  B' = B / kv_batch_div.  With ``k2`` / ``v2`` [B', Lk2, ...] (the IP-Adapter's image keys):
+    out = out_alpha * softmax(scale q k^T) v + alpha2 * softmax(scale q k2^T) v2 in ONE launch (fyc.h: second context)."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v"), (k2, "k2"), (v2, "v2")):
         _cuda(t, "attention." + n)
     B, Lq, _ = q.shape
     Lk = k.shape[1]
@@ -234,8 +235,15 @@ def attention(q, k, v, heads, scale, out=None, out_alpha=1.0, accumulate=False, 
     D = out.shape[2] // heads
     a = L.AttnArgs(ptr(q), ptr(k), ptr(v), ptr(out), B, heads, Lq, Lk, D, q.stride(1), k.stride(1), v.stride(1),
                    out.stride(1), q.stride(0), k.stride(0), v.stride(0), out.stride(0), kv_batch_div, float(scale),
-                   float(out_alpha), int(accumulate), dtype_code(q.dtype), _impl if impl is None else impl)
-    with _rec(f"attention[{B}x{heads}x{Lq}x{Lk}x{D}]" if _prof_shapes else "attention", 4.0 * B * heads * Lq * Lk * D, q.element_size() * (2 * B * Lq * heads * D + 2 * (B // kv_batch_div) * Lk * heads * D)):
+                   float(out_alpha), int(accumulate), dtype_code(q.dtype), _impl if impl is None else impl,
+                   ptr(k2), ptr(v2), 0, 0, 0, 0, 0, float(alpha2))
+    Lk2 = 0
+    if k2 is not None:
+        assert v2 is not None and k2.shape[0] == k.shape[0] and v2.shape[:2] == k2.shape[:2]
+        Lk2 = k2.shape[1]
+        a.Lk2, a.ldk2, a.ldv2, a.bsk2, a.bsv2 = Lk2, k2.stride(1), v2.stride(1), k2.stride(0), v2.stride(0)
+    with _rec(f"attention[{B}x{heads}x{Lq}x{Lk}{'+' + str(Lk2) if Lk2 else ''}x{D}]" if _prof_shapes else "attention", 4.0 * B * heads * Lq * (Lk + Lk2) * D,
+              q.element_size() * (2 * B * Lq * heads * D + 2 * (B // kv_batch_div) * (Lk + Lk2) * heads * D)):
         check(lib().fyc_attention(C.byref(a), stream_ptr()))
     return out
 

@@ -411,10 +411,11 @@ class UNet3DConditionModel(ParamTreeModel):
                 T = self._cfg["num_tokens"]
                 # reference quirk (animatediff/models/attention.py:43): without xformers the IP scale replaces d^-1/2
                 sc = d ** -0.5 if self._xformers_semantics else float(self._cfg["scale"])
-                ops.attention(qx, kv_r[:, :L - T, :C], kv_r[:, :L - T, C:], heads, sc, out=o_r, kv_batch_div=F)
                 kvi = ctx.kvi[p][r * Bq:(r + 1) * Bq]
-                ops.attention(qx, kvi[:, L - T:, :C], kvi[:, L - T:, C:], heads, sc, out=o_r, out_alpha=float(self._cfg["scale"]),
-                              accumulate=True, kv_batch_div=F)
+                # ONE launch: text keys [:, :-T] and image keys [:, -T:] staged together, two softmaxes over the same query
+                # fragments, o_text + scale * o_ip written once (attention.py:92-120)
+                ops.attention(qx, kv_r[:, :L - T, :C], kv_r[:, :L - T, C:], heads, sc, out=o_r, kv_batch_div=F,
+                              k2=kvi[:, L - T:, :C], v2=kvi[:, L - T:, C:], alpha2=float(self._cfg["scale"]))
             else:
                 ops.attention(qx, kv_r[:, :, :C], kv_r[:, :, C:], heads, d ** -0.5, out=o_r, kv_batch_div=F)
         w_o, b_o = self._w(q + ".attn2.to_out.0.weight"), self._f(q + ".attn2.to_out.0.bias")

@@ -123,7 +123,7 @@ int32_t fyc_layernorm(const void* x, const float* gamma, const float* beta, void
  * out[n, i, h*D + :] (=|+=) out_alpha * softmax_j(scale * q[n,i,h] . k[n',j,h]) v[n',j,h],  n' = n / kv_batch_div.
  * Replaces CrossAttention._attention (diffusers/models/attention.py:649-678) for attn1/attn2 and the two
  * softmaxes of IPCrossAttention.forward (animatediff/models/attention.py:98-120; second call with
- * accumulate=1, out_alpha = ip scale).  Never materialises the score matrix.
+ * accumulate=1, out_alpha = ip scale - or both at once through k2 / v2 / alpha2).  Never materialises the score matrix.
  */
 typedef struct {
   const void* q; const void* k; const void* v; void* out;
@@ -133,6 +133,14 @@ typedef struct {
   int64_t kv_batch_div;                  /* >= 1: context shared by F consecutive images (attention.py:264) */
   float scale, out_alpha;
   int32_t accumulate, dtype, impl;
+  /* optional SECOND context, fused (NULL: none): out = out_alpha * softmax(scale q k^T) v + alpha2 * softmax(scale q k2^T) v2, written once.
+     The IP-Adapter cross-attention - text keys [:, :-T] and image keys [:, -T:] with their own to_k_ip / to_v_ip projections, two
+     softmaxes, `hidden_states + self.scale * ip_hidden_states` (animatediff/models/attention.py:92-120,
+     ip_adapter/attention_processor.py:137-168) - as ONE kernel instead of two attention passes and an add.  Same batch / heads / D /
+     kv_batch_div as the first context. */
+  const void* k2; const void* v2;
+  int64_t Lk2, ldk2, ldv2, bsk2, bsv2;
+  float alpha2;
 } fyc_attention_args;
 int32_t fyc_attention(const fyc_attention_args* a, void* stream);
 

@@ -99,3 +99,55 @@ def pipeline_variant_inputs(variant):
         okw = dict(camera_movement_type=torch.tensor([3]))
         return ci, kw, okw, SCHED_EPS, 2, 7.5
     raise KeyError(variant)
+
+
+# IPAttnProcessor cases (tests/golden/ip_attn_processor.npz holds only the reference processor's OUTPUTS; weights and inputs are
+# regenerated from the case name, so the fixture stays small): name -> (C, heads, T image tokens, 4-D input spatial shape | None, residual)
+IP_ATTN_CASES = {"tok_t4": (160, 4, 4, None, False), "img_t16": (320, 4, 16, (8, 8), False), "res_t4": (160, 2, 4, None, True)}
+IP_ATTN_SCALE = 0.7
+
+
+def ip_attn_case(name, xd=768, B=2, L=64):
+    import zlib
+    C, heads, T, shape4d, residual = IP_ATTN_CASES[name]
+    g = torch.Generator().manual_seed(zlib.crc32(name.encode()) & 0x7FFFFFFF)
+    rn = lambda *s_, sc=1.0: torch.randn(*s_, generator=g) * sc
+    w = dict(to_q=rn(C, C, sc=C ** -0.5), to_k=rn(C, xd, sc=xd ** -0.5), to_v=rn(C, xd, sc=xd ** -0.5), to_out_w=rn(C, C, sc=C ** -0.5),
+             to_out_b=rn(C, sc=0.05), to_k_ip=rn(C, xd, sc=xd ** -0.5), to_v_ip=rn(C, xd, sc=xd ** -0.5))
+    x = rn(B, C, *shape4d) if shape4d else rn(B, L, C)
+    ctx = rn(B, 77 + T, xd)
+    return dict(C=C, heads=heads, T=T, shape4d=shape4d, residual=residual, xd=xd, w=w, x=x, ctx=ctx)
+
+
+class DuckAttention(torch.nn.Module):
+    """What an IP-Adapter attention processor is handed: the ``Attention`` module of modern pip diffusers (>= 0.19; NOT the vendored
+    0.11.1 CrossAttention, and absent from /root/reference), restated from its published helpers in plain torch.  Used to drive the
+    UNMODIFIED reference processor when the fixture is generated and to drive the engine's processor in the tests."""
+
+    def __init__(self, case):
+        super().__init__()
+        C, xd, w = case["C"], case["xd"], case["w"]
+        self.heads, self.scale = case["heads"], (C // case["heads"]) ** -0.5
+        self.to_q, self.to_k, self.to_v = torch.nn.Linear(C, C, bias=False), torch.nn.Linear(xd, C, bias=False), torch.nn.Linear(xd, C, bias=False)
+        self.to_out = torch.nn.ModuleList([torch.nn.Linear(C, C), torch.nn.Dropout(0.0)])
+        self.spatial_norm = self.group_norm = None
+        self.norm_cross, self.residual_connection, self.rescale_output_factor = False, case["residual"], 1.0
+        with torch.no_grad():
+            self.to_q.weight.copy_(w["to_q"]); self.to_k.weight.copy_(w["to_k"]); self.to_v.weight.copy_(w["to_v"])
+            self.to_out[0].weight.copy_(w["to_out_w"]); self.to_out[0].bias.copy_(w["to_out_b"])
+
+    def prepare_attention_mask(self, mask, target_length, batch_size):
+        return mask
+
+    def head_to_batch_dim(self, t):
+        b, L, c = t.shape
+        return t.reshape(b, L, self.heads, c // self.heads).permute(0, 2, 1, 3).reshape(b * self.heads, L, c // self.heads)
+
+    def batch_to_head_dim(self, t):
+        bh, L, d = t.shape
+        return t.reshape(bh // self.heads, self.heads, L, d).permute(0, 2, 1, 3).reshape(bh // self.heads, L, d * self.heads)
+
+    def get_attention_scores(self, q, k, mask=None):
+        assert mask is None
+        return torch.baddbmm(torch.empty(q.shape[0], q.shape[1], k.shape[1], device=q.device, dtype=q.dtype), q, k.transpose(-1, -2),
+                             beta=0, alpha=self.scale).softmax(dim=-1)

@@ -259,3 +259,25 @@ def run_pipeline_variant_case(variant, dtype, device="cuda", graph=True):
     s = stats(video, ref)
     mse = float(((video.float() - ref) ** 2).mean())
     return dict(video_maxabs=s["maxabs"], psnr=float(10 * np.log10(1.0 / max(mse, 1e-20))), finite=s["finite"], shape=tuple(video.shape))
+
+
+def run_ip_attn_processor_case(name, dtype, device="cuda"):
+    """followyourclick_b200.ip_adapter.IPAttnProcessor (the north star's named call surface) against the output of the
+    UNMODIFIED reference processor (tests/golden/ip_attn_processor.npz, ip_adapter/attention_processor.py:80-183) on the same duck-typed
+    ``attn`` module, weights and inputs."""
+    from followyourclick_b200.ip_adapter import IPAttnProcessor
+    from tests.cfgs import IP_ATTN_SCALE, DuckAttention, ip_attn_case
+    c = ip_attn_case(name)
+    attn = DuckAttention(c).to(device)
+    proc = IPAttnProcessor(hidden_size=c["C"], cross_attention_dim=c["xd"], scale=IP_ATTN_SCALE, num_tokens=c["T"]).to(device)
+    with torch.no_grad():
+        proc.to_k_ip.weight.copy_(c["w"]["to_k_ip"]); proc.to_v_ip.weight.copy_(c["w"]["to_v_ip"])
+    assert sorted(proc.state_dict()) == ["to_k_ip.weight", "to_v_ip.weight"]           # the adapter checkpoint's key names
+    y = proc(attn, c["x"].to(device=device, dtype=dtype), encoder_hidden_states=c["ctx"].to(device=device, dtype=dtype))
+    _sync(device)
+    ref = torch.from_numpy(golden("ip_attn_processor.npz")[name])
+    assert y.shape == ref.shape and y.dtype == dtype
+    last = y.float().cpu()
+    if c["shape4d"]:                       # channel-last for the per-row statistics
+        last, ref = last.permute(0, 2, 3, 1), ref.permute(0, 2, 3, 1)
+    return stats(last, ref)

@@ -229,6 +229,43 @@ def pipeline_variant_fixture(UNet, Pipe, VAE, DDIM, ImageProjModel, variant):
     return err
 
 
+def ip_attn_processor_fixture():
+    """the reference's ``IPAttnProcessor.__call__`` (ip_adapter/attention_processor.py:80-183), loaded from its
+    file (ip_adapter/__init__.py pulls modern-diffusers pipelines) and driven with a duck-typed ``attn`` (tests/cfgs.DuckAttention:
+    the helpers of the modern pip-diffusers ``Attention`` class the processor targets, absent from /root/reference).  Cases
+    (tests/cfgs.IP_ATTN_CASES): 3-D tokens with T = 4, 4-D (b, c, h, w) input with T = 16, residual_connection=True.  Only the
+    reference outputs are stored; the oracle's two-softmax formula is checked against them here."""
+    import importlib.util
+    from tests.cfgs import IP_ATTN_CASES, IP_ATTN_SCALE, DuckAttention, ip_attn_case
+    spec = importlib.util.spec_from_file_location("_ref_attention_processor", REF + "/ip_adapter/attention_processor.py")
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    out, worst = {}, 0.0
+    for name in IP_ATTN_CASES:
+        c = ip_attn_case(name)
+        C, heads, T, w, x, ctx = c["C"], c["heads"], c["T"], c["w"], c["x"], c["ctx"]
+        attn = DuckAttention(c)
+        proc = mod.IPAttnProcessor(hidden_size=C, cross_attention_dim=c["xd"], scale=IP_ATTN_SCALE, num_tokens=T)
+        with torch.no_grad():
+            proc.to_k_ip.weight.copy_(w["to_k_ip"]); proc.to_v_ip.weight.copy_(w["to_v_ip"])
+            y = proc(attn, x, encoder_hidden_states=ctx)
+            tok = x.reshape(x.shape[0], C, -1).transpose(1, 2) if c["shape4d"] else x
+            q = tok @ w["to_q"].t()
+            o = ref_unet.mha(q, ctx[:, :-T] @ w["to_k"].t(), ctx[:, :-T] @ w["to_v"].t(), heads) \
+                + IP_ATTN_SCALE * ref_unet.mha(q, ctx[:, -T:] @ w["to_k_ip"].t(), ctx[:, -T:] @ w["to_v_ip"].t(), heads)
+            yo = o @ w["to_out_w"].t() + w["to_out_b"]
+            if c["residual"]:
+                yo = yo + tok
+            if c["shape4d"]:
+                yo = yo.transpose(1, 2).reshape(x.shape)
+        worst = max(worst, maxabs(y, yo))
+        out[name] = y.numpy()
+    print(f"IPAttnProcessor fixture: oracle-vs-ref maxabs={worst:.3e}")
+    assert worst < 2e-5
+    np.savez_compressed(os.path.join(HERE, "ip_attn_processor.npz"), **out)
+    return worst
+
+
 def unet_ragged_fixture(UNet):
     """The unmodified reference UNet on a non-square, non-power-of-two latent grid with an odd frame count and batch 1 (320 x 192
     image, 3 frames): pins the oracle (and through it the engine's tile-picker fallbacks) away from the 16 x 16 x 4 fixture shape."""
@@ -261,6 +298,12 @@ def main():
         d = json.load(open(pj))
         for v in ("ip", "cam"):
             d["oracle_vs_reference_maxabs"][f"pipeline_{v}"] = pipeline_variant_fixture(UNet, Pipe, VAE, DDIM, ImageProjModel, v)
+        json.dump(d, open(pj, "w"), indent=1)
+        return
+    if "--only-ip-attn-processor" in sys.argv:
+        pj = os.path.join(HERE, "pins.json")
+        d = json.load(open(pj))
+        d["oracle_vs_reference_maxabs"]["ip_attn_processor"] = ip_attn_processor_fixture()
         json.dump(d, open(pj, "w"), indent=1)
         return
     if "--only-unet2d" in sys.argv:
@@ -426,6 +469,7 @@ def main():
     pins["resampler"] = resampler_fixture()
     pins["unet2d"] = unet2d_fixture()
     pins["unet_base_ragged"] = unet_ragged_fixture(UNet)
+    pins["ip_attn_processor"] = ip_attn_processor_fixture()
     for v in ("ip", "cam"):
         pins[f"pipeline_{v}"] = pipeline_variant_fixture(UNet, Pipe, VAE, DDIM, ImageProjModel, v)
     pins["pipeline_video_scale"] = video_scale_fixture(UNet, Pipe, VAE, DDIM)

@@ -122,13 +122,16 @@ def _mha(q, k, v, heads, D, scale, kv_batch_div):
     return (p @ vh).transpose(1, 2).reshape(B, Lq, heads * D)
 
 
-def attention(q, k, v, heads, scale, out=None, out_alpha=1.0, accumulate=False, kv_batch_div=1, impl=None):
+def attention(q, k, v, heads, scale, out=None, out_alpha=1.0, accumulate=False, kv_batch_div=1, impl=None, k2=None, v2=None, alpha2=1.0):
+    def both(D):        # fyc.h second context: out_alpha * softmax(q k^T) v + alpha2 * softmax(q k2^T) v2
+        y = out_alpha * _mha(q, k, v, heads, D, scale, kv_batch_div)
+        return y if k2 is None else y + alpha2 * _mha(q, k2, v2, heads, D, scale, kv_batch_div)
     if out is None:
         assert not accumulate and q.shape[2] % heads == 0
         D = q.shape[2] // heads
-        return _store(out_alpha * _mha(q, k, v, heads, D, scale, kv_batch_div), q.dtype)
+        return _store(both(D), q.dtype)
     D = out.shape[2] // heads
-    y = out_alpha * _mha(q, k, v, heads, D, scale, kv_batch_div)
+    y = both(D)
     out.copy_(_store((out.float() + y) if accumulate else y, out.dtype))
     return out
 

@@ -226,3 +226,14 @@ def test_unet_ragged_shapes_vs_oracle(dtype, tol, b, f, h, w):
     from tests.engine_helpers import run_unet_ragged_case
     s = run_unet_ragged_case(dtype, b=b, f=f, h=h, w=w)
     assert s["finite"] and s["rel_l2"] < tol, s
+
+
+@pytest.mark.parametrize("case", ["tok_t4", "img_t16", "res_t4"])
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 1.5e-2)])
+def test_ip_attn_processor_matches_reference_processor(cuda, case, dtype, tol):
+    """IPAttnProcessor(attn, hidden_states, encoder_hidden_states) - named in BASELINE.json's north_star - against the unmodified
+    reference processor's output: 3-D and 4-D inputs, T = 4 / 16 image tokens, residual_connection; the bf16 call runs the fused
+    two-context tensor-core kernel, the fp32 call the CUDA-core path."""
+    from tests.engine_helpers import run_ip_attn_processor_case
+    s = run_ip_attn_processor_case(case, dtype)
+    assert s["finite"] and s["rel_l2"] < tol and s["maxabs"] < (1e-4 if dtype == torch.float32 else 2 ** -6 * s["ref_max"]), s

@@ -256,3 +256,12 @@ def test_shared_cfg_prefix_with_two_clips():
     shared = unet.forward_nfhwc(x2, inp["timestep"], ctx4, cfg_dup=2, **kw)
     s = stats(shared, full)
     assert shared.shape == full.shape == (4, 4, 16, 16, 4) and s["rel_l2"] < 1e-6, s
+
+
+@pytest.mark.parametrize("case", ["tok_t4", "img_t16", "res_t4"])
+def test_ip_attn_processor_host_logic_vs_reference_processor(case):
+    """host side of IPAttnProcessor (token split [:, :-T] / [:, -T:], 4-D <-> token reshapes, residual_connection, the fused
+    second-context call) against the unmodified reference processor's fixture, kernels emulated"""
+    from tests.engine_helpers import run_ip_attn_processor_case
+    s = run_ip_attn_processor_case(case, torch.float32, device="cpu")
+    assert s["finite"] and s["rel_l2"] < 1e-5, s

@@ -342,6 +342,32 @@ def test_attention_short_context_persistent_kernel(cuda, heads, D, Lq, Lk, div, 
     assert rel(outs["1"], ref) < tol(dtype) * 1.5, rel(outs["1"], ref)
 
 
+@pytest.mark.parametrize("dtype,impl", MODES)
+@pytest.mark.parametrize("heads,D,Lq,Lk,T,div", [(8, 40, 4096, 77, 16, 2), (8, 40, 1024, 77, 4, 4), (8, 80, 1024, 77, 16, 2), (4, 80, 100, 77, 4, 1),
+                                                 (8, 160, 256, 77, 16, 2), (2, 160, 64, 77, 4, 1), (4, 40, 70, 64, 64, 1), (4, 40, 200, 150, 4, 2)])
+def test_attention_fused_ip_second_context(dtype, impl, heads, D, Lq, Lk, T, div):
+    """The IP-Adapter cross-attention as ONE launch (fyc.h second context): out = softmax(s q K_t^T) V_t + alpha2 softmax(s q K_i^T) V_i
+    (animatediff/models/attention.py:92-120, ip_adapter/attention_processor.py:137-168) against the fp32 two-softmax reference and
+    against the two-launch accumulate form it replaces.  Head dims of all UNet levels, T = 4 (vanilla) / 16 (plus), ragged Lq, shared
+    contexts, a context that is too long for the resident kernel (150 keys: the dispatcher's two-pass route)."""
+    from followyourclick_b200 import ops
+    ops.set_impl(impl)
+    B, C = 4, heads * D
+    q = rnd((B, Lq, C), 1, dtype)
+    kv, kvi = rnd((B // div, Lk + T, 2 * C), 2, dtype), rnd((B // div, Lk + T, 2 * C), 3, dtype)
+    scale, a2 = D ** -0.5, 0.6
+    k, v, k2, v2 = kv[:, :Lk, :C], kv[:, :Lk, C:], kvi[:, Lk:, :C], kvi[:, Lk:, C:]         # strided views, like the UNet's ClipContext
+    out = ops.attention(q, k, v, heads, scale, kv_batch_div=div, k2=k2, v2=v2, alpha2=a2)
+    rep = lambda t: t.repeat_interleave(div, 0)
+    ref = _mha_ref(q, rep(k), rep(v), heads, scale) + a2 * _mha_ref(q, rep(k2), rep(v2), heads, scale)
+    e = (out.float() - ref)
+    assert rel(out, ref) < tol(dtype), rel(out, ref)
+    assert float(e.abs().max()) < (1e-4 if dtype == torch.float32 else 2 ** -6 * float(ref.abs().max())), float(e.abs().max())
+    two = ops.attention(q, k, v, heads, scale, kv_batch_div=div)
+    ops.attention(q, k2, v2, heads, scale, out=two, out_alpha=a2, accumulate=True, kv_batch_div=div)
+    assert rel(out, two) < (1e-6 if dtype == torch.float32 else 4e-3), rel(out, two)
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("B,Fr,HW,heads,D", [(2, 4, 64, 4, 40), (2, 16, 16, 8, 40), (1, 8, 16, 4, 80), (2, 16, 4, 8, 160), (1, 24, 9, 2, 40),
                                              (1, 32, 4, 4, 160)])
