@@ -204,6 +204,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     // ================================================================== MMA issuer
     if (lane == 0) {
       const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BKV >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
+      const int kq = (p.D + 15) >> 4;      // k-steps of QK^T that hold data: q / k columns D..63 are zero, a 16-column step of zeros is skipped (D = 40: 3 of 4)
       const uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(DV >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
       const uint64_t q_desc = sw128_desc(smem_u32(smem));
       auto issue_s = [&](int j) {
@@ -213,7 +214,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
         tc_fence_after();
         const uint64_t k_desc = sw128_desc(smem_u32(smem + OFF_K + b * K_BYTES));
 #pragma unroll
-        for (int kk = 0; kk < DPAD / 16; ++kk)
+        for (int kk = 0; kk < kq; ++kk)
           umma(tmem_base + (b ? TM_S1 : TM_S0), q_desc + 2 * kk, k_desc + 2 * kk, idesc_s, kk > 0 ? 1u : 0u);
         tc_commit(&k_empty[b]);
         tc_commit(&s_full[b]);
@@ -415,6 +416,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     // ================================================================== MMA issuer
     if (lane == 0) {
       const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BKV >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
+      const int kq = (p.D + 15) >> 4;      // k-steps of QK^T that hold data: q / k columns D..63 are zero, a 16-column step of zeros is skipped (D = 40: 3 of 4)
       const uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(DV >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
       auto issue_s = [&](int j) {           // S_g(j) = Q_g K_j^T for both groups
         const int st = j & 1; const uint32_t ph = (j >> 1) & 1;
@@ -426,7 +428,7 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
           tc_fence_after();
           const uint64_t q_desc = sw128_desc(smem_u32(smem + g * Q_BYTES));
 #pragma unroll
-          for (int kk = 0; kk < DPAD / 16; ++kk)
+          for (int kk = 0; kk < kq; ++kk)
             umma(tmem_base + G2_TM_S + g * 128, q_desc + 2 * kk, k_desc + 2 * kk, idesc_s, kk > 0 ? 1u : 0u);
           tc_commit(&s_full[g]);
         }

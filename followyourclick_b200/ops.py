@@ -16,14 +16,27 @@ _impl = L.IMPL_AUTO
 L_SIMT = L.IMPL_SIMT
 _prof_shapes = False   # per-shape family names in the profile (diagnostics)
 _prof = None      # list of (family, algorithmic_flops, algorithmic_bytes, start_event, end_event) while profiling
+_pad_flops = 0.0  # FLOPs of the last profile that multiplied zero padding (q/k heads 40 -> 64, 9 -> 16 channel stem, 4 -> 16 channel head)
+
+
+def note_padding(flops):
+    """called by the models where they hand a zero-padded operand to a tensor-core kernel: bench.py reports executed and useful FLOPs"""
+    global _pad_flops
+    if _prof is not None:
+        _pad_flops += float(flops)
+
+
+def padded_flops():
+    return _pad_flops
 
 
 class profile:
     """Context manager: record a CUDA-event pair around every C-ABI call (bench.py's live per-kernel timing)."""
 
     def __enter__(self):
-        global _prof
+        global _prof, _pad_flops
         _prof = []
+        _pad_flops = 0.0
         self.records = _prof
         return self
 

@@ -135,6 +135,7 @@ class AnimationPipeline:
     _optional_components = []
     use_cuda_graph = True          # replay one captured UNet forward per DDIM step (set False to launch kernel by kernel)
     hoist_context = True           # build the step-invariant conditioning (ClipContext) once per clip instead of once per step
+    last_video_device = None       # the most recent decode's (b, 3, F, H, W) fp32 video, still on the device
     graph_cache_entries = 4        # captured UNet-step graphs kept per pipeline (least recently used shapes are dropped)
     # Shared CFG prefix (UNet3DConditionModel.forward_nfhwc cfg_dup): the uncond / cond halves of the reference's batch are identical
     # until the first cross-attention, so that prefix (incl. the first 64x64 self-attention) is computed once.  Exact, and verified
@@ -259,7 +260,8 @@ class AnimationPipeline:
         b, c, f, h, w = latents.shape
         z = ops.ncfhw_to_nfhwc(latents.to(torch.float32).contiguous(), self.vae.dtype, scale=1 / 0.18215).view(b * f, h, w, c)
         frames = self.vae.decode_nhwc(z)
-        return ops.frames_finalize(frames, b, f)
+        self.last_video_device = ops.frames_finalize(frames, b, f)      # kept for callers that continue on the device (gather, uint8 grid, GIF)
+        return self.last_video_device
 
     def decode_latents(self, latents):
         """pipeline_animation.py:400-413: returns a numpy array (b, 3, F, H, W) fp32 (device -> host boundary)."""

@@ -391,6 +391,7 @@ class UNet3DConditionModel(ParamTreeModel):
         if ops.self_attention_tc_ok(tok.dtype, HW, d):
             # tcgen05 path: q/k heads zero-padded to 64 columns by the packed weight, V transposed per image (keys contiguous)
             qkv = ops.gemm(n1, self._qkv_padded(q + ".attn1", heads, d)).view(NB, HW, 2 * heads * 64 + C)
+            ops.note_padding(2.0 * M * C * 2 * heads * (64 - d))
             vt = ops.transpose_tokens(qkv, 2 * heads * 64, C)
             o = ops.self_attention_tc(qkv, 0, heads * 64, vt, heads, d, d ** -0.5)
         else:
@@ -579,6 +580,7 @@ class UNet3DConditionModel(ParamTreeModel):
                 wp = torch.zeros(w.shape[:-1] + (c,), dtype=w.dtype, device=w.device)
                 wp[..., :w.shape[-1]] = w
                 return wp
+            ops.note_padding(2.0 * x.shape[0] * H * W * 9 * (Cin - w_in.shape[-1]) * w_in.shape[0])
             w_in = self._cached(("cin_pad", Cin, bool(use_first_frame_condition_concat)), pad)
         x = ops.conv3x3(x, w_in, bias=b_in)
         self._tap("conv_in", x)
@@ -629,6 +631,7 @@ class UNet3DConditionModel(ParamTreeModel):
         x = self._gn("conv_norm_out", x, B, True, False)
         w_out, b_out, cout = self._conv_head("conv_out", x.shape[0] * H * W)
         y = ops.conv3x3(x, w_out, bias=b_out, out_f32=True)
+        ops.note_padding(2.0 * x.shape[0] * H * W * 9 * x.shape[-1] * (w_out.shape[0] - cout))
         return y.view(B, F, H, W, -1)[..., :cout]          # a channel slice of the (possibly 16-wide) head output
 
     @torch.no_grad()

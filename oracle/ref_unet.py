@@ -86,9 +86,20 @@ def layer_norm(sd, p, x):
     return F.layer_norm(x, (x.shape[-1],), sd[p + ".weight"], sd[p + ".bias"], 1e-5)
 
 
+MHA_BATCH_CHUNK = None      # bench.py's CPU leg sets this: evaluate the batch entries in chunks (rows are independent, so the result is
+                            # the same arithmetic) - the reference materialises (B*heads, Lq, Lk) scores, 17 GB at the cfg2 level-0 shape
+
+
 def mha(q, k, v, heads, scale=None):
     """diffusers/models/attention.py:649-678 (== mm_attn_cross.py:148-177): softmax(q k^T * scale) v
     per head, heads packed along the channel axis; scale defaults to d^-1/2 (attention.py:544)."""
+    if MHA_BATCH_CHUNK and q.shape[0] > MHA_BATCH_CHUNK:
+        n = MHA_BATCH_CHUNK
+        return torch.cat([_mha(q[i:i + n], k[i:i + n], v[i:i + n], heads, scale) for i in range(0, q.shape[0], n)])
+    return _mha(q, k, v, heads, scale)
+
+
+def _mha(q, k, v, heads, scale=None):
     B, Lq, C = q.shape
     d = C // heads
     scale = d ** -0.5 if scale is None else scale

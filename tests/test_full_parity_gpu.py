@@ -181,6 +181,23 @@ def test_unet_forward_full_width(strict_torch, cfg, F, h, w, dtype):
         assert worst[0] <= TOL["unet_bf16_tap"], worst
 
 
+def test_shared_cfg_prefix_full_size(strict_torch):
+    """cfg_dup = 2 (one copy of the clip until the first cross-attention) against the duplicated CFG batch at the cfg2 shape, bf16:
+    the same kernels on the same rows - equal up to the tile-shape dependent accumulation order of the M-halved launches."""
+    from followyourclick_b200 import ops
+    dev = strict_torch
+    unet, _ = full_models(dev)
+    unet.to(torch.bfloat16)
+    inp = unet_case_inputs(16, 64, 64, dev)
+    x1 = ops.ncfhw_to_nfhwc(inp["sample"][:1].contiguous(), torch.bfloat16)
+    kw = dict(fps_tensor=inp["fps"], flow_control=inp["flow"], use_fps_condition=True)
+    full = unet.forward_nfhwc(torch.cat([x1, x1]), inp["t"], inp["ctx"], **kw)
+    shared = unet.forward_nfhwc(x1, inp["t"], inp["ctx"], cfg_dup=2, **kw)
+    e = err(shared.float().cpu(), full.float().cpu())
+    record("shared_cfg_prefix/cfg2/bf16_vs_duplicated_batch", e)
+    assert e["finite"] and e["rel_l2"] < 5e-3, e
+
+
 # ------------------------------------------------------------------------------------------------ (b) VAE decode, 16 frames 512x512
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_vae_decode_16_frames_512(strict_torch, dtype):

@@ -17,8 +17,6 @@ def _impl(cuda):
     ops.set_impl("auto")
 
 
-@pytest.mark.skipif(__import__("os").environ.get("FYC_SHARED_PREFIX") != "1",
-                    reason="shared CFG prefix is opt-in until it has had a GPU run (set FYC_SHARED_PREFIX=1)")
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_shared_cfg_prefix_on_gpu(dtype):
     """cfg_dup=2 on one copy of the input vs the duplicated batch (expected bit-identical: same kernels, row-independent), and the
@@ -36,11 +34,12 @@ def test_shared_cfg_prefix_on_gpu(dtype):
     shared = unet.forward_nfhwc(x1, inp["timestep"], kw["encoder_hidden_states"], cfg_dup=2, **nf)
     s = stats(shared, full)
     assert s["rel_l2"] < (1e-6 if dtype == torch.float32 else 2e-3), s
+    old = AnimationPipeline.share_cfg_prefix
     AnimationPipeline.share_cfg_prefix = True
     try:
         r = run_pipeline_case(dtype, steps=3, against="golden")
     finally:
-        AnimationPipeline.share_cfg_prefix = False
+        AnimationPipeline.share_cfg_prefix = old
     assert r["finite"] and (r["video_maxabs"] < 2e-3 if dtype == torch.float32 else r["psnr"] > 30.0), r
 
 
