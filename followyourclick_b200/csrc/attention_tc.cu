@@ -567,6 +567,228 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   }
 }
 
+// Four query tiles per CTA, 64-key tiles: 512 query rows, FOUR softmax warpgroups (16 warps: group g = rows 128 g .. 128 g + 127), so that
+// every scheduler holds four softmax warps instead of two.  ncu on attention_tc2 (profiles/round1_attention_tc2_full.md): the exponent
+// loop runs at 51 % issue utilisation with two warps per scheduler - 2900 clk per 256 x 128 tile pair against ~1300 clk of MUFU / issue
+// work and ~900 clk of MMA work - i.e. it is latency-bound, not throughput-bound.  Halving the key tile keeps a thread's score row at 64
+// registers, which is what lets 18 warps fit the register file (<= 102 registers per thread).  TMEM: S_g 4 x 64 columns + O_g 4 x 64.
+// Shared memory: Q 4 x 16 KB, P 4 x 16 KB (one buffer per group: only the 16-byte stores of tile j + 1 wait for PV_g(j), the exponentials
+// themselves do not), K / V^T rings of G4_STAGES x (8 + 6) KB - the 64-key tiles turn over in ~700 clk, below the TMA latency, so the
+// ring is four deep.
+constexpr int G4 = 4, G4_BKV = 64, G4_STAGES = 4;
+constexpr int G4_THREADS = 64 + G4 * 128;                       // 576
+constexpr int G4_K_BYTES = G4_BKV * DPAD * 2;                   // 8 KB
+constexpr int G4_V_BYTES = VBOX_BYTES;                          // 6 KB: 48 rows (d) x 64 keys
+constexpr int G4_P_BYTES = PHALF_BYTES;                         // 16 KB: 128 rows x 64 keys
+constexpr int G4_OFF_K = G4 * Q_BYTES, G4_OFF_V = G4_OFF_K + G4_STAGES * G4_K_BYTES, G4_OFF_P = G4_OFF_V + G4_STAGES * G4_V_BYTES;
+constexpr int G4_OFF_BAR = G4_OFF_P + G4 * G4_P_BYTES, G4_SMEM_BYTES = G4_OFF_BAR + 512 + 1024;
+constexpr int G4_TM_S = 0 /* + 64 g */, G4_TM_O = 256 /* + 64 g */;
+
+template <int POLYMASK>
+__global__ void __launch_bounds__(G4_THREADS, 1)
+attention_tc4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                     const __grid_constant__ CUtensorMap map_vt, const AttnTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024 - (raw & 1023)) & 1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G4_OFF_BAR);
+  uint64_t* q_full = bars;                          // [1]
+  uint64_t* k_full = bars + 1;                      // [G4_STAGES]
+  uint64_t* k_empty = k_full + G4_STAGES;
+  uint64_t* v_full = k_empty + G4_STAGES;
+  uint64_t* v_empty = v_full + G4_STAGES;
+  uint64_t* s_full = v_empty + G4_STAGES;           // [G4]  S_g(j) is in TMEM
+  uint64_t* s_empty = s_full + G4;                  // [G4]  S_g has been read into registers
+  uint64_t* p_full = s_empty + G4;                  // [G4]  P_g(j) is in shared memory (and O_g rescaled if needed)
+  uint64_t* p_empty = p_full + G4;                  // [G4]  PV_g(j) has retired: P_g may be overwritten, O_g is quiescent
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_empty + G4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
+  const int T = p.L / G4_BKV;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_q)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_k)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_vt)) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < G4_STAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
+    for (int i = 0; i < G4; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4); mbar_init(&p_full[i], 4); mbar_init(&p_empty[i], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================================================== TMA producer
+    if (lane == 0) {
+      mbar_expect_tx(q_full, G4 * Q_BYTES);
+#pragma unroll
+      for (int g = 0; g < G4; ++g) tma_load_4d(&map_q, q_full, smem + g * Q_BYTES, 0, qt * G4 * BQ + g * BQ, h, n);
+      int st = 0; uint32_t ph = 0;
+      for (int j = 0; j < T; ++j) {
+        mbar_wait(&k_empty[st], ph ^ 1);
+        mbar_expect_tx(&k_full[st], G4_K_BYTES);
+        tma_load_4d(&map_k, &k_full[st], smem + G4_OFF_K + st * G4_K_BYTES, 0, j * G4_BKV, h, n);
+        mbar_wait(&v_empty[st], ph ^ 1);
+        mbar_expect_tx(&v_full[st], G4_V_BYTES);
+        tma_load_3d(&map_vt, &v_full[st], smem + G4_OFF_V + st * G4_V_BYTES, j * G4_BKV, h * p.D, n);
+        if (++st == G4_STAGES) { st = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(G4_BKV >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
+      const uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(DV >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
+      const int kq = (p.D + 15) >> 4;      // k-steps of QK^T that hold data (q / k columns D..63 are zero)
+      auto issue_s = [&](int j) {           // S_g(j) = Q_g K_j^T for the four groups
+        const int st = j % G4_STAGES; const uint32_t ph = (uint32_t)((j / G4_STAGES) & 1);
+        mbar_wait(&k_full[st], ph);
+        const uint64_t k_desc = sw128_desc(smem_u32(smem + G4_OFF_K + st * G4_K_BYTES));
+#pragma unroll
+        for (int g = 0; g < G4; ++g) {
+          mbar_wait(&s_empty[g], (uint32_t)((j & 1) ^ 1));
+          tc_fence_after();
+          const uint64_t q_desc = sw128_desc(smem_u32(smem + g * Q_BYTES));
+          for (int kk = 0; kk < kq; ++kk)
+            umma(tmem_base + G4_TM_S + g * 64, q_desc + 2 * kk, k_desc + 2 * kk, idesc_s, kk > 0 ? 1u : 0u);
+          tc_commit(&s_full[g]);
+        }
+        tc_commit(&k_empty[st]);
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      for (int j = 0; j < T; ++j) {
+        if (j + 1 < T) issue_s(j + 1);
+        const int st = j % G4_STAGES; const uint32_t ph = (uint32_t)((j / G4_STAGES) & 1);
+        mbar_wait(&v_full[st], ph);
+        const uint64_t b_desc = sw128_desc(smem_u32(smem + G4_OFF_V + st * G4_V_BYTES));
+#pragma unroll
+        for (int g = 0; g < G4; ++g) {
+          mbar_wait(&p_full[g], (uint32_t)(j & 1));
+          tc_fence_after();
+          const uint64_t a_desc = sw128_desc(smem_u32(smem + G4_OFF_P + g * G4_P_BYTES));
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma(tmem_base + G4_TM_O + g * 64, a_desc + 2 * kk, b_desc + 2 * kk, idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+          tc_commit(&p_empty[g]);
+        }
+        tc_commit(&v_empty[st]);
+      }
+    }
+  } else {
+    // ================================================================== softmax / correction / epilogue (group g = warps 2 + 4g .. 5 + 4g)
+    const int g = (warp - 2) >> 2;
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    const float sl2 = p.scale_log2e;
+    float m_used = -INFINITY, l = 0.f;
+    const uint32_t s_addr = tmem_base + lane_base + G4_TM_S + g * 64;
+    const uint32_t o_addr = tmem_base + lane_base + G4_TM_O + g * 64;
+    uint8_t* const prow = smem + G4_OFF_P + g * G4_P_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
+    for (int j = 0; j < T; ++j) {
+      const uint32_t par = (uint32_t)(j & 1);
+      mbar_wait(&s_full[g], par);
+      tc_fence_after();
+      uint32_t sr[64];
+      tmem_ld32(s_addr, sr);
+      tmem_ld32(s_addr + 32, sr + 32);
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[g]);                // S_g may be overwritten by tile j + 1
+      float mt = __uint_as_float(sr[0]);
+#pragma unroll
+      for (int i = 1; i < 64; ++i) mt = fmaxf(mt, __uint_as_float(sr[i]));
+      float factor = 1.0f;
+      bool need = false;
+      if (j == 0) {
+        m_used = mt;
+      } else if ((mt - m_used) * sl2 > 8.0f) {                // lazy rescale: O is touched only when the running max grows by > 2^8
+        factor = ex2((m_used - mt) * sl2);
+        m_used = mt;
+        need = true;
+      }
+      l *= factor;
+      const float nbf = -m_used * sl2;
+      const f32x2 sl2p = pk2(sl2, sl2), nbp = pk2(nbf, nbf);
+      f32x2 sum2 = pk2(0.f, 0.f);
+      uint32_t pw[32];                                         // the row's 64 probabilities as bf16 pairs, stored once P_g is free
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const bool poly = ((POLYMASK >> c) & 1) != 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const f32x2 x = fma2(pk2(__uint_as_float(sr[c * 8 + 2 * i]), __uint_as_float(sr[c * 8 + 2 * i + 1])), sl2p, nbp);
+          f32x2 e;
+          float x0, x1; upk2(x, x0, x1);
+          if (poly) e = exp2_poly2(pk2(fmaxf(x0, -126.0f), fmaxf(x1, -126.0f)));
+          else e = pk2(ex2(x0), ex2(x1));
+          sum2 = add2(sum2, e);
+          float e0, e1; upk2(e, e0, e1);
+          __nv_bfloat162 t = __floats2bfloat162_rn(e0, e1);
+          pw[c * 4 + i] = *reinterpret_cast<uint32_t*>(&t);
+        }
+      }
+      { float a0, a1; upk2(sum2, a0, a1); l += a0 + a1; }
+      // PV_g(j - 1) must have retired before P_g is overwritten and before O_g may be rescaled (one wait serves both)
+      if (j > 0) mbar_wait(&p_empty[g], (uint32_t)((j - 1) & 1));
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<uint4*>(prow + ((c ^ (r & 7)) << 4)) = make_uint4(pw[c * 4], pw[c * 4 + 1], pw[c * 4 + 2], pw[c * 4 + 3]);
+      if (__any_sync(0xffffffffu, need)) {
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < DV / 16; ++c) {
+          uint32_t orr[16];
+          tmem_ld16(o_addr + c * 16, orr);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) orr[i] = __float_as_uint(__uint_as_float(orr[i]) * factor);
+          tmem_st16(o_addr + c * 16, orr);
+        }
+        tmem_wait_st();
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[g]);
+    }
+    mbar_wait(&p_empty[g], (uint32_t)((T - 1) & 1));
+    tc_fence_after();
+    const float inv = p.out_alpha / l;
+    bf16* orow = p.out + (int64_t)n * p.bso + ((int64_t)qt * G4 * BQ + g * BQ + r) * p.ldo + h * p.D;
+#pragma unroll
+    for (int c = 0; c < DV / 16; ++c) {
+      uint32_t orr[16];
+      tmem_ld16(o_addr + c * 16, orr);
+      tmem_wait_ld();
+      float f[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(orr[i]) * inv;
+      if (c * 16 + 8 <= p.D) Vec8<bf16>::store(orow + c * 16, f);
+      if (c * 16 + 16 <= p.D) Vec8<bf16>::store(orow + c * 16 + 8, f + 8);
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
 // [NB, L, ld] (columns col0 .. col0+C) -> [NB, C, L]   (V -> V^T so that keys are the contiguous, K-major dimension of PV)
 __global__ void __launch_bounds__(256) transpose_tokens_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int L, int C,
                                                                int64_t ld, int64_t col0) {
@@ -665,6 +887,37 @@ extern "C" int32_t fyc_self_attention_tc(const void* qk, int64_t ldqk, int64_t q
   AttnTcParams p;
   p.out = (bf16*)out; p.ldo = ldo; p.bso = L * ldo; p.L = (int)L; p.heads = (int)heads; p.D = (int)D;
   p.scale_log2e = scale * 1.4426950408889634f; p.out_alpha = 1.0f;
+  const char* g4e = getenv("FYC_ATTN_G4");
+  if (L % (G4 * BQ) == 0 && !(g4e && g4e[0] == '0')) {       // four query tiles per CTA, 64-key tiles (four softmax warps per scheduler)
+    CUtensorMap mk64;
+    {
+      uint64_t dims[4] = {64, (uint64_t)L, (uint64_t)heads, (uint64_t)NB};
+      uint64_t str[3] = {(uint64_t)ldqk * 2, 128, (uint64_t)L * ldqk * 2};
+      uint32_t box[4] = {64, (uint32_t)G4_BKV, 1, 1};
+      int32_t rc = make_map(&mk64, (const bf16*)qk + k_col0, 4, dims, str, box);
+      if (rc) return rc;
+    }
+    static bool attr4 = false;
+    if (!attr4) {
+      FYC_CUDA(cudaFuncSetAttribute(attention_tc4_kernel<0x00>, cudaFuncAttributeMaxDynamicSharedMemorySize, G4_SMEM_BYTES));
+      FYC_CUDA(cudaFuncSetAttribute(attention_tc4_kernel<0x02>, cudaFuncAttributeMaxDynamicSharedMemorySize, G4_SMEM_BYTES));
+      FYC_CUDA(cudaFuncSetAttribute(attention_tc4_kernel<0x12>, cudaFuncAttributeMaxDynamicSharedMemorySize, G4_SMEM_BYTES));
+      FYC_CUDA(cudaFuncSetAttribute(attention_tc4_kernel<0x52>, cudaFuncAttributeMaxDynamicSharedMemorySize, G4_SMEM_BYTES));
+      FYC_CUDA(cudaFuncSetAttribute(attention_tc4_kernel<0x5a>, cudaFuncAttributeMaxDynamicSharedMemorySize, G4_SMEM_BYTES));
+      attr4 = true;
+    }
+    dim3 grid4((unsigned)(L / (G4 * BQ)), (unsigned)heads, (unsigned)NB);
+    const char* pe = getenv("FYC_ATTN_POLY");
+    const int eighths = pe ? atoi(pe) : 3;          // share of the exponentials on the FMA pipe, in eighths
+    cudaStream_t s4 = (cudaStream_t)stream;
+    if (eighths <= 0) attention_tc4_kernel<0x00><<<grid4, G4_THREADS, G4_SMEM_BYTES, s4>>>(mq, mk64, mv, p);
+    else if (eighths == 1) attention_tc4_kernel<0x02><<<grid4, G4_THREADS, G4_SMEM_BYTES, s4>>>(mq, mk64, mv, p);
+    else if (eighths == 2) attention_tc4_kernel<0x12><<<grid4, G4_THREADS, G4_SMEM_BYTES, s4>>>(mq, mk64, mv, p);
+    else if (eighths == 3) attention_tc4_kernel<0x52><<<grid4, G4_THREADS, G4_SMEM_BYTES, s4>>>(mq, mk64, mv, p);
+    else attention_tc4_kernel<0x5a><<<grid4, G4_THREADS, G4_SMEM_BYTES, s4>>>(mq, mk64, mv, p);
+    FYC_LAUNCH_CHECK();
+    return FYC_OK;
+  }
   if (L % (2 * BQ) == 0) {       // two query tiles per CTA (ping-pong softmax warpgroups)
     static bool attr2 = false;
     if (!attr2) {

@@ -28,6 +28,12 @@ extern "C" int32_t fyc_gemm(const fyc_gemm_args* g, void* stream) {
   FYC_CHECK(!(g->epilogue & FYC_EPI_RESIDUAL) || g->residual, "gemm: FYC_EPI_RESIDUAL without residual");
   FYC_CHECK(!(g->epilogue & FYC_EPI_ROWBIAS) || (g->rowbias && g->rows_per_group > 0), "gemm: FYC_EPI_ROWBIAS without rowbias/rows_per_group");
   FYC_CHECK(!(g->epilogue & FYC_EPI_OUT_F32) || g->dtype == FYC_BF16 || g->dtype == FYC_F32, "gemm: bad dtype");
+  if (g->A2)
+    FYC_CHECK(g->impl != FYC_IMPL_SIMT && fyc_gemm_tc_eligible(g), "gemm: the two-segment A (A2) is a tcgen05-path feature (bf16, K1 %% 64 == 0); "
+              "other callers materialise the concatenation with fyc_concat_channels");
+  if (g->epilogue & FYC_EPI_LNFOLD)
+    FYC_CHECK(g->impl != FYC_IMPL_SIMT && fyc_gemm_tc_eligible(g), "gemm: FYC_EPI_LNFOLD is a tcgen05-path epilogue (bf16, N %% 8 == 0, alpha 1, "
+              "ln_rowstats / ln_colsum set); the CUDA-core path runs fyc_layernorm + fyc_gemm");
   if (g->impl == FYC_IMPL_TCGEN05) return fyc_gemm_tc(g, st);
   if (g->impl == FYC_IMPL_AUTO && fyc_gemm_tc_eligible(g)) return fyc_gemm_tc(g, st);
   if (g->impl == FYC_IMPL_AUTO && fyc_gemv_eligible(g)) return fyc_gemv(g, st);

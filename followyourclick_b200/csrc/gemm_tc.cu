@@ -51,6 +51,10 @@ struct TcParams {
   int64_t ldrb;              // row stride of rowbias (elements; N unless the caller passes a slice of a wider table)
   float alpha;
   int flags;
+  // two-segment K (fyc_gemm_args.A2): k blocks [0, cb_split) of a tap come from map_a, the rest from map_a2 (INT_MAX: single source)
+  int cb_split;
+  // LayerNorm folded into the epilogue (FYC_EPI_LNFOLD): per-row (rstd, -rstd * mean) and per-column sum of the gamma-scaled weight
+  const float* ln_rs; const float* ln_cs;
   // W-resident mode (small K): the CTA keeps its whole BN x K weight slab in shared memory and only streams A
   int resident, a_stages;
   // CTA-pair mode (tcgen05 cta_group::2): a cluster of two CTAs computes a 256 x BN tile; each CTA stages its own 128 rows of A
@@ -252,8 +256,12 @@ struct EpiRows {
   int n0;                     // first column of the tile
 };
 struct EpiPrefetch { float4 b0, b1; uint4 res[4]; };
+// LayerNorm fold: the 4 rows' (rstd, -rstd * mean), fetched with the row offsets one tile ahead, and the lane's 8 column sums per group
+struct EpiLnRows { float2 st[4]; };
+struct EpiLnCols { float4 s0, s1; };
 
-__device__ __forceinline__ void epi_rows(const TcParams& p, const TileCoord& tc, const uint32_t* whi, int q, EpiRows& t) {
+template <bool LNF>
+__device__ __forceinline__ void epi_rows(const TcParams& p, const TileCoord& tc, const uint32_t* whi, int q, EpiRows& t, EpiLnRows& ln) {
   const int n_blk = tc.n, wt = tc.w, ht = tc.h, it = tc.i;
   t.n0 = (int)n_blk * p.BN;
   t.ok = 0; t.rgu = -1;
@@ -269,6 +277,7 @@ __device__ __forceinline__ void epi_rows(const TcParams& p, const TileCoord& tc,
     const uint32_t px = ok ? (uint32_t)pix : 0u;
     t.oo[ps] = px * ldo8 + cq;
     t.ro[ps] = px * ldr8 + cq;
+    if constexpr (LNF) ln.st[ps] = ok ? __ldg(reinterpret_cast<const float2*>(p.ln_rs) + px) : make_float2(0.f, 0.f);
     if ((p.flags & FYC_EPI_ROWBIAS) && ok) {
       const int rg = (int)(px / (uint32_t)p.rows_per_group);
       mn = min(mn, rg); mx = max(mx, rg);
@@ -281,25 +290,32 @@ __device__ __forceinline__ void epi_rows(const TcParams& p, const TileCoord& tc,
 }
 
 // loads for 32-column group g of tile t: bias (+ the warp-uniform row bias) of this lane's 8 columns, residual of its 4 rows
-__device__ __forceinline__ void epi_prefetch(const TcParams& p, const EpiRows& t, int g, int q, EpiPrefetch& f) {
+template <bool LNF>
+__device__ __forceinline__ void epi_prefetch(const TcParams& p, const EpiRows& t, int g, int q, EpiPrefetch& f, EpiLnCols& lc) {
   const int c = g * 32 + q * 8, n = t.n0 + c;
   const bool col_ok = (c < p.BN) && (n < p.N);
   f.b0 = f.b1 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if constexpr (LNF) {
+    lc.s0 = lc.s1 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (col_ok) { lc.s0 = __ldg(reinterpret_cast<const float4*>(p.ln_cs + n)); lc.s1 = __ldg(reinterpret_cast<const float4*>(p.ln_cs + n + 4)); }
+  }
   if ((p.flags & FYC_EPI_BIAS) && col_ok) {
     f.b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
     f.b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
   }
-  if (p.flags & FYC_EPI_RESIDUAL) {
-    const uint4* rbase = reinterpret_cast<const uint4*>(p.residual);
+  if constexpr (!LNF) {      // (an LN-folded GEMM never carries a residual: q/k/v and FF1 projections - its registers go to the LN terms)
+    if (p.flags & FYC_EPI_RESIDUAL) {
+      const uint4* rbase = reinterpret_cast<const uint4*>(p.residual);
 #pragma unroll
-    for (int ps = 0; ps < 4; ++ps) {
-      f.res[ps] = make_uint4(0, 0, 0, 0);
-      if (col_ok && ((t.ok >> ps) & 1u)) f.res[ps] = __ldg(rbase + (t.ro[ps] + (uint32_t)g * 4u));
+      for (int ps = 0; ps < 4; ++ps) {
+        f.res[ps] = make_uint4(0, 0, 0, 0);
+        if (col_ok && ((t.ok >> ps) & 1u)) f.res[ps] = __ldg(rbase + (t.ro[ps] + (uint32_t)g * 4u));
+      }
     }
   }
 }
 
-template <int PAIR>
+template <int PAIR, bool LNF>
 __device__ __forceinline__ void epilogue_plain(const TcParams& p, const TileSched& ts, uint8_t* stage, uint64_t* tfull, uint64_t* tempty,
                                                uint32_t tmem_base, int warp, int lane) {
   const int64_t num_tiles = ts.num;
@@ -324,10 +340,12 @@ __device__ __forceinline__ void epilogue_plain(const TcParams& p, const TileSche
   int eg = egroup;                                  // the column half alternates per tile: NG is odd for N = 320 (3 + 2 groups)
   EpiRows cur, nxt;
   EpiPrefetch pf;
+  EpiLnRows lrc, lrn;          // LNF only (empty use otherwise: the compiler drops them)
+  EpiLnCols lcf;
   int64_t tile = ts.t0;
   TileCoord tcn = tile_coord(p, ts, tile);           // coordinates of the NEXT tile to be decoded
-  if (tile < num_tiles) { epi_rows(p, tcn, whi, q, cur); epi_prefetch(p, cur, eg, q, pf); }
-  nxt = cur;
+  if (tile < num_tiles) { epi_rows<LNF>(p, tcn, whi, q, cur, lrc); epi_prefetch<LNF>(p, cur, eg, q, pf, lcf); }
+  nxt = cur; lrn = lrc;
   for (; tile < num_tiles; tile += ts.stride) {
     mbar_wait(&tfull[acc], aphase);
     const long long te1 = p.debug ? clock64() : 0;
@@ -336,8 +354,8 @@ __device__ __forceinline__ void epilogue_plain(const TcParams& p, const TileSche
     const int64_t next_tile = tile + ts.stride;
     tile_advance(p, ts, tcn);
     if (next_tile < num_tiles) {
-      epi_rows(p, tcn, whi, q, nxt);
-      if (p.flags & FYC_EPI_RESIDUAL) {             // pull the next tile's residual rows into L2 a whole tile ahead: lane q takes its
+      epi_rows<LNF>(p, tcn, whi, q, nxt, lrn);
+      if (!LNF && (p.flags & FYC_EPI_RESIDUAL)) {             // pull the next tile's residual rows into L2 a whole tile ahead: lane q takes its
         const int g = (eg ^ 1) + 2 * q;             // q-th group, so one instruction per row covers all of this warp's groups
         if (g < NG && nxt.n0 + g * 32 < p.N) {
 #pragma unroll
@@ -349,18 +367,19 @@ __device__ __forceinline__ void epilogue_plain(const TcParams& p, const TileSche
         }
       }
     } else nxt.ok = 0;                               // nothing follows: the prefetch below degenerates to (valid) bias loads
-    if (eg >= NG) epi_prefetch(p, nxt, eg ^ 1, q, pf);
+    if (eg >= NG) epi_prefetch<LNF>(p, nxt, eg ^ 1, q, pf, lcf);
     for (int gi = eg; gi < NG; gi += 2) {
       // ---- P2
       uint32_t rr[32];
       tmem_ld32(taddr + gi * 32, rr);
       // ---- prefetch of the group after this one (possibly the next tile's first) while the TMEM load is in flight
       EpiPrefetch pn;
+      EpiLnCols lcn;
       {
         const bool last = gi + 2 >= NG;
         EpiRows src = cur;
         if (last) src = nxt;
-        epi_prefetch(p, src, last ? (eg ^ 1) : gi + 2, q, pn);
+        epi_prefetch<LNF>(p, src, last ? (eg ^ 1) : gi + 2, q, pn, lcn);
       }
       tmem_ld_wait32(rr);
 #pragma unroll
@@ -406,9 +425,18 @@ __device__ __forceinline__ void epilogue_plain(const TcParams& p, const TileSche
 #pragma unroll
       for (int ps = 0; ps < 4; ++ps) {
         const float4 x0 = xs[ps][0], x1 = xs[ps][1];
-        float v[8] = {fmaf(x0.x, a_eff, pf.b0.x), fmaf(x0.y, a_eff, pf.b0.y), fmaf(x0.z, a_eff, pf.b0.z), fmaf(x0.w, a_eff, pf.b0.w),
-                      fmaf(x1.x, a_eff, pf.b1.x), fmaf(x1.y, a_eff, pf.b1.y), fmaf(x1.z, a_eff, pf.b1.z), fmaf(x1.w, a_eff, pf.b1.w)};
-        if (p.flags & FYC_EPI_RESIDUAL) {
+        float v[8];
+        if constexpr (LNF) {       // LN(x) W^T = rstd * acc + (-rstd * mean) * colsum[n] + (beta W^T + bias)[n]
+          const float rs = lrc.st[ps].x, nr = lrc.st[ps].y;
+          v[0] = fmaf(x0.x, rs, fmaf(nr, lcf.s0.x, pf.b0.x)); v[1] = fmaf(x0.y, rs, fmaf(nr, lcf.s0.y, pf.b0.y));
+          v[2] = fmaf(x0.z, rs, fmaf(nr, lcf.s0.z, pf.b0.z)); v[3] = fmaf(x0.w, rs, fmaf(nr, lcf.s0.w, pf.b0.w));
+          v[4] = fmaf(x1.x, rs, fmaf(nr, lcf.s1.x, pf.b1.x)); v[5] = fmaf(x1.y, rs, fmaf(nr, lcf.s1.y, pf.b1.y));
+          v[6] = fmaf(x1.z, rs, fmaf(nr, lcf.s1.z, pf.b1.z)); v[7] = fmaf(x1.w, rs, fmaf(nr, lcf.s1.w, pf.b1.w));
+        } else {
+          v[0] = fmaf(x0.x, a_eff, pf.b0.x); v[1] = fmaf(x0.y, a_eff, pf.b0.y); v[2] = fmaf(x0.z, a_eff, pf.b0.z); v[3] = fmaf(x0.w, a_eff, pf.b0.w);
+          v[4] = fmaf(x1.x, a_eff, pf.b1.x); v[5] = fmaf(x1.y, a_eff, pf.b1.y); v[6] = fmaf(x1.z, a_eff, pf.b1.z); v[7] = fmaf(x1.w, a_eff, pf.b1.w);
+        }
+        if (!LNF && (p.flags & FYC_EPI_RESIDUAL)) {
           const uint32_t u[4] = {pf.res[ps].x, pf.res[ps].y, pf.res[ps].z, pf.res[ps].w};
 #pragma unroll
           for (int i = 0; i < 4; ++i) { v[2 * i] += __uint_as_float(u[i] << 16); v[2 * i + 1] += __uint_as_float(u[i] & 0xffff0000u); }
@@ -424,11 +452,13 @@ __device__ __forceinline__ void epilogue_plain(const TcParams& p, const TileSche
       }
       __syncwarp();
       pf = pn;
+      if constexpr (LNF) lcf = lcn;
     }
     epi_release<PAIR>(&tempty[acc], lane);
     if (p.debug) dbg_epi += clock64() - te1;
     if (++acc == 2) { acc = 0; aphase ^= 1; }
     cur = nxt;
+    if constexpr (LNF) lrc = lrn;
     eg ^= 1;
   }
   if (p.debug && lane == 0 && (warp == 2 || warp == 6)) p.debug[blockIdx.x * 8 + 5 + (warp == 6)] = dbg_epi;
@@ -440,38 +470,62 @@ __device__ __forceinline__ void epilogue_plain(const TcParams& p, const TileSche
 // trip; the bf16 results go through a 32 x 64 staging tile so that global stores cover full 128-byte row segments.
 // The 256 bias values of a tile are fetched one tile ahead (one register per epilogue thread), parked in shared memory
 // and read back as broadcast LDS.128 - as global loads at their point of use they were an L2 round trip per chunk.
-template <int PAIR>
+template <int PAIR, bool LNF>
 __device__ __forceinline__ void epilogue_geglu(const TcParams& p, const TileSched& ts, uint8_t* stage, float* sbias, uint64_t* tfull,
                                                uint64_t* tempty, uint32_t tmem_base, int warp, int lane) {
   const int64_t num_tiles = ts.num;
   const int quarter = warp & 3, egroup = (warp - 2) >> 2;
   const int r = quarter * 32 + lane;
   const int wl = r % p.bw, hl = (r / p.bw) % p.bh, il = r / (p.bw * p.bh);
-  const int et = (warp - 2) * 32 + lane;                 // 0..255: the bias element this thread carries
+  const int et = (warp - 2) * 32 + lane;                 // 0..255: the bias (and column-sum) element this thread carries
   const int sub = lane >> 3, ch8 = lane & 7;
   const int c0 = egroup * 64;                            // this warp's 64 output columns of the tile
   uint8_t* const srow = stage + lane * 128;
   uint4* const obase = reinterpret_cast<uint4*>(p.out);
   const uint32_t ldo8 = (uint32_t)(p.ldo >> 3);
+  float* const sb = sbias;                               // [256] bias of the current tile (single buffer: two named barriers per tile)
+  float* const ss = sbias + 256;                         // [256] LNF: column sums of the gamma-scaled weight
   long long dbg_epi = 0;
   int acc = 0; uint32_t aphase = 0;
   int64_t tile = ts.t0;
-  float bnext = 0.f;
+  float bnext = 0.f, snext = 0.f;
+  float2 stn = make_float2(1.f, 0.f);                    // LNF: (rstd, -rstd * mean) of this thread's row in the NEXT tile
   TileCoord tc = tile_coord(p, ts, tile);
-  if (tile < num_tiles) bnext = __ldg(p.bias + tc.n * 256 + et);
+  auto row_of = [&](const TileCoord& c, bool& ok) -> int64_t {
+    const int ow = c.w * p.bw + wl, oh = c.h * p.bh + hl, img = c.i * p.bn + il;
+    const int64_t pix = ((int64_t)img * p.Ho + oh) * p.Wo + ow;
+    ok = (ow < p.Wo) && (oh < p.Ho) && (pix < p.M);
+    return pix;
+  };
+  if (tile < num_tiles) {
+    bnext = __ldg(p.bias + tc.n * 256 + et);
+    if constexpr (LNF) {
+      snext = __ldg(p.ln_cs + tc.n * 256 + et);
+      bool ok; const int64_t pix = row_of(tc, ok);
+      if (ok) stn = __ldg(reinterpret_cast<const float2*>(p.ln_rs) + pix);
+    }
+  }
   for (; tile < num_tiles; tile += ts.stride) {
     const int n_blk = tc.n;
-    const int ow = tc.w * p.bw + wl, oh = tc.h * p.bh + hl, img = tc.i * p.bn + il;
-    const int64_t pix = ((int64_t)img * p.Ho + oh) * p.Wo + ow;
-    const bool row_ok = (ow < p.Wo) && (oh < p.Ho) && (pix < p.M);
+    bool row_ok;
+    const int64_t pix = row_of(tc, row_ok);
     const uint32_t rowoff = row_ok ? (uint32_t)pix * ldo8 : 0u;
     const uint32_t okmask = __ballot_sync(0xffffffffu, row_ok);
-    float* const sb = sbias + acc * 256;
+    const float rstd = stn.x, nrm = stn.y;
+    asm volatile("bar.sync 1, 256;" ::: "memory");       // the 8 epilogue warps have finished reading the previous tile's bias / sums
     sb[et] = bnext;
+    if constexpr (LNF) ss[et] = snext;
     const int64_t next_tile = tile + ts.stride;
-    tile_advance(p, ts, tc);                               // tc now describes next_tile; n_blk / ow / oh / img above are this tile's
-    if (next_tile < num_tiles) bnext = __ldg(p.bias + tc.n * 256 + et);
-    asm volatile("bar.sync 1, 256;" ::: "memory");       // the 8 epilogue warps: bias of this tile visible, previous reads done
+    tile_advance(p, ts, tc);                               // tc now describes next_tile; n_blk / pix above are this tile's
+    if (next_tile < num_tiles) {
+      bnext = __ldg(p.bias + tc.n * 256 + et);
+      if constexpr (LNF) {
+        snext = __ldg(p.ln_cs + tc.n * 256 + et);
+        bool ok; const int64_t pn = row_of(tc, ok);
+        stn = ok ? __ldg(reinterpret_cast<const float2*>(p.ln_rs) + pn) : make_float2(1.f, 0.f);
+      }
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");       // this tile's 256 bias values (and sums) are visible to all of them
     mbar_wait(&tfull[acc], aphase);
     const long long te1 = p.debug ? clock64() : 0;
     tcgen05_fence_after();
@@ -484,6 +538,7 @@ __device__ __forceinline__ void epilogue_geglu(const TcParams& p, const TileSche
       tmem_ld_wait32(ar);
       tmem_ld_wait32(gr);
       const float* ba_p = sb + c0 + hh * 32;                // packed (interleaved) bias of the `a` columns; gate = +128
+      const float* sa_p = ss + c0 + hh * 32;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {                          // 8 output columns = one 16-byte chunk of bf16
         float o[8];
@@ -491,10 +546,20 @@ __device__ __forceinline__ void epilogue_geglu(const TcParams& p, const TileSche
         for (int i = 0; i < 8; i += 4) {
           const float4 ba = *reinterpret_cast<const float4*>(ba_p + c * 8 + i);
           const float4 bg = *reinterpret_cast<const float4*>(ba_p + 128 + c * 8 + i);
-          const float av[4] = {ba.x, ba.y, ba.z, ba.w}, gv[4] = {bg.x, bg.y, bg.z, bg.w};
+          float av[4] = {ba.x, ba.y, ba.z, ba.w}, gv[4] = {bg.x, bg.y, bg.z, bg.w};
+          if constexpr (LNF) {                               // LN fold: bias := nrm * colsum + (beta W^T + bias), accumulator scaled by rstd
+            const float4 sa = *reinterpret_cast<const float4*>(sa_p + c * 8 + i);
+            const float4 sg = *reinterpret_cast<const float4*>(sa_p + 128 + c * 8 + i);
+            av[0] = fmaf(nrm, sa.x, av[0]); av[1] = fmaf(nrm, sa.y, av[1]); av[2] = fmaf(nrm, sa.z, av[2]); av[3] = fmaf(nrm, sa.w, av[3]);
+            gv[0] = fmaf(nrm, sg.x, gv[0]); gv[1] = fmaf(nrm, sg.y, gv[1]); gv[2] = fmaf(nrm, sg.z, gv[2]); gv[3] = fmaf(nrm, sg.w, gv[3]);
 #pragma unroll
-          for (int e = 0; e < 4; ++e)
-            o[i + e] = (__uint_as_float(ar[c * 8 + i + e]) + av[e]) * gelu_erf_fast(__uint_as_float(gr[c * 8 + i + e]) + gv[e]);
+            for (int e = 0; e < 4; ++e)
+              o[i + e] = fmaf(__uint_as_float(ar[c * 8 + i + e]), rstd, av[e]) * gelu_erf_fast(fmaf(__uint_as_float(gr[c * 8 + i + e]), rstd, gv[e]));
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              o[i + e] = (__uint_as_float(ar[c * 8 + i + e]) + av[e]) * gelu_erf_fast(__uint_as_float(gr[c * 8 + i + e]) + gv[e]);
+          }
         }
         Vec8<bf16>::store(reinterpret_cast<bf16*>(srow + (((hh * 4 + c) ^ (lane & 7)) << 4)), o);
       }
@@ -519,7 +584,8 @@ __device__ __forceinline__ void epilogue_geglu(const TcParams& p, const TileSche
 // ---------------------------------------------------------------------------------------------- kernel
 template <int PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const TcParams p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_a2,
+               const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   if (smem_u32(smem) & 1023u) __trap();   // SWIZZLE_128B operands need 1024-byte alignment
@@ -547,6 +613,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a2)) : "memory");
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -590,13 +657,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           for (int cb = 0; cb < p.cin_blocks; ++cb) {
             mbar_wait(&empty[stage], phase ^ 1);
             uint8_t* sa = smem + a_base + (uint32_t)stage * a_stride;
+            const bool seg2 = cb >= p.cb_split;                    // second K segment: the other source tensor, its own channel origin
+            const CUtensorMap* ma = seg2 ? &map_a2 : &map_a;
+            const int ka = (seg2 ? cb - p.cb_split : cb) * BK;
             if (pair) {
               if (ts.rank == 0) mbar_expect_tx(&full[stage], tx_bytes);
-              tma2_load_4d(&map_a, &full[stage], sa, cb * BK, ow0 + p.tap_dx[tap], oh0 + p.tap_dy[tap], img0 + p.tap_img[tap]);
+              tma2_load_4d(ma, &full[stage], sa, ka, ow0 + p.tap_dx[tap], oh0 + p.tap_dy[tap], img0 + p.tap_img[tap]);
               tma2_load_3d(&map_w, &full[stage], sa + A_BYTES, cb * BK, tap, wrow0);
             } else {
               mbar_expect_tx(&full[stage], tx_bytes);
-              tma_load_4d(&map_a, &full[stage], sa, cb * BK, ow0 + p.tap_dx[tap], oh0 + p.tap_dy[tap], img0 + p.tap_img[tap]);
+              tma_load_4d(ma, &full[stage], sa, ka, ow0 + p.tap_dx[tap], oh0 + p.tap_dy[tap], img0 + p.tap_img[tap]);
               if (!p.resident) tma_load_3d(&map_w, &full[stage], sa + A_BYTES, cb * BK, tap, wrow0);
             }
             if (++stage == nstages) { stage = 0; phase ^= 1; }
@@ -658,8 +728,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     int acc = 0; uint32_t aphase = 0;
     const bool geglu = (p.flags & FYC_EPI_GEGLU) != 0;
     const bool out_f32 = (p.flags & FYC_EPI_OUT_F32) != 0;
-    if (geglu) epilogue_geglu<PAIR>(p, ts, stage, reinterpret_cast<float*>(smem + OFF_BIAS), tfull, tempty, tmem_base, warp, lane);
-    else if (!out_f32) epilogue_plain<PAIR>(p, ts, stage, tfull, tempty, tmem_base, warp, lane);
+    const bool lnf = (p.flags & FYC_EPI_LNFOLD) != 0;
+    if (geglu && lnf) epilogue_geglu<PAIR, true>(p, ts, stage, reinterpret_cast<float*>(smem + OFF_BIAS), tfull, tempty, tmem_base, warp, lane);
+    else if (geglu) epilogue_geglu<PAIR, false>(p, ts, stage, reinterpret_cast<float*>(smem + OFF_BIAS), tfull, tempty, tmem_base, warp, lane);
+    else if (!out_f32 && lnf) epilogue_plain<PAIR, true>(p, ts, stage, tfull, tempty, tmem_base, warp, lane);
+    else if (!out_f32) epilogue_plain<PAIR, false>(p, ts, stage, tfull, tempty, tmem_base, warp, lane);
     else for (int64_t tile = ts.t0; tile < ts.num; tile += ts.stride) {
       const TileCoord tc = tile_coord(p, ts, tile);
       const int n_blk = tc.n, wt = tc.w, ht = tc.h, it = tc.i;
@@ -858,7 +931,9 @@ void choose_tiles(TcParams& p, int* grid_out) {
 
 long long* g_tc_debug = nullptr;
 
-int32_t launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, TcParams p, int grid, cudaStream_t st) {
+int32_t launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, TcParams p, int grid, cudaStream_t st, const CUtensorMap* ma2p = nullptr) {
+  const CUtensorMap& ma2 = ma2p ? *ma2p : ma;
+  if (!ma2p) p.cb_split = 0x7fffffff;
   if (p.pair) {
     p.debug = g_tc_debug;
     static bool attr_set2 = false;
@@ -878,7 +953,7 @@ int32_t launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, TcParams p, int 
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    FYC_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<1>, ma, mw, p));
+    FYC_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<1>, ma, mw, ma2, p));
     return FYC_OK;
   }
   p.debug = g_tc_debug;
@@ -899,7 +974,7 @@ int32_t launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, TcParams p, int 
     p.dg_h = (int)(g % p.h_tiles); g /= p.h_tiles;
     p.dg_i = (int)g;
   }
-  gemm_tc_kernel<0><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mw, p);
+  gemm_tc_kernel<0><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ma, mw, ma2, p);
   FYC_LAUNCH_CHECK();
   return FYC_OK;
 }
@@ -920,7 +995,15 @@ bool fyc_gemm_tc_eligible(const fyc_gemm_args* g) {
   const int64_t n_out = (g->epilogue & FYC_EPI_GEGLU) ? g->N / 2 : g->N;
   if (g->ldo % 8 || ((uintptr_t)g->out & 15)) return false;
   if ((g->epilogue & FYC_EPI_RESIDUAL) && (g->ldr % 8 || ((uintptr_t)g->residual & 15))) return false;
-  if ((g->epilogue & FYC_EPI_GEGLU) && (g->N % 256 || !(g->epilogue & FYC_EPI_BIAS) || (g->epilogue & ~(FYC_EPI_GEGLU | FYC_EPI_BIAS)))) return false;
+  if ((g->epilogue & FYC_EPI_GEGLU) && (g->N % 256 || !(g->epilogue & FYC_EPI_BIAS) || (g->epilogue & ~(FYC_EPI_GEGLU | FYC_EPI_BIAS | FYC_EPI_LNFOLD)))) return false;
+  if (g->A2) {
+    if (g->batch != 1 || g->K1 <= 0 || g->K1 >= g->K || g->K1 % BK || g->lda2 % 8 || (((uintptr_t)g->A2) & 15)) return false;
+  }
+  if (g->epilogue & FYC_EPI_LNFOLD) {
+    if (!g->ln_rowstats || !g->ln_colsum || (((uintptr_t)g->ln_rowstats) & 7) || (((uintptr_t)g->ln_colsum) & 15)) return false;
+    if (g->alpha != 1.0f || (g->epilogue & (FYC_EPI_OUT_F32 | FYC_EPI_RESIDUAL)) || g->N % 8) return false;
+    if ((g->epilogue & FYC_EPI_ROWBIAS) && g->rows_per_group % 128) return false;     // a warp's 32 rows never straddle two row-bias groups
+  }
   if ((g->epilogue & FYC_EPI_BIAS) && ((uintptr_t)g->bias & 15)) return false;
   if ((g->epilogue & FYC_EPI_ROWBIAS) && ((uintptr_t)g->rowbias & 15)) return false;
   (void)n_out;
@@ -935,12 +1018,20 @@ int32_t fyc_gemm_tc(const fyc_gemm_args* g, cudaStream_t st) {
   for (int64_t b = 0; b < g->batch; ++b) {
     const bf16* A = (const bf16*)g->A + b * g->strideA;
     const bf16* W = (const bf16*)g->W + b * g->strideW;
-    CUtensorMap ma, mw;
+    CUtensorMap ma, mw, ma2;
+    const int64_t Ka = g->A2 ? g->K1 : g->K;          // columns of the first (or only) source
     {
-      uint64_t dims[4] = {(uint64_t)g->K, (uint64_t)g->M, 1, 1};
+      uint64_t dims[4] = {(uint64_t)Ka, (uint64_t)g->M, 1, 1};
       uint64_t str[3] = {(uint64_t)g->lda * 2, (uint64_t)g->lda * 2 * (uint64_t)g->M, (uint64_t)g->lda * 2 * (uint64_t)g->M};
       uint32_t box[4] = {BK, BM, 1, 1};
       int32_t rc = encode_map(&ma, A, 4, dims, str, box);
+      if (rc) return rc;
+    }
+    if (g->A2) {
+      uint64_t dims[4] = {(uint64_t)(g->K - g->K1), (uint64_t)g->M, 1, 1};
+      uint64_t str[3] = {(uint64_t)g->lda2 * 2, (uint64_t)g->lda2 * 2 * (uint64_t)g->M, (uint64_t)g->lda2 * 2 * (uint64_t)g->M};
+      uint32_t box[4] = {BK, BM, 1, 1};
+      int32_t rc = encode_map(&ma2, g->A2, 4, dims, str, box);
       if (rc) return rc;
     }
     TcParams p{};
@@ -964,7 +1055,9 @@ int32_t fyc_gemm_tc(const fyc_gemm_args* g, cudaStream_t st) {
     p.residual = g->residual ? (f32 ? (const void*)((const float*)g->residual + b * g->strideO) : (const void*)((const bf16*)g->residual + b * g->strideO)) : nullptr;
     p.out = f32 ? (void*)((float*)g->out + b * g->strideO) : (void*)((bf16*)g->out + b * g->strideO);
     p.ldo = g->ldo; p.ldr = g->ldr; p.alpha = g->alpha; p.flags = g->epilogue;
-    int32_t rc = launch_tc(ma, mw, p, grid, st);
+    p.ln_rs = g->ln_rowstats ? g->ln_rowstats + 2 * b * g->M : nullptr; p.ln_cs = g->ln_colsum;
+    p.cb_split = g->A2 ? (int)(g->K1 / BK) : 0x7fffffff;
+    int32_t rc = launch_tc(ma, mw, p, grid, st, g->A2 ? &ma2 : nullptr);
     if (rc) return rc;
   }
   return FYC_OK;

@@ -38,9 +38,12 @@ __device__ __forceinline__ float rcp_fast(float x) { float y; asm("rcp.approx.ft
 // partial (sum, sumsq) per group.  No atomics anywhere: the per-thread channel sums are combined through shared
 // memory in a fixed order and the per-CTA partials are summed in chunk order by gn_finalize_kernel, so the
 // statistics (and therefore the whole engine) are bit-reproducible run to run.
+// Two-source form (x2 != nullptr): the normalised tensor is the channel concatenation [x (C1 channels) | x2 (C - C1 channels)] of two
+// tensors that are never concatenated in memory - the skip connections of the up blocks (torch.cat at unet_blocks.py:763,885 followed
+// by ResnetBlock3D.norm1).  A thread's channel vector lies wholly in one source (C1 % V == 0).
 template <typename T, int V>
 __global__ void __launch_bounds__(256, 4) gn_stats_kernel(const T* __restrict__ x, float2* __restrict__ partials, int64_t R,
-                                                       int C, int G, int64_t rows_per_cta, int rev) {
+                                                       int C, int G, int64_t rows_per_cta, int rev, const T* __restrict__ x2, int C1) {
   extern __shared__ float s_ch[];   // [RY][C][2]
   const int cpg = C / G;
   const int cvn = C / V;
@@ -52,9 +55,12 @@ __global__ void __launch_bounds__(256, 4) gn_stats_kernel(const T* __restrict__ 
   const int64_t bx = rev ? gridDim.x - 1 - blockIdx.x : blockIdx.x;
   const int64_t r0 = bx * rows_per_cta;
   const int64_t r1 = (r0 + rows_per_cta < R) ? r0 + rows_per_cta : R;
-  const T* base = x + nb * R * C;
   if (ry < RY) {
     for (int cv = tx; cv < cvn; cv += TX) {
+      // row pointer and row stride of this channel vector's source; below `base + r * C + cv * V` addresses row r
+      const bool second = x2 != nullptr && cv * V >= C1;
+      const int ldx = x2 == nullptr ? C : (second ? C - C1 : C1);
+      const T* base0 = second ? x2 + nb * R * ldx + (cv * V - C1) : x + nb * R * ldx + cv * V;
       float s[V], q[V];
 #pragma unroll
       for (int e = 0; e < V; ++e) { s[e] = 0.f; q[e] = 0.f; }
@@ -65,7 +71,7 @@ __global__ void __launch_bounds__(256, 4) gn_stats_kernel(const T* __restrict__ 
         for (; r + 7 * RY < r1; r += 8 * RY) {
           uint4 raw[8];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) raw[u] = __ldg(reinterpret_cast<const uint4*>(base + (r + (int64_t)u * RY) * C + cv * V));
+          for (int u = 0; u < 8; ++u) raw[u] = __ldg(reinterpret_cast<const uint4*>(base0 + (r + (int64_t)u * RY) * ldx));
           f32x2 sp[4], qp[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) { sp[e] = pk2(s[2 * e], s[2 * e + 1]); qp[e] = pk2(q[2 * e], q[2 * e + 1]); }
@@ -83,7 +89,7 @@ __global__ void __launch_bounds__(256, 4) gn_stats_kernel(const T* __restrict__ 
         float f[4][8];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const T* src = base + (r + (int64_t)u * RY) * C + cv * V;
+          const T* src = base0 + (r + (int64_t)u * RY) * ldx;
           if constexpr (V == 8) Vec8<T>::load(src, f[u]);
           else if constexpr (V == 4) Vec4<T>::load(src, f[u]);
           else f[u][0] = to_f(*src);
@@ -95,9 +101,9 @@ __global__ void __launch_bounds__(256, 4) gn_stats_kernel(const T* __restrict__ 
       }
       for (; r < r1; r += RY) {
         float f[8];
-        if constexpr (V == 8) Vec8<T>::load(base + r * C + cv * V, f);
-        else if constexpr (V == 4) Vec4<T>::load(base + r * C + cv * V, f);
-        else f[0] = to_f(base[r * C + cv]);
+        if constexpr (V == 8) Vec8<T>::load(base0 + r * ldx, f);
+        else if constexpr (V == 4) Vec4<T>::load(base0 + r * ldx, f);
+        else f[0] = to_f(base0[r * ldx]);
 #pragma unroll
         for (int e = 0; e < V; ++e) { s[e] += f[e]; q[e] = fmaf(f[e], f[e], q[e]); }
       }
@@ -156,7 +162,7 @@ __global__ void __launch_bounds__(128) gn_finalize_kernel(const float2* __restri
 template <typename T, int V, bool SILU>
 __global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ x, const float* __restrict__ scale,
                                                        const float* __restrict__ shift, T* __restrict__ out, int64_t R,
-                                                       int C, int64_t total_vec) {
+                                                       int C, int64_t total_vec, const T* __restrict__ x2, int C1) {
   const int cvn = C / V;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   constexpr int U = 4;     // vectors in flight per thread
@@ -173,9 +179,14 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ x, 
     for (int u = 0; u < U; ++u) {
       const int64_t i = i0 + u * stride;
       if (i < total_vec) {
-        if constexpr (V == 8) Vec8<T>::load(x + i * V, f[u]);
-        else if constexpr (V == 4) Vec4<T>::load(x + i * V, f[u]);
-        else f[u][0] = to_f(x[i]);
+        const T* src = x + i * V;
+        if (x2 != nullptr) {                      // two-source form: (row, channel vector) of vector i -> its source tensor
+          const int64_t rw = i / cvn; const int c = (int)(i - rw * cvn) * V;
+          src = c < C1 ? x + rw * C1 + c : x2 + rw * (C - C1) + (c - C1);
+        }
+        if constexpr (V == 8) Vec8<T>::load(src, f[u]);
+        else if constexpr (V == 4) Vec4<T>::load(src, f[u]);
+        else f[u][0] = to_f(*src);
       }
     }
 #pragma unroll
@@ -218,7 +229,7 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const T* __restrict__ x, 
 template <bool SILU>
 __global__ void __launch_bounds__(256) gn_apply_rows_kernel(const bf16* __restrict__ x, const float* __restrict__ scale,
                                                             const float* __restrict__ shift, bf16* __restrict__ out, int64_t R,
-                                                            int C, int64_t rows_per_cta) {
+                                                            int C, int64_t rows_per_cta, const bf16* __restrict__ x2, int C1) {
   constexpr int U = 4;
   const int cvn = C / 8;
   const int TX = cvn < 256 ? cvn : 256;
@@ -228,9 +239,11 @@ __global__ void __launch_bounds__(256) gn_apply_rows_kernel(const bf16* __restri
   const int64_t nb = blockIdx.y;
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
   const int64_t r1 = (r0 + rows_per_cta < R) ? r0 + rows_per_cta : R;
-  const bf16* xb = x + nb * R * C;
   bf16* ob = out + nb * R * C;
   for (int cv = tx; cv < cvn; cv += TX) {
+    const bool second = x2 != nullptr && cv * 8 >= C1;
+    const int ldx = x2 == nullptr ? C : (second ? C - C1 : C1);
+    const bf16* xb = second ? x2 + nb * R * ldx + (cv * 8 - C1) : x + nb * R * ldx + cv * 8;     // row r of this channel vector: xb + r * ldx
     f32x2 sc[4], sh[4];
     {
       const float4 a0 = __ldg(reinterpret_cast<const float4*>(scale + nb * C + cv * 8)), a1 = __ldg(reinterpret_cast<const float4*>(scale + nb * C + cv * 8 + 4));
@@ -245,7 +258,7 @@ __global__ void __launch_bounds__(256) gn_apply_rows_kernel(const bf16* __restri
       for (int u = 0; u < U; ++u) {
         const int64_t rr = r + (int64_t)u * RY;
         raw[u] = make_uint4(0, 0, 0, 0);
-        if (rr < r1) raw[u] = __ldg(reinterpret_cast<const uint4*>(xb + rr * C + cv * 8));
+        if (rr < r1) raw[u] = __ldg(reinterpret_cast<const uint4*>(xb + rr * ldx));
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -278,7 +291,7 @@ extern "C" size_t fyc_groupnorm_workspace_bytes(int64_t NB, int64_t C, int64_t G
 
 template <typename T, int V>
 static int32_t groupnorm_impl(const T* x, const float* gamma, const float* beta, T* out, int64_t NB, int64_t R, int C,
-                              int G, float eps, int silu, void* ws, cudaStream_t st) {
+                              int G, float eps, int silu, void* ws, cudaStream_t st, const T* x2 = nullptr, int C1 = 0) {
   float2* partials = (float2*)ws;
   float* scale = (float*)(partials + gn_partials(NB, G));
   float* shift = scale + NB * C;
@@ -296,7 +309,7 @@ static int32_t groupnorm_impl(const T* x, const float* gamma, const float* beta,
   auto kern = gn_stats_kernel<T, V>;
   if (smem > 48 * 1024) FYC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((unsigned)chunks, (unsigned)NB);
-  kern<<<grid, 256, smem, st>>>(x, partials, R, C, G, rows_per_cta, fyc_zigzag());
+  kern<<<grid, 256, smem, st>>>(x, partials, R, C, G, rows_per_cta, fyc_zigzag(), x2, C1);
   FYC_LAUNCH_CHECK();
   gn_finalize_kernel<<<dim3((unsigned)G, (unsigned)NB), 128, 0, st>>>(partials, chunks, gamma, beta, scale, shift, C, G,
                                                                        (double)R * (C / G), eps);
@@ -307,8 +320,8 @@ static int32_t groupnorm_impl(const T* x, const float* gamma, const float* beta,
     int64_t rpc = ceil_div64(R, want);
     rpc = ceil_div64(rpc, (int64_t)RY * 4) * RY * 4;
     dim3 ga((unsigned)ceil_div64(R, rpc), (unsigned)NB);
-    if (silu) gn_apply_rows_kernel<true><<<ga, 256, 0, st>>>((const bf16*)x, scale, shift, (bf16*)out, R, C, rpc);
-    else gn_apply_rows_kernel<false><<<ga, 256, 0, st>>>((const bf16*)x, scale, shift, (bf16*)out, R, C, rpc);
+    if (silu) gn_apply_rows_kernel<true><<<ga, 256, 0, st>>>((const bf16*)x, scale, shift, (bf16*)out, R, C, rpc, (const bf16*)x2, C1);
+    else gn_apply_rows_kernel<false><<<ga, 256, 0, st>>>((const bf16*)x, scale, shift, (bf16*)out, R, C, rpc, (const bf16*)x2, C1);
     FYC_LAUNCH_CHECK();
     return FYC_OK;
   }
@@ -316,8 +329,8 @@ static int32_t groupnorm_impl(const T* x, const float* gamma, const float* beta,
   int64_t blocks = ceil_div64(total_vec, 256);
   int64_t cap = (int64_t)fyc_sm_count() * 16;
   unsigned gb = (unsigned)(blocks > cap ? cap : blocks);
-  if (silu) gn_apply_kernel<T, V, true><<<gb, 256, 0, st>>>(x, scale, shift, out, R, C, total_vec);
-  else gn_apply_kernel<T, V, false><<<gb, 256, 0, st>>>(x, scale, shift, out, R, C, total_vec);
+  if (silu) gn_apply_kernel<T, V, true><<<gb, 256, 0, st>>>(x, scale, shift, out, R, C, total_vec, x2, C1);
+  else gn_apply_kernel<T, V, false><<<gb, 256, 0, st>>>(x, scale, shift, out, R, C, total_vec, x2, C1);
   FYC_LAUNCH_CHECK();
   return FYC_OK;
 }
@@ -337,6 +350,25 @@ extern "C" int32_t fyc_groupnorm(const void* x, const float* gamma, const float*
     return groupnorm_impl<float, 1>((const float*)x, gamma, beta, (float*)out, NB, R, (int)C, (int)G, eps, silu, workspace, st);
   }
   FYC_CHECK(false, "groupnorm: unknown dtype %d", dtype);
+}
+
+extern "C" int32_t fyc_groupnorm_concat(const void* x1, int64_t C1, const void* x2, int64_t C2, const float* gamma, const float* beta,
+                                        void* out, int64_t NB, int64_t R, int64_t G, float eps, int32_t silu, int32_t dtype,
+                                        void* workspace, size_t workspace_bytes, void* stream) {
+  const int64_t C = C1 + C2;
+  FYC_CHECK(x1 && x2 && C1 > 0 && C2 > 0, "groupnorm_concat: bad arguments");
+  FYC_CHECK(G > 0 && C % G == 0, "groupnorm_concat: C=%lld not divisible by G=%lld", (long long)C, (long long)G);
+  FYC_CHECK(workspace && workspace_bytes >= fyc_groupnorm_workspace_bytes(NB, C, G), "groupnorm_concat: workspace too small");
+  FYC_CHECK(NB > 0 && NB < 65536 && R > 0 && C < (1 << 20) && NB * R < (1ll << 31), "groupnorm_concat: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == FYC_BF16) {
+    FYC_CHECK(C1 % 8 == 0 && C2 % 8 == 0 && ((((uintptr_t)x1 | (uintptr_t)x2 | (uintptr_t)out)) & 15) == 0, "groupnorm_concat(bf16): channel counts must be multiples of 8, pointers 16-byte aligned");
+    return groupnorm_impl<bf16, 8>((const bf16*)x1, gamma, beta, (bf16*)out, NB, R, (int)C, (int)G, eps, silu, workspace, st, (const bf16*)x2, (int)C1);
+  } else if (dtype == FYC_F32) {
+    FYC_CHECK(C1 % 4 == 0 && C2 % 4 == 0, "groupnorm_concat(f32): channel counts must be multiples of 4");
+    return groupnorm_impl<float, 4>((const float*)x1, gamma, beta, (float*)out, NB, R, (int)C, (int)G, eps, silu, workspace, st, (const float*)x2, (int)C1);
+  }
+  FYC_CHECK(false, "groupnorm_concat: unknown dtype %d", dtype);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -559,6 +591,115 @@ __global__ void __launch_bounds__(256, 2) layernorm_lpr_kernel(const bf16* __res
       if (ok) *reinterpret_cast<uint4*>(orow + i * VS) = make_uint4(o[0], o[1], o[2], o[3]);
     }
   }
+}
+
+// LayerNorm STATISTICS only (fyc_layernorm_stats): per row float2(rstd, -rstd * mean), the two numbers the LN-folded GEMM epilogue
+// needs (fyc.h FYC_EPI_LNFOLD).  Same lane layout and the same two-pass arithmetic as layernorm_lpr_kernel - one read of x, no write
+// of a normalised copy.  PASSES x 5 independent 16-byte loads per lane are requested before the first is used.
+template <int LPR, int PASSES>
+__global__ void __launch_bounds__(256, 2) ln_stats_lpr_kernel(const bf16* __restrict__ x, float2* __restrict__ stats, int64_t M, float eps, int rev) {
+  constexpr int C = LPR * 40, RPP = 32 / LPR, VS = LPR * 8;
+  const int lane = threadIdx.x & 31, sub = lane % LPR, rr = lane / LPR;
+  const int64_t bxl = rev ? (int64_t)gridDim.x - 1 - blockIdx.x : (int64_t)blockIdx.x;
+  const int64_t row_base = (bxl * (blockDim.x >> 5) + (threadIdx.x >> 5)) * (RPP * PASSES);
+  if (row_base >= M) return;
+  const float inv_c = 1.0f / (float)C;
+  uint4 raw[PASSES][5];
+#pragma unroll
+  for (int ps = 0; ps < PASSES; ++ps) {
+    const int64_t row = row_base + ps * RPP + rr;
+    const int64_t rowc = row < M ? row : M - 1;
+    const bf16* xr = x + rowc * C + sub * 8;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) raw[ps][i] = __ldg(reinterpret_cast<const uint4*>(xr + i * VS));
+  }
+#pragma unroll
+  for (int ps = 0; ps < PASSES; ++ps) {
+    const int64_t row = row_base + ps * RPP + rr;
+    f32x2 v[5][4];
+    f32x2 s2 = pk2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const uint32_t w[4] = {raw[ps][i].x, raw[ps][i].y, raw[ps][i].z, raw[ps][i].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { v[i][e] = bf2_to_f2(w[e]); s2 = add2(s2, v[i][e]); }
+    }
+    float s0, s1; upk2(s2, s0, s1);
+    float sum = s0 + s1;
+#pragma unroll
+    for (int o = 1; o < LPR; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum * inv_c;
+    const f32x2 nmean = pk2(-mean, -mean);
+    f32x2 q2 = pk2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { const f32x2 d = add2(v[i][e], nmean); q2 = fma2(d, d, q2); }
+    float q0, q1; upk2(q2, q0, q1);
+    float sq = q0 + q1;
+#pragma unroll
+    for (int o = 1; o < LPR; o <<= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq * inv_c + eps);
+    if (sub == 0 && row < M) stats[row] = make_float2(rstd, -rstd * mean);
+  }
+}
+
+// generic widths (C % 8 == 0, C <= 2048; bf16) and fp32 rows: one warp per row
+template <typename T, int V, int NV>
+__global__ void __launch_bounds__(256) ln_stats_kernel(const T* __restrict__ x, float2* __restrict__ stats, int64_t M, int C, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int cvn = C / V;
+  const T* xr = x + row * C;
+  float v[NV][V];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int cv = lane + 32 * i;
+    if (cv < cvn) {
+      if constexpr (V == 8) Vec8<T>::load(xr + cv * V, v[i]); else Vec4<T>::load(xr + cv * V, v[i]);
+#pragma unroll
+      for (int e = 0; e < V; ++e) sum += v[i][e];
+    }
+  }
+  const float mean = warp_sum(sum) / (float)C;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+    if (lane + 32 * i < cvn) {
+#pragma unroll
+      for (int e = 0; e < V; ++e) { const float d = v[i][e] - mean; sq = fmaf(d, d, sq); }
+    }
+  const float rstd = rsqrtf(warp_sum(sq) / (float)C + eps);
+  if (lane == 0) stats[row] = make_float2(rstd, -rstd * mean);
+}
+
+extern "C" int32_t fyc_layernorm_stats(const void* x, float* stats, int64_t M, int64_t C, float eps, int32_t dtype, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  FYC_CHECK(x && stats && M > 0 && C > 0, "layernorm_stats: bad arguments");
+  FYC_CHECK((((uintptr_t)x) & 15) == 0 && (((uintptr_t)stats) & 7) == 0, "layernorm_stats: alignment");
+  float2* so = reinterpret_cast<float2*>(stats);
+  const unsigned grid = (unsigned)ceil_div64(M, 8);
+  if (dtype == FYC_BF16) {
+    FYC_CHECK(C % 8 == 0 && C <= 2048, "layernorm_stats(bf16): C=%lld must be a multiple of 8 and <= 2048", (long long)C);
+    const bf16* xb = (const bf16*)x;
+    constexpr int PASSES = 4;
+    if (C == 320) ln_stats_lpr_kernel<8, PASSES><<<(unsigned)ceil_div64(M, 8 * 4 * PASSES), 256, 0, st>>>(xb, so, M, eps, fyc_zigzag());
+    else if (C == 640) ln_stats_lpr_kernel<16, PASSES><<<(unsigned)ceil_div64(M, 8 * 2 * PASSES), 256, 0, st>>>(xb, so, M, eps, fyc_zigzag());
+    else if (C == 1280) ln_stats_lpr_kernel<32, PASSES><<<(unsigned)ceil_div64(M, 8 * 1 * PASSES), 256, 0, st>>>(xb, so, M, eps, fyc_zigzag());
+    else if (C <= 8 * 32 * 5) ln_stats_kernel<bf16, 8, 5><<<grid, 256, 0, st>>>(xb, so, M, (int)C, eps);
+    else ln_stats_kernel<bf16, 8, 8><<<grid, 256, 0, st>>>(xb, so, M, (int)C, eps);
+  } else if (dtype == FYC_F32) {
+    FYC_CHECK(C % 4 == 0 && C <= 2048, "layernorm_stats(f32): C=%lld must be a multiple of 4 and <= 2048", (long long)C);
+    if (C <= 4 * 32 * 5) ln_stats_kernel<float, 4, 5><<<grid, 256, 0, st>>>((const float*)x, so, M, (int)C, eps);
+    else if (C <= 4 * 32 * 10) ln_stats_kernel<float, 4, 10><<<grid, 256, 0, st>>>((const float*)x, so, M, (int)C, eps);
+    else ln_stats_kernel<float, 4, 16><<<grid, 256, 0, st>>>((const float*)x, so, M, (int)C, eps);
+  } else {
+    FYC_CHECK(false, "layernorm_stats: unknown dtype %d", dtype);
+  }
+  FYC_LAUNCH_CHECK();
+  return FYC_OK;
 }
 
 template <int LPR>

@@ -103,12 +103,50 @@ def tc_ok(dtype, M):
     return _impl != L.IMPL_SIMT and dtype == torch.bfloat16 and M >= 64 and lib().fyc_tcgen05_available() == 1
 
 
+use_ln_fold = os.environ.get("FYC_LN_FOLD", "1") != "0"          # A/B switch: LayerNorm folded into the consuming GEMM's epilogue
+
+
+def ln_fold_ok(dtype, M, C):
+    """can a LayerNorm over C channels feeding a GEMM on M rows be folded into that GEMM (fyc.h FYC_EPI_LNFOLD: tcgen05 path only)?"""
+    return use_ln_fold and tc_ok(dtype, M) and C % 8 == 0 and C <= 2048
+
+
+def layernorm_stats(x, eps=1e-5):
+    """x [..., C] -> fp32 [rows, 2] = (rstd, -rstd * mean) per row: the statistics pass of a LayerNorm whose scale / shift live in the
+    consuming GEMM's weights and epilogue (one read of x, no normalised copy)."""
+    _cuda(x, "layernorm_stats.x")
+    assert x.is_contiguous()
+    Cc = x.shape[-1]
+    M = x.numel() // Cc
+    out = torch.empty((M, 2), dtype=torch.float32, device=x.device)
+    fam = f"layernorm_stats[{M}x{Cc}]" if _prof_shapes else "layernorm_stats"
+    with _rec(fam, 0, x.numel() * x.element_size()):
+        check(lib().fyc_layernorm_stats(ptr(x), ptr(out), M, Cc, float(eps), dtype_code(x.dtype), stream_ptr()))
+    return out
+
+
+use_dual_source = os.environ.get("FYC_DUAL_SOURCE", "1") != "0"  # A/B switch: skip-concat read in place (two-source GroupNorm / shortcut GEMM)
+
+
 def gemm(A, W, bias=None, residual=None, rowbias=None, rows_per_group=0, alpha=1.0, geglu=False, out_f32=False,
-         out=None, impl=None):
+         out=None, impl=None, ln=None, A2=None):
     """out[M, N] = alpha * A[M, K] @ W[N, K]^T (+bias) (+rowbias[m // rows_per_group]) (+residual); GEGLU halves N.
-    A may be 2-D [M, K] or batched 3-D [B, M, K] with W [B, N, K] (one launch per batch on the tcgen05 path)."""
-    _cuda(A, "gemm.A"); _cuda(W, "gemm.W"); _cuda(residual, "gemm.residual")
+    A may be 2-D [M, K] or batched 3-D [B, M, K] with W [B, N, K] (one launch per batch on the tcgen05 path).
+    ``ln`` = (row stats [M, 2] from layernorm_stats, column sums [N] of W): A is the RAW input of a LayerNorm, W carries its gamma,
+    ``bias`` its beta term - out = rstd * (A W^T) + nrm * colsum + bias (fyc.h FYC_EPI_LNFOLD)."""
+    _cuda(A, "gemm.A"); _cuda(W, "gemm.W"); _cuda(residual, "gemm.residual"); _cuda(A2, "gemm.A2")
     _f32vec(bias, "gemm.bias"); _f32vec(rowbias, "gemm.rowbias")
+    K1 = 0
+    if A2 is not None:
+        # A = [A | A2] along K without the concatenation ever being written (fyc.h A2): tensor-core path with K1 % 64 == 0, else concatenate
+        assert A.dim() == 2 and A2.dim() == 2 and A2.shape[0] == A.shape[0] and A2.dtype == A.dtype
+        if (_impl if impl is None else impl) != L.IMPL_SIMT and tc_ok(A.dtype, A.shape[0]) and A.shape[1] % 64 == 0 and A2.shape[1] % 8 == 0 and use_dual_source:
+            K1 = A.shape[1]
+        else:
+            A, A2 = concat_channels(A.contiguous(), A2.contiguous()), None
+    if ln is not None:
+        _f32vec(ln[0], "gemm.ln_rowstats"); _f32vec(ln[1], "gemm.ln_colsum")
+        assert ln[0].shape == (A.shape[-2], 2) and ln[1].shape == (W.shape[-2],) and A.dim() == 2
     impl = _impl if impl is None else impl
     batched = A.dim() == 3
     if batched:
@@ -119,6 +157,8 @@ def gemm(A, W, bias=None, residual=None, rowbias=None, rows_per_group=0, alpha=1
         Bn, (M, K), N = 1, A.shape, W.shape[0]
         sA = sW = 0
         lda, ldw = A.stride(0), W.stride(0)
+    if K1:
+        K = K1 + A2.shape[1]
     assert W.shape[-1] == K and W.dtype == A.dtype
     fused_geglu = geglu and impl != L.IMPL_SIMT and tc_ok(A.dtype, M)
     n_out = N // 2 if fused_geglu else N
@@ -128,13 +168,16 @@ def gemm(A, W, bias=None, residual=None, rowbias=None, rows_per_group=0, alpha=1
     else:
         o = out
     epi = (L.EPI_BIAS if bias is not None else 0) | (L.EPI_RESIDUAL if residual is not None else 0) | \
-          (L.EPI_ROWBIAS if rowbias is not None else 0) | (L.EPI_GEGLU if fused_geglu else 0) | (L.EPI_OUT_F32 if out_f32 else 0)
+          (L.EPI_ROWBIAS if rowbias is not None else 0) | (L.EPI_GEGLU if fused_geglu else 0) | (L.EPI_OUT_F32 if out_f32 else 0) | \
+          (L.EPI_LNFOLD if ln is not None else 0)
     a = L.GemmArgs(ptr(A), ptr(W), ptr(o), ptr(bias), ptr(residual), ptr(rowbias), M, N, K, lda, ldw,
                    o.stride(-2), residual.stride(-2) if residual is not None else 0, Bn, sA, sW,
-                   o.stride(0) if batched else 0, rows_per_group, float(alpha), dtype_code(A.dtype), epi, impl)
+                   o.stride(0) if batched else 0, rows_per_group, float(alpha), dtype_code(A.dtype), epi, impl,
+                   ptr(A2) if K1 else None, A2.stride(0) if K1 else 0, K1,
+                   ptr(ln[0]) if ln is not None else None, ptr(ln[1]) if ln is not None else None)
     fam = "gemm_tc" if (impl != L.IMPL_SIMT and tc_ok(A.dtype, M) and N % 16 == 0 and K % 8 == 0) else "gemm_simt"
     if _prof_shapes:
-        fam += f"[{Bn}x{M}x{N}x{K}{'g' if fused_geglu else ''}{'r' if residual is not None else ''}]"
+        fam += f"[{Bn}x{M}x{N}x{K}{'g' if fused_geglu else ''}{'r' if residual is not None else ''}{'L' if ln is not None else ''}]"
     with _rec(fam, 2.0 * Bn * M * N * K, A.element_size() * Bn * (M * K + N * K + M * n_out)):
         check(lib().fyc_gemm(C.byref(a), stream_ptr()))
     if geglu and not fused_geglu:
@@ -204,20 +247,32 @@ def conv3x3(x, w, bias=None, residual=None, rowbias=None, images_per_group=0, st
     return out
 
 
-def groupnorm(x, gamma, beta, groups, eps, silu=False, stat_batches=None):
-    """x [..., C] contiguous; statistics per (stat batch, group) where x is viewed as [stat_batches, R, C]."""
-    _cuda(x, "groupnorm.x"); _f32vec(gamma, "groupnorm.gamma"); _f32vec(beta, "groupnorm.beta")
+def groupnorm(x, gamma, beta, groups, eps, silu=False, stat_batches=None, x2=None):
+    """x [..., C] contiguous; statistics per (stat batch, group) where x is viewed as [stat_batches, R, C].
+    ``x2`` [..., C2]: normalise the channel concatenation [x | x2] (gamma / beta of C + C2 channels) reading both tensors in place
+    (fyc_groupnorm_concat: the up blocks' skip concatenation is never written); returns [..., C + C2]."""
+    _cuda(x, "groupnorm.x"); _f32vec(gamma, "groupnorm.gamma"); _f32vec(beta, "groupnorm.beta"); _cuda(x2, "groupnorm.x2")
     assert x.is_contiguous()
-    Cc = x.shape[-1]
+    C1 = x.shape[-1]
+    vec = 8 if x.dtype == torch.bfloat16 else 4
+    if x2 is not None and not (use_dual_source and C1 % vec == 0 and x2.shape[-1] % vec == 0):
+        x, x2 = concat_channels(x, x2.contiguous()), None
+        C1 = x.shape[-1]
+    Cc = C1 + (x2.shape[-1] if x2 is not None else 0)
     NB = x.shape[0] if stat_batches is None else stat_batches
-    R = x.numel() // (NB * Cc)
-    out = torch.empty_like(x)
+    R = x.numel() // (NB * C1)
+    out = torch.empty(x.shape[:-1] + (Cc,), dtype=x.dtype, device=x.device)
     nbytes = lib().fyc_groupnorm_workspace_bytes(NB, Cc, groups)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
     fam = f"groupnorm[{NB}x{R}x{Cc}]" if _prof_shapes else "groupnorm"
-    with _rec(fam, 0, 3 * x.numel() * x.element_size()):
-        check(lib().fyc_groupnorm(ptr(x), ptr(gamma), ptr(beta), ptr(out), NB, R, Cc, groups, float(eps), int(silu),
-                                  dtype_code(x.dtype), ptr(ws), nbytes, stream_ptr()))
+    with _rec(fam, 0, 3 * out.numel() * x.element_size()):
+        if x2 is None:
+            check(lib().fyc_groupnorm(ptr(x), ptr(gamma), ptr(beta), ptr(out), NB, R, Cc, groups, float(eps), int(silu),
+                                      dtype_code(x.dtype), ptr(ws), nbytes, stream_ptr()))
+        else:
+            assert x2.is_contiguous() and x2.shape[:-1] == x.shape[:-1] and x2.dtype == x.dtype
+            check(lib().fyc_groupnorm_concat(ptr(x), C1, ptr(x2), x2.shape[-1], ptr(gamma), ptr(beta), ptr(out), NB, R, groups, float(eps),
+                                             int(silu), dtype_code(x.dtype), ptr(ws), nbytes, stream_ptr()))
     return out
 
 

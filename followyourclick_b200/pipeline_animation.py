@@ -138,10 +138,10 @@ class AnimationPipeline:
     last_video_device = None       # the most recent decode's (b, 3, F, H, W) fp32 video, still on the device
     graph_cache_entries = 4        # captured UNet-step graphs kept per pipeline (least recently used shapes are dropped)
     # Shared CFG prefix (UNet3DConditionModel.forward_nfhwc cfg_dup): the uncond / cond halves of the reference's batch are identical
-    # until the first cross-attention, so that prefix (incl. the first 64x64 self-attention) is computed once.  Exact, and verified
-    # against the reference fixtures through the CPU emulation of the kernels (tests/test_host_emulated_cpu.py); it has not had its
-    # GPU run yet (the round's GPU budget was spent), so it is opt-in: FYC_SHARED_PREFIX=1.
-    share_cfg_prefix = os.environ.get("FYC_SHARED_PREFIX", "0") == "1"
+    # until the first cross-attention, so that prefix (incl. the first 64x64 self-attention) is computed once.  Exact arithmetic on the
+    # same rows; GPU-verified in round 2 (tests/test_zz_late_gpu.py, tests/test_full_parity_gpu.py; cfg2 clip 1301 -> 1278 ms).
+    # FYC_SHARED_PREFIX=0 switches it off (A/B).
+    share_cfg_prefix = os.environ.get("FYC_SHARED_PREFIX", "1") != "0"
 
     def __init__(self, vae, text_encoder, tokenizer, unet, scheduler, image_encoder=None, text_encoder_2=None,
                  tokenizer_2=None, ip_adapter=None):

@@ -298,7 +298,11 @@ class UNet3DConditionModel(ParamTreeModel):
         """fp32 weight (time-embedding MLPs always run in fp32)"""
         return self._cached(("fw", key), lambda: self._p(key).detach().float().contiguous())
 
-    def _cat_w(self, name, keys, lora=None):
+    def _cat_w(self, name, keys, lora=None, dtype=None):
+        """rows of several projections stacked (q | k | v ...), temporal LoRA merged; ``dtype`` torch.float32: the unrounded stack (the
+        LN-fold packer scales it by gamma BEFORE the single rounding to the compute dtype)"""
+        dt = dtype or self._compute_dtype
+
         def make():
             ws = []
             for i, k in enumerate(keys):
@@ -306,11 +310,13 @@ class UNet3DConditionModel(ParamTreeModel):
                 if lora is not None and self._has(lora[i] + ".down.weight"):      # motion_module.py:389-456, scale 1.0
                     w = w + self._p(lora[i] + ".up.weight").detach().float() @ self._p(lora[i] + ".down.weight").detach().float()
                 ws.append(w)
-            return torch.cat(ws, dim=0).to(self._compute_dtype).contiguous()
-        return self._cached(("cat", name), make)
+            return torch.cat(ws, dim=0).to(dt).contiguous()
+        return self._cached(("cat", name, dt), make)
 
-    def _qkv_padded(self, p, heads, d, pad=64):
+    def _qkv_padded(self, p, heads, d, pad=64, dtype=None):
         """[Wq (heads x 64 rows, rows d..63 of every head zero) ; Wk (same) ; Wv] for the tcgen05 attention kernel."""
+        dt = dtype or self._compute_dtype
+
         def make():
             def padded(w):
                 C = w.shape[1]
@@ -318,14 +324,37 @@ class UNet3DConditionModel(ParamTreeModel):
                 wp[:, :d] = w.detach().float().view(heads, d, C)
                 return wp.view(heads * pad, C)
             ws = [padded(self._p(p + ".to_q.weight")), padded(self._p(p + ".to_k.weight")), self._p(p + ".to_v.weight").detach().float()]
-            return torch.cat(ws, dim=0).to(self._compute_dtype).contiguous()
-        return self._cached(("qkvpad", p), make)
+            return torch.cat(ws, dim=0).to(dt).contiguous()
+        return self._cached(("qkvpad", p, dt), make)
 
     def _geglu(self, p):
         def make():
             w, b = geglu_interleave(self._p(p + ".net.0.proj.weight").detach().float(), self._p(p + ".net.0.proj.bias").detach().float())
             return w.to(self._compute_dtype).contiguous(), b
         return self._cached(("geglu", p), make)
+
+    def _ln_fold(self, name, norm, make_w, make_bias=None, interleave=False, pe=None):
+        """LayerNorm folded into its consuming GEMM (fyc.h FYC_EPI_LNFOLD):  LN(x) W^T + b = rstd (x (gamma . W)^T) - rstd mean colsum + (beta W^T + b).
+        Returns (W' = gamma-scaled weight in the compute dtype, colsum[n] = sum_k W'[n, k] of the ROUNDED W' - the mean term then cancels
+        the accumulated product exactly -, cbias = beta W^T + b in fp32[, rowbias table (pe W^T) for the temporal position encoding:
+        (LN(x) + pe_f) W^T = LN(x) W^T + pe_f W^T]).  ``interleave``: GEGLU value / gate row interleave (modeling.geglu_interleave)."""
+        def make():
+            w = make_w().float()                                                     # [N, K] fp32 (q/k/v stacked, padded, LoRA merged ...)
+            g, b = self._p(norm + ".weight").detach().float(), self._p(norm + ".bias").detach().float()
+            wp = (w * g[None, :]).to(self._compute_dtype)
+            colsum = wp.float().sum(dim=1)
+            cb = w @ b
+            if make_bias is not None:
+                cb = cb + make_bias().float()
+            rb = None
+            if pe is not None:
+                rb = (pe.float() @ w.t()).contiguous()                               # [max_len, N]
+            if interleave:                                                           # a row permutation: applied to W' (already rounded), the bias, and
+                wi, cb = geglu_interleave(wp.float(), cb)                            # - by recomputing it - the column sums
+                wp = wi.to(self._compute_dtype)
+                colsum = wp.float().sum(dim=1)
+            return wp.contiguous(), colsum.contiguous(), cb.contiguous(), rb
+        return self._cached(("lnfold", name), make)
 
     def _freqs(self):
         def make():
@@ -335,11 +364,11 @@ class UNet3DConditionModel(ParamTreeModel):
         return self._cached(("freqs",), make)
 
     # ------------------------------------------------------------------------------------------ blocks
-    def _gn(self, p, x, B, silu, per_frame, eps=None, groups=None):
+    def _gn(self, p, x, B, silu, per_frame, eps=None, groups=None, x2=None):
         eps = self._cfg["norm_eps"] if eps is None else eps
         g = self._cfg["norm_num_groups"] if groups is None else groups
         nb = x.shape[0] if (per_frame or self._cfg["use_inflated_groupnorm"]) else B
-        return ops.groupnorm(x, self._f(p + ".weight"), self._f(p + ".bias"), g, eps, silu=silu, stat_batches=nb)
+        return ops.groupnorm(x, self._f(p + ".weight"), self._f(p + ".bias"), g, eps, silu=silu, stat_batches=nb, x2=x2)
 
     def _temb_pack(self):
         """Every ResnetBlock3D's time_emb_proj (resnet.py:307-313) stacked into one [sum Cout, temb] fp32 matrix: the forward runs
@@ -357,23 +386,35 @@ class UNet3DConditionModel(ParamTreeModel):
             return w, b, offs
         return self._cached(("temb_pack",), make)
 
-    def _resnet(self, p, x, temb_all, B, F):
+    def _resnet(self, p, x, temb_all, B, F, skip=None):
+        """``skip``: the up blocks' `torch.cat([hidden_states, res_hidden_states], dim=1)` (unet_blocks.py:763,885) is not materialised -
+        norm1 normalises [x | skip] reading both tensors in place, the 1x1 shortcut runs its K loop over the two sources."""
         NB, H, W, Cin = x.shape
         o, n = self._temb_pack()[2][p]
         temb = temb_all[:, o:o + n]                      # [B, Cout] fp32 view, row stride = sum Cout
-        h = self._gn(p + ".norm1", x, B, True, False)
+        h = self._gn(p + ".norm1", x, B, True, False, x2=skip)
         h = ops.conv3x3(h, self._conv_w(p + ".conv1.weight"), bias=self._f(p + ".conv1.bias"), rowbias=temb, images_per_group=F)
         h = self._gn(p + ".norm2", h, B, True, False)
         if self._has(p + ".conv_shortcut.weight"):
-            res = ops.gemm(x.view(-1, Cin), self._w1x1(p + ".conv_shortcut.weight"), bias=self._f(p + ".conv_shortcut.bias"))
+            res = ops.gemm(x.view(-1, Cin), self._w1x1(p + ".conv_shortcut.weight"), bias=self._f(p + ".conv_shortcut.bias"),
+                           A2=None if skip is None else skip.view(-1, skip.shape[-1]))
             res = res.view(NB, H, W, -1)
         else:
-            res = x
+            res = x if skip is None else ops.concat_channels(x, skip)
         return ops.conv3x3(h, self._conv_w(p + ".conv2.weight"), bias=self._f(p + ".conv2.bias"), residual=res)
 
-    def _ff(self, p, tok, n):
-        w1, b1 = self._geglu(p)
-        h = ops.gemm(n, w1, bias=b1, geglu=True)
+    def _ff(self, p, tok, norm):
+        """x + W2 (a . gelu(g)),  [a, g] = W1 LN(x) + b1  (attention.py:563, motion_module.py:282): LayerNorm `norm` folded into the GEGLU GEMM
+        in tensor-core mode"""
+        M, C = tok.shape
+        if ops.ln_fold_ok(tok.dtype, M, C) and C % 32 == 0:          # 8 C rows in 256-row GEGLU tiles
+            w1, cs, cb, _ = self._ln_fold(p + ".net.0.proj", norm, lambda: self._p(p + ".net.0.proj.weight").detach(),
+                                          lambda: self._p(p + ".net.0.proj.bias").detach(), interleave=True)
+            h = ops.gemm(tok, w1, bias=cb, geglu=True, ln=(ops.layernorm_stats(tok), cs))
+        else:
+            n = ops.layernorm(tok, self._f(norm + ".weight"), self._f(norm + ".bias"))
+            w1, b1 = self._geglu(p)
+            h = ops.gemm(n, w1, bias=b1, geglu=True)
         return ops.gemm(h, self._w(p + ".net.2.weight"), bias=self._f(p + ".net.2.bias"), residual=tok)
 
     def _transformer(self, p, x, ctx, heads, F, dup=1):
@@ -387,21 +428,34 @@ class UNet3DConditionModel(ParamTreeModel):
         tok = ops.gemm(h.view(M, C), self._w1x1(p + ".proj_in.weight"), bias=self._f(p + ".proj_in.bias"))
         q = p + ".transformer_blocks.0"
         # self attention (attention.py:507)
-        n1 = ops.layernorm(tok, self._f(q + ".norm1.weight"), self._f(q + ".norm1.bias"))
-        if ops.self_attention_tc_ok(tok.dtype, HW, d):
+        # LayerNorm -> projection pairs (norm1 -> q/k/v, norm2 -> to_q, norm3 -> GEGLU): in tensor-core mode the norm is folded into
+        # the GEMM (one read-only statistics pass + epilogue terms, _ln_fold) instead of writing and re-reading a normalised copy
+        fold = ops.ln_fold_ok(tok.dtype, M, C)
+        tc_attn = ops.self_attention_tc_ok(tok.dtype, HW, d)
+        qkv_w = (lambda dtype=None: self._qkv_padded(q + ".attn1", heads, d, dtype=dtype)) if tc_attn else \
+            (lambda dtype=None: self._cat_w(q + ".attn1", [q + ".attn1.to_q.weight", q + ".attn1.to_k.weight", q + ".attn1.to_v.weight"], dtype=dtype))
+        if fold:
+            w1_, cs1, cb1, _ = self._ln_fold(q + ".attn1.qkv" + (".pad" if tc_attn else ""), q + ".norm1", lambda: qkv_w(torch.float32))
+            qkv = ops.gemm(tok, w1_, bias=cb1, ln=(ops.layernorm_stats(tok), cs1))
+        else:
+            qkv = ops.gemm(ops.layernorm(tok, self._f(q + ".norm1.weight"), self._f(q + ".norm1.bias")), qkv_w())
+        if tc_attn:
             # tcgen05 path: q/k heads zero-padded to 64 columns by the packed weight, V transposed per image (keys contiguous)
-            qkv = ops.gemm(n1, self._qkv_padded(q + ".attn1", heads, d)).view(NB, HW, 2 * heads * 64 + C)
+            qkv = qkv.view(NB, HW, 2 * heads * 64 + C)
             ops.note_padding(2.0 * M * C * 2 * heads * (64 - d))
             vt = ops.transpose_tokens(qkv, 2 * heads * 64, C)
             o = ops.self_attention_tc(qkv, 0, heads * 64, vt, heads, d, d ** -0.5)
         else:
-            qkv = ops.gemm(n1, self._cat_w(q + ".attn1", [q + ".attn1.to_q.weight", q + ".attn1.to_k.weight", q + ".attn1.to_v.weight"]))
             qkv = qkv.view(NB, HW, 3 * C)
             o = ops.attention(qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:], heads, d ** -0.5)
         tok = ops.gemm(o.view(M, C), self._w(q + ".attn1.to_out.0.weight"), bias=self._f(q + ".attn1.to_out.0.bias"), residual=tok)
         # cross attention (attention.py:516-521; IPCrossAttention.forward :49-127); K/V of the context come from the per-clip cache
-        n2 = ops.layernorm(tok, self._f(q + ".norm2.weight"), self._f(q + ".norm2.bias"))
-        qx = ops.gemm(n2, self._w(q + ".attn2.to_q.weight")).view(NB, HW, C)
+        if fold:
+            w2_, cs2, cb2, _ = self._ln_fold(q + ".attn2.to_q", q + ".norm2", lambda: self._p(q + ".attn2.to_q.weight").detach())
+            qx = ops.gemm(tok, w2_, bias=cb2, ln=(ops.layernorm_stats(tok), cs2)).view(NB, HW, C)
+        else:
+            n2 = ops.layernorm(tok, self._f(q + ".norm2.weight"), self._f(q + ".norm2.bias"))
+            qx = ops.gemm(n2, self._w(q + ".attn2.to_q.weight")).view(NB, HW, C)
         kv = ctx.kv[p]
         L = kv.shape[1]
         Bq = kv.shape[0] // dup                 # clips per context replica
@@ -428,8 +482,7 @@ class UNet3DConditionModel(ParamTreeModel):
                 ops.gemm(o[r * NB:(r + 1) * NB].view(M, C), w_o, bias=b_o, residual=tok, out=tok_d[r * M:(r + 1) * M])
             tok = tok_d
         # feed forward (attention.py:563)
-        n3 = ops.layernorm(tok, self._f(q + ".norm3.weight"), self._f(q + ".norm3.bias"))
-        tok = self._ff(q + ".ff", tok, n3)
+        tok = self._ff(q + ".ff", tok, q + ".norm3")
         w_p, b_p = self._w1x1(p + ".proj_out.weight"), self._f(p + ".proj_out.bias")
         if dup == 1:
             out = ops.gemm(tok, w_p, bias=b_p, residual=res)
@@ -457,16 +510,24 @@ class UNet3DConditionModel(ParamTreeModel):
                     if F > self._p(a + ".pos_encoder.pe").shape[1]:
                         raise ValueError(f"video_length {F} exceeds temporal_position_encoding_max_len")
                     pe = self._cached(("pe", a), lambda a=a: self._p(a + ".pos_encoder.pe").detach()[0].float().contiguous())
-                n = ops.layernorm(tok, self._f(q + f".norms.{j}.weight"), self._f(q + f".norms.{j}.bias"), pe=pe,
-                                  rows_per_frame=HW, frames=F)
                 names = ["to_q", "to_k", "to_v"]
-                wqkv = self._cat_w(a, [a + f".{nm}.weight" for nm in names], lora=[a + f".{nm}_lora" for nm in names])
-                qkv = ops.gemm(n, wqkv).view(B, F, HW, 3 * C)
+                mk = lambda dtype=None, a=a: self._cat_w(a, [a + f".{nm}.weight" for nm in names], lora=[a + f".{nm}_lora" for nm in names], dtype=dtype)
+                if ops.ln_fold_ok(tok.dtype, M, C) and (pe is None or HW % 128 == 0):
+                    # (LN(x) + pe_f) Wqkv^T = LN-folded GEMM + the per-frame row-bias table pe Wqkv^T (motion_module.py:303,378)
+                    wq_, cs, cb, rbt = self._ln_fold(a + ".qkv", q + f".norms.{j}", lambda: mk(torch.float32), pe=pe)
+                    rb = None
+                    if pe is not None:
+                        rb = self._cached(("pe_rb", a, B, F), lambda rbt=rbt: rbt[:F].repeat(B, 1).contiguous())      # row group = (clip, frame)
+                    qkv = ops.gemm(tok, wq_, bias=cb, rowbias=rb, rows_per_group=HW if pe is not None else 0,
+                                   ln=(ops.layernorm_stats(tok), cs)).view(B, F, HW, 3 * C)
+                else:
+                    n = ops.layernorm(tok, self._f(q + f".norms.{j}.weight"), self._f(q + f".norms.{j}.bias"), pe=pe,
+                                      rows_per_frame=HW, frames=F)
+                    qkv = ops.gemm(n, mk()).view(B, F, HW, 3 * C)
                 o = ops.temporal_attention(qkv, heads, d ** -0.5)
                 wo = self._cat_w(a + ".out", [a + ".to_out.0.weight"], lora=[a + ".to_out_lora"])
                 tok = ops.gemm(o.view(M, C), wo, bias=self._f(a + ".to_out.0.bias"), residual=tok)
-            n = ops.layernorm(tok, self._f(q + ".ff_norm.weight"), self._f(q + ".ff_norm.bias"))
-            tok = self._ff(q + ".ff", tok, n)
+            tok = self._ff(q + ".ff", tok, q + ".ff_norm")
         out = ops.gemm(tok, self._w(p + ".proj_out.weight"), bias=self._f(p + ".proj_out.bias"), residual=res)
         return out.view(NB, H, W, C)
 
@@ -618,8 +679,7 @@ class UNet3DConditionModel(ParamTreeModel):
                 skip = skips.pop()
                 if skip.shape[0] != x.shape[0]:          # the conv_in output of the shared prefix: one copy per clip -> the CFG pair
                     skip = skip.repeat(dup, 1, 1, 1)     # (a 2 x 42 MB device copy per forward at cfg2)
-                x = ops.concat_channels(x, skip)
-                x = self._resnet(f"{p}.resnets.{j}", x, semb, B, F)
+                x = self._resnet(f"{p}.resnets.{j}", x, semb, B, F, skip=skip)
                 if i > 0:
                     x = self._transformer(f"{p}.attentions.{j}", x, ctx, self._heads[lvl], F)
                 if motion_on(lvl, True):

@@ -36,7 +36,14 @@ enum {
   FYC_EPI_RESIDUAL = 2,  /* + residual[m, n]                           */
   FYC_EPI_ROWBIAS = 4,   /* + rowbias[m / rows_per_group, n]  (time embedding broadcast, resnet.py:307,319) */
   FYC_EPI_GEGLU = 8,     /* out[m, j] = a * gelu_erf(gate); weight rows pre-interleaved in 128-col granules */
-  FYC_EPI_OUT_F32 = 16   /* write fp32 output regardless of `dtype`    */
+  FYC_EPI_OUT_F32 = 16,  /* write fp32 output regardless of `dtype`    */
+  FYC_EPI_LNFOLD = 32    /* A is the RAW input x of a LayerNorm whose output this GEMM consumes (attention.py:383,412,418, motion_module.py:261,
+                            267: norm1/2/3, norms.j, ff_norm -> to_q/k/v, ff.net.0.proj).  With W' = gamma (.) W (packed by the caller):
+                              LN(x) W^T = rstd_m * (x W'^T)[m, n] - rstd_m * mean_m * colsum[n] + (beta W^T)[n]
+                            so the epilogue computes  rstd_m * acc + nrm_m * ln_colsum[n] + bias[n]  with (rstd_m, nrm_m = -rstd_m mean_m) from
+                            fyc_layernorm_stats and bias := beta W^T + the layer's bias.  The normalised tensor is never written or re-read:
+                            one read-only statistics pass replaces LayerNorm's read + write pass.  tcgen05 path, alpha = 1, no fp32 output, no residual;
+                            with FYC_EPI_ROWBIAS (the temporal position table P W^T) rows_per_group must be a multiple of 128. */
 };
 enum { FYC_PRED_EPSILON = 0, FYC_PRED_SAMPLE = 1, FYC_PRED_V = 2 };
 
@@ -62,6 +69,12 @@ typedef struct {
   int64_t rows_per_group;
   float alpha;
   int32_t dtype, epilogue, impl;
+  const void* A2;               /* optional second K segment (NULL: none): A[:, :K1] comes from A (lda), A[:, K1:] from A2 (lda2) - the GEMM over
+                                   a channel concatenation that is never written (the up blocks' conv_shortcut on cat([x, skip]),
+                                   resnet.py:286 after unet_blocks.py:763,885).  tcgen05 path: K1 % 64 == 0.  W stays [N, K]. */
+  int64_t lda2, K1;
+  const float* ln_rowstats;     /* FYC_EPI_LNFOLD: [M][2] fp32 (rstd, -rstd * mean) per row, from fyc_layernorm_stats */
+  const float* ln_colsum;       /* FYC_EPI_LNFOLD: [N] fp32, colsum[n] = sum_k W'[n, k] (of the bf16-rounded packed weight) */
 } fyc_gemm_args;
 int32_t fyc_gemm(const fyc_gemm_args* a, void* stream);
 
@@ -113,11 +126,21 @@ size_t fyc_groupnorm_workspace_bytes(int64_t NB, int64_t C, int64_t G);
 int32_t fyc_groupnorm(const void* x, const float* gamma, const float* beta, void* out, int64_t NB, int64_t R,
                       int64_t C, int64_t G, float eps, int32_t silu, int32_t dtype, void* workspace,
                       size_t workspace_bytes, void* stream);
+/* GroupNorm of the channel concatenation [x1 (C1) | x2 (C2)] WITHOUT materialising it: the up blocks' `torch.cat([hidden_states,
+ * res_hidden_states], dim=1)` (animatediff/models/unet_blocks.py:763,885) feeds ResnetBlock3D.norm1 (and the 1x1 shortcut, see
+ * fyc_gemm_args.A2); both read the two tensors in place.  out: [NB, R, C1 + C2].  Same workspace as fyc_groupnorm with C = C1 + C2. */
+int32_t fyc_groupnorm_concat(const void* x1, int64_t C1, const void* x2, int64_t C2, const float* gamma, const float* beta, void* out,
+                             int64_t NB, int64_t R, int64_t G, float eps, int32_t silu, int32_t dtype, void* workspace,
+                             size_t workspace_bytes, void* stream);
 /* LayerNorm over the last dim (attention.py:383,412,418; motion_module.py:261,267), optional sinusoidal
  * position table added AFTER the norm: out = LN(x) + pe[(row / rows_per_frame) % frames]  (motion_module.py:303,378). */
 int32_t fyc_layernorm(const void* x, const float* gamma, const float* beta, void* out, int64_t M, int64_t C,
                       float eps, const float* pe, int64_t rows_per_frame, int64_t frames, int32_t dtype,
                       void* stream);
+
+/* LayerNorm statistics only: stats[m] = (rstd_m, -rstd_m * mean_m), biased variance + eps like nn.LayerNorm - the row scalars of a GEMM
+ * launched with FYC_EPI_LNFOLD. */
+int32_t fyc_layernorm_stats(const void* x, float* stats, int64_t M, int64_t C, float eps, int32_t dtype, void* stream);
 
 /* ---- attention ----------------------------------------------------------------------------------------
  * out[n, i, h*D + :] (=|+=) out_alpha * softmax_j(scale * q[n,i,h] . k[n',j,h]) v[n',j,h],  n' = n / kv_batch_div.

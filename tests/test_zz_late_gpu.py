@@ -35,12 +35,13 @@ def test_shared_cfg_prefix_on_gpu(dtype):
     s = stats(shared, full)
     assert s["rel_l2"] < (1e-6 if dtype == torch.float32 else 2e-3), s
     old = AnimationPipeline.share_cfg_prefix
-    AnimationPipeline.share_cfg_prefix = True
-    try:
-        r = run_pipeline_case(dtype, steps=3, against="golden")
-    finally:
-        AnimationPipeline.share_cfg_prefix = old
-    assert r["finite"] and (r["video_maxabs"] < 2e-3 if dtype == torch.float32 else r["psnr"] > 30.0), r
+    for share in (True, False):            # default on; off = the reference's duplicated CFG batch
+        AnimationPipeline.share_cfg_prefix = share
+        try:
+            r = run_pipeline_case(dtype, steps=3, against="golden")
+        finally:
+            AnimationPipeline.share_cfg_prefix = old
+        assert r["finite"] and (r["video_maxabs"] < 2e-3 if dtype == torch.float32 else r["psnr"] > 30.0), (share, r)
 
 
 @pytest.mark.parametrize("variant", ["ip", "cam"])
