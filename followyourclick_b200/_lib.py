@@ -23,7 +23,7 @@ class GemmArgs(C.Structure):
     _fields_ = [("A", _vp), ("W", _vp), ("out", _vp), ("bias", _vp), ("residual", _vp), ("rowbias", _vp),
                 ("M", _i64), ("N", _i64), ("K", _i64), ("lda", _i64), ("ldw", _i64), ("ldo", _i64), ("ldr", _i64),
                 ("batch", _i64), ("strideA", _i64), ("strideW", _i64), ("strideO", _i64), ("rows_per_group", _i64),
-                ("alpha", _f32), ("dtype", _i32), ("epilogue", _i32), ("impl", _i32), ("A2", _vp), ("lda2", _i64), ("K1", _i64), ("ln_rowstats", _vp), ("ln_colsum", _vp)]
+                ("alpha", _f32), ("dtype", _i32), ("epilogue", _i32), ("impl", _i32), ("A2", _vp), ("lda2", _i64), ("K1", _i64), ("ln_rowstats", _vp)]
 
 
 class ConvArgs(C.Structure):
@@ -59,7 +59,7 @@ SIGNATURES = {
     "fyc_groupnorm": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _f32, _i32, _i32, _vp, _sz, _vp]),
     "fyc_groupnorm_concat": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _i64, _i64, _i64, _f32, _i32, _i32, _vp, _sz, _vp]),
     "fyc_layernorm": (_i32, [_vp, _vp, _vp, _vp, _i64, _i64, _f32, _vp, _i64, _i64, _i32, _vp]),
-    "fyc_layernorm_stats": (_i32, [_vp, _vp, _i64, _i64, _f32, _i32, _vp]),
+    "fyc_layernorm_stats": (_i32, [_vp, _vp, _vp, _i64, _i64, _f32, _i32, _vp]),
     "fyc_attention": (_i32, [C.POINTER(AttnArgs), _vp]),
     "fyc_temporal_attention": (_i32, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _f32, _i32, _vp]),
     "fyc_self_attention_tc": (_i32, [_vp, _i64, _i64, _i64, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _f32, _vp]),

@@ -43,6 +43,7 @@ struct TcParams {
   int BN, n_tiles;
   // output-pixel tiling: tile = bn images x bh rows x bw cols; Wt = ceil(Wo / bw) tiles per row, etc.
   int bw, bh, bn, Wo, Ho, w_tiles, h_tiles;
+  int lg_bw, lg_bh;          // log2 of bw, bh (both powers of two)
   int64_t m_tiles;
   int tap_dy[9], tap_dx[9], tap_img[9];
   // epilogue
@@ -53,8 +54,8 @@ struct TcParams {
   int flags;
   // two-segment K (fyc_gemm_args.A2): k blocks [0, cb_split) of a tap come from map_a, the rest from map_a2 (INT_MAX: single source)
   int cb_split;
-  // LayerNorm folded into the epilogue (FYC_EPI_LNFOLD): per-row (rstd, -rstd * mean) and per-column sum of the gamma-scaled weight
-  const float* ln_rs; const float* ln_cs;
+  // LayerNorm folded into the GEMM (FYC_EPI_LNFOLD): per-row rstd; the mean term is an extra K block (A2 = fyc_layernorm_stats' aug rows)
+  const float* ln_rs;
   // W-resident mode (small K): the CTA keeps its whole BN x K weight slab in shared memory and only streams A
   int resident, a_stages;
   // CTA-pair mode (tcgen05 cta_group::2): a cluster of two CTAs computes a 256 x BN tile; each CTA stages its own 128 rows of A
@@ -256,12 +257,11 @@ struct EpiRows {
   int n0;                     // first column of the tile
 };
 struct EpiPrefetch { float4 b0, b1; uint4 res[4]; };
-// LayerNorm fold: the 4 rows' (rstd, -rstd * mean), fetched with the row offsets one tile ahead, and the lane's 8 column sums per group
-struct EpiLnRows { float2 st[4]; };
-struct EpiLnCols { float4 s0, s1; };
+// LayerNorm fold: the 4 rows' rstd, fetched with the row offsets one tile ahead (the mean term is already in the accumulator, see fyc.h)
+struct EpiLnRows { float rs[4]; };
 
 template <bool LNF>
-__device__ __forceinline__ void epi_rows(const TcParams& p, const TileCoord& tc, const uint32_t* whi, int q, EpiRows& t, EpiLnRows& ln) {
+__device__ __forceinline__ void epi_rows(const TcParams& p, const TileCoord& tc, int r0, int q, EpiRows& t, EpiLnRows& ln) {
   const int n_blk = tc.n, wt = tc.w, ht = tc.h, it = tc.i;
   t.n0 = (int)n_blk * p.BN;
   t.ok = 0; t.rgu = -1;
@@ -269,15 +269,18 @@ __device__ __forceinline__ void epi_rows(const TcParams& p, const TileCoord& tc,
   int mn = 0x7fffffff, mx = -1;
 #pragma unroll
   for (int ps = 0; ps < 4; ++ps) {
-    const int ow = (int)wt * p.bw + (int)(whi[ps] & 1023u), oh = (int)ht * p.bh + (int)((whi[ps] >> 10) & 1023u);
-    const int img = (int)it * p.bn + (int)(whi[ps] >> 20);
+    // (w, h, image) of patch row r0 + 8 ps: bw, bh are powers of two (pick_patch), so three shifts / masks per row per tile - cheaper than
+    // four live registers in a loop that is at the register cap (they were being spilled: a local-memory round trip per tile)
+    const int r = r0 + ps * 8;
+    const int ow = (int)wt * p.bw + (r & (p.bw - 1)), oh = (int)ht * p.bh + ((r >> p.lg_bw) & (p.bh - 1));
+    const int img = (int)it * p.bn + (r >> (p.lg_bw + p.lg_bh));
     const int64_t pix = ((int64_t)img * p.Ho + oh) * p.Wo + ow;
     const bool ok = (ow < p.Wo) && (oh < p.Ho) && (pix < p.M);
     t.ok |= (ok ? 1u : 0u) << ps;
     const uint32_t px = ok ? (uint32_t)pix : 0u;
     t.oo[ps] = px * ldo8 + cq;
     t.ro[ps] = px * ldr8 + cq;
-    if constexpr (LNF) ln.st[ps] = ok ? __ldg(reinterpret_cast<const float2*>(p.ln_rs) + px) : make_float2(0.f, 0.f);
+    if constexpr (LNF) ln.rs[ps] = ok ? __ldg(p.ln_rs + px) : 0.f;
     if ((p.flags & FYC_EPI_ROWBIAS) && ok) {
       const int rg = (int)(px / (uint32_t)p.rows_per_group);
       mn = min(mn, rg); mx = max(mx, rg);
@@ -291,14 +294,10 @@ __device__ __forceinline__ void epi_rows(const TcParams& p, const TileCoord& tc,
 
 // loads for 32-column group g of tile t: bias (+ the warp-uniform row bias) of this lane's 8 columns, residual of its 4 rows
 template <bool LNF>
-__device__ __forceinline__ void epi_prefetch(const TcParams& p, const EpiRows& t, int g, int q, EpiPrefetch& f, EpiLnCols& lc) {
+__device__ __forceinline__ void epi_prefetch(const TcParams& p, const EpiRows& t, int g, int q, EpiPrefetch& f) {
   const int c = g * 32 + q * 8, n = t.n0 + c;
   const bool col_ok = (c < p.BN) && (n < p.N);
   f.b0 = f.b1 = make_float4(0.f, 0.f, 0.f, 0.f);
-  if constexpr (LNF) {
-    lc.s0 = lc.s1 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (col_ok) { lc.s0 = __ldg(reinterpret_cast<const float4*>(p.ln_cs + n)); lc.s1 = __ldg(reinterpret_cast<const float4*>(p.ln_cs + n + 4)); }
-  }
   if ((p.flags & FYC_EPI_BIAS) && col_ok) {
     f.b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
     f.b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
@@ -323,12 +322,7 @@ __device__ __forceinline__ void epilogue_plain(const TcParams& p, const TileSche
   const int rip = lane >> 2, q = lane & 3;
   const int NG = (p.BN + 31) >> 5;
   const float alpha = p.alpha;
-  uint32_t whi[4];                                  // (w, h, image) of this lane's 4 rows inside the 128-pixel patch, 10 bits each
-#pragma unroll
-  for (int ps = 0; ps < 4; ++ps) {
-    const int r = quarter * 32 + ps * 8 + rip;
-    whi[ps] = (uint32_t)(r % p.bw) | ((uint32_t)((r / p.bw) % p.bh) << 10) | ((uint32_t)(r / (p.bw * p.bh)) << 20);
-  }
+  const int r0 = quarter * 32 + rip;                // this lane's rows inside the 128-pixel patch: r0 + 8 ps
   // staging addresses: P2 writes row `lane`, P3 reads rows ps*8 + rip (row & 7 == rip for every ps)
   uint8_t* const srow = stage + lane * 128;
   const int sw = lane & 7;
@@ -340,11 +334,10 @@ __device__ __forceinline__ void epilogue_plain(const TcParams& p, const TileSche
   int eg = egroup;                                  // the column half alternates per tile: NG is odd for N = 320 (3 + 2 groups)
   EpiRows cur, nxt;
   EpiPrefetch pf;
-  EpiLnRows lrc, lrn;          // LNF only (empty use otherwise: the compiler drops them)
-  EpiLnCols lcf;
+  EpiLnRows lrc, lrn;          // LNF only (unused otherwise: the compiler drops them)
   int64_t tile = ts.t0;
   TileCoord tcn = tile_coord(p, ts, tile);           // coordinates of the NEXT tile to be decoded
-  if (tile < num_tiles) { epi_rows<LNF>(p, tcn, whi, q, cur, lrc); epi_prefetch<LNF>(p, cur, eg, q, pf, lcf); }
+  if (tile < num_tiles) { epi_rows<LNF>(p, tcn, r0, q, cur, lrc); epi_prefetch<LNF>(p, cur, eg, q, pf); }
   nxt = cur; lrn = lrc;
   for (; tile < num_tiles; tile += ts.stride) {
     mbar_wait(&tfull[acc], aphase);
@@ -354,7 +347,7 @@ __device__ __forceinline__ void epilogue_plain(const TcParams& p, const TileSche
     const int64_t next_tile = tile + ts.stride;
     tile_advance(p, ts, tcn);
     if (next_tile < num_tiles) {
-      epi_rows<LNF>(p, tcn, whi, q, nxt, lrn);
+      epi_rows<LNF>(p, tcn, r0, q, nxt, lrn);
       if (!LNF && (p.flags & FYC_EPI_RESIDUAL)) {             // pull the next tile's residual rows into L2 a whole tile ahead: lane q takes its
         const int g = (eg ^ 1) + 2 * q;             // q-th group, so one instruction per row covers all of this warp's groups
         if (g < NG && nxt.n0 + g * 32 < p.N) {
@@ -367,19 +360,18 @@ __device__ __forceinline__ void epilogue_plain(const TcParams& p, const TileSche
         }
       }
     } else nxt.ok = 0;                               // nothing follows: the prefetch below degenerates to (valid) bias loads
-    if (eg >= NG) epi_prefetch<LNF>(p, nxt, eg ^ 1, q, pf, lcf);
+    if (eg >= NG) epi_prefetch<LNF>(p, nxt, eg ^ 1, q, pf);
     for (int gi = eg; gi < NG; gi += 2) {
       // ---- P2
       uint32_t rr[32];
       tmem_ld32(taddr + gi * 32, rr);
       // ---- prefetch of the group after this one (possibly the next tile's first) while the TMEM load is in flight
       EpiPrefetch pn;
-      EpiLnCols lcn;
       {
         const bool last = gi + 2 >= NG;
         EpiRows src = cur;
         if (last) src = nxt;
-        epi_prefetch<LNF>(p, src, last ? (eg ^ 1) : gi + 2, q, pn, lcn);
+        epi_prefetch<LNF>(p, src, last ? (eg ^ 1) : gi + 2, q, pn);
       }
       tmem_ld_wait32(rr);
 #pragma unroll
@@ -426,12 +418,10 @@ __device__ __forceinline__ void epilogue_plain(const TcParams& p, const TileSche
       for (int ps = 0; ps < 4; ++ps) {
         const float4 x0 = xs[ps][0], x1 = xs[ps][1];
         float v[8];
-        if constexpr (LNF) {       // LN(x) W^T = rstd * acc + (-rstd * mean) * colsum[n] + (beta W^T + bias)[n]
-          const float rs = lrc.st[ps].x, nr = lrc.st[ps].y;
-          v[0] = fmaf(x0.x, rs, fmaf(nr, lcf.s0.x, pf.b0.x)); v[1] = fmaf(x0.y, rs, fmaf(nr, lcf.s0.y, pf.b0.y));
-          v[2] = fmaf(x0.z, rs, fmaf(nr, lcf.s0.z, pf.b0.z)); v[3] = fmaf(x0.w, rs, fmaf(nr, lcf.s0.w, pf.b0.w));
-          v[4] = fmaf(x1.x, rs, fmaf(nr, lcf.s1.x, pf.b1.x)); v[5] = fmaf(x1.y, rs, fmaf(nr, lcf.s1.y, pf.b1.y));
-          v[6] = fmaf(x1.z, rs, fmaf(nr, lcf.s1.z, pf.b1.z)); v[7] = fmaf(x1.w, rs, fmaf(nr, lcf.s1.w, pf.b1.w));
+        if constexpr (LNF) {       // LN(x) W^T + b = rstd * (x W'^T - mean colsum) + (beta W^T + b): the bracket is the accumulator
+          const float rs = lrc.rs[ps];
+          v[0] = fmaf(x0.x, rs, pf.b0.x); v[1] = fmaf(x0.y, rs, pf.b0.y); v[2] = fmaf(x0.z, rs, pf.b0.z); v[3] = fmaf(x0.w, rs, pf.b0.w);
+          v[4] = fmaf(x1.x, rs, pf.b1.x); v[5] = fmaf(x1.y, rs, pf.b1.y); v[6] = fmaf(x1.z, rs, pf.b1.z); v[7] = fmaf(x1.w, rs, pf.b1.w);
         } else {
           v[0] = fmaf(x0.x, a_eff, pf.b0.x); v[1] = fmaf(x0.y, a_eff, pf.b0.y); v[2] = fmaf(x0.z, a_eff, pf.b0.z); v[3] = fmaf(x0.w, a_eff, pf.b0.w);
           v[4] = fmaf(x1.x, a_eff, pf.b1.x); v[5] = fmaf(x1.y, a_eff, pf.b1.y); v[6] = fmaf(x1.z, a_eff, pf.b1.z); v[7] = fmaf(x1.w, a_eff, pf.b1.w);
@@ -452,7 +442,6 @@ __device__ __forceinline__ void epilogue_plain(const TcParams& p, const TileSche
       }
       __syncwarp();
       pf = pn;
-      if constexpr (LNF) lcf = lcn;
     }
     epi_release<PAIR>(&tempty[acc], lane);
     if (p.debug) dbg_epi += clock64() - te1;
@@ -477,55 +466,44 @@ __device__ __forceinline__ void epilogue_geglu(const TcParams& p, const TileSche
   const int quarter = warp & 3, egroup = (warp - 2) >> 2;
   const int r = quarter * 32 + lane;
   const int wl = r % p.bw, hl = (r / p.bw) % p.bh, il = r / (p.bw * p.bh);
-  const int et = (warp - 2) * 32 + lane;                 // 0..255: the bias (and column-sum) element this thread carries
+  const int et = (warp - 2) * 32 + lane;                 // 0..255: the bias element this thread carries
   const int sub = lane >> 3, ch8 = lane & 7;
   const int c0 = egroup * 64;                            // this warp's 64 output columns of the tile
   uint8_t* const srow = stage + lane * 128;
   uint4* const obase = reinterpret_cast<uint4*>(p.out);
   const uint32_t ldo8 = (uint32_t)(p.ldo >> 3);
-  float* const sb = sbias;                               // [256] bias of the current tile (single buffer: two named barriers per tile)
-  float* const ss = sbias + 256;                         // [256] LNF: column sums of the gamma-scaled weight
   long long dbg_epi = 0;
   int acc = 0; uint32_t aphase = 0;
   int64_t tile = ts.t0;
-  float bnext = 0.f, snext = 0.f;
-  float2 stn = make_float2(1.f, 0.f);                    // LNF: (rstd, -rstd * mean) of this thread's row in the NEXT tile
+  float bnext = 0.f;
+  float rnext = 1.0f;                                      // LNF: rstd of this thread's row in the NEXT tile (fetched one tile ahead like the bias)
   TileCoord tc = tile_coord(p, ts, tile);
-  auto row_of = [&](const TileCoord& c, bool& ok) -> int64_t {
+  auto row_rstd = [&](const TileCoord& c) -> float {
     const int ow = c.w * p.bw + wl, oh = c.h * p.bh + hl, img = c.i * p.bn + il;
-    const int64_t pix = ((int64_t)img * p.Ho + oh) * p.Wo + ow;
-    ok = (ow < p.Wo) && (oh < p.Ho) && (pix < p.M);
-    return pix;
+    const int64_t px = ((int64_t)img * p.Ho + oh) * p.Wo + ow;
+    return ((ow < p.Wo) && (oh < p.Ho) && (px < p.M)) ? __ldg(p.ln_rs + px) : 1.0f;
   };
   if (tile < num_tiles) {
     bnext = __ldg(p.bias + tc.n * 256 + et);
-    if constexpr (LNF) {
-      snext = __ldg(p.ln_cs + tc.n * 256 + et);
-      bool ok; const int64_t pix = row_of(tc, ok);
-      if (ok) stn = __ldg(reinterpret_cast<const float2*>(p.ln_rs) + pix);
-    }
+    if constexpr (LNF) rnext = row_rstd(tc);
   }
   for (; tile < num_tiles; tile += ts.stride) {
     const int n_blk = tc.n;
-    bool row_ok;
-    const int64_t pix = row_of(tc, row_ok);
+    const int ow = tc.w * p.bw + wl, oh = tc.h * p.bh + hl, img = tc.i * p.bn + il;
+    const int64_t pix = ((int64_t)img * p.Ho + oh) * p.Wo + ow;
+    const bool row_ok = (ow < p.Wo) && (oh < p.Ho) && (pix < p.M);
     const uint32_t rowoff = row_ok ? (uint32_t)pix * ldo8 : 0u;
     const uint32_t okmask = __ballot_sync(0xffffffffu, row_ok);
-    const float rstd = stn.x, nrm = stn.y;
-    asm volatile("bar.sync 1, 256;" ::: "memory");       // the 8 epilogue warps have finished reading the previous tile's bias / sums
+    float* const sb = sbias + acc * 256;
     sb[et] = bnext;
-    if constexpr (LNF) ss[et] = snext;
+    const float rstd = rnext;
     const int64_t next_tile = tile + ts.stride;
-    tile_advance(p, ts, tc);                               // tc now describes next_tile; n_blk / pix above are this tile's
+    tile_advance(p, ts, tc);                               // tc now describes next_tile; n_blk / ow / oh / img above are this tile's
     if (next_tile < num_tiles) {
       bnext = __ldg(p.bias + tc.n * 256 + et);
-      if constexpr (LNF) {
-        snext = __ldg(p.ln_cs + tc.n * 256 + et);
-        bool ok; const int64_t pn = row_of(tc, ok);
-        stn = ok ? __ldg(reinterpret_cast<const float2*>(p.ln_rs) + pn) : make_float2(1.f, 0.f);
-      }
+      if constexpr (LNF) rnext = row_rstd(tc);
     }
-    asm volatile("bar.sync 1, 256;" ::: "memory");       // this tile's 256 bias values (and sums) are visible to all of them
+    asm volatile("bar.sync 1, 256;" ::: "memory");       // the 8 epilogue warps: bias of this tile visible, previous reads done
     mbar_wait(&tfull[acc], aphase);
     const long long te1 = p.debug ? clock64() : 0;
     tcgen05_fence_after();
@@ -538,7 +516,6 @@ __device__ __forceinline__ void epilogue_geglu(const TcParams& p, const TileSche
       tmem_ld_wait32(ar);
       tmem_ld_wait32(gr);
       const float* ba_p = sb + c0 + hh * 32;                // packed (interleaved) bias of the `a` columns; gate = +128
-      const float* sa_p = ss + c0 + hh * 32;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {                          // 8 output columns = one 16-byte chunk of bf16
         float o[8];
@@ -546,19 +523,12 @@ __device__ __forceinline__ void epilogue_geglu(const TcParams& p, const TileSche
         for (int i = 0; i < 8; i += 4) {
           const float4 ba = *reinterpret_cast<const float4*>(ba_p + c * 8 + i);
           const float4 bg = *reinterpret_cast<const float4*>(ba_p + 128 + c * 8 + i);
-          float av[4] = {ba.x, ba.y, ba.z, ba.w}, gv[4] = {bg.x, bg.y, bg.z, bg.w};
-          if constexpr (LNF) {                               // LN fold: bias := nrm * colsum + (beta W^T + bias), accumulator scaled by rstd
-            const float4 sa = *reinterpret_cast<const float4*>(sa_p + c * 8 + i);
-            const float4 sg = *reinterpret_cast<const float4*>(sa_p + 128 + c * 8 + i);
-            av[0] = fmaf(nrm, sa.x, av[0]); av[1] = fmaf(nrm, sa.y, av[1]); av[2] = fmaf(nrm, sa.z, av[2]); av[3] = fmaf(nrm, sa.w, av[3]);
-            gv[0] = fmaf(nrm, sg.x, gv[0]); gv[1] = fmaf(nrm, sg.y, gv[1]); gv[2] = fmaf(nrm, sg.z, gv[2]); gv[3] = fmaf(nrm, sg.w, gv[3]);
+          const float av[4] = {ba.x, ba.y, ba.z, ba.w}, gv[4] = {bg.x, bg.y, bg.z, bg.w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-              o[i + e] = fmaf(__uint_as_float(ar[c * 8 + i + e]), rstd, av[e]) * gelu_erf_fast(fmaf(__uint_as_float(gr[c * 8 + i + e]), rstd, gv[e]));
-          } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              o[i + e] = (__uint_as_float(ar[c * 8 + i + e]) + av[e]) * gelu_erf_fast(__uint_as_float(gr[c * 8 + i + e]) + gv[e]);
+          for (int e = 0; e < 4; ++e) {
+            // LNF: the accumulator already holds x W'^T - mean * colsum (the mean term rides in the extra K block); one FMA applies rstd
+            if constexpr (LNF) o[i + e] = fmaf(__uint_as_float(ar[c * 8 + i + e]), rstd, av[e]) * gelu_erf_fast(fmaf(__uint_as_float(gr[c * 8 + i + e]), rstd, gv[e]));
+            else o[i + e] = (__uint_as_float(ar[c * 8 + i + e]) + av[e]) * gelu_erf_fast(__uint_as_float(gr[c * 8 + i + e]) + gv[e]);
           }
         }
         Vec8<bf16>::store(reinterpret_cast<bf16*>(srow + (((hh * 4 + c) ^ (lane & 7)) << 4)), o);
@@ -881,7 +851,7 @@ void choose_tiles(TcParams& p, int* grid_out) {
     // W-resident candidate
     int rbn = 0;
     for (int bn = 256; bn >= 128; bn -= 16)
-      if (p.N % bn == 0 && (int64_t)k_iters * bn * 128 <= RING_BYTES - 4 * A_BYTES) { rbn = bn; break; }
+      if (p.N % bn == 0 && (int64_t)k_iters * bn * 128 <= RING_BYTES - 3 * A_BYTES) { rbn = bn; break; }     // slab + at least 3 A stages
     if (rbn) {
       const int nt = p.N / rbn;
       const int grid = (sms / nt) * nt;
@@ -934,6 +904,9 @@ long long* g_tc_debug = nullptr;
 int32_t launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, TcParams p, int grid, cudaStream_t st, const CUtensorMap* ma2p = nullptr) {
   const CUtensorMap& ma2 = ma2p ? *ma2p : ma;
   if (!ma2p) p.cb_split = 0x7fffffff;
+  FYC_CHECK((p.bw & (p.bw - 1)) == 0 && (p.bh & (p.bh - 1)) == 0 && p.bw > 0 && p.bh > 0, "tcgen05 GEMM: patch dims must be powers of two");
+  p.lg_bw = 0; while ((1 << p.lg_bw) < p.bw) ++p.lg_bw;
+  p.lg_bh = 0; while ((1 << p.lg_bh) < p.bh) ++p.lg_bh;
   if (p.pair) {
     p.debug = g_tc_debug;
     static bool attr_set2 = false;
@@ -1000,7 +973,7 @@ bool fyc_gemm_tc_eligible(const fyc_gemm_args* g) {
     if (g->batch != 1 || g->K1 <= 0 || g->K1 >= g->K || g->K1 % BK || g->lda2 % 8 || (((uintptr_t)g->A2) & 15)) return false;
   }
   if (g->epilogue & FYC_EPI_LNFOLD) {
-    if (!g->ln_rowstats || !g->ln_colsum || (((uintptr_t)g->ln_rowstats) & 7) || (((uintptr_t)g->ln_colsum) & 15)) return false;
+    if (!g->ln_rowstats || !g->A2 || (((uintptr_t)g->ln_rowstats) & 3)) return false;
     if (g->alpha != 1.0f || (g->epilogue & (FYC_EPI_OUT_F32 | FYC_EPI_RESIDUAL)) || g->N % 8) return false;
     if ((g->epilogue & FYC_EPI_ROWBIAS) && g->rows_per_group % 128) return false;     // a warp's 32 rows never straddle two row-bias groups
   }
@@ -1055,7 +1028,7 @@ int32_t fyc_gemm_tc(const fyc_gemm_args* g, cudaStream_t st) {
     p.residual = g->residual ? (f32 ? (const void*)((const float*)g->residual + b * g->strideO) : (const void*)((const bf16*)g->residual + b * g->strideO)) : nullptr;
     p.out = f32 ? (void*)((float*)g->out + b * g->strideO) : (void*)((bf16*)g->out + b * g->strideO);
     p.ldo = g->ldo; p.ldr = g->ldr; p.alpha = g->alpha; p.flags = g->epilogue;
-    p.ln_rs = g->ln_rowstats ? g->ln_rowstats + 2 * b * g->M : nullptr; p.ln_cs = g->ln_colsum;
+    p.ln_rs = g->ln_rowstats;
     p.cb_split = g->A2 ? (int)(g->K1 / BK) : 0x7fffffff;
     int32_t rc = launch_tc(ma, mw, p, grid, st, g->A2 ? &ma2 : nullptr);
     if (rc) return rc;

@@ -593,11 +593,21 @@ __global__ void __launch_bounds__(256, 2) layernorm_lpr_kernel(const bf16* __res
   }
 }
 
-// LayerNorm STATISTICS only (fyc_layernorm_stats): per row float2(rstd, -rstd * mean), the two numbers the LN-folded GEMM epilogue
-// needs (fyc.h FYC_EPI_LNFOLD).  Same lane layout and the same two-pass arithmetic as layernorm_lpr_kernel - one read of x, no write
-// of a normalised copy.  PASSES x 5 independent 16-byte loads per lane are requested before the first is used.
+// LayerNorm STATISTICS only (fyc_layernorm_stats): per row rstd (fp32) and the 8-column bf16 "aug" row [m_hi, m_hi, m_lo, m_lo, 0, 0, 0, 0]
+// (mean = m_hi + m_lo) that the LN-folded GEMM appends to its K dimension (fyc.h FYC_EPI_LNFOLD).  Same lane layout and the same
+// two-pass arithmetic as layernorm_lpr_kernel - one read of x, no write of a normalised copy.  PASSES x 5 independent 16-byte loads
+// per lane are requested before the first is used.
+__device__ __forceinline__ void ln_write_stats(float* __restrict__ rstd_out, bf16* __restrict__ aug, int64_t row, float mean, float rstd) {
+  rstd_out[row] = rstd;
+  const bf16 hi = __float2bfloat16_rn(mean);
+  const bf16 lo = __float2bfloat16_rn(mean - __bfloat162float(hi));
+  const uint32_t hh = (uint32_t)__bfloat16_as_ushort(hi) * 0x10001u, ll = (uint32_t)__bfloat16_as_ushort(lo) * 0x10001u;
+  *reinterpret_cast<uint4*>(aug + row * 8) = make_uint4(hh, ll, 0u, 0u);
+}
+
 template <int LPR, int PASSES>
-__global__ void __launch_bounds__(256, 2) ln_stats_lpr_kernel(const bf16* __restrict__ x, float2* __restrict__ stats, int64_t M, float eps, int rev) {
+__global__ void __launch_bounds__(256, 2) ln_stats_lpr_kernel(const bf16* __restrict__ x, float* __restrict__ rstd_out, bf16* __restrict__ aug,
+                                                              int64_t M, float eps, int rev) {
   constexpr int C = LPR * 40, RPP = 32 / LPR, VS = LPR * 8;
   const int lane = threadIdx.x & 31, sub = lane % LPR, rr = lane / LPR;
   const int64_t bxl = rev ? (int64_t)gridDim.x - 1 - blockIdx.x : (int64_t)blockIdx.x;
@@ -640,13 +650,13 @@ __global__ void __launch_bounds__(256, 2) ln_stats_lpr_kernel(const bf16* __rest
 #pragma unroll
     for (int o = 1; o < LPR; o <<= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
     const float rstd = rsqrtf(sq * inv_c + eps);
-    if (sub == 0 && row < M) stats[row] = make_float2(rstd, -rstd * mean);
+    if (sub == 0 && row < M) ln_write_stats(rstd_out, aug, row, mean, rstd);
   }
 }
 
 // generic widths (C % 8 == 0, C <= 2048; bf16) and fp32 rows: one warp per row
 template <typename T, int V, int NV>
-__global__ void __launch_bounds__(256) ln_stats_kernel(const T* __restrict__ x, float2* __restrict__ stats, int64_t M, int C, float eps) {
+__global__ void __launch_bounds__(256) ln_stats_kernel(const T* __restrict__ x, float* __restrict__ rstd_out, bf16* __restrict__ aug, int64_t M, int C, float eps) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -672,29 +682,29 @@ __global__ void __launch_bounds__(256) ln_stats_kernel(const T* __restrict__ x, 
       for (int e = 0; e < V; ++e) { const float d = v[i][e] - mean; sq = fmaf(d, d, sq); }
     }
   const float rstd = rsqrtf(warp_sum(sq) / (float)C + eps);
-  if (lane == 0) stats[row] = make_float2(rstd, -rstd * mean);
+  if (lane == 0) ln_write_stats(rstd_out, aug, row, mean, rstd);
 }
 
-extern "C" int32_t fyc_layernorm_stats(const void* x, float* stats, int64_t M, int64_t C, float eps, int32_t dtype, void* stream) {
+extern "C" int32_t fyc_layernorm_stats(const void* x, float* rstd, void* aug, int64_t M, int64_t C, float eps, int32_t dtype, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  FYC_CHECK(x && stats && M > 0 && C > 0, "layernorm_stats: bad arguments");
-  FYC_CHECK((((uintptr_t)x) & 15) == 0 && (((uintptr_t)stats) & 7) == 0, "layernorm_stats: alignment");
-  float2* so = reinterpret_cast<float2*>(stats);
+  FYC_CHECK(x && rstd && aug && M > 0 && C > 0, "layernorm_stats: bad arguments");
+  FYC_CHECK((((uintptr_t)x | (uintptr_t)aug) & 15) == 0 && (((uintptr_t)rstd) & 3) == 0, "layernorm_stats: alignment");
+  bf16* ao = (bf16*)aug;
   const unsigned grid = (unsigned)ceil_div64(M, 8);
   if (dtype == FYC_BF16) {
     FYC_CHECK(C % 8 == 0 && C <= 2048, "layernorm_stats(bf16): C=%lld must be a multiple of 8 and <= 2048", (long long)C);
     const bf16* xb = (const bf16*)x;
     constexpr int PASSES = 4;
-    if (C == 320) ln_stats_lpr_kernel<8, PASSES><<<(unsigned)ceil_div64(M, 8 * 4 * PASSES), 256, 0, st>>>(xb, so, M, eps, fyc_zigzag());
-    else if (C == 640) ln_stats_lpr_kernel<16, PASSES><<<(unsigned)ceil_div64(M, 8 * 2 * PASSES), 256, 0, st>>>(xb, so, M, eps, fyc_zigzag());
-    else if (C == 1280) ln_stats_lpr_kernel<32, PASSES><<<(unsigned)ceil_div64(M, 8 * 1 * PASSES), 256, 0, st>>>(xb, so, M, eps, fyc_zigzag());
-    else if (C <= 8 * 32 * 5) ln_stats_kernel<bf16, 8, 5><<<grid, 256, 0, st>>>(xb, so, M, (int)C, eps);
-    else ln_stats_kernel<bf16, 8, 8><<<grid, 256, 0, st>>>(xb, so, M, (int)C, eps);
+    if (C == 320) ln_stats_lpr_kernel<8, PASSES><<<(unsigned)ceil_div64(M, 8 * 4 * PASSES), 256, 0, st>>>(xb, rstd, ao, M, eps, fyc_zigzag());
+    else if (C == 640) ln_stats_lpr_kernel<16, PASSES><<<(unsigned)ceil_div64(M, 8 * 2 * PASSES), 256, 0, st>>>(xb, rstd, ao, M, eps, fyc_zigzag());
+    else if (C == 1280) ln_stats_lpr_kernel<32, PASSES><<<(unsigned)ceil_div64(M, 8 * 1 * PASSES), 256, 0, st>>>(xb, rstd, ao, M, eps, fyc_zigzag());
+    else if (C <= 8 * 32 * 5) ln_stats_kernel<bf16, 8, 5><<<grid, 256, 0, st>>>(xb, rstd, ao, M, (int)C, eps);
+    else ln_stats_kernel<bf16, 8, 8><<<grid, 256, 0, st>>>(xb, rstd, ao, M, (int)C, eps);
   } else if (dtype == FYC_F32) {
     FYC_CHECK(C % 4 == 0 && C <= 2048, "layernorm_stats(f32): C=%lld must be a multiple of 4 and <= 2048", (long long)C);
-    if (C <= 4 * 32 * 5) ln_stats_kernel<float, 4, 5><<<grid, 256, 0, st>>>((const float*)x, so, M, (int)C, eps);
-    else if (C <= 4 * 32 * 10) ln_stats_kernel<float, 4, 10><<<grid, 256, 0, st>>>((const float*)x, so, M, (int)C, eps);
-    else ln_stats_kernel<float, 4, 16><<<grid, 256, 0, st>>>((const float*)x, so, M, (int)C, eps);
+    if (C <= 4 * 32 * 5) ln_stats_kernel<float, 4, 5><<<grid, 256, 0, st>>>((const float*)x, rstd, ao, M, (int)C, eps);
+    else if (C <= 4 * 32 * 10) ln_stats_kernel<float, 4, 10><<<grid, 256, 0, st>>>((const float*)x, rstd, ao, M, (int)C, eps);
+    else ln_stats_kernel<float, 4, 16><<<grid, 256, 0, st>>>((const float*)x, rstd, ao, M, (int)C, eps);
   } else {
     FYC_CHECK(false, "layernorm_stats: unknown dtype %d", dtype);
   }

@@ -108,21 +108,34 @@ use_ln_fold = os.environ.get("FYC_LN_FOLD", "1") != "0"          # A/B switch: L
 
 def ln_fold_ok(dtype, M, C):
     """can a LayerNorm over C channels feeding a GEMM on M rows be folded into that GEMM (fyc.h FYC_EPI_LNFOLD: tcgen05 path only)?"""
-    return use_ln_fold and tc_ok(dtype, M) and C % 8 == 0 and C <= 2048
+    return use_ln_fold and tc_ok(dtype, M) and C % 64 == 0 and C <= 2048
 
 
 def layernorm_stats(x, eps=1e-5):
-    """x [..., C] -> fp32 [rows, 2] = (rstd, -rstd * mean) per row: the statistics pass of a LayerNorm whose scale / shift live in the
-    consuming GEMM's weights and epilogue (one read of x, no normalised copy)."""
+    """x [..., C] -> (rstd fp32 [rows], aug bf16 [rows, 8] = [m_hi, m_hi, m_lo, m_lo, 0, 0, 0, 0] with mean = m_hi + m_lo): the statistics
+    pass of a LayerNorm whose scale / shift live in the consuming GEMM's weights and whose mean subtraction is an extra K block of that GEMM
+    (one read of x, no normalised copy; fyc.h FYC_EPI_LNFOLD)."""
     _cuda(x, "layernorm_stats.x")
     assert x.is_contiguous()
     Cc = x.shape[-1]
     M = x.numel() // Cc
-    out = torch.empty((M, 2), dtype=torch.float32, device=x.device)
+    rstd = torch.empty((M,), dtype=torch.float32, device=x.device)
+    aug = torch.empty((M, 8), dtype=torch.bfloat16, device=x.device)
     fam = f"layernorm_stats[{M}x{Cc}]" if _prof_shapes else "layernorm_stats"
     with _rec(fam, 0, x.numel() * x.element_size()):
-        check(lib().fyc_layernorm_stats(ptr(x), ptr(out), M, Cc, float(eps), dtype_code(x.dtype), stream_ptr()))
-    return out
+        check(lib().fyc_layernorm_stats(ptr(x), ptr(rstd), ptr(aug), M, Cc, float(eps), dtype_code(x.dtype), stream_ptr()))
+    return rstd, aug
+
+
+def ln_aug_weight(wp):
+    """[N, K] gamma-scaled weight (already rounded to the compute dtype) -> [N, K + 8]: the mean-term columns [-c_hi, -c_lo, -c_hi, -c_lo, 0..]
+    appended, colsum[n] = sum_k wp[n, k] = c_hi + c_lo (hi / lo bf16 split: the cancellation against x W'^T keeps ~16 mantissa bits)."""
+    cs = wp.float().sum(dim=1)
+    hi = cs.to(torch.bfloat16)
+    lo = (cs - hi.float()).to(torch.bfloat16)
+    cols = torch.zeros((wp.shape[0], 8), dtype=torch.bfloat16, device=wp.device)
+    cols[:, 0], cols[:, 1], cols[:, 2], cols[:, 3] = -hi, -lo, -hi, -lo
+    return torch.cat([wp.to(torch.bfloat16), cols], dim=1).contiguous()
 
 
 use_dual_source = os.environ.get("FYC_DUAL_SOURCE", "1") != "0"  # A/B switch: skip-concat read in place (two-source GroupNorm / shortcut GEMM)
@@ -132,8 +145,9 @@ def gemm(A, W, bias=None, residual=None, rowbias=None, rows_per_group=0, alpha=1
          out=None, impl=None, ln=None, A2=None):
     """out[M, N] = alpha * A[M, K] @ W[N, K]^T (+bias) (+rowbias[m // rows_per_group]) (+residual); GEGLU halves N.
     A may be 2-D [M, K] or batched 3-D [B, M, K] with W [B, N, K] (one launch per batch on the tcgen05 path).
-    ``ln`` = (row stats [M, 2] from layernorm_stats, column sums [N] of W): A is the RAW input of a LayerNorm, W carries its gamma,
-    ``bias`` its beta term - out = rstd * (A W^T) + nrm * colsum + bias (fyc.h FYC_EPI_LNFOLD)."""
+    ``ln`` = (rstd [M], aug [M, 8]) from layernorm_stats: A is the RAW input of a LayerNorm, W = ln_aug_weight(gamma-scaled weight)
+    [N, K + 8], ``bias`` carries the beta term - out = rstd * ([A | aug] W^T) + bias (fyc.h FYC_EPI_LNFOLD).
+    ``A2`` [M, K2]: the K dimension is the concatenation [A | A2] read in place."""
     _cuda(A, "gemm.A"); _cuda(W, "gemm.W"); _cuda(residual, "gemm.residual"); _cuda(A2, "gemm.A2")
     _f32vec(bias, "gemm.bias"); _f32vec(rowbias, "gemm.rowbias")
     K1 = 0
@@ -145,8 +159,9 @@ def gemm(A, W, bias=None, residual=None, rowbias=None, rows_per_group=0, alpha=1
         else:
             A, A2 = concat_channels(A.contiguous(), A2.contiguous()), None
     if ln is not None:
-        _f32vec(ln[0], "gemm.ln_rowstats"); _f32vec(ln[1], "gemm.ln_colsum")
-        assert ln[0].shape == (A.shape[-2], 2) and ln[1].shape == (W.shape[-2],) and A.dim() == 2
+        _f32vec(ln[0], "gemm.ln_rstd")
+        assert A2 is None and A.dim() == 2 and ln[0].shape == (A.shape[0],) and ln[1].shape == (A.shape[0], 8) and A.shape[1] % 64 == 0
+        A2, K1 = ln[1], A.shape[1]                     # the mean term is a second K segment
     impl = _impl if impl is None else impl
     batched = A.dim() == 3
     if batched:
@@ -173,8 +188,7 @@ def gemm(A, W, bias=None, residual=None, rowbias=None, rows_per_group=0, alpha=1
     a = L.GemmArgs(ptr(A), ptr(W), ptr(o), ptr(bias), ptr(residual), ptr(rowbias), M, N, K, lda, ldw,
                    o.stride(-2), residual.stride(-2) if residual is not None else 0, Bn, sA, sW,
                    o.stride(0) if batched else 0, rows_per_group, float(alpha), dtype_code(A.dtype), epi, impl,
-                   ptr(A2) if K1 else None, A2.stride(0) if K1 else 0, K1,
-                   ptr(ln[0]) if ln is not None else None, ptr(ln[1]) if ln is not None else None)
+                   ptr(A2) if K1 else None, A2.stride(0) if K1 else 0, K1, ptr(ln[0]) if ln is not None else None)
     fam = "gemm_tc" if (impl != L.IMPL_SIMT and tc_ok(A.dtype, M) and N % 16 == 0 and K % 8 == 0) else "gemm_simt"
     if _prof_shapes:
         fam += f"[{Bn}x{M}x{N}x{K}{'g' if fused_geglu else ''}{'r' if residual is not None else ''}{'L' if ln is not None else ''}]"

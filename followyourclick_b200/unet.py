@@ -334,26 +334,25 @@ class UNet3DConditionModel(ParamTreeModel):
         return self._cached(("geglu", p), make)
 
     def _ln_fold(self, name, norm, make_w, make_bias=None, interleave=False, pe=None):
-        """LayerNorm folded into its consuming GEMM (fyc.h FYC_EPI_LNFOLD):  LN(x) W^T + b = rstd (x (gamma . W)^T) - rstd mean colsum + (beta W^T + b).
-        Returns (W' = gamma-scaled weight in the compute dtype, colsum[n] = sum_k W'[n, k] of the ROUNDED W' - the mean term then cancels
-        the accumulated product exactly -, cbias = beta W^T + b in fp32[, rowbias table (pe W^T) for the temporal position encoding:
-        (LN(x) + pe_f) W^T = LN(x) W^T + pe_f W^T]).  ``interleave``: GEGLU value / gate row interleave (modeling.geglu_interleave)."""
+        """LayerNorm folded into its consuming GEMM (fyc.h FYC_EPI_LNFOLD):
+            LN(x) W^T + b = rstd (x (gamma . W)^T - mean colsum) + (beta W^T + b).
+        Returns (W_aug = [gamma-scaled weight in the compute dtype | 8 mean-term columns] (ops.ln_aug_weight: colsum of the ROUNDED weight, so
+        the mean term cancels the accumulated product to ~16 bits), cbias = beta W^T + b in fp32[, row-bias table pe W^T for the temporal
+        position encoding: (LN(x) + pe_f) W^T = LN(x) W^T + pe_f W^T]).  ``interleave``: GEGLU value / gate row interleave."""
         def make():
             w = make_w().float()                                                     # [N, K] fp32 (q/k/v stacked, padded, LoRA merged ...)
             g, b = self._p(norm + ".weight").detach().float(), self._p(norm + ".bias").detach().float()
             wp = (w * g[None, :]).to(self._compute_dtype)
-            colsum = wp.float().sum(dim=1)
             cb = w @ b
             if make_bias is not None:
                 cb = cb + make_bias().float()
             rb = None
             if pe is not None:
                 rb = (pe.float() @ w.t()).contiguous()                               # [max_len, N]
-            if interleave:                                                           # a row permutation: applied to W' (already rounded), the bias, and
-                wi, cb = geglu_interleave(wp.float(), cb)                            # - by recomputing it - the column sums
+            if interleave:                                                           # a row permutation of W' and of the bias
+                wi, cb = geglu_interleave(wp.float(), cb)
                 wp = wi.to(self._compute_dtype)
-                colsum = wp.float().sum(dim=1)
-            return wp.contiguous(), colsum.contiguous(), cb.contiguous(), rb
+            return ops.ln_aug_weight(wp), cb.contiguous(), rb
         return self._cached(("lnfold", name), make)
 
     def _freqs(self):
@@ -408,9 +407,9 @@ class UNet3DConditionModel(ParamTreeModel):
         in tensor-core mode"""
         M, C = tok.shape
         if ops.ln_fold_ok(tok.dtype, M, C) and C % 32 == 0:          # 8 C rows in 256-row GEGLU tiles
-            w1, cs, cb, _ = self._ln_fold(p + ".net.0.proj", norm, lambda: self._p(p + ".net.0.proj.weight").detach(),
-                                          lambda: self._p(p + ".net.0.proj.bias").detach(), interleave=True)
-            h = ops.gemm(tok, w1, bias=cb, geglu=True, ln=(ops.layernorm_stats(tok), cs))
+            w1, cb, _ = self._ln_fold(p + ".net.0.proj", norm, lambda: self._p(p + ".net.0.proj.weight").detach(),
+                                      lambda: self._p(p + ".net.0.proj.bias").detach(), interleave=True)
+            h = ops.gemm(tok, w1, bias=cb, geglu=True, ln=ops.layernorm_stats(tok))
         else:
             n = ops.layernorm(tok, self._f(norm + ".weight"), self._f(norm + ".bias"))
             w1, b1 = self._geglu(p)
@@ -435,8 +434,8 @@ class UNet3DConditionModel(ParamTreeModel):
         qkv_w = (lambda dtype=None: self._qkv_padded(q + ".attn1", heads, d, dtype=dtype)) if tc_attn else \
             (lambda dtype=None: self._cat_w(q + ".attn1", [q + ".attn1.to_q.weight", q + ".attn1.to_k.weight", q + ".attn1.to_v.weight"], dtype=dtype))
         if fold:
-            w1_, cs1, cb1, _ = self._ln_fold(q + ".attn1.qkv" + (".pad" if tc_attn else ""), q + ".norm1", lambda: qkv_w(torch.float32))
-            qkv = ops.gemm(tok, w1_, bias=cb1, ln=(ops.layernorm_stats(tok), cs1))
+            w1_, cb1, _ = self._ln_fold(q + ".attn1.qkv" + (".pad" if tc_attn else ""), q + ".norm1", lambda: qkv_w(torch.float32))
+            qkv = ops.gemm(tok, w1_, bias=cb1, ln=ops.layernorm_stats(tok))
         else:
             qkv = ops.gemm(ops.layernorm(tok, self._f(q + ".norm1.weight"), self._f(q + ".norm1.bias")), qkv_w())
         if tc_attn:
@@ -451,8 +450,8 @@ class UNet3DConditionModel(ParamTreeModel):
         tok = ops.gemm(o.view(M, C), self._w(q + ".attn1.to_out.0.weight"), bias=self._f(q + ".attn1.to_out.0.bias"), residual=tok)
         # cross attention (attention.py:516-521; IPCrossAttention.forward :49-127); K/V of the context come from the per-clip cache
         if fold:
-            w2_, cs2, cb2, _ = self._ln_fold(q + ".attn2.to_q", q + ".norm2", lambda: self._p(q + ".attn2.to_q.weight").detach())
-            qx = ops.gemm(tok, w2_, bias=cb2, ln=(ops.layernorm_stats(tok), cs2)).view(NB, HW, C)
+            w2_, cb2, _ = self._ln_fold(q + ".attn2.to_q", q + ".norm2", lambda: self._p(q + ".attn2.to_q.weight").detach())
+            qx = ops.gemm(tok, w2_, bias=cb2, ln=ops.layernorm_stats(tok)).view(NB, HW, C)
         else:
             n2 = ops.layernorm(tok, self._f(q + ".norm2.weight"), self._f(q + ".norm2.bias"))
             qx = ops.gemm(n2, self._w(q + ".attn2.to_q.weight")).view(NB, HW, C)
@@ -514,12 +513,12 @@ class UNet3DConditionModel(ParamTreeModel):
                 mk = lambda dtype=None, a=a: self._cat_w(a, [a + f".{nm}.weight" for nm in names], lora=[a + f".{nm}_lora" for nm in names], dtype=dtype)
                 if ops.ln_fold_ok(tok.dtype, M, C) and (pe is None or HW % 128 == 0):
                     # (LN(x) + pe_f) Wqkv^T = LN-folded GEMM + the per-frame row-bias table pe Wqkv^T (motion_module.py:303,378)
-                    wq_, cs, cb, rbt = self._ln_fold(a + ".qkv", q + f".norms.{j}", lambda: mk(torch.float32), pe=pe)
+                    wq_, cb, rbt = self._ln_fold(a + ".qkv", q + f".norms.{j}", lambda: mk(torch.float32), pe=pe)
                     rb = None
                     if pe is not None:
                         rb = self._cached(("pe_rb", a, B, F), lambda rbt=rbt: rbt[:F].repeat(B, 1).contiguous())      # row group = (clip, frame)
                     qkv = ops.gemm(tok, wq_, bias=cb, rowbias=rb, rows_per_group=HW if pe is not None else 0,
-                                   ln=(ops.layernorm_stats(tok), cs)).view(B, F, HW, 3 * C)
+                                   ln=ops.layernorm_stats(tok)).view(B, F, HW, 3 * C)
                 else:
                     n = ops.layernorm(tok, self._f(q + f".norms.{j}.weight"), self._f(q + f".norms.{j}.bias"), pe=pe,
                                       rows_per_frame=HW, frames=F)

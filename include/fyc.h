@@ -38,12 +38,15 @@ enum {
   FYC_EPI_GEGLU = 8,     /* out[m, j] = a * gelu_erf(gate); weight rows pre-interleaved in 128-col granules */
   FYC_EPI_OUT_F32 = 16,  /* write fp32 output regardless of `dtype`    */
   FYC_EPI_LNFOLD = 32    /* A is the RAW input x of a LayerNorm whose output this GEMM consumes (attention.py:383,412,418, motion_module.py:261,
-                            267: norm1/2/3, norms.j, ff_norm -> to_q/k/v, ff.net.0.proj).  With W' = gamma (.) W (packed by the caller):
-                              LN(x) W^T = rstd_m * (x W'^T)[m, n] - rstd_m * mean_m * colsum[n] + (beta W^T)[n]
-                            so the epilogue computes  rstd_m * acc + nrm_m * ln_colsum[n] + bias[n]  with (rstd_m, nrm_m = -rstd_m mean_m) from
-                            fyc_layernorm_stats and bias := beta W^T + the layer's bias.  The normalised tensor is never written or re-read:
-                            one read-only statistics pass replaces LayerNorm's read + write pass.  tcgen05 path, alpha = 1, no fp32 output, no residual;
-                            with FYC_EPI_ROWBIAS (the temporal position table P W^T) rows_per_group must be a multiple of 128. */
+                            267: norm1/2/3, norms.j, ff_norm -> to_q/k/v, ff.net.0.proj).  With W' = gamma (.) W packed by the caller:
+                              LN(x) W^T + b = rstd_m * ( (x W'^T)[m, n] - mean_m * colsum[n] ) + (beta W^T + b)[n],   colsum[n] = sum_k W'[n, k].
+                            The bracket is ONE accumulator: the mean term rides in an extra 8-column K block - A2 = the `aug` rows of
+                            fyc_layernorm_stats, [m_hi, m_hi, m_lo, m_lo, 0 ..] with mean = m_hi + m_lo in bf16, against the weight columns
+                            [-c_hi, -c_lo, -c_hi, -c_lo, 0 ..] (colsum = c_hi + c_lo) appended to W' - so the tensor core subtracts it and
+                            the epilogue only scales by rstd_m (ln_rowstats) and adds the bias: no extra work per output element.  The
+                            normalised tensor is never written or re-read: one read-only statistics pass replaces LayerNorm's read +
+                            write pass.  tcgen05 path; A2 / K1 = C / K = C + 8 as for any two-segment GEMM; alpha = 1, no fp32 output, no
+                            residual; with FYC_EPI_ROWBIAS (the temporal position table P W^T) rows_per_group must be a multiple of 128. */
 };
 enum { FYC_PRED_EPSILON = 0, FYC_PRED_SAMPLE = 1, FYC_PRED_V = 2 };
 
@@ -73,8 +76,7 @@ typedef struct {
                                    a channel concatenation that is never written (the up blocks' conv_shortcut on cat([x, skip]),
                                    resnet.py:286 after unet_blocks.py:763,885).  tcgen05 path: K1 % 64 == 0.  W stays [N, K]. */
   int64_t lda2, K1;
-  const float* ln_rowstats;     /* FYC_EPI_LNFOLD: [M][2] fp32 (rstd, -rstd * mean) per row, from fyc_layernorm_stats */
-  const float* ln_colsum;       /* FYC_EPI_LNFOLD: [N] fp32, colsum[n] = sum_k W'[n, k] (of the bf16-rounded packed weight) */
+  const float* ln_rowstats;     /* FYC_EPI_LNFOLD: [M] fp32 rstd per row, from fyc_layernorm_stats */
 } fyc_gemm_args;
 int32_t fyc_gemm(const fyc_gemm_args* a, void* stream);
 
@@ -138,9 +140,9 @@ int32_t fyc_layernorm(const void* x, const float* gamma, const float* beta, void
                       float eps, const float* pe, int64_t rows_per_frame, int64_t frames, int32_t dtype,
                       void* stream);
 
-/* LayerNorm statistics only: stats[m] = (rstd_m, -rstd_m * mean_m), biased variance + eps like nn.LayerNorm - the row scalars of a GEMM
- * launched with FYC_EPI_LNFOLD. */
-int32_t fyc_layernorm_stats(const void* x, float* stats, int64_t M, int64_t C, float eps, int32_t dtype, void* stream);
+/* LayerNorm statistics only (biased variance + eps like nn.LayerNorm) for a GEMM launched with FYC_EPI_LNFOLD: rstd[m] (fp32) and
+ * aug[m][8] (bf16) = [m_hi, m_hi, m_lo, m_lo, 0, 0, 0, 0], mean_m = m_hi + m_lo - the GEMM's second K segment (A2, lda2 = 8). */
+int32_t fyc_layernorm_stats(const void* x, float* rstd, void* aug, int64_t M, int64_t C, float eps, int32_t dtype, void* stream);
 
 /* ---- attention ----------------------------------------------------------------------------------------
  * out[n, i, h*D + :] (=|+=) out_alpha * softmax_j(scale * q[n,i,h] . k[n',j,h]) v[n',j,h],  n' = n / kv_batch_div.

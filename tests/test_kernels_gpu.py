@@ -383,22 +383,25 @@ def test_gemm_two_segment_k(cuda, M, N, K1, K2, pair, monkeypatch):
 
 
 def _ln_pack(w, gamma, beta, bias, dtype):
-    """what UNet3DConditionModel._ln_fold packs: gamma-scaled weight (rounded once), column sums of the ROUNDED weight, beta W^T + bias"""
+    """what UNet3DConditionModel._ln_fold packs: gamma-scaled weight (rounded once), beta W^T + bias"""
     wp = (w * gamma[None, :]).to(dtype)
-    return wp.contiguous(), wp.float().sum(dim=1).contiguous(), (w @ beta + (bias if bias is not None else 0)).contiguous()
+    return wp.contiguous(), (w @ beta + (bias if bias is not None else 0)).contiguous()
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("M,C", [(4096, 320), (1000, 640), (515, 1280), (300, 768), (64, 160)])
+@pytest.mark.parametrize("M,C", [(4096, 320), (1000, 640), (515, 1280), (300, 768), (64, 192)])
 def test_layernorm_stats(cuda, dtype, M, C):
     from followyourclick_b200 import ops
     x = (rnd((M, C), 1) * 1.7 + rnd((M, 1), 2) * 3.0).to(dtype)       # per-row offsets: the mean term matters
-    st = ops.layernorm_stats(x)
+    rs, aug = ops.layernorm_stats(x)
     xf = x.float()
     mean = xf.mean(dim=1)
     rstd = torch.rsqrt(xf.var(dim=1, unbiased=False) + 1e-5)
-    assert st.shape == (M, 2) and st.dtype == torch.float32
-    assert rel(st[:, 0], rstd) < 1e-5 and float((st[:, 1] + rstd * mean).abs().max()) < 1e-4 * float((rstd * mean).abs().max() + 1)
+    assert rs.shape == (M,) and rs.dtype == torch.float32 and aug.shape == (M, 8) and aug.dtype == torch.bfloat16
+    assert rel(rs, rstd) < 1e-5
+    af = aug.float()
+    assert torch.equal(af[:, 0], af[:, 1]) and torch.equal(af[:, 2], af[:, 3]) and float(af[:, 4:].abs().max()) == 0.0
+    assert float((af[:, 0] + af[:, 2] - mean).abs().max()) < 2e-5 * float(mean.abs().max() + 1)         # hi + lo = mean to ~2^-16
 
 
 @pytest.mark.parametrize("M,N,K,rpg", [(4096, 960, 320, 0), (8192, 1344, 320, 0), (2048, 1920, 640, 256), (8192, 3840, 1280, 128), (1000, 320, 320, 0),
@@ -413,9 +416,9 @@ def test_gemm_layernorm_fold(cuda, M, N, K, rpg):
     x = (rnd((M, K), 1) * 1.3 + rnd((M, 1), 2) * 4.0).to(dt)           # row means up to several sigma
     w = rnd((N, K), 3, torch.float32, K ** -0.5)
     gamma, beta, bias = 1 + 0.1 * rnd((K,), 4), 0.05 * rnd((K,), 5), 0.05 * rnd((N,), 6)
-    wp, cs, cb = _ln_pack(w, gamma, beta, bias, dt)
+    wp, cb = _ln_pack(w, gamma, beta, bias, dt)
     rb = rnd((M // rpg, N), 7) if rpg else None
-    out = ops.gemm(x, wp, bias=cb, rowbias=rb, rows_per_group=rpg, ln=(ops.layernorm_stats(x), cs))
+    out = ops.gemm(x, ops.ln_aug_weight(wp), bias=cb, rowbias=rb, rows_per_group=rpg, ln=ops.layernorm_stats(x))
     ref = Fn.layer_norm(x.float(), (K,), gamma, beta, 1e-5) @ w.t() + bias
     if rpg:
         ref = ref + rb.repeat_interleave(rpg, dim=0)
@@ -437,10 +440,9 @@ def test_geglu_layernorm_fold(cuda, M, C):
     x = (rnd((M, C), 1) + rnd((M, 1), 2) * 2.0).to(dt)
     w, b = rnd((8 * C, C), 3, torch.float32, C ** -0.5), 0.05 * rnd((8 * C,), 4)
     gamma, beta = 1 + 0.1 * rnd((C,), 5), 0.05 * rnd((C,), 6)
-    wp, _, cb = _ln_pack(w, gamma, beta, b, dt)
+    wp, cb = _ln_pack(w, gamma, beta, b, dt)
     wi, cbi = geglu_interleave(wp.float(), cb)
-    wi = wi.to(dt).contiguous()
-    out = ops.gemm(x, wi, bias=cbi.contiguous(), geglu=True, ln=(ops.layernorm_stats(x), wi.float().sum(dim=1).contiguous()))
+    out = ops.gemm(x, ops.ln_aug_weight(wi.to(dt)), bias=cbi.contiguous(), geglu=True, ln=ops.layernorm_stats(x))
     h = Fn.layer_norm(x.float(), (C,), gamma, beta, 1e-5) @ w.t() + b
     a, g = h.chunk(2, dim=-1)
     ref = a * Fn.gelu(g)
