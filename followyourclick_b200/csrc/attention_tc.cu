@@ -506,7 +506,9 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
         for (int i = 0; i < 4; ++i) {
           const f32x2 x = fma2(pk2(__uint_as_float(sr[c * 8 + 2 * i]), __uint_as_float(sr[c * 8 + 2 * i + 1])), sl2p, nbp);
           f32x2 e;
-          if (poly) {
+          if (POLYMASK & 0x100) {              // DIAGNOSTIC build (FYC_ATTN_DBG): no exponentials - wrong results, times the rest of the pipeline
+            e = x;
+          } else if (poly) {
             float x0, x1; upk2(x, x0, x1);
             e = exp2_poly2(pk2(fmaxf(x0, -126.0f), fmaxf(x1, -126.0f)));
           } else {
@@ -519,7 +521,8 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
           pw[i] = *reinterpret_cast<uint32_t*>(&t);
         }
         const int half = c >> 3, cc = c & 7;
-        *reinterpret_cast<uint4*>(prow + half * PHALF_BYTES + ((cc ^ (r & 7)) << 4)) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+        if (!(POLYMASK & 0x200) || c == 0)     // DIAGNOSTIC 0x200: one of the sixteen P stores only
+          *reinterpret_cast<uint4*>(prow + half * PHALF_BYTES + ((cc ^ (r & 7)) << 4)) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
       }
       { float a0, a1; upk2(sum2, a0, a1); l += a0 + a1; }
       if (__any_sync(0xffffffffu, need)) {
@@ -888,7 +891,10 @@ extern "C" int32_t fyc_self_attention_tc(const void* qk, int64_t ldqk, int64_t q
   p.out = (bf16*)out; p.ldo = ldo; p.bso = L * ldo; p.L = (int)L; p.heads = (int)heads; p.D = (int)D;
   p.scale_log2e = scale * 1.4426950408889634f; p.out_alpha = 1.0f;
   const char* g4e = getenv("FYC_ATTN_G4");
-  if (L % (G4 * BQ) == 0 && !(g4e && g4e[0] == '0')) {       // four query tiles per CTA, 64-key tiles (four softmax warps per scheduler)
+  // Four query tiles per CTA with 64-key tiles: measured SLOWER than the two-tile kernel (1.70 vs 1.43 ms at 32 x 8 x 4096, round 2:
+  // profiles/round2_attention.md - half of its warp samples wait for MMA completions, the 64-key tiles double the MMA instruction count and
+  // the shared-memory operand reads per key); kept as an opt-in experiment, FYC_ATTN_G4=1.
+  if (L % (G4 * BQ) == 0 && g4e && g4e[0] == '1') {
     CUtensorMap mk64;
     {
       uint64_t dims[4] = {64, (uint64_t)L, (uint64_t)heads, (uint64_t)NB};
@@ -932,6 +938,21 @@ extern "C" int32_t fyc_self_attention_tc(const void* qk, int64_t ldqk, int64_t q
     const char* pe = getenv("FYC_ATTN_POLY");
     const int eighths = pe ? atoi(pe) : 3;          // 0: 1.574 ms, 1: 1.480, 2: 1.452, 3: 1.422 ms at 32 x 8 heads x 4096 tokens
     cudaStream_t s2 = (cudaStream_t)stream;
+    const char* dbg = getenv("FYC_ATTN_DBG");      // diagnostics only (WRONG results): 1 = no exponentials, 2 = 1/16 of the P stores, 3 = both
+    if (dbg && dbg[0] >= '1' && dbg[0] <= '3') {
+      static bool attrd = false;
+      if (!attrd) {
+        FYC_CUDA(cudaFuncSetAttribute(attention_tc2_kernel<0x152>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES));
+        FYC_CUDA(cudaFuncSetAttribute(attention_tc2_kernel<0x252>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES));
+        FYC_CUDA(cudaFuncSetAttribute(attention_tc2_kernel<0x352>, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_BYTES));
+        attrd = true;
+      }
+      if (dbg[0] == '1') attention_tc2_kernel<0x152><<<grid2, G2_THREADS, G2_SMEM_BYTES, s2>>>(mq, mk, mv, p);
+      else if (dbg[0] == '2') attention_tc2_kernel<0x252><<<grid2, G2_THREADS, G2_SMEM_BYTES, s2>>>(mq, mk, mv, p);
+      else attention_tc2_kernel<0x352><<<grid2, G2_THREADS, G2_SMEM_BYTES, s2>>>(mq, mk, mv, p);
+      FYC_LAUNCH_CHECK();
+      return FYC_OK;
+    }
     if (eighths <= 0) attention_tc2_kernel<0x00><<<grid2, G2_THREADS, G2_SMEM_BYTES, s2>>>(mq, mk, mv, p);
     else if (eighths == 1) attention_tc2_kernel<0x02><<<grid2, G2_THREADS, G2_SMEM_BYTES, s2>>>(mq, mk, mv, p);
     else if (eighths == 2) attention_tc2_kernel<0x12><<<grid2, G2_THREADS, G2_SMEM_BYTES, s2>>>(mq, mk, mv, p);

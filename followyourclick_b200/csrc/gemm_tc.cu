@@ -52,6 +52,9 @@ struct TcParams {
   int64_t ldrb;              // row stride of rowbias (elements; N unless the caller passes a slice of a wider table)
   float alpha;
   int flags;
+  // 16-wide k-steps of the LAST k block of a tap that hold data (1..4): K % 64 != 0 leaves TMA-zero-filled columns there - an LN-folded GEMM's
+  // 8-column mean block would otherwise cost a full 64-deep block of MMA work
+  int last_ksteps;
   // two-segment K (fyc_gemm_args.A2): k blocks [0, cb_split) of a tap come from map_a, the rest from map_a2 (INT_MAX: single source)
   int cb_split;
   // LayerNorm folded into the GEMM (FYC_EPI_LNFOLD): per-row rstd; the mean term is an extra K block (A2 = fyc_layernorm_stats' aug rows)
@@ -667,17 +670,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           const uint32_t sa = smem_u32(smem + a_base + (uint32_t)stage * a_stride);
           const uint64_t a_desc = make_sw128_desc(sa);
           const uint64_t b_desc = make_sw128_desc(p.resident ? smem_u32(smem) + (uint32_t)k * slab_kb : sa + A_BYTES);
+          const int nks = ((k + 1) % p.cin_blocks == 0) ? p.last_ksteps : BK / 16;     // last k block of a tap: skip the all-zero k-steps
           if (pair) {
 #pragma unroll
             for (int kk = 0; kk < BK / 16; ++kk)
-              umma_bf16_pair(d_tmem, a_desc + (uint64_t)(2 * kk), b_desc + (uint64_t)(2 * kk), idesc, (k > 0 || kk > 0) ? 1u : 0u);
+              if (kk < nks) umma_bf16_pair(d_tmem, a_desc + (uint64_t)(2 * kk), b_desc + (uint64_t)(2 * kk), idesc, (k > 0 || kk > 0) ? 1u : 0u);
             tcgen05_commit_pair(&empty[stage]);                     // frees this stage in BOTH CTAs
             if (k == k_iters - 1) tcgen05_commit_pair(&tfull[acc]); // accumulator complete, both CTAs' epilogues may drain
           } else {
 #pragma unroll
             for (int kk = 0; kk < BK / 16; ++kk) {
               // advance 16 elements (32 B) along K inside the 128B swizzle atom: +2 in the (addr >> 4) field
-              umma_bf16(d_tmem, a_desc + (uint64_t)(2 * kk), b_desc + (uint64_t)(2 * kk), idesc, (k > 0 || kk > 0) ? 1u : 0u);
+              if (kk < nks) umma_bf16(d_tmem, a_desc + (uint64_t)(2 * kk), b_desc + (uint64_t)(2 * kk), idesc, (k > 0 || kk > 0) ? 1u : 0u);
             }
             tcgen05_commit(&empty[stage]);                     // frees the smem stage when these MMAs retire
             if (k == k_iters - 1) tcgen05_commit(&tfull[acc]); // accumulator complete
@@ -905,6 +909,7 @@ int32_t launch_tc(const CUtensorMap& ma, const CUtensorMap& mw, TcParams p, int 
   const CUtensorMap& ma2 = ma2p ? *ma2p : ma;
   if (!ma2p) p.cb_split = 0x7fffffff;
   FYC_CHECK((p.bw & (p.bw - 1)) == 0 && (p.bh & (p.bh - 1)) == 0 && p.bw > 0 && p.bh > 0, "tcgen05 GEMM: patch dims must be powers of two");
+  if (p.last_ksteps < 1 || p.last_ksteps > BK / 16) p.last_ksteps = BK / 16;
   p.lg_bw = 0; while ((1 << p.lg_bw) < p.bw) ++p.lg_bw;
   p.lg_bh = 0; while ((1 << p.lg_bh) < p.bh) ++p.lg_bh;
   if (p.pair) {
@@ -1030,6 +1035,7 @@ int32_t fyc_gemm_tc(const fyc_gemm_args* g, cudaStream_t st) {
     p.ldo = g->ldo; p.ldr = g->ldr; p.alpha = g->alpha; p.flags = g->epilogue;
     p.ln_rs = g->ln_rowstats;
     p.cb_split = g->A2 ? (int)(g->K1 / BK) : 0x7fffffff;
+    p.last_ksteps = (g->K % BK) ? (int)ceil_div64(g->K % BK, 16) : BK / 16;
     int32_t rc = launch_tc(ma, mw, p, grid, st, g->A2 ? &ma2 : nullptr);
     if (rc) return rc;
   }
@@ -1070,6 +1076,7 @@ int32_t fyc_conv3x3_tc(const fyc_conv3x3_args* c, const void* x_planes, cudaStre
   pick_patch(c->NB, Ho, Wo, &p.bw, &p.bh, &p.bn);
   p.M = c->NB * Ho * Wo; p.N = (int)c->Cout; p.N_out = p.N;
   p.taps = 9; p.cin_blocks = (int)ceil_div64(c->Cin, BK);
+  p.last_ksteps = (c->Cin % BK) ? (int)ceil_div64(c->Cin % BK, 16) : BK / 16;          // e.g. the 16-channel stem: one k-step per tap instead of four
   p.Wo = (int)Wo; p.Ho = (int)Ho; p.w_tiles = (int)(Wo / p.bw); p.h_tiles = (int)(Ho / p.bh);
   p.m_tiles = (int64_t)p.w_tiles * p.h_tiles * (c->NB / p.bn);
   p.flags = c->epilogue;
@@ -1137,6 +1144,7 @@ int32_t fyc_conv3x3_up2_tc(const fyc_conv3x3_args* c, cudaStream_t st) {
   pick_patch(c->NB, H, W, &p.bw, &p.bh, &p.bn);
   p.M = c->NB * H * W; p.N = (int)c->Cout; p.N_out = p.N;
   p.taps = 4; p.cin_blocks = (int)ceil_div64(c->Cin, BK);
+  p.last_ksteps = (c->Cin % BK) ? (int)ceil_div64(c->Cin % BK, 16) : BK / 16;
   p.Wo = (int)W; p.Ho = (int)H; p.w_tiles = (int)(W / p.bw); p.h_tiles = (int)(H / p.bh);
   p.m_tiles = (int64_t)p.w_tiles * p.h_tiles * (c->NB / p.bn);
   p.flags = c->epilogue;
