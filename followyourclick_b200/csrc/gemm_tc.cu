@@ -854,8 +854,9 @@ void choose_tiles(TcParams& p, int* grid_out) {
   if (!geglu) {
     // W-resident candidate
     int rbn = 0;
-    for (int bn = 256; bn >= 128; bn -= 16)
-      if (p.N % bn == 0 && (int64_t)k_iters * bn * 128 <= RING_BYTES - 3 * A_BYTES) { rbn = bn; break; }     // slab + at least 3 A stages
+    for (int min_stages = 4; min_stages >= 3 && !rbn; --min_stages)      // prefer a slab that leaves the full 4-stage A ring; settle for 3
+      for (int bn = 256; bn >= 128; bn -= 16)
+        if (p.N % bn == 0 && (int64_t)k_iters * bn * 128 <= RING_BYTES - min_stages * A_BYTES) { rbn = bn; break; }
     if (rbn) {
       const int nt = p.N / rbn;
       const int grid = (sms / nt) * nt;
