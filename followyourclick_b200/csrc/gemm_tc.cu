@@ -57,7 +57,7 @@ struct TcParams {
   int last_ksteps;
   // two-segment K (fyc_gemm_args.A2): k blocks [0, cb_split) of a tap come from map_a, the rest from map_a2 (INT_MAX: single source)
   int cb_split;
-  // LayerNorm folded into the GEMM (FYC_EPI_LNFOLD): per-row rstd; the mean term is an extra K block (A2 = fyc_layernorm_stats' aug rows)
+  // LayerNorm folded into the GEMM (FYC_EPI_LNFOLD): per-row rstd; the mean subtraction is in the (row-centred) weights
   const float* ln_rs;
   // W-resident mode (small K): the CTA keeps its whole BN x K weight slab in shared memory and only streams A
   int resident, a_stages;
@@ -421,7 +421,7 @@ __device__ __forceinline__ void epilogue_plain(const TcParams& p, const TileSche
       for (int ps = 0; ps < 4; ++ps) {
         const float4 x0 = xs[ps][0], x1 = xs[ps][1];
         float v[8];
-        if constexpr (LNF) {       // LN(x) W^T + b = rstd * (x W'^T - mean colsum) + (beta W^T + b): the bracket is the accumulator
+        if constexpr (LNF) {       // LN(x) W^T + b = rstd * (x W"^T) + (beta W^T + b), W" row-centred: the bracket is the accumulator
           const float rs = lrc.rs[ps];
           v[0] = fmaf(x0.x, rs, pf.b0.x); v[1] = fmaf(x0.y, rs, pf.b0.y); v[2] = fmaf(x0.z, rs, pf.b0.z); v[3] = fmaf(x0.w, rs, pf.b0.w);
           v[4] = fmaf(x1.x, rs, pf.b1.x); v[5] = fmaf(x1.y, rs, pf.b1.y); v[6] = fmaf(x1.z, rs, pf.b1.z); v[7] = fmaf(x1.w, rs, pf.b1.w);
@@ -529,7 +529,7 @@ __device__ __forceinline__ void epilogue_geglu(const TcParams& p, const TileSche
           const float av[4] = {ba.x, ba.y, ba.z, ba.w}, gv[4] = {bg.x, bg.y, bg.z, bg.w};
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            // LNF: the accumulator already holds x W'^T - mean * colsum (the mean term rides in the extra K block); one FMA applies rstd
+            // LNF: the accumulator already holds x W'^T - mean * colsum (row-centred weights); one FMA applies rstd
             if constexpr (LNF) o[i + e] = fmaf(__uint_as_float(ar[c * 8 + i + e]), rstd, av[e]) * gelu_erf_fast(fmaf(__uint_as_float(gr[c * 8 + i + e]), rstd, gv[e]));
             else o[i + e] = (__uint_as_float(ar[c * 8 + i + e]) + av[e]) * gelu_erf_fast(__uint_as_float(gr[c * 8 + i + e]) + gv[e]);
           }
@@ -979,7 +979,7 @@ bool fyc_gemm_tc_eligible(const fyc_gemm_args* g) {
     if (g->batch != 1 || g->K1 <= 0 || g->K1 >= g->K || g->K1 % BK || g->lda2 % 8 || (((uintptr_t)g->A2) & 15)) return false;
   }
   if (g->epilogue & FYC_EPI_LNFOLD) {
-    if (!g->ln_rowstats || !g->A2 || (((uintptr_t)g->ln_rowstats) & 3)) return false;
+    if (!g->ln_rowstats || (((uintptr_t)g->ln_rowstats) & 3)) return false;
     if (g->alpha != 1.0f || (g->epilogue & (FYC_EPI_OUT_F32 | FYC_EPI_RESIDUAL)) || g->N % 8) return false;
     if ((g->epilogue & FYC_EPI_ROWBIAS) && g->rows_per_group % 128) return false;     // a warp's 32 rows never straddle two row-bias groups
   }

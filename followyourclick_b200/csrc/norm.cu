@@ -599,6 +599,7 @@ __global__ void __launch_bounds__(256, 2) layernorm_lpr_kernel(const bf16* __res
 // per lane are requested before the first is used.
 __device__ __forceinline__ void ln_write_stats(float* __restrict__ rstd_out, bf16* __restrict__ aug, int64_t row, float mean, float rstd) {
   rstd_out[row] = rstd;
+  if (aug == nullptr) return;
   const bf16 hi = __float2bfloat16_rn(mean);
   const bf16 lo = __float2bfloat16_rn(mean - __bfloat162float(hi));
   const uint32_t hh = (uint32_t)__bfloat16_as_ushort(hi) * 0x10001u, ll = (uint32_t)__bfloat16_as_ushort(lo) * 0x10001u;
@@ -687,7 +688,7 @@ __global__ void __launch_bounds__(256) ln_stats_kernel(const T* __restrict__ x, 
 
 extern "C" int32_t fyc_layernorm_stats(const void* x, float* rstd, void* aug, int64_t M, int64_t C, float eps, int32_t dtype, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  FYC_CHECK(x && rstd && aug && M > 0 && C > 0, "layernorm_stats: bad arguments");
+  FYC_CHECK(x && rstd && M > 0 && C > 0, "layernorm_stats: bad arguments");
   FYC_CHECK((((uintptr_t)x | (uintptr_t)aug) & 15) == 0 && (((uintptr_t)rstd) & 3) == 0, "layernorm_stats: alignment");
   bf16* ao = (bf16*)aug;
   const unsigned grid = (unsigned)ceil_div64(M, 8);

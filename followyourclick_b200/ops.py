@@ -108,38 +108,53 @@ use_ln_fold = os.environ.get("FYC_LN_FOLD", "1") != "0"          # A/B switch: L
 
 def ln_fold_ok(dtype, M, C):
     """can a LayerNorm over C channels feeding a GEMM on M rows be folded into that GEMM (fyc.h FYC_EPI_LNFOLD: tcgen05 path only)?"""
-    return use_ln_fold and tc_ok(dtype, M) and C % 64 == 0 and C <= 2048
+    return use_ln_fold and tc_ok(dtype, M) and C % 8 == 0 and C <= 2048
 
 
 def layernorm_stats(x, eps=1e-5):
-    """x [..., C] -> (rstd fp32 [rows], aug bf16 [rows, 8] = [m_hi, m_hi, m_lo, m_lo, 0, 0, 0, 0] with mean = m_hi + m_lo): the statistics
-    pass of a LayerNorm whose scale / shift live in the consuming GEMM's weights and whose mean subtraction is an extra K block of that GEMM
-    (one read of x, no normalised copy; fyc.h FYC_EPI_LNFOLD)."""
+    """x [..., C] -> rstd fp32 [rows]: the statistics pass of a LayerNorm whose scale / shift AND mean subtraction live in the consuming
+    GEMM's weights (gamma-scaled, row-centred: fyc.h FYC_EPI_LNFOLD) - one read of x, no normalised copy."""
     _cuda(x, "layernorm_stats.x")
     assert x.is_contiguous()
     Cc = x.shape[-1]
     M = x.numel() // Cc
     rstd = torch.empty((M,), dtype=torch.float32, device=x.device)
-    aug = torch.empty((M, 8), dtype=torch.bfloat16, device=x.device)
     fam = f"layernorm_stats[{M}x{Cc}]" if _prof_shapes else "layernorm_stats"
     with _rec(fam, 0, x.numel() * x.element_size()):
-        check(lib().fyc_layernorm_stats(ptr(x), ptr(rstd), ptr(aug), M, Cc, float(eps), dtype_code(x.dtype), stream_ptr()))
-    return rstd, aug
+        check(lib().fyc_layernorm_stats(ptr(x), ptr(rstd), None, M, Cc, float(eps), dtype_code(x.dtype), stream_ptr()))
+    return rstd
 
 
-def ln_aug_weight(wp):
-    """[N, K] gamma-scaled weight (already rounded to the compute dtype) -> [N, K + 8] VIEW of an [N, K + 64] buffer: the mean-term columns
-    [-c_hi, -c_lo, -c_hi, -c_lo, 0..] appended, colsum[n] = sum_k wp[n, k] = c_hi + c_lo (hi / lo bf16 split: the cancellation against x W'^T
-    keeps ~16 mantissa bits).  The row stride stays a multiple of 64 elements so that every 128-byte TMA box row of the weight is one
-    aligned 128-byte line (with a stride of K + 8 the K = 320 GEMMs, which are bound by L2 -> SM operand traffic, lost 25 %)."""
-    N, K = wp.shape
-    cs = wp.float().sum(dim=1)
-    hi = cs.to(torch.bfloat16)
-    lo = (cs - hi.float()).to(torch.bfloat16)
-    buf = torch.zeros((N, K + 64), dtype=torch.bfloat16, device=wp.device)
-    buf[:, :K] = wp
-    buf[:, K], buf[:, K + 1], buf[:, K + 2], buf[:, K + 3] = -hi, -lo, -hi, -lo
-    return buf[:, :K + 8]
+def _balance_rows_bf16(w, iters=12):
+    """w: fp32 tensor holding bf16-representable values [N, K] -> the same with a handful of elements per row moved by ONE bf16 ulp so
+    that every row sums to ~0 (<= a few 1e-6 instead of ~sqrt(K) * 2^-10 * |w|).  Each step picks, per row, the element whose ulp is
+    closest to the remaining row sum and steps it against the sum's sign; a one-ulp step of a bf16 value is always representable."""
+    w = w.clone()
+    rows = torch.arange(w.shape[0], device=w.device)
+    inf = torch.tensor(float("inf"), device=w.device)
+    for _ in range(iters):
+        r = w.sum(dim=1)
+        ulp = torch.exp2(torch.floor(torch.log2(w.abs().clamp_min(1e-30))) - 7)
+        ulp = torch.where(w == 0, inf, ulp)
+        target = r.abs()[:, None]
+        score = torch.where(ulp <= 1.5 * target, (target - ulp).abs(), inf)
+        idx = score.argmin(dim=1)
+        good = torch.isfinite(score[rows, idx])
+        step = torch.where(good, ulp[rows, idx] * torch.sign(r), torch.zeros_like(r))
+        w[rows, idx] -= torch.where(torch.isfinite(step), step, torch.zeros_like(step))
+    return w
+
+
+def ln_fold_weight(w, gamma, dtype):
+    """[N, K] fp32 weight, [K] LayerNorm gain -> the LN-folded GEMM operand: gamma-scaled, every row centred (the mean of LN's input then
+    cancels inside the product: x W"^T = x W'^T - mean colsum), rounded ONCE to the compute dtype; in bf16 the rounded rows are
+    re-balanced to sum to zero (_balance_rows_bf16): the leftover row sum is what a large row mean would multiply - with it the fold is
+    as accurate as LN -> bf16 -> GEMM for row means of 100 sigma, without it only for means below ~2 sigma (tests/test_kernels_gpu.py)."""
+    wp = w.float() * gamma.float()[None, :]
+    wc = (wp - wp.mean(dim=1, keepdim=True)).to(dtype)
+    if dtype == torch.bfloat16:
+        wc = _balance_rows_bf16(wc.float()).to(dtype)
+    return wc.contiguous()
 
 
 use_dual_source = os.environ.get("FYC_DUAL_SOURCE", "1") != "0"  # A/B switch: skip-concat read in place (two-source GroupNorm / shortcut GEMM)
@@ -149,8 +164,8 @@ def gemm(A, W, bias=None, residual=None, rowbias=None, rows_per_group=0, alpha=1
          out=None, impl=None, ln=None, A2=None):
     """out[M, N] = alpha * A[M, K] @ W[N, K]^T (+bias) (+rowbias[m // rows_per_group]) (+residual); GEGLU halves N.
     A may be 2-D [M, K] or batched 3-D [B, M, K] with W [B, N, K] (one launch per batch on the tcgen05 path).
-    ``ln`` = (rstd [M], aug [M, 8]) from layernorm_stats: A is the RAW input of a LayerNorm, W = ln_aug_weight(gamma-scaled weight)
-    [N, K + 8], ``bias`` carries the beta term - out = rstd * ([A | aug] W^T) + bias (fyc.h FYC_EPI_LNFOLD).
+    ``ln`` = rstd [M] from layernorm_stats: A is the RAW input of a LayerNorm, W = ln_fold_weight(...) (gamma-scaled, row-centred),
+    ``bias`` carries the beta term - out = rstd * (A W^T) + bias (fyc.h FYC_EPI_LNFOLD).
     ``A2`` [M, K2]: the K dimension is the concatenation [A | A2] read in place."""
     _cuda(A, "gemm.A"); _cuda(W, "gemm.W"); _cuda(residual, "gemm.residual"); _cuda(A2, "gemm.A2")
     _f32vec(bias, "gemm.bias"); _f32vec(rowbias, "gemm.rowbias")
@@ -163,9 +178,8 @@ def gemm(A, W, bias=None, residual=None, rowbias=None, rows_per_group=0, alpha=1
         else:
             A, A2 = concat_channels(A.contiguous(), A2.contiguous()), None
     if ln is not None:
-        _f32vec(ln[0], "gemm.ln_rstd")
-        assert A2 is None and A.dim() == 2 and ln[0].shape == (A.shape[0],) and ln[1].shape == (A.shape[0], 8) and A.shape[1] % 64 == 0
-        A2, K1 = ln[1], A.shape[1]                     # the mean term is a second K segment
+        _f32vec(ln, "gemm.ln_rstd")
+        assert A2 is None and A.dim() == 2 and ln.shape == (A.shape[0],)
     impl = _impl if impl is None else impl
     batched = A.dim() == 3
     if batched:
@@ -192,7 +206,7 @@ def gemm(A, W, bias=None, residual=None, rowbias=None, rows_per_group=0, alpha=1
     a = L.GemmArgs(ptr(A), ptr(W), ptr(o), ptr(bias), ptr(residual), ptr(rowbias), M, N, K, lda, ldw,
                    o.stride(-2), residual.stride(-2) if residual is not None else 0, Bn, sA, sW,
                    o.stride(0) if batched else 0, rows_per_group, float(alpha), dtype_code(A.dtype), epi, impl,
-                   ptr(A2) if K1 else None, A2.stride(0) if K1 else 0, K1, ptr(ln[0]) if ln is not None else None)
+                   ptr(A2) if K1 else None, A2.stride(0) if K1 else 0, K1, ptr(ln))
     fam = "gemm_tc" if (impl != L.IMPL_SIMT and tc_ok(A.dtype, M) and N % 16 == 0 and K % 8 == 0) else "gemm_simt"
     if _prof_shapes:
         fam += f"[{Bn}x{M}x{N}x{K}{'g' if fused_geglu else ''}{'r' if residual is not None else ''}{'L' if ln is not None else ''}]"

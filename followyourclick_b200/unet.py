@@ -335,24 +335,23 @@ class UNet3DConditionModel(ParamTreeModel):
 
     def _ln_fold(self, name, norm, make_w, make_bias=None, interleave=False, pe=None):
         """LayerNorm folded into its consuming GEMM (fyc.h FYC_EPI_LNFOLD):
-            LN(x) W^T + b = rstd (x (gamma . W)^T - mean colsum) + (beta W^T + b).
-        Returns (W_aug = [gamma-scaled weight in the compute dtype | 8 mean-term columns] (ops.ln_aug_weight: colsum of the ROUNDED weight, so
-        the mean term cancels the accumulated product to ~16 bits), cbias = beta W^T + b in fp32[, row-bias table pe W^T for the temporal
-        position encoding: (LN(x) + pe_f) W^T = LN(x) W^T + pe_f W^T]).  ``interleave``: GEGLU value / gate row interleave."""
+            LN(x) W^T + b = rstd (x W"^T) + (beta W^T + b),   W" = gamma . W with every row centred (ops.ln_fold_weight).
+        Returns (W" in the compute dtype, cbias = beta W^T + b in fp32[, row-bias table pe W^T for the temporal position encoding:
+        (LN(x) + pe_f) W^T = LN(x) W^T + pe_f W^T]).  ``interleave``: GEGLU value / gate row interleave."""
         def make():
             w = make_w().float()                                                     # [N, K] fp32 (q/k/v stacked, padded, LoRA merged ...)
             g, b = self._p(norm + ".weight").detach().float(), self._p(norm + ".bias").detach().float()
-            wp = (w * g[None, :]).to(self._compute_dtype)
+            wp = ops.ln_fold_weight(w, g, self._compute_dtype)
             cb = w @ b
             if make_bias is not None:
                 cb = cb + make_bias().float()
             rb = None
             if pe is not None:
                 rb = (pe.float() @ w.t()).contiguous()                               # [max_len, N]
-            if interleave:                                                           # a row permutation of W' and of the bias
+            if interleave:                                                           # a row permutation of W" and of the bias
                 wi, cb = geglu_interleave(wp.float(), cb)
-                wp = wi.to(self._compute_dtype)
-            return ops.ln_aug_weight(wp), cb.contiguous(), rb
+                wp = wi.to(self._compute_dtype).contiguous()
+            return wp, cb.contiguous(), rb
         return self._cached(("lnfold", name), make)
 
     def _freqs(self):

@@ -38,15 +38,13 @@ enum {
   FYC_EPI_GEGLU = 8,     /* out[m, j] = a * gelu_erf(gate); weight rows pre-interleaved in 128-col granules */
   FYC_EPI_OUT_F32 = 16,  /* write fp32 output regardless of `dtype`    */
   FYC_EPI_LNFOLD = 32    /* A is the RAW input x of a LayerNorm whose output this GEMM consumes (attention.py:383,412,418, motion_module.py:261,
-                            267: norm1/2/3, norms.j, ff_norm -> to_q/k/v, ff.net.0.proj).  With W' = gamma (.) W packed by the caller:
-                              LN(x) W^T + b = rstd_m * ( (x W'^T)[m, n] - mean_m * colsum[n] ) + (beta W^T + b)[n],   colsum[n] = sum_k W'[n, k].
-                            The bracket is ONE accumulator: the mean term rides in an extra 8-column K block - A2 = the `aug` rows of
-                            fyc_layernorm_stats, [m_hi, m_hi, m_lo, m_lo, 0 ..] with mean = m_hi + m_lo in bf16, against the weight columns
-                            [-c_hi, -c_lo, -c_hi, -c_lo, 0 ..] (colsum = c_hi + c_lo) appended to W' - so the tensor core subtracts it and
-                            the epilogue only scales by rstd_m (ln_rowstats) and adds the bias: no extra work per output element.  The
-                            normalised tensor is never written or re-read: one read-only statistics pass replaces LayerNorm's read +
-                            write pass.  tcgen05 path; A2 / K1 = C / K = C + 8 as for any two-segment GEMM; alpha = 1, no fp32 output, no
-                            residual; with FYC_EPI_ROWBIAS (the temporal position table P W^T) rows_per_group must be a multiple of 128. */
+                            267: norm1/2/3, norms.j, ff_norm -> to_q/k/v, ff.net.0.proj).  The caller packs W" = gamma (.) W with every row
+                            CENTRED (W"[n, k] -= mean_k of the row): since mean_m = (1/C) sum_k x[m, k],
+                              x W"^T = x W'^T - mean_m * colsum(W')[n]   and   LN(x) W^T + b = rstd_m * (x W"^T)[m, n] + (beta W^T + b)[n],
+                            i.e. the mean subtraction lives in the weights, the tensor core computes the bracket, and the epilogue only scales
+                            by rstd_m (ln_rowstats, from fyc_layernorm_stats) and adds the bias: the GEMM costs what the plain one costs,
+                            and LayerNorm's read + write pass shrinks to one read-only statistics pass.  tcgen05 path; alpha = 1, no fp32
+                            output, no residual; with FYC_EPI_ROWBIAS (the temporal position table P W^T) rows_per_group % 128 == 0. */
 };
 enum { FYC_PRED_EPSILON = 0, FYC_PRED_SAMPLE = 1, FYC_PRED_V = 2 };
 
@@ -140,8 +138,9 @@ int32_t fyc_layernorm(const void* x, const float* gamma, const float* beta, void
                       float eps, const float* pe, int64_t rows_per_frame, int64_t frames, int32_t dtype,
                       void* stream);
 
-/* LayerNorm statistics only (biased variance + eps like nn.LayerNorm) for a GEMM launched with FYC_EPI_LNFOLD: rstd[m] (fp32) and
- * aug[m][8] (bf16) = [m_hi, m_hi, m_lo, m_lo, 0, 0, 0, 0], mean_m = m_hi + m_lo - the GEMM's second K segment (A2, lda2 = 8). */
+/* LayerNorm statistics only (biased variance + eps like nn.LayerNorm) for a GEMM launched with FYC_EPI_LNFOLD: rstd[m] (fp32).  `aug` is
+ * optional (NULL: not written): [m][8] bf16 = [m_hi, m_hi, m_lo, m_lo, 0, 0, 0, 0] with mean_m = m_hi + m_lo, for callers that want the
+ * row mean as a second K segment of a GEMM (fyc_gemm_args.A2) instead of centred weights. */
 int32_t fyc_layernorm_stats(const void* x, float* rstd, void* aug, int64_t M, int64_t C, float eps, int32_t dtype, void* stream);
 
 /* ---- attention ----------------------------------------------------------------------------------------
