@@ -305,6 +305,14 @@ __device__ __forceinline__ void epi_prefetch(const TcParams& p, const EpiRows& t
     f.b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
     f.b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
   }
+  if ((p.flags & FYC_EPI_ROWBIAS) && col_ok && t.rgu >= 0) {
+    // the warp's 32 rows share one row-bias vector (time embedding of a clip, position-table row of a frame): fetched here, one group
+    // AHEAD like the bias, and folded into it - at its point of use this load was an exposed L2 round trip per 32-column group
+    const float* rbp = p.rowbias + (int64_t)t.rgu * p.ldrb + n;
+    const float4 r0 = __ldg(reinterpret_cast<const float4*>(rbp)), r1 = __ldg(reinterpret_cast<const float4*>(rbp + 4));
+    f.b0.x += r0.x; f.b0.y += r0.y; f.b0.z += r0.z; f.b0.w += r0.w;
+    f.b1.x += r1.x; f.b1.y += r1.y; f.b1.z += r1.z; f.b1.w += r1.w;
+  }
   if constexpr (!LNF) {      // (an LN-folded GEMM never carries a residual: q/k/v and FF1 projections - its registers go to the LN terms)
     if (p.flags & FYC_EPI_RESIDUAL) {
       const uint4* rbase = reinterpret_cast<const uint4*>(p.residual);
@@ -386,15 +394,9 @@ __device__ __forceinline__ void epilogue_plain(const TcParams& p, const TileSche
       const bool col_ok = (c0 < p.BN) && (cur.n0 + c0 < p.N);
       const uint32_t g4 = (uint32_t)gi * 4u;
       float a_eff = alpha;
-      if (p.flags & FYC_EPI_ROWBIAS) {
-        if (cur.rgu >= 0) {                                // the 32 rows share one row-bias vector (the usual case)
-          if (col_ok) {
-            const float* rbp = p.rowbias + (int64_t)cur.rgu * p.ldrb + cur.n0 + c0;
-            const float4 r0 = __ldg(reinterpret_cast<const float4*>(rbp)), r1 = __ldg(reinterpret_cast<const float4*>(rbp + 4));
-            pf.b0.x += r0.x; pf.b0.y += r0.y; pf.b0.z += r0.z; pf.b0.w += r0.w;
-            pf.b1.x += r1.x; pf.b1.y += r1.y; pf.b1.z += r1.z; pf.b1.w += r1.w;
-          }
-        } else {                                           // rare: rows straddle two groups - fold alpha and the row bias into the staged tile
+      if ((p.flags & FYC_EPI_ROWBIAS) && cur.rgu < 0) {
+        {                                                  // rare: rows straddle two groups - fold alpha and the row bias into the staged tile
+                                                           // (the usual case, one group per warp, is part of the prefetched bias)
 #pragma unroll
           for (int ps = 0; ps < 4; ++ps) {
             if (!(((cur.ok >> ps) & 1u) && col_ok)) continue;
