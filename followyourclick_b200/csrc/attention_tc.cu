@@ -570,45 +570,55 @@ attention_tc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   }
 }
 
-// Four query tiles per CTA, 64-key tiles: 512 query rows, FOUR softmax warpgroups (16 warps: group g = rows 128 g .. 128 g + 127), so that
-// every scheduler holds four softmax warps instead of two.  ncu on attention_tc2 (profiles/round1_attention_tc2_full.md): the exponent
-// loop runs at 51 % issue utilisation with two warps per scheduler - 2900 clk per 256 x 128 tile pair against ~1300 clk of MUFU / issue
-// work and ~900 clk of MMA work - i.e. it is latency-bound, not throughput-bound.  Halving the key tile keeps a thread's score row at 64
-// registers, which is what lets 18 warps fit the register file (<= 102 registers per thread).  TMEM: S_g 4 x 64 columns + O_g 4 x 64.
-// Shared memory: Q 4 x 16 KB, P 4 x 16 KB (one buffer per group: only the 16-byte stores of tile j + 1 wait for PV_g(j), the exponentials
-// themselves do not), K / V^T rings of G4_STAGES x (8 + 6) KB - the 64-key tiles turn over in ~700 clk, below the TMA latency, so the
-// ring is four deep.
-constexpr int G4 = 4, G4_BKV = 64, G4_STAGES = 4;
-constexpr int G4_THREADS = 64 + G4 * 128;                       // 576
-constexpr int G4_K_BYTES = G4_BKV * DPAD * 2;                   // 8 KB
-constexpr int G4_V_BYTES = VBOX_BYTES;                          // 6 KB: 48 rows (d) x 64 keys
-constexpr int G4_P_BYTES = PHALF_BYTES;                         // 16 KB: 128 rows x 64 keys
-constexpr int G4_OFF_K = G4 * Q_BYTES, G4_OFF_V = G4_OFF_K + G4_STAGES * G4_K_BYTES, G4_OFF_P = G4_OFF_V + G4_STAGES * G4_V_BYTES;
-constexpr int G4_OFF_BAR = G4_OFF_P + G4 * G4_P_BYTES, G4_SMEM_BYTES = G4_OFF_BAR + 512 + 1024;
-constexpr int G4_TM_S = 0 /* + 64 g */, G4_TM_O = 256 /* + 64 g */;
+// Generalised ping-pong kernel with 64-key tiles: G query tiles (groups of 128 rows, one softmax warpgroup each) per CTA, head dims that
+// span KA 64-column swizzle atoms, PV accumulators DVN columns wide.  Two instantiations:
+//   <G = 2, KA = 2, DVN = 80>  head dim 80 (level-1 self-attention, 1024 tokens): q / k heads UNPADDED in the fused [q | k | v] buffer - the
+//       head's second atom (columns 64..127 of its 160-byte-strided row) holds 16 of its own columns and 48 of the next head's, and QK^T
+//       issues only the k-steps that hold data (5 x 16 columns), so the foreign columns are never multiplied.  Replaces the legacy
+//       mma.sync kernel for this shape (214 TFLOP/s, profiles/round1_probe_c_shapes.txt).
+//   <G = 4, KA = 1, DVN = 48>  head dim 40 with four softmax warps per scheduler - an EXPERIMENT that measured slower than
+//       attention_tc2 (1.70 vs 1.43 ms at 32 x 8 x 4096, profiles/round2_attention.md): opt-in, FYC_ATTN_G4=1.
+// TMEM: S_g G x 64 columns, O_g at 256 + g x (64 | 128).  Shared memory: Q G x KA x 16 KB, P G x 16 KB (one buffer per group: only the 16-byte
+// stores of tile j + 1 wait for PV_g(j), the exponentials themselves do not), K / V^T rings of GK_STAGES x (KA x 8 KB + DVN x 128 B) -
+// the 64-key tiles turn over in well under the TMA latency, so the ring is four deep.
+constexpr int GK_BKV = 64, GK_STAGES = 4;
+constexpr int GK_P_BYTES = PHALF_BYTES;                          // 16 KB: 128 rows x 64 keys
+template <int G, int KA, int DVN> struct GkCfg {
+  static constexpr int THREADS = 64 + G * 128;
+  static constexpr int Q_TILE = KA * Q_BYTES;                     // per group
+  static constexpr int K_STAGE = KA * GK_BKV * 128;               // KA atoms of 64 keys x 128 B
+  static constexpr int V_STAGE = DVN * 128;                       // DVN rows (d) x 64 keys
+  static constexpr int OFF_K = G * Q_TILE, OFF_V = OFF_K + GK_STAGES * K_STAGE, OFF_P = OFF_V + GK_STAGES * V_STAGE;
+  static constexpr int OFF_BAR = OFF_P + G * GK_P_BYTES, SMEM = OFF_BAR + 512 + 1024;
+  static_assert(V_STAGE % 1024 == 0 && K_STAGE % 1024 == 0, "SWIZZLE_128B tiles need 1024-byte aligned bases");
+  static_assert(SMEM <= 227 * 1024, "shared memory budget");
+  static constexpr int O_STRIDE = DVN <= 64 ? 64 : 128;         // TMEM columns between the groups' O accumulators
+  static_assert(G * 64 <= 256 && 256 + G * O_STRIDE <= 512, "TMEM column budget");
+};
 
-template <int POLYMASK>
-__global__ void __launch_bounds__(G4_THREADS, 1)
-attention_tc4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+template <int G, int KA, int DVN, int POLYMASK>
+__global__ void __launch_bounds__(GkCfg<G, KA, DVN>::THREADS, 1)
+attention_tcg_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                      const __grid_constant__ CUtensorMap map_vt, const AttnTcParams p) {
+  using Cfg = GkCfg<G, KA, DVN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024 - (raw & 1023)) & 1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G4_OFF_BAR);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
   uint64_t* q_full = bars;                          // [1]
-  uint64_t* k_full = bars + 1;                      // [G4_STAGES]
-  uint64_t* k_empty = k_full + G4_STAGES;
-  uint64_t* v_full = k_empty + G4_STAGES;
-  uint64_t* v_empty = v_full + G4_STAGES;
-  uint64_t* s_full = v_empty + G4_STAGES;           // [G4]  S_g(j) is in TMEM
-  uint64_t* s_empty = s_full + G4;                  // [G4]  S_g has been read into registers
-  uint64_t* p_full = s_empty + G4;                  // [G4]  P_g(j) is in shared memory (and O_g rescaled if needed)
-  uint64_t* p_empty = p_full + G4;                  // [G4]  PV_g(j) has retired: P_g may be overwritten, O_g is quiescent
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_empty + G4);
+  uint64_t* k_full = bars + 1;                      // [GK_STAGES]
+  uint64_t* k_empty = k_full + GK_STAGES;
+  uint64_t* v_full = k_empty + GK_STAGES;
+  uint64_t* v_empty = v_full + GK_STAGES;
+  uint64_t* s_full = v_empty + GK_STAGES;           // [G]  S_g(j) is in TMEM
+  uint64_t* s_empty = s_full + G;                   // [G]  S_g has been read into registers
+  uint64_t* p_full = s_empty + G;                   // [G]  P_g(j) is in shared memory (and O_g rescaled if needed)
+  uint64_t* p_empty = p_full + G;                   // [G]  PV_g(j) has retired: P_g may be overwritten, O_g is quiescent
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_empty + G);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, h = blockIdx.y, n = blockIdx.z;
-  const int T = p.L / G4_BKV;
+  const int T = p.L / GK_BKV;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_q)) : "memory");
@@ -617,8 +627,8 @@ attention_tc4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   }
   if (warp == 1 && lane == 0) {
     mbar_init(q_full, 1);
-    for (int i = 0; i < G4_STAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
-    for (int i = 0; i < G4; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4); mbar_init(&p_full[i], 4); mbar_init(&p_empty[i], 1); }
+    for (int i = 0; i < GK_STAGES; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
+    for (int i = 0; i < G; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 4); mbar_init(&p_full[i], 4); mbar_init(&p_empty[i], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
@@ -633,37 +643,45 @@ attention_tc4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   if (warp == 0) {
     // ================================================================== TMA producer
     if (lane == 0) {
-      mbar_expect_tx(q_full, G4 * Q_BYTES);
+      mbar_expect_tx(q_full, G * Cfg::Q_TILE);
 #pragma unroll
-      for (int g = 0; g < G4; ++g) tma_load_4d(&map_q, q_full, smem + g * Q_BYTES, 0, qt * G4 * BQ + g * BQ, h, n);
+      for (int g = 0; g < G; ++g)
+#pragma unroll
+        for (int a = 0; a < KA; ++a)
+          tma_load_4d(&map_q, q_full, smem + g * Cfg::Q_TILE + a * Q_BYTES, a * 64, qt * G * BQ + g * BQ, h, n);
       int st = 0; uint32_t ph = 0;
       for (int j = 0; j < T; ++j) {
         mbar_wait(&k_empty[st], ph ^ 1);
-        mbar_expect_tx(&k_full[st], G4_K_BYTES);
-        tma_load_4d(&map_k, &k_full[st], smem + G4_OFF_K + st * G4_K_BYTES, 0, j * G4_BKV, h, n);
+        mbar_expect_tx(&k_full[st], Cfg::K_STAGE);
+#pragma unroll
+        for (int a = 0; a < KA; ++a)
+          tma_load_4d(&map_k, &k_full[st], smem + Cfg::OFF_K + st * Cfg::K_STAGE + a * (GK_BKV * 128), a * 64, j * GK_BKV, h, n);
         mbar_wait(&v_empty[st], ph ^ 1);
-        mbar_expect_tx(&v_full[st], G4_V_BYTES);
-        tma_load_3d(&map_vt, &v_full[st], smem + G4_OFF_V + st * G4_V_BYTES, j * G4_BKV, h * p.D, n);
-        if (++st == G4_STAGES) { st = 0; ph ^= 1; }
+        mbar_expect_tx(&v_full[st], Cfg::V_STAGE);
+        tma_load_3d(&map_vt, &v_full[st], smem + Cfg::OFF_V + st * Cfg::V_STAGE, j * GK_BKV, h * p.D, n);
+        if (++st == GK_STAGES) { st = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ================================================================== MMA issuer
     if (lane == 0) {
-      const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(G4_BKV >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
-      const uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(DV >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
-      const int kq = (p.D + 15) >> 4;      // k-steps of QK^T that hold data (q / k columns D..63 are zero)
-      auto issue_s = [&](int j) {           // S_g(j) = Q_g K_j^T for the four groups
-        const int st = j % G4_STAGES; const uint32_t ph = (uint32_t)((j / G4_STAGES) & 1);
+      const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(GK_BKV >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
+      const uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(DVN >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
+      const int kq = (p.D + 15) >> 4;      // k-steps of QK^T that hold this head's data; later columns of the last atom are never read
+      auto issue_s = [&](int j) {           // S_g(j) = Q_g K_j^T for all groups
+        const int st = j % GK_STAGES; const uint32_t ph = (uint32_t)((j / GK_STAGES) & 1);
         mbar_wait(&k_full[st], ph);
-        const uint64_t k_desc = sw128_desc(smem_u32(smem + G4_OFF_K + st * G4_K_BYTES));
+        const uint32_t k_base = smem_u32(smem + Cfg::OFF_K + st * Cfg::K_STAGE);
 #pragma unroll
-        for (int g = 0; g < G4; ++g) {
+        for (int g = 0; g < G; ++g) {
           mbar_wait(&s_empty[g], (uint32_t)((j & 1) ^ 1));
           tc_fence_after();
-          const uint64_t q_desc = sw128_desc(smem_u32(smem + g * Q_BYTES));
-          for (int kk = 0; kk < kq; ++kk)
-            umma(tmem_base + G4_TM_S + g * 64, q_desc + 2 * kk, k_desc + 2 * kk, idesc_s, kk > 0 ? 1u : 0u);
+          const uint32_t q_base = smem_u32(smem + g * Cfg::Q_TILE);
+          for (int kk = 0; kk < kq; ++kk) {
+            const int atom = kk >> 2, within = kk & 3;
+            umma(tmem_base + g * 64, sw128_desc(q_base + atom * Q_BYTES) + 2 * within, sw128_desc(k_base + atom * (GK_BKV * 128)) + 2 * within,
+                 idesc_s, kk > 0 ? 1u : 0u);
+          }
           tc_commit(&s_full[g]);
         }
         tc_commit(&k_empty[st]);
@@ -672,17 +690,17 @@ attention_tc4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       issue_s(0);
       for (int j = 0; j < T; ++j) {
         if (j + 1 < T) issue_s(j + 1);
-        const int st = j % G4_STAGES; const uint32_t ph = (uint32_t)((j / G4_STAGES) & 1);
+        const int st = j % GK_STAGES; const uint32_t ph = (uint32_t)((j / GK_STAGES) & 1);
         mbar_wait(&v_full[st], ph);
-        const uint64_t b_desc = sw128_desc(smem_u32(smem + G4_OFF_V + st * G4_V_BYTES));
+        const uint64_t b_desc = sw128_desc(smem_u32(smem + Cfg::OFF_V + st * Cfg::V_STAGE));
 #pragma unroll
-        for (int g = 0; g < G4; ++g) {
+        for (int g = 0; g < G; ++g) {
           mbar_wait(&p_full[g], (uint32_t)(j & 1));
           tc_fence_after();
-          const uint64_t a_desc = sw128_desc(smem_u32(smem + G4_OFF_P + g * G4_P_BYTES));
+          const uint64_t a_desc = sw128_desc(smem_u32(smem + Cfg::OFF_P + g * GK_P_BYTES));
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
-            umma(tmem_base + G4_TM_O + g * 64, a_desc + 2 * kk, b_desc + 2 * kk, idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
+            umma(tmem_base + 256 + g * Cfg::O_STRIDE, a_desc + 2 * kk, b_desc + 2 * kk, idesc_o, (j > 0 || kk > 0) ? 1u : 0u);
           tc_commit(&p_empty[g]);
         }
         tc_commit(&v_empty[st]);
@@ -696,9 +714,9 @@ attention_tc4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     const float sl2 = p.scale_log2e;
     float m_used = -INFINITY, l = 0.f;
-    const uint32_t s_addr = tmem_base + lane_base + G4_TM_S + g * 64;
-    const uint32_t o_addr = tmem_base + lane_base + G4_TM_O + g * 64;
-    uint8_t* const prow = smem + G4_OFF_P + g * G4_P_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
+    const uint32_t s_addr = tmem_base + lane_base + g * 64;
+    const uint32_t o_addr = tmem_base + lane_base + 256 + g * Cfg::O_STRIDE;
+    uint8_t* const prow = smem + Cfg::OFF_P + g * GK_P_BYTES + (r >> 3) * 1024 + (r & 7) * 128;
     for (int j = 0; j < T; ++j) {
       const uint32_t par = (uint32_t)(j & 1);
       mbar_wait(&s_full[g], par);
@@ -752,7 +770,7 @@ attention_tc4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
       if (__any_sync(0xffffffffu, need)) {
         tc_fence_after();
 #pragma unroll
-        for (int c = 0; c < DV / 16; ++c) {
+        for (int c = 0; c < DVN / 16; ++c) {
           uint32_t orr[16];
           tmem_ld16(o_addr + c * 16, orr);
           tmem_wait_ld();
@@ -770,9 +788,9 @@ attention_tc4_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
     mbar_wait(&p_empty[g], (uint32_t)((T - 1) & 1));
     tc_fence_after();
     const float inv = p.out_alpha / l;
-    bf16* orow = p.out + (int64_t)n * p.bso + ((int64_t)qt * G4 * BQ + g * BQ + r) * p.ldo + h * p.D;
+    bf16* orow = p.out + (int64_t)n * p.bso + ((int64_t)qt * G * BQ + g * BQ + r) * p.ldo + h * p.D;
 #pragma unroll
-    for (int c = 0; c < DV / 16; ++c) {
+    for (int c = 0; c < DVN / 16; ++c) {
       uint32_t orr[16];
       tmem_ld16(o_addr + c * 16, orr);
       tmem_wait_ld();
@@ -894,33 +912,21 @@ extern "C" int32_t fyc_self_attention_tc(const void* qk, int64_t ldqk, int64_t q
   // Four query tiles per CTA with 64-key tiles: measured SLOWER than the two-tile kernel (1.70 vs 1.43 ms at 32 x 8 x 4096, round 2:
   // profiles/round2_attention.md - half of its warp samples wait for MMA completions, the 64-key tiles double the MMA instruction count and
   // the shared-memory operand reads per key); kept as an opt-in experiment, FYC_ATTN_G4=1.
-  if (L % (G4 * BQ) == 0 && g4e && g4e[0] == '1') {
+  if (L % (4 * BQ) == 0 && g4e && g4e[0] == '1') {
+    using Cfg = GkCfg<4, 1, DV>;
     CUtensorMap mk64;
     {
       uint64_t dims[4] = {64, (uint64_t)L, (uint64_t)heads, (uint64_t)NB};
       uint64_t str[3] = {(uint64_t)ldqk * 2, 128, (uint64_t)L * ldqk * 2};
-      uint32_t box[4] = {64, (uint32_t)G4_BKV, 1, 1};
+      uint32_t box[4] = {64, (uint32_t)GK_BKV, 1, 1};
       int32_t rc = make_map(&mk64, (const bf16*)qk + k_col0, 4, dims, str, box);
       if (rc) return rc;
     }
+    auto kern = attention_tcg_kernel<4, 1, DV, 0x52>;
     static bool attr4 = false;
-    if (!attr4) {
-      FYC_CUDA(cudaFuncSetAttribute(attention_tc4_kernel<0x00>, cudaFuncAttributeMaxDynamicSharedMemorySize, G4_SMEM_BYTES));
-      FYC_CUDA(cudaFuncSetAttribute(attention_tc4_kernel<0x02>, cudaFuncAttributeMaxDynamicSharedMemorySize, G4_SMEM_BYTES));
-      FYC_CUDA(cudaFuncSetAttribute(attention_tc4_kernel<0x12>, cudaFuncAttributeMaxDynamicSharedMemorySize, G4_SMEM_BYTES));
-      FYC_CUDA(cudaFuncSetAttribute(attention_tc4_kernel<0x52>, cudaFuncAttributeMaxDynamicSharedMemorySize, G4_SMEM_BYTES));
-      FYC_CUDA(cudaFuncSetAttribute(attention_tc4_kernel<0x5a>, cudaFuncAttributeMaxDynamicSharedMemorySize, G4_SMEM_BYTES));
-      attr4 = true;
-    }
-    dim3 grid4((unsigned)(L / (G4 * BQ)), (unsigned)heads, (unsigned)NB);
-    const char* pe = getenv("FYC_ATTN_POLY");
-    const int eighths = pe ? atoi(pe) : 3;          // share of the exponentials on the FMA pipe, in eighths
-    cudaStream_t s4 = (cudaStream_t)stream;
-    if (eighths <= 0) attention_tc4_kernel<0x00><<<grid4, G4_THREADS, G4_SMEM_BYTES, s4>>>(mq, mk64, mv, p);
-    else if (eighths == 1) attention_tc4_kernel<0x02><<<grid4, G4_THREADS, G4_SMEM_BYTES, s4>>>(mq, mk64, mv, p);
-    else if (eighths == 2) attention_tc4_kernel<0x12><<<grid4, G4_THREADS, G4_SMEM_BYTES, s4>>>(mq, mk64, mv, p);
-    else if (eighths == 3) attention_tc4_kernel<0x52><<<grid4, G4_THREADS, G4_SMEM_BYTES, s4>>>(mq, mk64, mv, p);
-    else attention_tc4_kernel<0x5a><<<grid4, G4_THREADS, G4_SMEM_BYTES, s4>>>(mq, mk64, mv, p);
+    if (!attr4) { FYC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM)); attr4 = true; }
+    dim3 grid4((unsigned)(L / (4 * BQ)), (unsigned)heads, (unsigned)NB);
+    kern<<<grid4, Cfg::THREADS, Cfg::SMEM, (cudaStream_t)stream>>>(mq, mk64, mv, p);
     FYC_LAUNCH_CHECK();
     return FYC_OK;
   }
@@ -962,6 +968,49 @@ extern "C" int32_t fyc_self_attention_tc(const void* qk, int64_t ldqk, int64_t q
   }
   dim3 grid((unsigned)(L / BQ), (unsigned)heads, (unsigned)NB);
   attention_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, (cudaStream_t)stream>>>(mq, mk, mv, p);
+  FYC_LAUNCH_CHECK();
+  return FYC_OK;
+}
+
+// Head dim 80 (level-1 self-attention): qkv [NB, L, ldqkv] bf16 with q head h at columns [q_col0 + 80 h, +80), k at [k_col0 + 80 h, +80) -
+// UNPADDED, the fused [q | k | v] projection as the GEMM wrote it (reads up to column k_col0 + 80 heads + 47: the buffer must hold at
+// least 48 more columns after k's last head, which the v block provides); vt: [NB, heads * 80, L]; out: [NB, L, ldo].
+extern "C" int32_t fyc_self_attention_tc_d80(const void* qkv, int64_t ldqkv, int64_t q_col0, int64_t k_col0, const void* vt, void* out,
+                                             int64_t ldo, int64_t NB, int64_t heads, int64_t L, float scale, void* stream) {
+  constexpr int D = 80;
+  using Cfg = GkCfg<2, 2, D>;
+  FYC_CHECK(L % (2 * BQ) == 0 && L >= 2 * BQ, "self_attention_tc_d80: sequence length %lld must be a multiple of 256", (long long)L);
+  FYC_CHECK(ldqkv % 8 == 0 && q_col0 % 8 == 0 && k_col0 % 8 == 0 && ldo % 8 == 0, "self_attention_tc_d80: 16-byte alignment");
+  FYC_CHECK((((uintptr_t)qkv | (uintptr_t)vt | (uintptr_t)out) & 15) == 0, "self_attention_tc_d80: pointers must be 16-byte aligned");
+  FYC_CHECK(NB < 65536 && heads < 65536, "self_attention_tc_d80: grid too large");
+  FYC_CHECK(q_col0 + heads * D + 48 <= ldqkv && k_col0 + heads * D + 48 <= ldqkv, "self_attention_tc_d80: the row must extend 48 columns past the last head");
+  CUtensorMap mq, mk, mv;
+  {
+    // inner extent 128 columns per head although heads are 160 bytes apart: overlapping tensor-map dimensions are legal, and the second
+    // atom's foreign columns are never multiplied (5 k-steps)
+    uint64_t dims[4] = {128, (uint64_t)L, (uint64_t)heads, (uint64_t)NB};
+    uint64_t str[3] = {(uint64_t)ldqkv * 2, (uint64_t)D * 2, (uint64_t)L * ldqkv * 2};
+    uint32_t boxq[4] = {64, (uint32_t)BQ, 1, 1}, boxk[4] = {64, (uint32_t)GK_BKV, 1, 1};
+    int32_t rc = make_map(&mq, (const bf16*)qkv + q_col0, 4, dims, str, boxq);
+    if (rc) return rc;
+    rc = make_map(&mk, (const bf16*)qkv + k_col0, 4, dims, str, boxk);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)L, (uint64_t)(heads * D), (uint64_t)NB};
+    uint64_t str[2] = {(uint64_t)L * 2, (uint64_t)L * heads * D * 2};
+    uint32_t box[3] = {64, (uint32_t)D, 1};
+    int32_t rc = make_map(&mv, vt, 3, dims, str, box);
+    if (rc) return rc;
+  }
+  AttnTcParams p;
+  p.out = (bf16*)out; p.ldo = ldo; p.bso = L * ldo; p.L = (int)L; p.heads = (int)heads; p.D = D;
+  p.scale_log2e = scale * 1.4426950408889634f; p.out_alpha = 1.0f;
+  auto kern = attention_tcg_kernel<2, 2, D, 0x52>;
+  static bool attr = false;
+  if (!attr) { FYC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM)); attr = true; }
+  dim3 grid((unsigned)(L / (2 * BQ)), (unsigned)heads, (unsigned)NB);
+  kern<<<grid, Cfg::THREADS, Cfg::SMEM, (cudaStream_t)stream>>>(mq, mk, mv, p);
   FYC_LAUNCH_CHECK();
   return FYC_OK;
 }

@@ -279,7 +279,7 @@ def conv3x3(x, w, bias=None, residual=None, rowbias=None, images_per_group=0, st
     return out
 
 
-def groupnorm(x, gamma, beta, groups, eps, silu=False, stat_batches=None, x2=None):
+def groupnorm(x, gamma, beta, groups, eps, silu=False, stat_batches=None, x2=None, out=None):
     """x [..., C] contiguous; statistics per (stat batch, group) where x is viewed as [stat_batches, R, C].
     ``x2`` [..., C2]: normalise the channel concatenation [x | x2] (gamma / beta of C + C2 channels) reading both tensors in place
     (fyc_groupnorm_concat: the up blocks' skip concatenation is never written); returns [..., C + C2]."""
@@ -293,7 +293,9 @@ def groupnorm(x, gamma, beta, groups, eps, silu=False, stat_batches=None, x2=Non
     Cc = C1 + (x2.shape[-1] if x2 is not None else 0)
     NB = x.shape[0] if stat_batches is None else stat_batches
     R = x.numel() // (NB * C1)
-    out = torch.empty(x.shape[:-1] + (Cc,), dtype=x.dtype, device=x.device)
+    if out is None:
+        out = torch.empty(x.shape[:-1] + (Cc,), dtype=x.dtype, device=x.device)
+    assert out.is_contiguous() and tuple(out.shape) == tuple(x.shape[:-1]) + (Cc,) and out.dtype == x.dtype
     nbytes = lib().fyc_groupnorm_workspace_bytes(NB, Cc, groups)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
     fam = f"groupnorm[{NB}x{R}x{Cc}]" if _prof_shapes else "groupnorm"
@@ -369,6 +371,25 @@ def self_attention_tc(qk, q_col0, k_col0, vt, heads, D, scale):
     with _rec("attention_tc", 4.0 * NB * heads * L * L * D, qk.element_size() * (4 * NB * L * heads * D)):
         check(lib().fyc_self_attention_tc(ptr(qk), qk.stride(1), q_col0, k_col0, ptr(vt), ptr(out), out.stride(1), NB, heads, L, D,
                                           float(scale), stream_ptr()))
+    return out
+
+
+use_attn_d80 = os.environ.get("FYC_ATTN_D80", "1") != "0"        # A/B switch: head-dim-80 self-attention on tcgen05 (else the mma.sync kernel)
+
+
+def self_attention_tc80_ok(dtype, L, D):
+    return use_attn_d80 and _impl != L_SIMT and dtype == torch.bfloat16 and D == 80 and L % 256 == 0 and lib().fyc_tcgen05_available() == 1
+
+
+def self_attention_tc_d80(qkv, q_col0, k_col0, vt, heads, scale):
+    """tcgen05 self-attention for head dim 80: qkv [NB, L, ld] with UNPADDED 80-wide q / k heads (the fused projection as is), vt
+    [NB, heads * 80, L] -> [NB, L, heads * 80]."""
+    NB, L, _ = qkv.shape
+    D = 80
+    out = torch.empty((NB, L, heads * D), dtype=qkv.dtype, device=qkv.device)
+    with _rec(f"attention_tc80[{NB}x{heads}x{L}]" if _prof_shapes else "attention_tc", 4.0 * NB * heads * L * L * D, qkv.element_size() * (4 * NB * L * heads * D)):
+        check(lib().fyc_self_attention_tc_d80(ptr(qkv), qkv.stride(1), q_col0, k_col0, ptr(vt), ptr(out), out.stride(1), NB, heads, L,
+                                              float(scale), stream_ptr()))
     return out
 
 

@@ -386,19 +386,36 @@ class UNet3DConditionModel(ParamTreeModel):
 
     def _resnet(self, p, x, temb_all, B, F, skip=None):
         """``skip``: the up blocks' `torch.cat([hidden_states, res_hidden_states], dim=1)` (unet_blocks.py:763,885) is not materialised -
-        norm1 normalises [x | skip] reading both tensors in place, the 1x1 shortcut runs its K loop over the two sources."""
+        norm1 normalises [x | skip] reading both tensors in place, the 1x1 shortcut runs its K loop over the two sources.  A skip with
+        fewer images than x (the conv_in output under the shared CFG prefix: ONE copy for the `rep` CFG replicas of x) is read once per
+        replica instead of being duplicated."""
         NB, H, W, Cin = x.shape
         o, n = self._temb_pack()[2][p]
         temb = temb_all[:, o:o + n]                      # [B, Cout] fp32 view, row stride = sum Cout
-        h = self._gn(p + ".norm1", x, B, True, False, x2=skip)
+        rep = 1 if skip is None else NB // skip.shape[0]
+        if rep == 1:
+            h = self._gn(p + ".norm1", x, B, True, False, x2=skip)
+        else:                                            # per CFG replica: statistics are per clip, so the replicas are independent launches
+            nb = NB // rep
+            h = torch.empty((NB, H, W, Cin + skip.shape[-1]), dtype=x.dtype, device=x.device)
+            for r in range(rep):
+                ops.groupnorm(x[r * nb:(r + 1) * nb], self._f(p + ".norm1.weight"), self._f(p + ".norm1.bias"), self._cfg["norm_num_groups"],
+                              self._cfg["norm_eps"], silu=True, stat_batches=nb if self._cfg["use_inflated_groupnorm"] else B // rep,
+                              x2=skip, out=h[r * nb:(r + 1) * nb])
         h = ops.conv3x3(h, self._conv_w(p + ".conv1.weight"), bias=self._f(p + ".conv1.bias"), rowbias=temb, images_per_group=F)
         h = self._gn(p + ".norm2", h, B, True, False)
         if self._has(p + ".conv_shortcut.weight"):
-            res = ops.gemm(x.view(-1, Cin), self._w1x1(p + ".conv_shortcut.weight"), bias=self._f(p + ".conv_shortcut.bias"),
-                           A2=None if skip is None else skip.view(-1, skip.shape[-1]))
+            w_s, b_s = self._w1x1(p + ".conv_shortcut.weight"), self._f(p + ".conv_shortcut.bias")
+            if rep == 1:
+                res = ops.gemm(x.view(-1, Cin), w_s, bias=b_s, A2=None if skip is None else skip.view(-1, skip.shape[-1]))
+            else:
+                rows = (NB // rep) * H * W
+                res = torch.empty((NB * H * W, w_s.shape[0]), dtype=x.dtype, device=x.device)
+                for r in range(rep):
+                    ops.gemm(x.view(-1, Cin)[r * rows:(r + 1) * rows], w_s, bias=b_s, A2=skip.view(-1, skip.shape[-1]), out=res[r * rows:(r + 1) * rows])
             res = res.view(NB, H, W, -1)
         else:
-            res = x if skip is None else ops.concat_channels(x, skip)
+            res = x if skip is None else ops.concat_channels(x, skip if rep == 1 else skip.repeat(rep, 1, 1, 1))
         return ops.conv3x3(h, self._conv_w(p + ".conv2.weight"), bias=self._f(p + ".conv2.bias"), residual=res)
 
     def _ff(self, p, tok, norm):
@@ -443,6 +460,11 @@ class UNet3DConditionModel(ParamTreeModel):
             ops.note_padding(2.0 * M * C * 2 * heads * (64 - d))
             vt = ops.transpose_tokens(qkv, 2 * heads * 64, C)
             o = ops.self_attention_tc(qkv, 0, heads * 64, vt, heads, d, d ** -0.5)
+        elif ops.self_attention_tc80_ok(tok.dtype, HW, d):
+            # head dim 80 on tcgen05: the fused [q | k | v] buffer as the GEMM wrote it (no padding), V transposed per image
+            qkv = qkv.view(NB, HW, 3 * C)
+            vt = ops.transpose_tokens(qkv, 2 * C, C)
+            o = ops.self_attention_tc_d80(qkv, 0, C, vt, heads, d ** -0.5)
         else:
             qkv = qkv.view(NB, HW, 3 * C)
             o = ops.attention(qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:], heads, d ** -0.5)
@@ -674,9 +696,7 @@ class UNet3DConditionModel(ParamTreeModel):
             p = f"up_blocks.{i}"
             lvl = n - 1 - i
             for j in range(cfg["layers_per_block"] + 1):
-                skip = skips.pop()
-                if skip.shape[0] != x.shape[0]:          # the conv_in output of the shared prefix: one copy per clip -> the CFG pair
-                    skip = skip.repeat(dup, 1, 1, 1)     # (a 2 x 42 MB device copy per forward at cfg2)
+                skip = skips.pop()                       # (under the shared CFG prefix the conv_in output exists once: _resnet reads it per replica)
                 x = self._resnet(f"{p}.resnets.{j}", x, semb, B, F, skip=skip)
                 if i > 0:
                     x = self._transformer(f"{p}.attentions.{j}", x, ctx, self._heads[lvl], F)

@@ -180,6 +180,12 @@ int32_t fyc_temporal_attention(const void* qkv, void* out, int64_t B, int64_t F,
  * out: [NB, L, ldo], head h at columns [h*D, (h+1)*D). */
 int32_t fyc_self_attention_tc(const void* qk, int64_t ldqk, int64_t q_col0, int64_t k_col0, const void* vt, void* out,
                               int64_t ldo, int64_t NB, int64_t heads, int64_t L, int64_t D, float scale, void* stream);
+/* The same for head dim 80, L % 256 == 0 - the level-1 attn1 (1024 tokens at cfg2, 2304 at cfg5).  qkv: [NB, L, ldqkv] bf16, the fused
+ * [q | k | v] projection UNPADDED: q head h at columns [q_col0 + 80 h, +80), k at [k_col0 + 80 h, +80); each head's second 64-column
+ * TMA atom overlaps the next head, whose columns are never multiplied (QK^T issues 5 k-steps of 16), so the row only has to extend 48
+ * columns past the last k head (the v block does).  vt: [NB, heads * 80, L]; out: [NB, L, ldo]. */
+int32_t fyc_self_attention_tc_d80(const void* qkv, int64_t ldqkv, int64_t q_col0, int64_t k_col0, const void* vt, void* out,
+                                  int64_t ldo, int64_t NB, int64_t heads, int64_t L, float scale, void* stream);
 /* in [NB, L, ld] columns [col0, col0 + C) (bf16) -> out [NB, C, L] */
 int32_t fyc_transpose_tokens(const void* in, void* out, int64_t NB, int64_t L, int64_t C, int64_t ld, int64_t col0,
                              void* stream);

@@ -111,7 +111,10 @@ def conv3x3(x, w, bias=None, residual=None, rowbias=None, images_per_group=0, st
     return _store(y, torch.float32 if out_f32 else x.dtype).contiguous()
 
 
-def groupnorm(x, gamma, beta, groups, eps, silu=False, stat_batches=None, x2=None):
+def groupnorm(x, gamma, beta, groups, eps, silu=False, stat_batches=None, x2=None, out=None):
+    if out is not None:
+        out.copy_(groupnorm(x, gamma, beta, groups, eps, silu=silu, stat_batches=stat_batches, x2=x2))
+        return out
     if x2 is not None:          # fyc_groupnorm_concat
         x = torch.cat([x, x2], dim=-1)
     C = x.shape[-1]
@@ -170,6 +173,20 @@ def self_attention_tc(qk, q_col0, k_col0, vt, heads, D, scale):
     v = vt.float().reshape(NB, heads, D, L).transpose(2, 3)
     p = torch.softmax(q @ k.transpose(-1, -2) * scale, dim=-1)
     return _store((p @ v).transpose(1, 2).reshape(NB, L, heads * D), qk.dtype)
+
+
+def self_attention_tc80_ok(dtype, L, D):
+    return TC_EMULATED and ops.use_attn_d80 and ops._impl != _lib.IMPL_SIMT and dtype == torch.bfloat16 and D == 80 and L % 256 == 0
+
+
+def self_attention_tc_d80(qkv, q_col0, k_col0, vt, heads, scale):
+    NB, L, _ = qkv.shape
+    D = 80
+    q = qkv[:, :, q_col0:q_col0 + heads * D].float().reshape(NB, L, heads, D).transpose(1, 2)
+    k = qkv[:, :, k_col0:k_col0 + heads * D].float().reshape(NB, L, heads, D).transpose(1, 2)
+    v = vt.float().reshape(NB, heads, D, L).transpose(2, 3)
+    p = torch.softmax(q @ k.transpose(-1, -2) * scale, dim=-1)
+    return _store((p @ v).transpose(1, 2).reshape(NB, L, heads * D), qkv.dtype)
 
 
 def temporal_attention(qkv, heads, scale):
@@ -279,7 +296,7 @@ def video_grid_u8(video, nrow=6, padding=2, rescale=False):
 
 
 _NAMES = ["tc_ok", "require_cuda", "ln_fold_ok", "layernorm_stats", "gemm", "conv3x3", "groupnorm", "layernorm", "attention", "transpose_tokens", "self_attention_tc_ok",
-          "self_attention_tc", "temporal_attention", "softmax_rows", "timestep_embed", "silu", "gelu", "upsample_nearest2x",
+          "self_attention_tc", "self_attention_tc80_ok", "self_attention_tc_d80", "temporal_attention", "softmax_rows", "timestep_embed", "silu", "gelu", "upsample_nearest2x",
           "concat_channels", "ncfhw_to_nfhwc", "nfhwc_to_ncfhw", "build_unet_input", "cfg_ddim_step", "frames_finalize", "video_grid_u8"]
 
 

@@ -510,6 +510,25 @@ def test_self_attention_tcgen05(cuda, L, heads, NB, gain):
     assert rel(out, o2) < BF16_TOL
 
 
+@pytest.mark.parametrize("L,heads,NB,gain", [(256, 2, 2, 1.0), (1024, 8, 3, 1.0), (512, 4, 1, 3.0), (2304, 8, 1, 1.0)])
+def test_self_attention_tcgen05_d80(cuda, L, heads, NB, gain):
+    """head dim 80 (level-1 attn1) on tcgen05: UNPADDED heads in the fused [q | k | v] buffer - the second 64-column atom of a head
+    overlaps the next head (or, for the last k head, the v block), whose columns must not leak into the scores; against fp32
+    softmax(q k^T / sqrt(80)) v on the same bf16 operands, and against the mma.sync kernel it replaces.  2304 = the cfg5 level-1 length."""
+    from followyourclick_b200 import ops
+    D = 80
+    C = heads * D
+    qkv = rnd((NB, L, 3 * C), 1, torch.bfloat16)
+    qkv[:, :, :C] *= gain
+    vt = ops.transpose_tokens(qkv, 2 * C, C)
+    out = ops.self_attention_tc_d80(qkv, 0, C, vt, heads, D ** -0.5)
+    ref = _mha_ref(qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:], heads, D ** -0.5)
+    old = ops.attention(qkv[:, :, :C], qkv[:, :, C:2 * C], qkv[:, :, 2 * C:], heads, D ** -0.5)
+    e = (out.float() - ref)
+    assert rel(out, ref) < BF16_TOL and float(e.abs().max()) < 2 ** -6 * float(ref.abs().max()) + 1e-3, (rel(out, ref), float(e.abs().max()))
+    assert rel(out, old) < 1e-2, rel(out, old)
+
+
 def test_softmax_rows_and_misc(cuda):
     from followyourclick_b200 import ops
     s = rnd((64, 300), 1) * 4
