@@ -206,13 +206,21 @@ class AutoencoderKL(ParamTreeModel):
         t = self._gn(p + ".group_norm", x, False).view(NB * HW, C)
         q = ops.gemm(t, self._w(p + ".query.weight"), bias=self._f(p + ".query.bias")).view(NB, HW, C)
         k = ops.gemm(t, self._w(p + ".key.weight"), bias=self._f(p + ".key.bias")).view(NB, HW, C)
-        scores = ops.gemm(q, k, alpha=C ** -0.5, out_f32=True)                         # [NB, HW, HW] fp32
-        probs = ops.softmax_rows(scores, x.dtype)
-        del scores
-        # V^T[n] = Wv @ t[n]^T (bias folded into the next GEMM: softmax rows sum to 1, so P (V + 1 b^T) = P V + b^T)
+        # V^T[n] = Wv @ t[n]^T (bias folded into the P V GEMM: softmax rows sum to 1, so P (V + 1 b^T) = P V + b^T)
         wv = self._w(p + ".value.weight")
         vt = ops.gemm(wv.unsqueeze(0).expand(NB, C, C), t.view(NB, HW, C))            # [NB, C, HW]
-        o = ops.gemm(probs, vt, bias=self._f(p + ".value.bias"))                       # [NB, HW, C]
+        # one head of width C = 512 (attention.py:331-379, fp32 softmax :366): TMEM cannot hold a 512-wide O accumulator next to S, so the
+        # scores go through memory - but only for a few frames at a time (<= 256 MB of fp32 scores live, instead of [NB, HW, HW] at once:
+        # 1.07 GB at 16 frames of 512x512, 10.9 GB at 32 frames of 768x768)
+        o = torch.empty((NB, HW, C), dtype=x.dtype, device=x.device)
+        fc = max(1, (1 << 26) // (HW * HW))
+        for f0 in range(0, NB, fc):
+            f1 = min(NB, f0 + fc)
+            scores = ops.gemm(q[f0:f1], k[f0:f1], alpha=C ** -0.5, out_f32=True)       # [fc, HW, HW] fp32
+            probs = ops.softmax_rows(scores, x.dtype)
+            del scores
+            ops.gemm(probs, vt[f0:f1], bias=self._f(p + ".value.bias"), out=o[f0:f1])  # [fc, HW, C]
+            del probs
         out = ops.gemm(o.view(NB * HW, C), self._w(p + ".proj_attn.weight"), bias=self._f(p + ".proj_attn.bias"),
                        residual=x.view(NB * HW, C))
         return out.view(NB, H, W, C)
