@@ -64,6 +64,8 @@ SIGNATURES = {
     "fyc_temporal_attention": (_i32, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _f32, _i32, _vp]),
     "fyc_self_attention_tc": (_i32, [_vp, _i64, _i64, _i64, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _f32, _vp]),
     "fyc_self_attention_tc_d80": (_i32, [_vp, _i64, _i64, _i64, _vp, _vp, _i64, _i64, _i64, _i64, _f32, _vp]),
+    "fyc_cross_attention_tc": (_i32, [_vp, _i64, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _i64, _f32, _f32,
+                                      _f32, _vp]),
     "fyc_transpose_tokens": (_i32, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _vp]),
     "fyc_softmax_rows": (_i32, [_vp, _vp, _i64, _i64, _i32, _vp]),
     "fyc_timestep_embed": (_i32, [_vp, _vp, _vp, _i64, _i64, _i32, _vp]),

@@ -810,6 +810,279 @@ attention_tcg_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_con
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------------------
+// Cross-attention on tcgen05: a SHORT, step-invariant context (the 77 text tokens, padded to 80 keys; optionally the IP-Adapter's
+// 4 / 16 image tokens, padded to 16) against long query sequences.  Replaces the mma.sync `attention_mma_shortk_kernel` for head dims
+// 40 and 80 (CrossAttention._attention diffusers/models/attention.py:649-678 for attn2; IPCrossAttention.forward
+// animatediff/models/attention.py:92-120 == IPAttnProcessor.__call__ ip_adapter/attention_processor.py:137-168).
+//
+// One CTA = one (image, head): K_t, V_t^T (and K_i, V_i^T) are loaded ONCE and stay in shared memory; two softmax warpgroups ping-pong
+// over the CTA's query tiles (128 rows each).  Per tile:  S_t = Q K_t^T (N = 80) and S_i = Q K_i^T (N = 16) into TMEM -> one row per
+// thread: two INDEPENDENT softmaxes, normalised in registers (the whole context is one tile: no online rescaling) and pre-scaled by
+// out_alpha / l_t and alpha2 / l_i -> P_t, P_i (bf16) to shared memory -> O = P_t V_t + P_i V_i accumulated in ONE TMEM accumulator ->
+// bf16 out, written once.  Padding keys (77..79, T..15) are masked to -inf before the softmax.
+// Operands (prepared once per clip by the host, unet.py::prepare_context): q UNPADDED [NB, Lq, heads * D] (head h at columns D h): the
+// 64-column TMA box of a head reads 24 foreign columns for D = 40, of which k-step 2 multiplies columns 40..47 - against ZERO columns
+// of K, which the host pads per head to 64 (D = 80: two atoms, 5 k-steps, no padding, as in the self-attention kernel above);
+// k [NBc, 80, heads * DKP] (DKP = 64 | 80), vt [NBc, heads * D, 80]; k2 [NBc, 16, heads * DKP], vt2 [NBc, heads * D, 16].
+template <int KA, int DVN> struct CxCfg {
+  static constexpr int LKT = 80, LKI = 16;                        // padded key counts (text, image)
+  static constexpr int THREADS = 64 + 2 * 128;
+  static constexpr int KT_BYTES = KA * LKT * 128;                 // K_t: KA atoms of 80 keys x 128 B
+  static constexpr int VT_BYTES = 2 * DVN * 128;                  // V_t^T: two 64-key atoms (keys 0..63 | 64..79 + zero fill) of DVN rows
+  static constexpr int KI_BYTES = KA * LKI * 128;
+  static constexpr int VI_BYTES = DVN * 128;
+  static constexpr int Q_TILE = KA * Q_BYTES;                     // per group
+  static constexpr int P_TILE = 3 * PHALF_BYTES;                  // per group: P_t atoms 0, 1 and P_i
+  static constexpr int OFF_KT = 0, OFF_VT = OFF_KT + KT_BYTES, OFF_KI = OFF_VT + VT_BYTES, OFF_VI = OFF_KI + KI_BYTES;
+  static constexpr int OFF_Q = OFF_VI + VI_BYTES, OFF_P = OFF_Q + 2 * Q_TILE, OFF_BAR = OFF_P + 2 * P_TILE, SMEM = OFF_BAR + 256 + 1024;
+  static constexpr int TM_ST = 0, TM_SI = 96, TM_O = 128, TM_GROUP = 256;      // TMEM columns inside a group's 256
+  static_assert(KT_BYTES % 1024 == 0 && VT_BYTES % 1024 == 0 && KI_BYTES % 1024 == 0 && VI_BYTES % 1024 == 0, "SWIZZLE_128B tile bases");
+  static_assert(SMEM <= 227 * 1024, "shared memory budget");
+  static_assert(TM_O + DVN <= TM_GROUP, "TMEM column budget");
+};
+
+struct AttnCxParams {
+  bf16* out; int64_t ldo, bso;
+  int Lq, heads, D, Lk, Lk2;        // Lk <= 80 real text keys, Lk2 = 0 (no second context) or <= 16 real image keys
+  int dkp;                          // column stride between the heads of k / k2 (64 for D = 40: zero-padded heads; 80 for D = 80)
+  int kv_div;                       // images per context (= F)
+  float scale_log2e, out_alpha, alpha2;
+};
+
+template <int KA, int DVN, int POLYMASK>
+__global__ void __launch_bounds__(CxCfg<KA, DVN>::THREADS, 1)
+attention_cx_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k, const __grid_constant__ CUtensorMap map_vt,
+                    const __grid_constant__ CUtensorMap map_k2, const __grid_constant__ CUtensorMap map_vt2, const AttnCxParams p) {
+  using Cfg = CxCfg<KA, DVN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024 - (raw & 1023)) & 1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint64_t* kv_full = bars;              // [1]
+  uint64_t* q_full = bars + 1;           // [2] per group: the group's Q tile has landed
+  uint64_t* q_empty = bars + 3;          // [2] QK^T of the tile has retired: the Q slot may be refilled
+  uint64_t* s_full = bars + 5;           // [2] S_t, S_i are in TMEM
+  uint64_t* s_empty = bars + 7;          // [2] ... and have been read into registers
+  uint64_t* p_full = bars + 9;           // [2] P_t, P_i are in shared memory and O_g has been drained
+  uint64_t* o_full = bars + 11;          // [2] PV has retired: O_g is complete, P_g may be overwritten
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.y, n = blockIdx.z;
+  const int nc = n / p.kv_div;
+  const int nqt = (p.Lq + BQ - 1) / BQ;
+  const bool ip = p.Lk2 > 0;
+  // this CTA's query tiles: blockIdx.x, + gridDim.x, ...; group g takes every other one of them
+  auto tile_of = [&](int g, int it) { return (int)blockIdx.x + (2 * it + g) * (int)gridDim.x; };
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_q)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_k)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_vt)) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(kv_full, 1);
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&q_full[g], 1); mbar_init(&q_empty[g], 1); mbar_init(&s_full[g], 1); mbar_init(&s_empty[g], 4);
+      mbar_init(&p_full[g], 4); mbar_init(&o_full[g], 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================================================== TMA producer
+    if (lane == 0) {
+      const uint32_t kv_bytes = Cfg::KT_BYTES + Cfg::VT_BYTES + (ip ? Cfg::KI_BYTES + Cfg::VI_BYTES : 0);
+      mbar_expect_tx(kv_full, kv_bytes);
+#pragma unroll
+      for (int a = 0; a < KA; ++a) tma_load_3d(&map_k, kv_full, smem + Cfg::OFF_KT + a * (Cfg::LKT * 128), h * p.dkp + a * 64, 0, nc);
+      tma_load_3d(&map_vt, kv_full, smem + Cfg::OFF_VT, 0, h * p.D, nc);
+      tma_load_3d(&map_vt, kv_full, smem + Cfg::OFF_VT + DVN * 128, 64, h * p.D, nc);
+      if (ip) {
+#pragma unroll
+        for (int a = 0; a < KA; ++a) tma_load_3d(&map_k2, kv_full, smem + Cfg::OFF_KI + a * (Cfg::LKI * 128), h * p.dkp + a * 64, 0, nc);
+        tma_load_3d(&map_vt2, kv_full, smem + Cfg::OFF_VI, 0, h * p.D, nc);
+      }
+      for (int it = 0;; ++it) {
+        bool any = false;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          const int t = tile_of(g, it);
+          if (t >= nqt) continue;
+          any = true;
+          mbar_wait(&q_empty[g], (uint32_t)((it & 1) ^ 1));
+          mbar_expect_tx(&q_full[g], Cfg::Q_TILE);
+#pragma unroll
+          for (int a = 0; a < KA; ++a) tma_load_3d(&map_q, &q_full[g], smem + Cfg::OFF_Q + g * Cfg::Q_TILE + a * Q_BYTES, h * p.D + a * 64, t * BQ, n);
+        }
+        if (!any) break;
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc_st = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(Cfg::LKT >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
+      const uint32_t idesc_si = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(Cfg::LKI >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
+      const uint32_t idesc_o = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(DVN >> 3) << 17) | ((uint32_t)(BQ >> 4) << 24);
+      const int kq = (p.D + 15) >> 4;
+      const uint32_t kt_base = smem_u32(smem + Cfg::OFF_KT), ki_base = smem_u32(smem + Cfg::OFF_KI);
+      mbar_wait(kv_full, 0);
+      auto issue_s = [&](int g, int it) {
+        mbar_wait(&q_full[g], (uint32_t)(it & 1));
+        mbar_wait(&s_empty[g], (uint32_t)((it & 1) ^ 1));
+        tc_fence_after();
+        const uint32_t q_base = smem_u32(smem + Cfg::OFF_Q + g * Cfg::Q_TILE);
+        const uint32_t tm = tmem_base + g * Cfg::TM_GROUP;
+        for (int kk = 0; kk < kq; ++kk) {
+          const int atom = kk >> 2, within = kk & 3;
+          umma(tm + Cfg::TM_ST, sw128_desc(q_base + atom * Q_BYTES) + 2 * within, sw128_desc(kt_base + atom * (Cfg::LKT * 128)) + 2 * within, idesc_st, kk > 0 ? 1u : 0u);
+        }
+        if (ip)
+          for (int kk = 0; kk < kq; ++kk) {
+            const int atom = kk >> 2, within = kk & 3;
+            umma(tm + Cfg::TM_SI, sw128_desc(q_base + atom * Q_BYTES) + 2 * within, sw128_desc(ki_base + atom * (Cfg::LKI * 128)) + 2 * within, idesc_si, kk > 0 ? 1u : 0u);
+          }
+        tc_commit(&s_full[g]);
+        tc_commit(&q_empty[g]);
+      };
+      auto issue_o = [&](int g, int it) {
+        mbar_wait(&p_full[g], (uint32_t)(it & 1));
+        tc_fence_after();
+        const uint32_t p_base = smem_u32(smem + Cfg::OFF_P + g * Cfg::P_TILE);
+        const uint32_t tm = tmem_base + g * Cfg::TM_GROUP + Cfg::TM_O;
+        const uint32_t vt_base = smem_u32(smem + Cfg::OFF_VT);
+#pragma unroll
+        for (int kk = 0; kk < Cfg::LKT / 16; ++kk) {       // 80 keys: four k-steps in atom 0, one in atom 1
+          const int atom = kk >> 2, within = kk & 3;
+          umma(tm, sw128_desc(p_base + atom * PHALF_BYTES) + 2 * within, sw128_desc(vt_base + atom * (DVN * 128)) + 2 * within, idesc_o, kk > 0 ? 1u : 0u);
+        }
+        if (ip) umma(tm, sw128_desc(p_base + 2 * PHALF_BYTES), sw128_desc(smem_u32(smem + Cfg::OFF_VI)), idesc_o, 1u);
+        tc_commit(&o_full[g]);
+      };
+      // order: S(g0, 0), S(g1, 0), then per iteration O(g, it) followed by S(g, it + 1) - the other group's softmax overlaps
+      for (int g = 0; g < 2; ++g) if (tile_of(g, 0) < nqt) issue_s(g, 0);
+      for (int it = 0;; ++it) {
+        bool any = false;
+        for (int g = 0; g < 2; ++g) {
+          if (tile_of(g, it) >= nqt) continue;
+          any = true;
+          issue_o(g, it);
+          if (tile_of(g, it + 1) < nqt) issue_s(g, it + 1);
+        }
+        if (!any) break;
+      }
+    }
+  } else {
+    // ================================================================== softmax + epilogue (group g = warps 2-5 | 6-9)
+    const int g = (warp - 2) >> 2;
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    const float sl2 = p.scale_log2e;
+    const uint32_t tm = tmem_base + lane_base + g * Cfg::TM_GROUP;
+    uint8_t* const prow = smem + Cfg::OFF_P + g * Cfg::P_TILE + (r >> 3) * 1024 + (r & 7) * 128;
+    for (int it = 0;; ++it) {
+      const int t = tile_of(g, it);
+      if (t >= nqt) break;
+      const uint32_t par = (uint32_t)(it & 1);
+      mbar_wait(&s_full[g], par);
+      tc_fence_after();
+      uint32_t st[80], si[16];
+      tmem_ld32(tm + Cfg::TM_ST, st);
+      tmem_ld32(tm + Cfg::TM_ST + 32, st + 32);
+      tmem_ld16(tm + Cfg::TM_ST + 64, st + 64);
+      if (ip) tmem_ld16(tm + Cfg::TM_SI, si);
+      tmem_wait_ld();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[g]);
+      // ---- text softmax over Lk keys (padding keys are TMA-zero rows of K: score 0 -> masked here)
+      float mt = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 80; ++i) { if (i >= p.Lk) st[i] = 0xff800000u; mt = fmaxf(mt, __uint_as_float(st[i])); }
+      const float nb = -mt * sl2;
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < 80; ++i) { const float e = ex2(fmaf(__uint_as_float(st[i]), sl2, nb)); sum += e; st[i] = __float_as_uint(e); }
+      const float wt = p.out_alpha / sum;
+      float mi = -INFINITY, wi = 0.f;
+      if (ip) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { if (i >= p.Lk2) si[i] = 0xff800000u; mi = fmaxf(mi, __uint_as_float(si[i])); }
+        const float nbi = -mi * sl2;
+        float sumi = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { const float e = ex2(fmaf(__uint_as_float(si[i]), sl2, nbi)); sumi += e; si[i] = __float_as_uint(e); }
+        wi = p.alpha2 / sumi;
+      }
+      // ---- P (normalised, weighted) -> shared memory; the previous tile's PV must have retired (it also means O was ... see below)
+      if (it > 0) mbar_wait(&o_full[g], (uint32_t)((it - 1) & 1));      // (already passed in the epilogue of tile it - 1: kept for clarity)
+#pragma unroll
+      for (int c = 0; c < 10; ++c) {                   // 80 keys = 10 chunks of 8: chunks 0-7 -> atom 0, 8-9 -> atom 1
+        uint32_t pw[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          __nv_bfloat162 v = __floats2bfloat162_rn(__uint_as_float(st[c * 8 + 2 * i]) * wt, __uint_as_float(st[c * 8 + 2 * i + 1]) * wt);
+          pw[i] = *reinterpret_cast<uint32_t*>(&v);
+        }
+        const int atom = c >> 3, cc = c & 7;
+        *reinterpret_cast<uint4*>(prow + atom * PHALF_BYTES + ((cc ^ (r & 7)) << 4)) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+      }
+      if (ip) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t pw[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            __nv_bfloat162 v = __floats2bfloat162_rn(__uint_as_float(si[c * 8 + 2 * i]) * wi, __uint_as_float(si[c * 8 + 2 * i + 1]) * wi);
+            pw[i] = *reinterpret_cast<uint32_t*>(&v);
+          }
+          *reinterpret_cast<uint4*>(prow + 2 * PHALF_BYTES + ((c ^ (r & 7)) << 4)) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[g]);
+      // ---- epilogue of THIS tile: O = P_t V_t + P_i V_i is already normalised and weighted
+      mbar_wait(&o_full[g], par);
+      tc_fence_after();
+      const int64_t row = (int64_t)t * BQ + r;
+      bf16* orow = p.out + (int64_t)n * p.bso + row * p.ldo + h * p.D;
+#pragma unroll
+      for (int c = 0; c < DVN / 16; ++c) {
+        uint32_t orr[16];
+        tmem_ld16(tm + Cfg::TM_O + c * 16, orr);
+        tmem_wait_ld();
+        float f[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(orr[i]);
+        if (row < p.Lq) {
+          if (c * 16 + 8 <= p.D) Vec8<bf16>::store(orow + c * 16, f);
+          if (c * 16 + 16 <= p.D) Vec8<bf16>::store(orow + c * 16 + 8, f + 8);
+        }
+      }
+      tc_fence_before();      // the O reads are ordered before the next p_full arrival (PV of the next tile overwrites O only after it)
+    }
+  }
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
 // [NB, L, ld] (columns col0 .. col0+C) -> [NB, C, L]   (V -> V^T so that keys are the contiguous, K-major dimension of PV)
 __global__ void __launch_bounds__(256) transpose_tokens_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int L, int C,
                                                                int64_t ld, int64_t col0) {
@@ -1011,6 +1284,86 @@ extern "C" int32_t fyc_self_attention_tc_d80(const void* qkv, int64_t ldqkv, int
   if (!attr) { FYC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM)); attr = true; }
   dim3 grid((unsigned)(L / (2 * BQ)), (unsigned)heads, (unsigned)NB);
   kern<<<grid, Cfg::THREADS, Cfg::SMEM, (cudaStream_t)stream>>>(mq, mk, mv, p);
+  FYC_LAUNCH_CHECK();
+  return FYC_OK;
+}
+
+// Cross-attention with a resident short context on tcgen05 (head dim 40 or 80).  q: [NB, Lq, ldq] bf16, head h at columns [q_col0 + D h, +D),
+// UNPADDED, ldq >= heads * D;
+// k: [NBc, 80, ldk] with head h at columns [DKP h, +D), DKP = 64 for D = 40 (columns D..63 ZERO) or 80 for D = 80, rows Lk..79 zero;
+// vt: [NBc, heads * D, 80]; optional second context k2 [NBc, 16, ldk2], vt2 [NBc, heads * D, 16] (rows / columns Lk2..15 zero).
+// out[n, i, h D + :] = out_alpha softmax_j<Lk(scale q k^T) v + alpha2 softmax_j<Lk2(scale q k2^T) v2, NBc = NB / kv_batch_div.
+extern "C" int32_t fyc_cross_attention_tc(const void* q, int64_t ldq, int64_t q_col0, const void* k, int64_t ldk, const void* vt,
+                                          const void* k2, int64_t ldk2, const void* vt2, void* out, int64_t ldo, int64_t NB, int64_t heads,
+                                          int64_t Lq, int64_t D, int64_t Lk, int64_t Lk2, int64_t kv_batch_div, float scale, float out_alpha,
+                                          float alpha2, void* stream) {
+  FYC_CHECK(D == 40 || D == 80, "cross_attention_tc: head dim %lld (40 or 80)", (long long)D);
+  FYC_CHECK(Lk >= 1 && Lk <= 80 && Lk2 >= 0 && Lk2 <= 16 && Lq >= 1 && kv_batch_div >= 1 && NB % kv_batch_div == 0, "cross_attention_tc: bad shape");
+  FYC_CHECK((k2 != nullptr) == (Lk2 > 0) && (vt2 != nullptr) == (Lk2 > 0), "cross_attention_tc: second context needs k2, vt2 and Lk2 > 0");
+  FYC_CHECK(ldq % 8 == 0 && q_col0 % 8 == 0 && ldk % 8 == 0 && ldo % 8 == 0 && (k2 == nullptr || ldk2 % 8 == 0), "cross_attention_tc: 16-byte alignment");
+  FYC_CHECK((((uintptr_t)q | (uintptr_t)k | (uintptr_t)vt | (uintptr_t)out | (uintptr_t)k2 | (uintptr_t)vt2) & 15) == 0, "cross_attention_tc: pointers must be 16-byte aligned");
+  FYC_CHECK(NB < 65536 && heads < 65536, "cross_attention_tc: grid too large");
+  const int64_t NBc = NB / kv_batch_div;
+  const int KA = D == 40 ? 1 : 2;
+  const int64_t DKP = D == 40 ? 64 : 80;
+  CUtensorMap mq, mk, mv, mk2, mv2;
+  {
+    // q and k as 3-D maps over the WHOLE head-packed row (box origin = the head's first column): columns past the row end - the tail
+    // of the last head's 64-column atom - are out of bounds for TMA and zero-filled instead of read
+    uint64_t dims[3] = {(uint64_t)(heads * D), (uint64_t)Lq, (uint64_t)NB};
+    uint64_t str[2] = {(uint64_t)ldq * 2, (uint64_t)Lq * ldq * 2};
+    uint32_t box[3] = {64, (uint32_t)BQ, 1};
+    int32_t rc = make_map(&mq, (const bf16*)q + q_col0, 3, dims, str, box);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)(heads * DKP), 80, (uint64_t)NBc};
+    uint64_t str[2] = {(uint64_t)ldk * 2, (uint64_t)80 * ldk * 2};
+    uint32_t box[3] = {64, 80, 1};
+    int32_t rc = make_map(&mk, k, 3, dims, str, box);
+    if (rc) return rc;
+    uint64_t vd[3] = {80, (uint64_t)(heads * D), (uint64_t)NBc};
+    uint64_t vs[2] = {160, (uint64_t)(80 * heads * D * 2)};
+    uint32_t vb[3] = {64, (uint32_t)(D == 40 ? 48 : 80), 1};
+    rc = make_map(&mv, vt, 3, vd, vs, vb);
+    if (rc) return rc;
+  }
+  mk2 = mk; mv2 = mv;
+  if (k2) {
+    uint64_t dims[3] = {(uint64_t)(heads * DKP), 16, (uint64_t)NBc};
+    uint64_t str[2] = {(uint64_t)ldk2 * 2, (uint64_t)16 * ldk2 * 2};
+    uint32_t box[3] = {64, 16, 1};
+    int32_t rc = make_map(&mk2, k2, 3, dims, str, box);
+    if (rc) return rc;
+    uint64_t vd[3] = {16, (uint64_t)(heads * D), (uint64_t)NBc};
+    uint64_t vs[2] = {32, (uint64_t)(16 * heads * D * 2)};
+    uint32_t vb[3] = {64, (uint32_t)(D == 40 ? 48 : 80), 1};
+    rc = make_map(&mv2, vt2, 3, vd, vs, vb);
+    if (rc) return rc;
+  }
+  AttnCxParams p;
+  p.out = (bf16*)out; p.ldo = ldo; p.bso = Lq * ldo; p.Lq = (int)Lq; p.heads = (int)heads; p.D = (int)D; p.Lk = (int)Lk; p.Lk2 = (int)Lk2;
+  p.dkp = (int)DKP; p.kv_div = (int)kv_batch_div; p.scale_log2e = scale * 1.4426950408889634f; p.out_alpha = out_alpha; p.alpha2 = alpha2;
+  const int nqt = (int)((Lq + BQ - 1) / BQ);
+  // CTAs per (image, head): enough to fill the machine once (one CTA per SM), at most one per pair of query tiles
+  int64_t gx = ((int64_t)fyc_sm_count() + heads * NB - 1) / (heads * NB);
+  if (gx < 1) gx = 1;
+  if (gx > (nqt + 1) / 2) gx = (nqt + 1) / 2;
+  dim3 grid((unsigned)gx, (unsigned)heads, (unsigned)NB);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (D == 40) {
+    using Cfg = CxCfg<1, 48>;
+    auto kern = attention_cx_kernel<1, 48, 0>;
+    static bool attr = false;
+    if (!attr) { FYC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM)); attr = true; }
+    kern<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(mq, mk, mv, mk2, mv2, p);
+  } else {
+    using Cfg = CxCfg<2, 80>;
+    auto kern = attention_cx_kernel<2, 80, 0>;
+    static bool attr = false;
+    if (!attr) { FYC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM)); attr = true; }
+    kern<<<grid, Cfg::THREADS, Cfg::SMEM, st>>>(mq, mk, mv, mk2, mv2, p);
+  }
   FYC_LAUNCH_CHECK();
   return FYC_OK;
 }

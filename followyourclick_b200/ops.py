@@ -393,6 +393,38 @@ def self_attention_tc_d80(qkv, q_col0, k_col0, vt, heads, scale):
     return out
 
 
+use_cross_tc = os.environ.get("FYC_CROSS_TC", "1") != "0"        # A/B switch: text / image cross-attention on tcgen05 (else the mma.sync kernel)
+CROSS_LK, CROSS_LK2 = 80, 16                                      # padded key counts of the resident-context kernel
+
+
+def cross_attention_tc_ok(dtype, D, Lk, Lk2):
+    return (use_cross_tc and _impl != L_SIMT and dtype == torch.bfloat16 and D in (40, 80) and 1 <= Lk <= CROSS_LK and 0 <= Lk2 <= CROSS_LK2
+            and lib().fyc_tcgen05_available() == 1)
+
+
+def cross_dkp(D):
+    """column stride between the heads of the packed context keys: 64 (zero-padded heads) for D = 40, 80 for D = 80"""
+    return 64 if D == 40 else D
+
+
+def cross_attention_tc(q, k, vt, heads, D, scale, Lk, out, k2=None, vt2=None, Lk2=0, out_alpha=1.0, alpha2=1.0, kv_batch_div=1):
+    """tcgen05 cross-attention with a resident short context (fyc.h fyc_cross_attention_tc).  q [NB, Lq, >= heads D]; k [NBc, 80, ...] (a view is
+    fine: its row stride is passed), vt [NBc, heads D, 80]; k2 [NBc, 16, ...], vt2 [NBc, heads D, 16]; out [NB, Lq, heads D] is written."""
+    for t, nme in ((q, "q"), (k, "k"), (vt, "vt"), (k2, "k2"), (vt2, "vt2"), (out, "out")):
+        _cuda(t, "cross_attention_tc." + nme)
+    NB, Lq, _ = q.shape
+    assert k.shape[1] == CROSS_LK and vt.is_contiguous() and tuple(vt.shape[1:]) == (heads * D, CROSS_LK) and k.stride(0) == CROSS_LK * k.stride(1)
+    if k2 is not None:
+        assert k2.shape[1] == CROSS_LK2 and vt2.is_contiguous() and tuple(vt2.shape[1:]) == (heads * D, CROSS_LK2) and k2.stride(0) == CROSS_LK2 * k2.stride(1)
+    assert q.stride(0) == Lq * q.stride(1) and out.stride(0) == Lq * out.stride(1) and k.shape[0] * kv_batch_div == NB
+    with _rec(f"cross_attention_tc[{NB}x{heads}x{Lq}x{Lk}+{Lk2}x{D}]" if _prof_shapes else "cross_attention_tc", 4.0 * NB * heads * Lq * (Lk + Lk2) * D,
+              q.element_size() * 2 * NB * Lq * heads * D):
+        check(lib().fyc_cross_attention_tc(ptr(q), q.stride(1), 0, ptr(k), k.stride(1), ptr(vt), ptr(k2), k2.stride(1) if k2 is not None else 0,
+                                           ptr(vt2), ptr(out), out.stride(1), NB, heads, Lq, D, Lk, Lk2, kv_batch_div, float(scale), float(out_alpha),
+                                           float(alpha2), stream_ptr()))
+    return out
+
+
 def temporal_attention(qkv, heads, scale):
     """qkv [B, F, HW, 3C] -> [B, F, HW, C]; softmax over the F frames of each (clip, pixel, head)."""
     _cuda(qkv, "temporal_attention.qkv")

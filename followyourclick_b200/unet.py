@@ -39,11 +39,17 @@ class ClipContext:
     recomputes all of it in every forward (unet.py:592-594, attention.py:60-75,98-106); the engine builds it once per clip
     (``UNet3DConditionModel.prepare_context``) and the per-step forward only reads it."""
 
-    def __init__(self, ctx, kv, kvi, ip_tokens):
+    def __init__(self, ctx, kv, kvi, ip_tokens, kx=None, kxi=None):
         self.ctx, self.kv, self.kvi, self.ip_tokens = ctx, kv, kvi, ip_tokens
+        # packed operands of the tcgen05 cross-attention (ops.cross_attention_tc), per block: (k_and_v [Bc, 80 | 16, heads DKP + C], V^T [Bc, C, 80 | 16])
+        self.kx, self.kxi = kx or {}, kxi or {}
 
     def tensors(self):
-        return [self.ctx] + [self.kv[k] for k in sorted(self.kv)] + [self.kvi[k] for k in sorted(self.kvi)]
+        out = [self.ctx] + [self.kv[k] for k in sorted(self.kv)] + [self.kvi[k] for k in sorted(self.kvi)]
+        for d in (self.kx, self.kxi):
+            for k in sorted(d):
+                out += list(d[k])
+        return out
 
     def copy_(self, other):
         """refresh in place (the static buffers a captured CUDA graph reads)"""
@@ -476,11 +482,22 @@ class UNet3DConditionModel(ParamTreeModel):
         else:
             n2 = ops.layernorm(tok, self._f(q + ".norm2.weight"), self._f(q + ".norm2.bias"))
             qx = ops.gemm(n2, self._w(q + ".attn2.to_q.weight")).view(NB, HW, C)
-        kv = ctx.kv[p]
-        L = kv.shape[1]
-        Bq = kv.shape[0] // dup                 # clips per context replica
         o = torch.empty((dup * NB, HW, C), dtype=qx.dtype, device=qx.device)
-        for r in range(dup):                    # one pass per context replica over the SAME queries (dup = 1: the plain case)
+        L = ctx.ctx.shape[1]
+        Bq = ctx.ctx.shape[0] // dup            # clips per context replica
+        ipx = self._cfg["use_ip_cross_attention"]
+        for r in range(dup if p in ctx.kx else 0):       # tcgen05 path (head dims 40 / 80): resident packed context, text + image keys in one launch
+            T = self._cfg["num_tokens"] if ipx else 0
+            sc = d ** -0.5 if (self._xformers_semantics or not ipx) else float(self._cfg["scale"])     # reference quirk, see below
+            kvp, vt = (t[r * Bq:(r + 1) * Bq] for t in ctx.kx[p])
+            k2 = vt2 = None
+            if ipx:
+                kvpi, vt2 = (t[r * Bq:(r + 1) * Bq] for t in ctx.kxi[p])
+                k2 = kvpi[:, :, :heads * ops.cross_dkp(d)]
+            ops.cross_attention_tc(qx, kvp[:, :, :heads * ops.cross_dkp(d)], vt, heads, d, sc, L - T, o[r * NB:(r + 1) * NB], k2=k2, vt2=vt2, Lk2=T,
+                                   alpha2=float(self._cfg["scale"]), kv_batch_div=F)
+        kv = ctx.kv.get(p)
+        for r in range(dup if kv is not None else 0):    # one pass per context replica over the SAME queries (dup = 1: the plain case)
             o_r, kv_r = o[r * NB:(r + 1) * NB], kv[r * Bq:(r + 1) * Bq]
             if self._cfg["use_ip_cross_attention"]:
                 T = self._cfg["num_tokens"]
@@ -585,13 +602,57 @@ class UNet3DConditionModel(ParamTreeModel):
             tokens = self._to_compute(ip_tokens.float())
             ctx = ops.concat_channels(ctx.view(B, -1), tokens.view(B, -1)).view(B, -1, ctx.shape[-1])   # unet.py:592-594
         Bc, L, xd = ctx.shape
-        kv, kvi = {}, {}
+        kv, kvi, kx, kxi = {}, {}, {}, {}
+        ip = self._cfg["use_ip_cross_attention"]
+        T = self._cfg["num_tokens"] if ip else 0
+        # tcgen05 cross-attention (head dims 40 / 80): the text tokens zero-padded to 80 keys, the image tokens to 16, projected with the
+        # per-head padded K weight, V transposed so that the keys are contiguous - once per clip, read by every step
+        pad_t = pad_i = None
         for p in self._transformer_prefixes():
             q = p + ".transformer_blocks.0"
+            C = self._p(q + ".attn2.to_q.weight").shape[0]
+            heads = self._heads_of(p)
+            d = C // heads
+            if ops.cross_attention_tc_ok(ctx.dtype, d, L - T, T):
+                if pad_t is None:
+                    pad_t = torch.zeros((Bc, ops.CROSS_LK, xd), dtype=ctx.dtype, device=ctx.device)
+                    pad_t[:, :L - T] = ctx[:, :L - T]
+                    if ip:
+                        pad_i = torch.zeros((Bc, ops.CROSS_LK2, xd), dtype=ctx.dtype, device=ctx.device)
+                        pad_i[:, :T] = ctx[:, L - T:]
+                kx[p] = self._cross_pack(q + ".attn2", ("to_k", "to_v"), pad_t, heads, d)
+                if ip:
+                    kxi[p] = self._cross_pack(q + ".attn2", ("to_k_ip", "to_v_ip"), pad_i, heads, d)
+                continue
             kv[p] = ops.gemm(ctx.view(Bc * L, xd), self._cat_w(q + ".attn2", [q + ".attn2.to_k.weight", q + ".attn2.to_v.weight"])).view(Bc, L, -1)
-            if self._cfg["use_ip_cross_attention"]:
+            if ip:
                 kvi[p] = ops.gemm(ctx.view(Bc * L, xd), self._cat_w(q + ".attn2ip", [q + ".attn2.to_k_ip.weight", q + ".attn2.to_v_ip.weight"])).view(Bc, L, -1)
-        return ClipContext(ctx, kv, kvi, tokens)
+        return ClipContext(ctx, kv, kvi, tokens, kx, kxi)
+
+    def _heads_of(self, prefix):
+        """number of heads of the transformer block at ``prefix`` (attention_head_dim is per level in this diffusers vintage)"""
+        n = len(self._cfg["block_out_channels"])
+        if prefix.startswith("down_blocks."):
+            return self._heads[int(prefix.split(".")[1])]
+        if prefix.startswith("up_blocks."):
+            return self._heads[n - 1 - int(prefix.split(".")[1])]
+        return self._heads[-1]
+
+    def _cross_pack(self, a, names, ctx_pad, heads, d):
+        """(k_and_v, V^T) of a zero-padded context for ops.cross_attention_tc: one GEMM with [Wk (per head padded to DKP rows) ; Wv], K a
+        column view of its output, V^T [Bc, C, keys] by the token transpose."""
+        dkp = ops.cross_dkp(d)
+        C = heads * d
+
+        def make():
+            wk, wv = self._p(a + f".{names[0]}.weight").detach().float(), self._p(a + f".{names[1]}.weight").detach().float()
+            wkp = torch.zeros(heads, dkp, wk.shape[1], dtype=torch.float32, device=wk.device)
+            wkp[:, :d] = wk.view(heads, d, -1)
+            return torch.cat([wkp.view(heads * dkp, -1), wv], dim=0).to(self._compute_dtype).contiguous()
+        w = self._cached(("crosspack", a, names), make)
+        Bc, Lp, xd = ctx_pad.shape
+        kvp = ops.gemm(ctx_pad.view(Bc * Lp, xd), w).view(Bc, Lp, heads * dkp + C)
+        return kvp, ops.transpose_tokens(kvp, heads * dkp, C)
 
     def input_channel_pad(self):
         """Channel count the engine wants for its channels-last input: 16 (zero padded) in tensor-core mode so the stem

@@ -186,6 +186,20 @@ int32_t fyc_self_attention_tc(const void* qk, int64_t ldqk, int64_t q_col0, int6
  * columns past the last k head (the v block does).  vt: [NB, heads * 80, L]; out: [NB, L, ldo]. */
 int32_t fyc_self_attention_tc_d80(const void* qkv, int64_t ldqkv, int64_t q_col0, int64_t k_col0, const void* vt, void* out,
                                   int64_t ldo, int64_t NB, int64_t heads, int64_t L, float scale, void* stream);
+/* Cross-attention against a SHORT, step-invariant context on tcgen05 (head dim 40 or 80; bf16): attn2 of every transformer block
+ * (diffusers/models/attention.py:649-678) and, with the second context, the whole IP-Adapter cross-attention in one launch
+ * (animatediff/models/attention.py:92-120, ip_adapter/attention_processor.py:137-168):
+ *   out[n, i, h D + :] = out_alpha softmax_{j < Lk}(scale q k^T) v + alpha2 softmax_{j < Lk2}(scale q k2^T) v2,   context n / kv_batch_div.
+ * One CTA per (image, head) keeps K, V^T (and K2, V2^T) in shared memory and ping-pongs two softmax warpgroups over its query tiles; S and
+ * O live in TMEM, the probabilities are normalised in registers (one key tile: no online rescaling) and both contexts accumulate into ONE
+ * O accumulator, written once.  Operands, packed once per clip by the caller:
+ *   q   [NB, Lq, ldq], head h at columns [q_col0 + D h, +D), unpadded;
+ *   k   [NBc, 80, ldk], head h at columns [DKP h, +D) with DKP = 64 for D = 40 (columns D..63 of every head ZERO) | 80 for D = 80, rows Lk..79 zero;
+ *   vt  [NBc, heads D, 80] (V transposed: keys contiguous), columns Lk..79 zero;
+ *   k2  [NBc, 16, ldk2], vt2 [NBc, heads D, 16] likewise (NULL / Lk2 = 0: no second context). */
+int32_t fyc_cross_attention_tc(const void* q, int64_t ldq, int64_t q_col0, const void* k, int64_t ldk, const void* vt, const void* k2,
+                               int64_t ldk2, const void* vt2, void* out, int64_t ldo, int64_t NB, int64_t heads, int64_t Lq, int64_t D,
+                               int64_t Lk, int64_t Lk2, int64_t kv_batch_div, float scale, float out_alpha, float alpha2, void* stream);
 /* in [NB, L, ld] columns [col0, col0 + C) (bf16) -> out [NB, C, L] */
 int32_t fyc_transpose_tokens(const void* in, void* out, int64_t NB, int64_t L, int64_t C, int64_t ld, int64_t col0,
                              void* stream);

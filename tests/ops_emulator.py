@@ -189,6 +189,29 @@ def self_attention_tc_d80(qkv, q_col0, k_col0, vt, heads, scale):
     return _store((p @ v).transpose(1, 2).reshape(NB, L, heads * D), qkv.dtype)
 
 
+def cross_attention_tc_ok(dtype, D, Lk, Lk2):
+    return (TC_EMULATED and ops.use_cross_tc and ops._impl != _lib.IMPL_SIMT and dtype == torch.bfloat16 and D in (40, 80)
+            and 1 <= Lk <= ops.CROSS_LK and 0 <= Lk2 <= ops.CROSS_LK2)
+
+
+def cross_attention_tc(q, k, vt, heads, D, scale, Lk, out, k2=None, vt2=None, Lk2=0, out_alpha=1.0, alpha2=1.0, kv_batch_div=1):
+    """fyc_cross_attention_tc: packed context keys (head stride 64 | 80), V^T with the keys contiguous; keys >= Lk / Lk2 are padding"""
+    NB, Lq, _ = q.shape
+    dkp = ops.cross_dkp(D)
+
+    def one(kk, vv, L):
+        qh = q[..., :heads * D].float().reshape(NB, Lq, heads, D).transpose(1, 2)
+        kh = kk.float()[:, :L].reshape(kk.shape[0], L, -1)[..., :heads * dkp].reshape(kk.shape[0], L, heads, dkp)[..., :D].transpose(1, 2)
+        vh = vv.float().reshape(vv.shape[0], heads, D, -1)[..., :L].transpose(2, 3)
+        kh, vh = kh.repeat_interleave(kv_batch_div, 0), vh.repeat_interleave(kv_batch_div, 0)
+        return (torch.softmax(qh @ kh.transpose(-1, -2) * scale, dim=-1) @ vh).transpose(1, 2).reshape(NB, Lq, heads * D)
+    y = out_alpha * one(k, vt, Lk)
+    if k2 is not None:
+        y = y + alpha2 * one(k2, vt2, Lk2)
+    out.copy_(_store(y, out.dtype))
+    return out
+
+
 def temporal_attention(qkv, heads, scale):
     B, Fr, HW, C3 = qkv.shape
     C = C3 // 3
@@ -296,7 +319,7 @@ def video_grid_u8(video, nrow=6, padding=2, rescale=False):
 
 
 _NAMES = ["tc_ok", "require_cuda", "ln_fold_ok", "layernorm_stats", "gemm", "conv3x3", "groupnorm", "layernorm", "attention", "transpose_tokens", "self_attention_tc_ok",
-          "self_attention_tc", "self_attention_tc80_ok", "self_attention_tc_d80", "temporal_attention", "softmax_rows", "timestep_embed", "silu", "gelu", "upsample_nearest2x",
+          "self_attention_tc", "self_attention_tc80_ok", "self_attention_tc_d80", "cross_attention_tc_ok", "cross_attention_tc", "temporal_attention", "softmax_rows", "timestep_embed", "silu", "gelu", "upsample_nearest2x",
           "concat_channels", "ncfhw_to_nfhwc", "nfhwc_to_ncfhw", "build_unet_input", "cfg_ddim_step", "frames_finalize", "video_grid_u8"]
 
 

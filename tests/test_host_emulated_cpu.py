@@ -102,7 +102,9 @@ def test_context_hoisting_and_ip_plus_host_logic(dtype, tol):
     ctx = unet.prepare_context(inp["ctx"], clip, True)
     b = unet.forward_nfhwc(x, inp["timestep"], None, context=ctx, **args)
     assert torch.equal(a, b)
-    assert len(ctx.kv) == len(ctx.kvi) == len(unet._transformer_prefixes()) == 10
+    # every block's context projections are hoisted: packed for the tcgen05 cross-attention (head dims 40 / 80, tensor-core mode) or plain [K | V]
+    assert len(ctx.kv) + len(ctx.kx) == len(ctx.kvi) + len(ctx.kxi) == len(unet._transformer_prefixes()) == 10
+    assert (len(ctx.kx) == 6) == (dtype == torch.bfloat16)
     tokens = ref_resampler.resampler_forward(rsd, MINI_RESAMPLER, clip)
     ocfg = dict(mini_unet_oracle_cfg("ip"), num_tokens=MINI_RESAMPLER["num_queries"])
     ref = ref_unet.unet3d_forward(sd, ocfg, inp["sample"], inp["timestep"], torch.cat([inp["ctx"], tokens], dim=1),

@@ -529,6 +529,48 @@ def test_self_attention_tcgen05_d80(cuda, L, heads, NB, gain):
     assert rel(out, old) < 1e-2, rel(out, old)
 
 
+def _cross_pack(k, v, heads, D, Lpad):
+    """test-side packing of a context for ops.cross_attention_tc: keys zero-padded to Lpad rows, heads to DKP columns; V transposed"""
+    from followyourclick_b200 import ops
+    NBc, Lk, C = k.shape
+    dkp = ops.cross_dkp(D)
+    kp = torch.zeros((NBc, Lpad, heads * dkp), dtype=k.dtype, device=k.device)
+    kp.view(NBc, Lpad, heads, dkp)[:, :Lk, :, :D] = k.view(NBc, Lk, heads, D)
+    vt = torch.zeros((NBc, C, Lpad), dtype=v.dtype, device=v.device)
+    vt[:, :, :Lk] = v.transpose(1, 2)
+    return kp, vt.contiguous()
+
+
+@pytest.mark.parametrize("heads,D,Lq,Lk,T,div", [(8, 40, 4096, 77, 16, 2), (8, 40, 1024, 77, 4, 4), (8, 80, 1024, 77, 16, 2), (4, 80, 1000, 77, 0, 1),
+                                                 (4, 40, 300, 80, 16, 1), (8, 40, 128, 5, 1, 2), (2, 80, 130, 77, 4, 1), (8, 80, 2304, 77, 4, 2)])
+def test_cross_attention_tcgen05(cuda, heads, D, Lq, Lk, T, div):
+    """tcgen05 cross-attention with a resident short context (fyc_cross_attention_tc): text keys + optional image keys in one launch,
+    UNPADDED q heads (the 64-column box of a D = 40 head reads 24 foreign columns that meet zero key columns), padding keys masked,
+    ragged query counts, shared contexts - against the fp32 two-softmax reference and the mma.sync kernel it replaces."""
+    from followyourclick_b200 import ops
+    dt = torch.bfloat16
+    B, C = 4, heads * D
+    q = rnd((B, Lq, C), 1, dt)
+    kt, vtx = rnd((B // div, Lk, C), 2, dt), rnd((B // div, Lk, C), 3, dt)
+    scale, a1, a2 = D ** -0.5, 1.0, 0.6
+    kp, vt = _cross_pack(kt, vtx, heads, D, ops.CROSS_LK)
+    k2 = vt2 = ki = vi = None
+    if T:
+        ki, vi = rnd((B // div, T, C), 4, dt), rnd((B // div, T, C), 5, dt)
+        k2, vt2 = _cross_pack(ki, vi, heads, D, ops.CROSS_LK2)
+    out = torch.full((B, Lq, C), float("nan"), dtype=dt, device="cuda")
+    ops.cross_attention_tc(q, kp, vt, heads, D, scale, Lk, out, k2=k2, vt2=vt2, Lk2=T, out_alpha=a1, alpha2=a2, kv_batch_div=div)
+    rep = lambda t: t.repeat_interleave(div, 0)
+    ref = a1 * _mha_ref(q, rep(kt), rep(vtx), heads, scale)
+    if T:
+        ref = ref + a2 * _mha_ref(q, rep(ki), rep(vi), heads, scale)
+    assert bool(torch.isfinite(out).all())
+    e = (out.float() - ref)
+    assert rel(out, ref) < BF16_TOL and float(e.abs().max()) < 2 ** -6 * float(ref.abs().max()) + 1e-3, (rel(out, ref), float(e.abs().max()))
+    old = ops.attention(q, kt, vtx, heads, scale, kv_batch_div=div, k2=ki, v2=vi, alpha2=a2)
+    assert rel(out, old) < 1e-2, rel(out, old)
+
+
 def test_softmax_rows_and_misc(cuda):
     from followyourclick_b200 import ops
     s = rnd((64, 300), 1) * 4
