@@ -158,7 +158,9 @@ def test_context_hoisting_is_bit_identical_and_ip_plus_matches_oracle(dtype):
     ctx = unet.prepare_context(inp["ctx"].cuda(), clip.cuda(), True)
     b = unet.forward_nfhwc(x, inp["timestep"], None, context=ctx, **args)
     assert torch.equal(a, b)
-    assert ctx.ip_tokens.shape == (2, MINI_RESAMPLER["num_queries"], 768) and len(ctx.kv) == len(ctx.kvi) == len(unet._transformer_prefixes())
+    # every block's context projections are hoisted: packed for the tcgen05 cross-attention (head dims 40 / 80, tensor-core mode) or plain [K | V]
+    assert ctx.ip_tokens.shape == (2, MINI_RESAMPLER["num_queries"], 768)
+    assert len(ctx.kv) + len(ctx.kx) == len(ctx.kvi) + len(ctx.kxi) == len(unet._transformer_prefixes())
     # oracle: tokens from the oracle Resampler appended to the text context; the oracle UNet is told not to project again
     tokens = ref_resampler.resampler_forward(rsd, MINI_RESAMPLER, clip)
     ocfg = dict(mini_unet_oracle_cfg("ip"), num_tokens=MINI_RESAMPLER["num_queries"])
