@@ -990,28 +990,6 @@ attention_cx_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
     const float sl2 = p.scale_log2e;
     const uint32_t tm = tmem_base + lane_base + g * Cfg::TM_GROUP;
     uint8_t* const prow = smem + Cfg::OFF_P + g * Cfg::P_TILE + (r >> 3) * 1024 + (r & 7) * 128;
-    // epilogue of tile `te` (iteration `ie`): O = P_t V_t + P_i V_i is already normalised and weighted - convert and store
-    auto epilogue = [&](int te, int ie) {
-      mbar_wait(&o_full[g], (uint32_t)(ie & 1));
-      tc_fence_after();
-      const int64_t row = (int64_t)te * BQ + r;
-      bf16* orow = p.out + (int64_t)n * p.bso + row * p.ldo + h * p.D;
-#pragma unroll
-      for (int c = 0; c < DVN / 16; ++c) {
-        uint32_t orr[16];
-        tmem_ld16(tm + Cfg::TM_O + c * 16, orr);
-        tmem_wait_ld();
-        float f[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(orr[i]);
-        if (row < p.Lq) {
-          if (c * 16 + 8 <= p.D) Vec8<bf16>::store(orow + c * 16, f);
-          if (c * 16 + 16 <= p.D) Vec8<bf16>::store(orow + c * 16 + 8, f + 8);
-        }
-      }
-      tc_fence_before();      // the O reads are ordered before the next p_full arrival (the next PV overwrites O only after it)
-    };
-    int prev_t = -1, prev_it = 0;
     for (int it = 0;; ++it) {
       const int t = tile_of(g, it);
       if (t >= nqt) break;
@@ -1027,7 +1005,7 @@ attention_cx_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[g]);
-      // ---- text softmax over Lk keys (padding keys are zero rows of K: score 0 -> masked here), normalised and weighted in registers
+      // ---- text softmax over Lk keys (padding keys are TMA-zero rows of K: score 0 -> masked here)
       float mt = -INFINITY;
 #pragma unroll
       for (int i = 0; i < 80; ++i) { if (i >= p.Lk) st[i] = 0xff800000u; mt = fmaxf(mt, __uint_as_float(st[i])); }
@@ -1036,47 +1014,65 @@ attention_cx_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_cons
 #pragma unroll
       for (int i = 0; i < 80; ++i) { const float e = ex2(fmaf(__uint_as_float(st[i]), sl2, nb)); sum += e; st[i] = __float_as_uint(e); }
       const float wt = p.out_alpha / sum;
-      uint32_t pt[40], pi[8];
-#pragma unroll
-      for (int i = 0; i < 40; ++i) {
-        __nv_bfloat162 v = __floats2bfloat162_rn(__uint_as_float(st[2 * i]) * wt, __uint_as_float(st[2 * i + 1]) * wt);
-        pt[i] = *reinterpret_cast<uint32_t*>(&v);
-      }
+      float mi = -INFINITY, wi = 0.f;
       if (ip) {
-        float mi = -INFINITY;
 #pragma unroll
         for (int i = 0; i < 16; ++i) { if (i >= p.Lk2) si[i] = 0xff800000u; mi = fmaxf(mi, __uint_as_float(si[i])); }
         const float nbi = -mi * sl2;
         float sumi = 0.f;
 #pragma unroll
         for (int i = 0; i < 16; ++i) { const float e = ex2(fmaf(__uint_as_float(si[i]), sl2, nbi)); sumi += e; si[i] = __float_as_uint(e); }
-        const float wi = p.alpha2 / sumi;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          __nv_bfloat162 v = __floats2bfloat162_rn(__uint_as_float(si[2 * i]) * wi, __uint_as_float(si[2 * i + 1]) * wi);
-          pi[i] = *reinterpret_cast<uint32_t*>(&v);
-        }
+        wi = p.alpha2 / sumi;
       }
-      // ---- software pipeline: the PREVIOUS tile's epilogue runs here, after this tile's softmax math - its PV has long retired, and its
-      // o_full wait also guarantees that P_g (read by that PV) may now be overwritten
-      if (prev_t >= 0) epilogue(prev_t, prev_it);
+      // ---- P (normalised, weighted) -> shared memory; the previous tile's PV must have retired (it also means O was ... see below)
+      if (it > 0) mbar_wait(&o_full[g], (uint32_t)((it - 1) & 1));      // (already passed in the epilogue of tile it - 1: kept for clarity)
 #pragma unroll
       for (int c = 0; c < 10; ++c) {                   // 80 keys = 10 chunks of 8: chunks 0-7 -> atom 0, 8-9 -> atom 1
+        uint32_t pw[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          __nv_bfloat162 v = __floats2bfloat162_rn(__uint_as_float(st[c * 8 + 2 * i]) * wt, __uint_as_float(st[c * 8 + 2 * i + 1]) * wt);
+          pw[i] = *reinterpret_cast<uint32_t*>(&v);
+        }
         const int atom = c >> 3, cc = c & 7;
-        *reinterpret_cast<uint4*>(prow + atom * PHALF_BYTES + ((cc ^ (r & 7)) << 4)) = make_uint4(pt[c * 4], pt[c * 4 + 1], pt[c * 4 + 2], pt[c * 4 + 3]);
+        *reinterpret_cast<uint4*>(prow + atom * PHALF_BYTES + ((cc ^ (r & 7)) << 4)) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
       }
       if (ip) {
 #pragma unroll
-        for (int c = 0; c < 2; ++c)
-          *reinterpret_cast<uint4*>(prow + 2 * PHALF_BYTES + ((c ^ (r & 7)) << 4)) = make_uint4(pi[c * 4], pi[c * 4 + 1], pi[c * 4 + 2], pi[c * 4 + 3]);
+        for (int c = 0; c < 2; ++c) {
+          uint32_t pw[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            __nv_bfloat162 v = __floats2bfloat162_rn(__uint_as_float(si[c * 8 + 2 * i]) * wi, __uint_as_float(si[c * 8 + 2 * i + 1]) * wi);
+            pw[i] = *reinterpret_cast<uint32_t*>(&v);
+          }
+          *reinterpret_cast<uint4*>(prow + 2 * PHALF_BYTES + ((c ^ (r & 7)) << 4)) = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+        }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[g]);
-      prev_t = t; prev_it = it;
+      // ---- epilogue of THIS tile: O = P_t V_t + P_i V_i is already normalised and weighted
+      mbar_wait(&o_full[g], par);
+      tc_fence_after();
+      const int64_t row = (int64_t)t * BQ + r;
+      bf16* orow = p.out + (int64_t)n * p.bso + row * p.ldo + h * p.D;
+#pragma unroll
+      for (int c = 0; c < DVN / 16; ++c) {
+        uint32_t orr[16];
+        tmem_ld16(tm + Cfg::TM_O + c * 16, orr);
+        tmem_wait_ld();
+        float f[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(orr[i]);
+        if (row < p.Lq) {
+          if (c * 16 + 8 <= p.D) Vec8<bf16>::store(orow + c * 16, f);
+          if (c * 16 + 16 <= p.D) Vec8<bf16>::store(orow + c * 16 + 8, f + 8);
+        }
+      }
+      tc_fence_before();      // the O reads are ordered before the next p_full arrival (PV of the next tile overwrites O only after it)
     }
-    if (prev_t >= 0) epilogue(prev_t, prev_it);
   }
   __syncwarp();
   tc_fence_before();
@@ -1349,16 +1345,12 @@ extern "C" int32_t fyc_cross_attention_tc(const void* q, int64_t ldq, int64_t q_
   p.out = (bf16*)out; p.ldo = ldo; p.bso = Lq * ldo; p.Lq = (int)Lq; p.heads = (int)heads; p.D = (int)D; p.Lk = (int)Lk; p.Lk2 = (int)Lk2;
   p.dkp = (int)DKP; p.kv_div = (int)kv_batch_div; p.scale_log2e = scale * 1.4426950408889634f; p.out_alpha = out_alpha; p.alpha2 = alpha2;
   const int nqt = (int)((Lq + BQ - 1) / BQ);
-  // CTAs per (image, head): the smallest count (fewest reloads of the context) whose last wave is >= 95 % full (one CTA per SM: 256
-  // pairs on 148 SMs would run as two waves at 86 %), at most one CTA per pair of query tiles
-  const int64_t sms = fyc_sm_count(), pairs = heads * NB, gmax = (nqt + 1) / 2 > 0 ? (nqt + 1) / 2 : 1;
-  int64_t gx = 1; double best = 0.0;
-  for (int64_t c = 1; c <= gmax && c <= 16; ++c) {
-    const int64_t tot = pairs * c, waves = (tot + sms - 1) / sms;
-    const double eff = (double)tot / (double)(waves * sms);
-    if (eff > best + 1e-9) { best = eff; gx = c; }
-    if (eff >= 0.95) { gx = c; break; }
-  }
+  // CTAs per (image, head): enough to fill the machine once (one CTA per SM), at most one per pair of query tiles.  More, smaller CTAs were
+  // measured slower (round 2, call K: 4 CTAs per pair for a fuller last wave: 94 vs 83 us at 32 x 8 x 4096) - the per-CTA prologue (TMEM
+  // allocation, barrier init, context load) is not small against ~30 us of work per CTA
+  int64_t gx = ((int64_t)fyc_sm_count() + heads * NB - 1) / (heads * NB);
+  if (gx < 1) gx = 1;
+  if (gx > (nqt + 1) / 2) gx = (nqt + 1) / 2;
   dim3 grid((unsigned)gx, (unsigned)heads, (unsigned)NB);
   cudaStream_t st = (cudaStream_t)stream;
   if (D == 40) {
