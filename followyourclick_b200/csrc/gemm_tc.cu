@@ -259,11 +259,23 @@ struct EpiRows {
   uint32_t ok;                // bit ps: the row exists
   int n0;                     // first column of the tile
 };
-struct EpiPrefetch { float4 b0, b1; uint4 res[4]; };
+struct EpiPrefetch { float4 b0, b1; uint4 res[4]; float4 rb0, rb1; };      // rb*: raw row bias, carried only by the LNF + ROWB variant
+// Forces every load of `f` to have landed HERE.  The group loop rotates `pf = pn` with register moves, which wait for the loads of `pn` at the
+// END of a group; a prefetch that is still in flight on a path INTO the loop (first tile, a warp half without groups) makes ptxas guard the first
+// use of `pf` inside the loop with the same scoreboard the in-loop prefetch re-arms - and every group then waits, in its middle, for the loads it
+// issued itself (ncu, round 2 call L: 9 % of all samples of the K = 320 residual GEMM sat on that wait).
+template <bool LNF>
+__device__ __forceinline__ void epi_settle(const EpiPrefetch& f) {
+  asm volatile("" ::"f"(f.b0.x), "f"(f.b0.y), "f"(f.b0.z), "f"(f.b0.w), "f"(f.b1.x), "f"(f.b1.y), "f"(f.b1.z), "f"(f.b1.w));
+  if constexpr (!LNF)         // (an LN-folded GEMM carries no residual)
+    asm volatile("" ::"r"(f.res[0].x), "r"(f.res[0].y), "r"(f.res[0].z), "r"(f.res[0].w), "r"(f.res[1].x), "r"(f.res[1].y), "r"(f.res[1].z),
+                 "r"(f.res[1].w), "r"(f.res[2].x), "r"(f.res[2].y), "r"(f.res[2].z), "r"(f.res[2].w), "r"(f.res[3].x), "r"(f.res[3].y),
+                 "r"(f.res[3].z), "r"(f.res[3].w));
+}
 // LayerNorm fold: the 4 rows' rstd, fetched with the row offsets one tile ahead (the mean term is already in the accumulator, see fyc.h)
 struct EpiLnRows { float rs[4]; };
 
-template <bool LNF>
+template <bool LNF, bool ROWB>
 __device__ __forceinline__ void epi_rows(const TcParams& p, const TileCoord& tc, int r0, int q, EpiRows& t, EpiLnRows& ln) {
   const int n_blk = tc.n, wt = tc.w, ht = tc.h, it = tc.i;
   t.n0 = (int)n_blk * p.BN;
@@ -284,19 +296,24 @@ __device__ __forceinline__ void epi_rows(const TcParams& p, const TileCoord& tc,
     t.oo[ps] = px * ldo8 + cq;
     t.ro[ps] = px * ldr8 + cq;
     if constexpr (LNF) ln.rs[ps] = ok ? __ldg(p.ln_rs + px) : 0.f;
-    if ((p.flags & FYC_EPI_ROWBIAS) && ok) {
-      const int rg = (int)(px / (uint32_t)p.rows_per_group);
-      mn = min(mn, rg); mx = max(mx, rg);
+    if constexpr (ROWB) {
+      if (ok) {
+        const int rg = (int)(px / (uint32_t)p.rows_per_group);
+        mn = min(mn, rg); mx = max(mx, rg);
+      }
     }
   }
-  if (p.flags & FYC_EPI_ROWBIAS) {
+  if constexpr (ROWB) {
     mn = __reduce_min_sync(0xffffffffu, mn); mx = __reduce_max_sync(0xffffffffu, mx);
     t.rgu = (mn == mx) ? mn : -1;
   }
 }
 
-// loads for 32-column group g of tile t: bias (+ the warp-uniform row bias) of this lane's 8 columns, residual of its 4 rows
-template <bool LNF>
+// loads for 32-column group g of tile t: bias (+ the warp-uniform row bias) of this lane's 8 columns, residual of its 4 rows.
+// ROWB is a template parameter, not a flag test: as predicated-off `@!P FADD bias, bias, rowbias` instructions the fold below still carried the
+// scoreboard wait for the bias load that precedes it, i.e. every GEMM WITHOUT a row bias waited for its bias right after issuing the "prefetch"
+// (ncu, round 2 call L: another 9 % of the samples of the K = 320 residual GEMM).
+template <bool LNF, bool ROWB>
 __device__ __forceinline__ void epi_prefetch(const TcParams& p, const EpiRows& t, int g, int q, EpiPrefetch& f) {
   const int c = g * 32 + q * 8, n = t.n0 + c;
   const bool col_ok = (c < p.BN) && (n < p.N);
@@ -305,13 +322,21 @@ __device__ __forceinline__ void epi_prefetch(const TcParams& p, const EpiRows& t
     f.b0 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
     f.b1 = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4));
   }
-  if ((p.flags & FYC_EPI_ROWBIAS) && col_ok && t.rgu >= 0) {
-    // the warp's 32 rows share one row-bias vector (time embedding of a clip, position-table row of a frame): fetched here, one group
-    // AHEAD like the bias, and folded into it - at its point of use this load was an exposed L2 round trip per 32-column group
-    const float* rbp = p.rowbias + (int64_t)t.rgu * p.ldrb + n;
-    const float4 r0 = __ldg(reinterpret_cast<const float4*>(rbp)), r1 = __ldg(reinterpret_cast<const float4*>(rbp + 4));
-    f.b0.x += r0.x; f.b0.y += r0.y; f.b0.z += r0.z; f.b0.w += r0.w;
-    f.b1.x += r1.x; f.b1.y += r1.y; f.b1.z += r1.z; f.b1.w += r1.w;
+  if constexpr (ROWB) {
+    // the warp's 32 rows share one row-bias vector (time embedding of a clip, position-table row of a frame): fetched here, one group AHEAD like
+    // the bias - at its point of use this load was an exposed L2 round trip per 32-column group.  LNF (the temporal q/k/v projections, whose
+    // epilogue is the bottleneck at K = 320) keeps it raw and folds it when the registers rotate (epi_fold); the other row-bias users (conv1 +
+    // time embedding: MMA-bound, and their residual registers are live) fold at once.
+    float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
+    if (col_ok && t.rgu >= 0) {
+      const float* rbp = p.rowbias + (int64_t)t.rgu * p.ldrb + n;
+      r0 = __ldg(reinterpret_cast<const float4*>(rbp)); r1 = __ldg(reinterpret_cast<const float4*>(rbp + 4));
+    }
+    if constexpr (LNF) { f.rb0 = r0; f.rb1 = r1; }
+    else {
+      f.b0.x += r0.x; f.b0.y += r0.y; f.b0.z += r0.z; f.b0.w += r0.w;
+      f.b1.x += r1.x; f.b1.y += r1.y; f.b1.z += r1.z; f.b1.w += r1.w;
+    }
   }
   if constexpr (!LNF) {      // (an LN-folded GEMM never carries a residual: q/k/v and FF1 projections - its registers go to the LN terms)
     if (p.flags & FYC_EPI_RESIDUAL) {
@@ -324,8 +349,16 @@ __device__ __forceinline__ void epi_prefetch(const TcParams& p, const EpiRows& t
     }
   }
 }
+// bias += raw row bias (LNF + ROWB only), at the point where the loads must have landed anyway
+template <bool LNF, bool ROWB>
+__device__ __forceinline__ void epi_fold(EpiPrefetch& f) {
+  if constexpr (LNF && ROWB) {
+    f.b0.x += f.rb0.x; f.b0.y += f.rb0.y; f.b0.z += f.rb0.z; f.b0.w += f.rb0.w;
+    f.b1.x += f.rb1.x; f.b1.y += f.rb1.y; f.b1.z += f.rb1.z; f.b1.w += f.rb1.w;
+  }
+}
 
-template <int PAIR, bool LNF>
+template <int PAIR, bool LNF, bool ROWB>
 __device__ __forceinline__ void epilogue_plain(const TcParams& p, const TileSched& ts, uint8_t* stage, uint64_t* tfull, uint64_t* tempty,
                                                uint32_t tmem_base, int warp, int lane) {
   const int64_t num_tiles = ts.num;
@@ -348,7 +381,7 @@ __device__ __forceinline__ void epilogue_plain(const TcParams& p, const TileSche
   EpiLnRows lrc, lrn;          // LNF only (unused otherwise: the compiler drops them)
   int64_t tile = ts.t0;
   TileCoord tcn = tile_coord(p, ts, tile);           // coordinates of the NEXT tile to be decoded
-  if (tile < num_tiles) { epi_rows<LNF>(p, tcn, r0, q, cur, lrc); epi_prefetch<LNF>(p, cur, eg, q, pf); }
+  if (tile < num_tiles) { epi_rows<LNF, ROWB>(p, tcn, r0, q, cur, lrc); epi_prefetch<LNF, ROWB>(p, cur, eg, q, pf); epi_fold<LNF, ROWB>(pf); epi_settle<LNF>(pf); }
   nxt = cur; lrn = lrc;
   for (; tile < num_tiles; tile += ts.stride) {
     mbar_wait(&tfull[acc], aphase);
@@ -358,7 +391,7 @@ __device__ __forceinline__ void epilogue_plain(const TcParams& p, const TileSche
     const int64_t next_tile = tile + ts.stride;
     tile_advance(p, ts, tcn);
     if (next_tile < num_tiles) {
-      epi_rows<LNF>(p, tcn, r0, q, nxt, lrn);
+      epi_rows<LNF, ROWB>(p, tcn, r0, q, nxt, lrn);
       if (!LNF && (p.flags & FYC_EPI_RESIDUAL)) {             // pull the next tile's residual rows into L2 a whole tile ahead: lane q takes its
         const int g = (eg ^ 1) + 2 * q;             // q-th group, so one instruction per row covers all of this warp's groups
         if (g < NG && nxt.n0 + g * 32 < p.N) {
@@ -371,7 +404,7 @@ __device__ __forceinline__ void epilogue_plain(const TcParams& p, const TileSche
         }
       }
     } else nxt.ok = 0;                               // nothing follows: the prefetch below degenerates to (valid) bias loads
-    if (eg >= NG) epi_prefetch<LNF>(p, nxt, eg ^ 1, q, pf);
+    if (eg >= NG) { epi_prefetch<LNF, ROWB>(p, nxt, eg ^ 1, q, pf); epi_fold<LNF, ROWB>(pf); epi_settle<LNF>(pf); }
     for (int gi = eg; gi < NG; gi += 2) {
       // ---- P2
       uint32_t rr[32];
@@ -382,7 +415,7 @@ __device__ __forceinline__ void epilogue_plain(const TcParams& p, const TileSche
         const bool last = gi + 2 >= NG;
         EpiRows src = cur;
         if (last) src = nxt;
-        epi_prefetch<LNF>(p, src, last ? (eg ^ 1) : gi + 2, q, pn);
+        epi_prefetch<LNF, ROWB>(p, src, last ? (eg ^ 1) : gi + 2, q, pn);
       }
       tmem_ld_wait32(rr);
 #pragma unroll
@@ -394,8 +427,8 @@ __device__ __forceinline__ void epilogue_plain(const TcParams& p, const TileSche
       const bool col_ok = (c0 < p.BN) && (cur.n0 + c0 < p.N);
       const uint32_t g4 = (uint32_t)gi * 4u;
       float a_eff = alpha;
-      if ((p.flags & FYC_EPI_ROWBIAS) && cur.rgu < 0) {
-        {                                                  // rare: rows straddle two groups - fold alpha and the row bias into the staged tile
+      if constexpr (ROWB) {
+        if (cur.rgu < 0) {                                                  // rare: rows straddle two groups - fold alpha and the row bias into the staged tile
                                                            // (the usual case, one group per warp, is part of the prefetched bias)
 #pragma unroll
           for (int ps = 0; ps < 4; ++ps) {
@@ -447,6 +480,7 @@ __device__ __forceinline__ void epilogue_plain(const TcParams& p, const TileSche
       }
       __syncwarp();
       pf = pn;
+      epi_fold<LNF, ROWB>(pf);
     }
     epi_release<PAIR>(&tempty[acc], lane);
     if (p.debug) dbg_epi += clock64() - te1;
@@ -705,10 +739,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const bool geglu = (p.flags & FYC_EPI_GEGLU) != 0;
     const bool out_f32 = (p.flags & FYC_EPI_OUT_F32) != 0;
     const bool lnf = (p.flags & FYC_EPI_LNFOLD) != 0;
+    const bool rowb = (p.flags & FYC_EPI_ROWBIAS) != 0;
     if (geglu && lnf) epilogue_geglu<PAIR, true>(p, ts, stage, reinterpret_cast<float*>(smem + OFF_BIAS), tfull, tempty, tmem_base, warp, lane);
     else if (geglu) epilogue_geglu<PAIR, false>(p, ts, stage, reinterpret_cast<float*>(smem + OFF_BIAS), tfull, tempty, tmem_base, warp, lane);
-    else if (!out_f32 && lnf) epilogue_plain<PAIR, true>(p, ts, stage, tfull, tempty, tmem_base, warp, lane);
-    else if (!out_f32) epilogue_plain<PAIR, false>(p, ts, stage, tfull, tempty, tmem_base, warp, lane);
+    else if (!out_f32 && lnf && rowb) epilogue_plain<PAIR, true, true>(p, ts, stage, tfull, tempty, tmem_base, warp, lane);
+    else if (!out_f32 && lnf) epilogue_plain<PAIR, true, false>(p, ts, stage, tfull, tempty, tmem_base, warp, lane);
+    else if (!out_f32 && rowb) epilogue_plain<PAIR, false, true>(p, ts, stage, tfull, tempty, tmem_base, warp, lane);
+    else if (!out_f32) epilogue_plain<PAIR, false, false>(p, ts, stage, tfull, tempty, tmem_base, warp, lane);
     else for (int64_t tile = ts.t0; tile < ts.num; tile += ts.stride) {
       const TileCoord tc = tile_coord(p, ts, tile);
       const int n_blk = tc.n, wt = tc.w, ht = tc.h, it = tc.i;
