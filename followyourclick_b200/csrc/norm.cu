@@ -13,6 +13,16 @@ static int fyc_zigzag() {
   return (e && e[0] == '0') ? 0 : 1;
 }
 
+// Waves of resident statistics CTAs (4 per SM) the GroupNorm statistics pass is cut into (A/B switch FYC_GN_WAVES=1|2|3).
+static int fyc_gn_waves() {
+  static int w = -1;
+  if (w < 0) {
+    const char* e = getenv("FYC_GN_WAVES");
+    w = (e && e[0] >= '1' && e[0] <= '3') ? e[0] - '0' : 3;
+  }
+  return w;
+}
+
 namespace {
 // Blackwell packed fp32 pairs (FFMA2 / FADD2 / FMUL2): one issue slot for two lanes' worth of work.  The norm kernels were
 // instruction-bound (ncu: 18-20 issued instructions per element at ~50 % issue utilisation, 2.5-3 TB/s), not memory-bound.
@@ -311,7 +321,7 @@ static int32_t groupnorm_impl(const T* x, const float* gamma, const float* beta,
   const int cvn = C / V;
   const int TX = cvn < 256 ? cvn : 256;
   const int RY = 256 / TX;
-  int64_t target = gn_max_chunks(NB) - 1;                                 // CTAs per nb
+  int64_t target = ceil_div64((int64_t)fyc_sm_count() * 4 * fyc_gn_waves(), NB);   // CTAs per nb (<= gn_max_chunks(NB) - 1, the workspace bound)
   int64_t rows_per_cta = ceil_div64(R, target);
   if (rows_per_cta < 8 * RY) rows_per_cta = 8 * RY;
   rows_per_cta = ceil_div64(rows_per_cta, RY) * RY;
