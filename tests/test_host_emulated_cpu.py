@@ -271,3 +271,15 @@ def test_ip_attn_processor_host_logic_vs_reference_processor(case):
     from tests.engine_helpers import run_ip_attn_processor_case
     s = run_ip_attn_processor_case(case, torch.float32, device="cpu")
     assert s["finite"] and s["rel_l2"] < 1e-5, s
+
+
+def test_smoke_entry_logic_emulated():
+    """`__graft_entry__.smoke()` minus the device: the same three helper calls with the same thresholds, kernels emulated (its oracle leg -
+    `run_pipeline_case(..., steps=1, against="oracle")` - is not what the `-m gpu` engine tests run, so it is kept alive here)."""
+    from tests.engine_helpers import run_pipeline_case, run_unet_case
+    u16 = run_unet_case("base", torch.bfloat16, device="cpu")
+    assert u16["finite"] and u16["rel_l2"] < 3e-2, u16
+    r16 = run_pipeline_case(dtype=torch.bfloat16, steps=1, device="cpu")
+    assert r16["video_maxabs"] < 0.1, r16
+    r = run_pipeline_case(dtype=torch.float32, steps=1, device="cpu")
+    assert r["video_maxabs"] < 2e-3, r
